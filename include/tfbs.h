@@ -1,0 +1,234 @@
+/*
+ * tfbs.h -- C ABI of the B200-native find-tfbs hot path.
+ *
+ * This header is the drop-in boundary for the reference's per-region pipeline
+ * (all citations are paths under the reference repository, Helkafen/find-tfbs):
+ *
+ *   find_all_matches          src/main.rs:94-154      (haplotype build + PWM scan)
+ *     load_haplotypes         src/haplotype.rs:77-88
+ *     patch_haplotype         src/haplotype.rs:94-156
+ *     matches / apply_pwm     src/pattern.rs:119-171
+ *   count_matches_by_sample   src/main.rs:500-534
+ *   counts_as_genotypes       src/main.rs:439-458     (v = l + r, min == max filter)
+ *
+ * The reference has no FFI of its own; the seam is the Rust call sequence inside
+ * process_peak (src/main.rs:409-420).  A Rust driver would bind these entry points
+ * with bindgen and feed one tfbs_block per chunk of merged regions (the reference
+ * hands out chunks of 50 regions, src/main.rs:375-381).  See INTEGRATION.md.
+ *
+ * Plain C only: fixed-width integers, pointers and sizes.  No C++ or torch types.
+ */
+#ifndef TFBS_H
+#define TFBS_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TFBS_ABI_VERSION 1
+
+/* Nucleotide codes: enum Nucleotide { A, C, G, T, N } (src/types.rs:5-8). */
+enum { TFBS_NUC_A = 0, TFBS_NUC_C = 1, TFBS_NUC_G = 2, TFBS_NUC_T = 3, TFBS_NUC_N = 4 };
+
+/* enum Pattern { PWM{..}, OtherPattern{..} } (src/types.rs:86-90). */
+enum { TFBS_PATTERN_PWM = 0, TFBS_PATTERN_OTHER = 1 };
+/* enum PWMDirection { P, N } (src/types.rs:72-75). */
+enum { TFBS_DIR_P = 0, TFBS_DIR_N = 1 };
+
+/* Status codes (negative = the condition on which the reference panics). */
+enum {
+    TFBS_OK = 0,
+    TFBS_ERR_INVALID_ARGUMENT = -1,
+    TFBS_ERR_CUDA = -2,              /* CUDA runtime failure or no usable device */
+    TFBS_ERR_UNKNOWN_NUCLEOTIDE = -3,/* util.rs:15 "Unknown nucleotide" */
+    TFBS_ERR_REF_MISMATCH = -4,      /* haplotype.rs:126-128 */
+    TFBS_ERR_MISSING_CASE = -5,      /* haplotype.rs:141-143 "Missing case in haplotype patcher" */
+    TFBS_ERR_SCORE_RANGE = -6,       /* weights too large for exact 32-bit scoring */
+    TFBS_ERR_STATE = -7,             /* call order violated (e.g. collect before submit) */
+    TFBS_ERR_INTERNAL = -8           /* hash collision retry exhausted etc. */
+};
+
+/*
+ * One pattern, laid out as the reference holds it: Pattern::PWM { weights, name, pattern_id,
+ * min_score, direction } with Weight { acgtn: [a, c, g, t, 0] } (src/types.rs:86-113).
+ * Forward (P) and reverse-complement (N) patterns are separate entries that share
+ * pattern_id (src/pattern.rs:73-77); the caller passes them exactly as parse_pwm_files
+ * would have produced them.  A window scores sum_c weights[c][nuc(i+c)] with N -> 0 and
+ * is a hit iff score > min_score (src/pattern.rs:125-129,151).
+ */
+typedef struct tfbs_pattern {
+    const int32_t* weights; /* len x 4, row-major [column][A,C,G,T]; may be NULL if kind != PWM */
+    uint32_t len;           /* pattern_length(); 0 for OtherPattern (src/types.rs:92-101) */
+    int32_t min_score;
+    uint16_t pattern_id;
+    uint8_t direction;      /* TFBS_DIR_* (informational) */
+    uint8_t kind;           /* TFBS_PATTERN_*; OtherPattern never matches (src/pattern.rs:166-168) */
+} tfbs_pattern;
+
+/*
+ * One original BED region that select_inner_peaks (src/main.rs:62-72) attached to a merged
+ * region.  `multiplicity` is how many times the identical (bed, start, end) occurs in that
+ * BED file: the reference visits such a region once per occurrence and so multiplies its
+ * counts (src/main.rs:503-505).  Use 1 unless the BED file holds duplicates.
+ */
+typedef struct tfbs_inner_region {
+    int64_t start;          /* inclusive, 0-based (src/bed.rs:15) */
+    int64_t end;            /* inclusive */
+    uint32_t bed_index;     /* which BED file (caller-defined numbering) */
+    uint32_t multiplicity;
+} tfbs_inner_region;
+
+/*
+ * One biallelic record returned by the BCF fetch of a region's extended window
+ * (src/haplotype.rs:16-28), i.e. a Diff { pos, reference, alternative } (src/types.rs:39-44)
+ * plus the row of the carrier bit matrix that says which haplotypes carry ALT.
+ */
+typedef struct tfbs_variant {
+    int64_t pos;            /* 0-based record.pos() */
+    uint32_t ref_off;       /* REF allele: allele_bases[ref_off .. ref_off + ref_len) */
+    uint32_t ref_len;
+    uint32_t alt_off;       /* ALT allele */
+    uint32_t alt_len;
+    uint32_t carrier_row;   /* row of tfbs_block.carriers */
+    uint32_t reserved;
+} tfbs_variant;
+
+/*
+ * A block of merged regions with everything process_peak (src/main.rs:395-436) reads for
+ * them.  Haplotype index h = 2 * sample_id + side, side 0 = Left, 1 = Right
+ * (src/types.rs:29-30,66-70); sample_id indexes the *selected* samples (src/main.rs:293-313).
+ * Bit h of carrier row v is set iff the reference's load_diffs would push that Diff for h:
+ * left iff the first GT value is Unphased(1), right iff the second is Phased(1)
+ * (src/haplotype.rs:34-49).
+ */
+typedef struct tfbs_block {
+    uint32_t n_regions;
+    uint32_t n_samples;
+    const int64_t* region_start;   /* [n_regions] extended window start = merged.start - Lmax + 1 (main.rs:407) */
+    const int64_t* region_end;     /* [n_regions] extended window end   = merged.end + Lmax - 1, inclusive */
+    const uint64_t* ref_off;       /* [n_regions + 1] window r = ref_bases[ref_off[r] .. ref_off[r+1]) */
+    const uint8_t* ref_bases;      /* ASCII ACGTNacgtn as read from the FASTA (util.rs:4-16); base i of a
+                                      window has pos = region_start + i (util.rs:22-31).  A window may be
+                                      shorter than region_end - region_start + 1 (haplotype.rs:183-185). */
+    const uint32_t* inner_off;     /* [n_regions + 1] */
+    const tfbs_inner_region* inner;/* inner regions per merged region */
+    const uint32_t* var_off;       /* [n_regions + 1] */
+    const tfbs_variant* variants;  /* per region, in BCF record order */
+    const uint8_t* allele_bases;   /* ASCII */
+    uint64_t allele_bytes;
+    const uint32_t* carriers;      /* [n_carrier_rows][carrier_pitch] little-endian bit h -> word h/32, bit h%32 */
+    uint32_t n_carrier_rows;
+    uint32_t carrier_pitch;        /* 32-bit words per row, >= ceil(2 * n_samples / 32) */
+} tfbs_block;
+
+/*
+ * Result rows: one per key (merged region, inner region, pattern_id) of
+ * count_matches_by_sample (src/main.rs:500-534) that survives the filter.  left/right are the
+ * reference's (Vec<u32>, Vec<u32>) value.  Rows come in a deterministic order: by region,
+ * then pattern_id ascending, then inner index.  Pointers stay valid until the next
+ * tfbs_submit_block / tfbs_run_resident / tfbs_destroy on the same context.
+ */
+typedef struct tfbs_rows {
+    uint64_t n_rows;
+    uint32_t n_samples;
+    uint32_t reserved;
+    const uint32_t* region;        /* [n_rows] index of the merged region inside the block */
+    const uint32_t* inner;         /* [n_rows] index into tfbs_block.inner */
+    const uint16_t* pattern_id;    /* [n_rows] */
+    const uint32_t* vmin;          /* [n_rows] min over samples of left + right (main.rs:450) */
+    const uint32_t* vmax;          /* [n_rows] max over samples of left + right (main.rs:451) */
+    const uint32_t* left;          /* [n_rows * n_samples] */
+    const uint32_t* right;         /* [n_rows * n_samples] */
+} tfbs_rows;
+
+/* Individual hits (struct Match, src/types.rs:32-37), for debugging and parity tests. */
+typedef struct tfbs_matches {
+    uint64_t n_matches;
+    const uint32_t* region;        /* [n_matches] */
+    const uint32_t* pattern_index; /* [n_matches] index into the array given to tfbs_set_patterns */
+    const uint32_t* group;         /* [n_matches] distinct-haplotype group inside the region, 0 = reference */
+    const int64_t* start;          /* [n_matches] range.start = pos of the window's first base (pattern.rs:156) */
+    /* carrier lists: group of haplotype h in region r is hap_group[r * 2 * n_samples + h] */
+    const uint32_t* hap_group;
+    uint32_t n_samples;
+    uint32_t truncated;            /* 1 if the match buffer overflowed (n_matches is then a lower bound) */
+} tfbs_matches;
+
+/* Row filter: which keys tfbs_collect returns. */
+enum {
+    TFBS_ROWS_VARYING = 0, /* only keys with min != max, i.e. those counts_as_genotypes keeps (main.rs:456-458) */
+    TFBS_ROWS_ALL_KEYS = 1 /* every key count_matches_by_sample creates (>= 1 hit, main.rs:517-528) */
+};
+
+/* Per-stage device timings and work counters of the most recent run. */
+typedef struct tfbs_stats {
+    uint64_t n_regions;
+    uint64_t n_groups;          /* distinct haplotype sequences scanned, incl. one reference per region */
+    uint64_t executed_cells;    /* sum over scanned (group, pattern) of max(0, len - L + 1) * L */
+    uint64_t nominal_cells;     /* the same sum over every haplotype of every sample (2 * n_samples per region) */
+    uint64_t n_hits;            /* above-threshold windows over all scanned groups */
+    uint64_t n_keys;            /* candidate (region, inner, pattern_id) keys */
+    uint64_t n_rows;
+    uint64_t h2d_bytes;
+    uint64_t d2h_bytes;
+    uint32_t scan_launches;     /* launches of the PWM scan kernel */
+    uint32_t total_launches;    /* all kernel launches of the run */
+    float ms_group;             /* K0: signature hash + grouping */
+    float ms_build;             /* K1: haplotype build */
+    float ms_scan;              /* K2: PWM scan (sum over launches) */
+    float ms_count;             /* K3: fan-out, filter, row compaction */
+    float ms_total;             /* first launch to last, device time */
+    uint32_t sm_count;
+    uint32_t scan_ctas;
+} tfbs_stats;
+
+typedef struct tfbs_ctx tfbs_ctx;
+
+/* Library / ABI version; never touches CUDA. */
+int tfbs_abi_version(void);
+
+/* Create a context on CUDA device `device`.  Fails (TFBS_ERR_CUDA) when no device is usable:
+ * there is no CPU fallback. */
+int tfbs_create(int device, tfbs_ctx** out);
+void tfbs_destroy(tfbs_ctx* ctx);
+
+/* Message of the last failing call on this context ("" if none); for ctx == NULL the message
+ * of the last failing tfbs_create of the calling thread.  Mirrors the reference's panic text. */
+const char* tfbs_last_error(const tfbs_ctx* ctx);
+
+/* Options: "rows_mode" (TFBS_ROWS_*), "record_matches" (0/1), "max_matches" (capacity of the
+ * match buffer), "verify_groups" (0/1, exact check of hash-grouped haplotypes, default 1),
+ * "scan_format" (0 auto, 1 force 32-bit tables). */
+int tfbs_set_option(tfbs_ctx* ctx, const char* key, int64_t value);
+
+/* Replace the pattern list (the reference's pwm_list, src/main.rs:237). */
+int tfbs_set_patterns(tfbs_ctx* ctx, const tfbs_pattern* patterns, uint32_t n_patterns);
+
+/* Host-buffer path: copy the block to the device and launch the whole pipeline
+ * asynchronously.  The caller's buffers may be reused after this returns. */
+int tfbs_submit_block(tfbs_ctx* ctx, const tfbs_block* block);
+
+/* Wait for the submitted block and expose its rows (device -> host copy included). */
+int tfbs_collect(tfbs_ctx* ctx, tfbs_rows* out);
+
+/* Matches of the last run when "record_matches" was on (call after tfbs_collect). */
+int tfbs_get_matches(tfbs_ctx* ctx, tfbs_matches* out);
+
+/* Device-resident path for benchmarking: upload once, run the device pipeline on the
+ * resident block any number of times.  tfbs_run_resident returns after the device work of
+ * this run has been enqueued and its row count is known; tfbs_collect then fetches rows. */
+int tfbs_upload_block(tfbs_ctx* ctx, const tfbs_block* block);
+int tfbs_run_resident(tfbs_ctx* ctx);
+
+int tfbs_get_stats(const tfbs_ctx* ctx, tfbs_stats* out);
+
+/* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
+void* tfbs_stream(const tfbs_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TFBS_H */
