@@ -1,0 +1,289 @@
+#!/usr/bin/env python
+"""bench.py -- find-tfbs hot path on B200: PWM cells/s (haplotype bp x PWM columns).
+
+A step = one pass of the whole hot path (haplotype grouping + build, PWM scan on both strands, per-haplotype counts,
+row filter) over one synthetic cohort block: BASELINE.json configs[1] = 100 samples x 10k DHS regions (200-2000 bp) x
+50 random PWMs, per GPU (weak scaling: every rank owns its own 10k-region shard, no collective on the data path).
+
+  value  nominal cells/s (every haplotype of every sample x every pattern, both strands), inputs resident in HBM
+  e2e    same metric through tfbs_submit_block / tfbs_collect with host buffers (H2D + D2H inside the timed region)
+  roofline  the scan kernel against its lookup-add roof, timed with CUDA events on the library's stream
+  cpu_baseline  the C++ oracle (a restatement of the reference: the Rust binary cannot be built here) on the host cores
+
+`--impl reference` times that CPU restatement alone.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "pwm_cells_per_s"
+UNIT = "cells/s"
+SM_COUNT = 148
+CELLS_PER_LDS64 = 6          # 3 packed patterns x 2 columns per 64-bit shared-memory read
+LDS64_PER_CLK_PER_SM = 16    # 128 B/clk/SM of shared-memory bandwidth
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 10k regions of configs[1] (debugging only)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target duration of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--option", action="append", default=[], help="library option key=value")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d.get("hbm_gbs", 6650.0), "sm_max_mhz": d.get("sm_max_mhz", 1965.0), "source": "MEASURED_PEAKS.json"}
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        # median over the samples taken under load (upper half), the idle tail of a short run would bias it down
+        med = sm[len(sm) // 2] if sm else None
+        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_rate(ps, blk, seconds, threads):
+    """Oracle (C++ restatement of the reference, multi-threaded like main.rs:333-382) on a bounded sample of the block."""
+    import parity_helpers as hp
+    # the reference hands out 50-region chunks (main.rs:378); a bounded sample is cut finer so that every thread has work
+    n0 = min(blk.n_regions, max(2 * threads, 16))
+    t = time.perf_counter()
+    o = hp.run_oracle(ps, blk.slice(0, n0), 0, False, threads, 1)
+    dt = time.perf_counter() - t
+    rate = o["nominal_cells"] / max(dt, 1e-9)
+    n = int(min(blk.n_regions, max(n0, n0 * seconds / max(dt, 1e-6))))
+    if n > n0:
+        t = time.perf_counter()
+        o = hp.run_oracle(ps, blk.slice(0, n), 0, False, threads, max(1, min(50, n // (4 * threads))))
+        dt = time.perf_counter() - t
+        rate = o["nominal_cells"] / max(dt, 1e-9)
+    else:
+        n = n0
+    return {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "seconds": dt, "executed_cells_per_s": o["executed_cells"] / max(dt, 1e-9),
+            "sample": "first %d of %d regions of the rank-0 block, all %d samples, all patterns, %d threads pulling region chunks from a shared queue" %
+                      (n, blk.n_regions, blk.n_samples, threads)}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    from find_tfbs_b200 import binding, synth
+
+    config = {"workload": "configs[1]: synthetic 100 samples x %d DHS regions (200-2000 bp) x 50 random PWMs (L 8-30, both strands, p=1e-4) per GPU"
+                          % int(10000 * args.scale),
+              "regions_per_gpu": int(10000 * args.scale), "samples": 100, "pwms": 50, "patterns": 100,
+              "sharding": "region blocks per GPU, no collective", "l2": "inputs larger than L2 (packed haplotypes ~0.9 GB per step)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        pats, blk = synth.config2(scale=args.scale, seed=2)
+        ps = binding.PatternSet(pats)
+        threads = os.cpu_count() or 1
+        per_step = max(2.0, min(30.0, 120.0 / max(1, args.steps + args.warmup)))
+        vals = []
+        info = None
+        for i in range(args.warmup + args.steps):
+            info = cpu_reference_rate(ps, blk, per_step, threads)
+            if i >= args.warmup:
+                vals.append((info["value"], info["seconds"]))
+        v = sum(x[0] for x in vals) / max(1, len(vals))
+        ms = 1000.0 * sum(x[1] for x in vals) / max(1, len(vals))
+        info["value"] = v
+        out = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+               "impl": "reference", "cpu_baseline": info,
+               "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+               "note": "CPU restatement (oracle/) of the reference algorithm; the Rust reference cannot be compiled in this image (no cargo/rustc)"}
+        print(json.dumps(out))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    pats, blk = synth.config2(scale=args.scale, seed=2 + rank)
+    ps = binding.PatternSet(pats)
+    ctx = binding.Context(local_rank)
+    for kv in args.option:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
+    ctx.set_patterns(ps)
+    stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps bracketed by barrier + synchronize; device time from CUDA events on the library's stream; max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def total(x):
+        if world == 1:
+            return x
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- resident path: inputs in HBM ----
+    ctx.upload_block(blk)
+
+    def step_resident():
+        ctx.run_resident()
+        ctx.collect(copy=False)
+
+    for _ in range(args.warmup):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    scan_ms, launches = [], 0
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_resident()
+        st = ctx.stats()
+        scan_ms.append(st["ms_scan"])
+        launches += st["total_launches"]
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    st = ctx.stats()
+    nominal = total(st["nominal_cells"])
+    executed = total(st["executed_cells"])
+    ms_step = ms_total / args.steps
+    value = nominal / (ms_step * 1e-3)
+
+    # ---- end to end: host buffers in, rows out ----
+    def step_e2e():
+        ctx.submit_block(blk)
+        ctx.collect(copy=False)
+
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps) / args.steps
+    st2 = ctx.stats()
+    e2e = {"value": nominal / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(total(st2["h2d_bytes"])),
+           "d2h_bytes_per_step": int(total(st2["d2h_bytes"])), "ms_per_step": ms_e2e}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    pk = peaks()
+    scan_s = (sum(scan_ms) / len(scan_ms)) * 1e-3
+    achieved = st["executed_cells"] / scan_s  # this rank's scan kernel
+    f_max = pk["sm_max_mhz"] * 1e6
+    roof = SM_COUNT * LDS64_PER_CLK_PER_SM * CELLS_PER_LDS64 * f_max
+    f_obs = (clocks["sm_mhz"] or pk["sm_max_mhz"]) * 1e6
+    # algorithmic HBM bytes of the scan: 3 bits per base read once per pattern chunk + count rows written
+    roofline = {"bound": "lookup-add (shared-memory table bandwidth; not hbm, not tensor: see DESIGN.md)", "kernel": "k_scan",
+                "achieved": achieved / 1e12, "peak": roof / 1e12, "unit": "Tcell/s", "frac": achieved / roof,
+                "peak_basis": "148 SMs x 128 B/clk shared memory = 16 LDS.64/clk/SM x 6 cells per LDS.64 (3 packed patterns x 2 columns) at sm_max_mhz from %s" % pk["source"],
+                "frac_at_observed_clock": achieved / (roof * f_obs / f_max), "observed_sm_mhz": clocks["sm_mhz"],
+                "frac_of_one_lookup_per_cell_roof": achieved / (SM_COUNT * 32 * f_max), "frac_of_int32_issue_roof": achieved / (SM_COUNT * 128 * f_max),
+                "ms_per_launch": scan_s * 1e3, "cells_per_launch": st["executed_cells"], "traffic": None,
+                "hbm": {"achieved_gbs": None, "peak_gbs": pk["hbm_gbs"]}}
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic", "config": config,
+           "executed_cells_per_s": executed / (ms_step * 1e-3), "nominal_cells_per_step": nominal, "executed_cells_per_step": executed,
+           "stages_ms": {k: st[k] for k in ("ms_group", "ms_build", "ms_scan", "ms_count", "ms_total")},
+           "groups_per_step": st["n_groups"], "hits_per_step": st["n_hits"], "rows_per_step": st["n_rows"],
+           "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_reference_rate(ps, blk, args.cpu_seconds, os.cpu_count() or 1)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,283 @@
+"""ctypes binding of the product library (find_tfbs_b200/libtfbs_b200.so, C ABI in include/tfbs.h).
+
+This is what a host program binds; the Rust driver of the reference would bind the same symbols with
+bindgen.  There is no fallback: if the CUDA library is missing or no B200 is usable,
+construction fails loudly.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtfbs_b200.so")
+
+TFBS_OK = 0
+ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNKNOWN_NUCLEOTIDE, ERR_REF_MISMATCH = -1, -2, -3, -4
+ERR_MISSING_CASE, ERR_SCORE_RANGE, ERR_STATE, ERR_INTERNAL = -5, -6, -7, -8
+ROWS_VARYING, ROWS_ALL_KEYS = 0, 1
+PATTERN_PWM, PATTERN_OTHER = 0, 1
+DIR_P, DIR_N = 0, 1
+
+EXPORTS = ["tfbs_abi_version", "tfbs_create", "tfbs_destroy", "tfbs_last_error", "tfbs_set_option", "tfbs_set_patterns",
+           "tfbs_submit_block", "tfbs_collect", "tfbs_get_matches", "tfbs_upload_block", "tfbs_run_resident", "tfbs_get_stats",
+           "tfbs_stream"]
+
+
+class TfbsPattern(C.Structure):
+    _fields_ = [("weights", C.POINTER(C.c_int32)), ("len", C.c_uint32), ("min_score", C.c_int32),
+                ("pattern_id", C.c_uint16), ("direction", C.c_uint8), ("kind", C.c_uint8)]
+
+
+class TfbsInnerRegion(C.Structure):
+    _fields_ = [("start", C.c_int64), ("end", C.c_int64), ("bed_index", C.c_uint32), ("multiplicity", C.c_uint32)]
+
+
+class TfbsVariant(C.Structure):
+    _fields_ = [("pos", C.c_int64), ("ref_off", C.c_uint32), ("ref_len", C.c_uint32), ("alt_off", C.c_uint32),
+                ("alt_len", C.c_uint32), ("carrier_row", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class TfbsBlock(C.Structure):
+    _fields_ = [("n_regions", C.c_uint32), ("n_samples", C.c_uint32),
+                ("region_start", C.POINTER(C.c_int64)), ("region_end", C.POINTER(C.c_int64)),
+                ("ref_off", C.POINTER(C.c_uint64)), ("ref_bases", C.POINTER(C.c_uint8)),
+                ("inner_off", C.POINTER(C.c_uint32)), ("inner", C.POINTER(TfbsInnerRegion)),
+                ("var_off", C.POINTER(C.c_uint32)), ("variants", C.POINTER(TfbsVariant)),
+                ("allele_bases", C.POINTER(C.c_uint8)), ("allele_bytes", C.c_uint64),
+                ("carriers", C.POINTER(C.c_uint32)), ("n_carrier_rows", C.c_uint32), ("carrier_pitch", C.c_uint32)]
+
+
+class TfbsRows(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64), ("n_samples", C.c_uint32), ("reserved", C.c_uint32),
+                ("region", C.POINTER(C.c_uint32)), ("inner", C.POINTER(C.c_uint32)), ("pattern_id", C.POINTER(C.c_uint16)),
+                ("vmin", C.POINTER(C.c_uint32)), ("vmax", C.POINTER(C.c_uint32)),
+                ("left", C.POINTER(C.c_uint32)), ("right", C.POINTER(C.c_uint32))]
+
+
+class TfbsMatches(C.Structure):
+    _fields_ = [("n_matches", C.c_uint64), ("region", C.POINTER(C.c_uint32)), ("pattern_index", C.POINTER(C.c_uint32)),
+                ("group", C.POINTER(C.c_uint32)), ("start", C.POINTER(C.c_int64)), ("hap_group", C.POINTER(C.c_uint32)),
+                ("n_samples", C.c_uint32), ("truncated", C.c_uint32)]
+
+
+class TfbsStats(C.Structure):
+    _fields_ = [("n_regions", C.c_uint64), ("n_groups", C.c_uint64), ("executed_cells", C.c_uint64), ("nominal_cells", C.c_uint64),
+                ("n_hits", C.c_uint64), ("n_keys", C.c_uint64), ("n_rows", C.c_uint64), ("h2d_bytes", C.c_uint64),
+                ("d2h_bytes", C.c_uint64), ("scan_launches", C.c_uint32), ("total_launches", C.c_uint32),
+                ("ms_group", C.c_float), ("ms_build", C.c_float), ("ms_scan", C.c_float), ("ms_count", C.c_float),
+                ("ms_total", C.c_float), ("sm_count", C.c_uint32), ("scan_ctas", C.c_uint32)]
+
+
+INNER_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("bed_index", "<u4"), ("multiplicity", "<u4")])
+VARIANT_DTYPE = np.dtype([("pos", "<i8"), ("ref_off", "<u4"), ("ref_len", "<u4"), ("alt_off", "<u4"), ("alt_len", "<u4"),
+                          ("carrier_row", "<u4"), ("reserved", "<u4")])
+
+
+def build(force=False):
+    """Compile libtfbs_b200.so for sm_100a with nvcc (in-tree, so that the .so travels with the repo)."""
+    csrc = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(csrc, f) for f in ("tfbs.cu", "kernels.cuh", "tables.cpp", "tables.hpp", "Makefile")]
+    srcs.append(os.path.join(_HERE, "..", "include", "tfbs.h"))
+    if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
+        subprocess.check_call(["make", "-C", csrc], stdout=subprocess.DEVNULL)
+    return LIB_PATH
+
+
+_LIB = None
+
+
+def lib():
+    """Load the C-ABI library.  Missing library = hard error (no CPU or PyTorch fallback exists)."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` (nvcc, sm_100a). "
+                               "There is no fallback implementation." % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.tfbs_last_error.restype = C.c_char_p
+        L.tfbs_last_error.argtypes = [C.c_void_p]
+        L.tfbs_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.tfbs_destroy.argtypes = [C.c_void_p]
+        L.tfbs_destroy.restype = None
+        L.tfbs_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int64]
+        L.tfbs_set_patterns.argtypes = [C.c_void_p, C.POINTER(TfbsPattern), C.c_uint32]
+        L.tfbs_submit_block.argtypes = [C.c_void_p, C.POINTER(TfbsBlock)]
+        L.tfbs_upload_block.argtypes = [C.c_void_p, C.POINTER(TfbsBlock)]
+        L.tfbs_run_resident.argtypes = [C.c_void_p]
+        L.tfbs_collect.argtypes = [C.c_void_p, C.POINTER(TfbsRows)]
+        L.tfbs_get_matches.argtypes = [C.c_void_p, C.POINTER(TfbsMatches)]
+        L.tfbs_get_stats.argtypes = [C.c_void_p, C.POINTER(TfbsStats)]
+        L.tfbs_stream.argtypes = [C.c_void_p]
+        L.tfbs_stream.restype = C.c_void_p
+        _LIB = L
+    return _LIB
+
+
+class TfbsError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("tfbs error %d: %s" % (code, msg))
+        self.code = code
+        self.message = msg
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class PatternSet:
+    """pwm_list of the reference (main.rs:237) as a C array; keeps the weight buffers alive."""
+
+    def __init__(self, patterns):
+        # patterns: list of dicts {weights: (L,4) int32 | None, min_score, pattern_id, direction, kind}
+        self.n = len(patterns)
+        self.items = patterns
+        self._keep = []
+        self.c = (TfbsPattern * max(1, self.n))()
+        for i, p in enumerate(patterns):
+            kind = p.get("kind", PATTERN_PWM)
+            if kind == PATTERN_PWM:
+                w = np.ascontiguousarray(np.asarray(p["weights"], dtype=np.int32).reshape(-1, 4))
+                self._keep.append(w)
+                self.c[i].weights = _ptr(w, C.c_int32)
+                self.c[i].len = w.shape[0]
+            else:
+                self.c[i].weights = None
+                self.c[i].len = 0
+            self.c[i].min_score = int(p.get("min_score", 0))
+            self.c[i].pattern_id = int(p["pattern_id"])
+            self.c[i].direction = int(p.get("direction", DIR_P))
+            self.c[i].kind = kind
+
+
+class Block:
+    """A tfbs_block over numpy arrays (kept alive by this object)."""
+
+    def __init__(self, n_samples, region_start, region_end, ref_off, ref_bases, inner_off, inner, var_off, variants, allele_bases,
+                 carriers):
+        self.n_samples = int(n_samples)
+        self.region_start = np.ascontiguousarray(region_start, dtype=np.int64)
+        self.region_end = np.ascontiguousarray(region_end, dtype=np.int64)
+        self.ref_off = np.ascontiguousarray(ref_off, dtype=np.uint64)
+        self.ref_bases = np.ascontiguousarray(ref_bases, dtype=np.uint8)
+        self.inner_off = np.ascontiguousarray(inner_off, dtype=np.uint32)
+        self.inner = np.ascontiguousarray(inner, dtype=INNER_DTYPE)
+        self.var_off = np.ascontiguousarray(var_off, dtype=np.uint32)
+        self.variants = np.ascontiguousarray(variants, dtype=VARIANT_DTYPE)
+        self.allele_bases = np.ascontiguousarray(allele_bases, dtype=np.uint8)
+        carriers = np.ascontiguousarray(carriers, dtype=np.uint32)
+        if carriers.ndim != 2:
+            carriers = carriers.reshape(-1, max(1, (2 * self.n_samples + 31) // 32))
+        self.carriers = carriers
+        self.n_regions = len(self.region_start)
+        b = TfbsBlock()
+        b.n_regions = self.n_regions
+        b.n_samples = self.n_samples
+        b.region_start = _ptr(self.region_start, C.c_int64)
+        b.region_end = _ptr(self.region_end, C.c_int64)
+        b.ref_off = _ptr(self.ref_off, C.c_uint64)
+        b.ref_bases = _ptr(self.ref_bases, C.c_uint8)
+        b.inner_off = _ptr(self.inner_off, C.c_uint32)
+        b.inner = C.cast(self.inner.ctypes.data, C.POINTER(TfbsInnerRegion))
+        b.var_off = _ptr(self.var_off, C.c_uint32)
+        b.variants = C.cast(self.variants.ctypes.data, C.POINTER(TfbsVariant))
+        b.allele_bases = _ptr(self.allele_bases, C.c_uint8)
+        b.allele_bytes = self.allele_bases.size
+        b.carriers = _ptr(self.carriers, C.c_uint32)
+        b.n_carrier_rows = self.carriers.shape[0]
+        b.carrier_pitch = self.carriers.shape[1]
+        self.c = b
+
+    def input_bytes(self):
+        return sum(a.nbytes for a in (self.region_start, self.region_end, self.ref_off, self.ref_bases, self.inner_off, self.inner,
+                                      self.var_off, self.variants, self.allele_bases, self.carriers))
+
+    def slice(self, r0, r1):
+        """Sub-block of regions [r0, r1) (variants keep their global carrier rows)."""
+        ro, io, vo = self.ref_off, self.inner_off, self.var_off
+        return Block(self.n_samples, self.region_start[r0:r1], self.region_end[r0:r1], ro[r0:r1 + 1] - ro[r0],
+                     self.ref_bases[int(ro[r0]):int(ro[r1])], io[r0:r1 + 1] - io[r0], self.inner[int(io[r0]):int(io[r1])],
+                     vo[r0:r1 + 1] - vo[r0], self.variants[int(vo[r0]):int(vo[r1])], self.allele_bases, self.carriers)
+
+
+class Context:
+    """tfbs_ctx: one CUDA device, one stream."""
+
+    def __init__(self, device=0):
+        self._lib = lib()
+        self._h = C.c_void_p()
+        rc = self._lib.tfbs_create(device, C.byref(self._h))
+        if rc != TFBS_OK:
+            raise TfbsError(rc, self._lib.tfbs_last_error(None).decode())
+        self._patterns = None
+
+    def close(self):
+        if self._h:
+            self._lib.tfbs_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != TFBS_OK:
+            raise TfbsError(rc, self._lib.tfbs_last_error(self._h).decode())
+
+    def set_option(self, key, value):
+        self._check(self._lib.tfbs_set_option(self._h, key.encode(), int(value)))
+
+    def set_patterns(self, pattern_set):
+        self._patterns = pattern_set
+        self._check(self._lib.tfbs_set_patterns(self._h, pattern_set.c, pattern_set.n))
+
+    def submit_block(self, block):
+        self._check(self._lib.tfbs_submit_block(self._h, C.byref(block.c)))
+
+    def upload_block(self, block):
+        self._block = block
+        self._check(self._lib.tfbs_upload_block(self._h, C.byref(block.c)))
+
+    def run_resident(self):
+        self._check(self._lib.tfbs_run_resident(self._h))
+
+    def collect(self, copy=True):
+        rows = TfbsRows()
+        self._check(self._lib.tfbs_collect(self._h, C.byref(rows)))
+        n, S = rows.n_rows, rows.n_samples
+
+        def arr(p, cnt, dt):
+            if cnt == 0:
+                return np.zeros(0, dtype=dt)
+            a = np.ctypeslib.as_array(p, shape=(cnt,))
+            return a.astype(dt, copy=True) if copy else a
+
+        return {"region": arr(rows.region, n, np.uint32), "inner": arr(rows.inner, n, np.uint32),
+                "pattern_id": arr(rows.pattern_id, n, np.uint16), "vmin": arr(rows.vmin, n, np.uint32),
+                "vmax": arr(rows.vmax, n, np.uint32), "left": arr(rows.left, n * S, np.uint32).reshape(n, S),
+                "right": arr(rows.right, n * S, np.uint32).reshape(n, S)}
+
+    def matches(self, n_regions):
+        m = TfbsMatches()
+        self._check(self._lib.tfbs_get_matches(self._h, C.byref(m)))
+        n = m.n_matches
+
+        def arr(p, cnt, dt):
+            if cnt == 0:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(p, shape=(cnt,)).astype(dt, copy=True)
+
+        return {"region": arr(m.region, n, np.uint32), "pattern_index": arr(m.pattern_index, n, np.uint32),
+                "group": arr(m.group, n, np.uint32), "start": arr(m.start, n, np.int64),
+                "hap_group": arr(m.hap_group, n_regions * 2 * m.n_samples, np.uint32), "truncated": bool(m.truncated)}
+
+    def stats(self):
+        s = TfbsStats()
+        self._check(self._lib.tfbs_get_stats(self._h, C.byref(s)))
+        return {f: getattr(s, f) for f, _ in TfbsStats._fields_}
+
+    def stream(self):
+        return self._lib.tfbs_stream(self._h)

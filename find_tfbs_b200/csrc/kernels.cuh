@@ -1,0 +1,924 @@
+// kernels.cuh -- sm_100a kernels of the find-tfbs hot path.
+//
+//   K0  grouping      sig/group kernels     replaces load_diffs + group_by_diffs      (haplotype.rs:13-75)
+//   K1  build         k_walk + k_emit       replaces patch_haplotype                  (haplotype.rs:94-156)
+//       dedup         k_seq_*               the sequence-keyed map of load_haplotypes (haplotype.rs:81-85)
+//   K2  scan          k_scan                replaces matches / apply_pwm              (pattern.rs:119-171)
+//                                           + the hit -> inner-region test            (main.rs:500-505)
+//   K3  count/rows    k_rows_*              count_matches_by_sample fan-out           (main.rs:506-531)
+//                                           + min/max filter of counts_as_genotypes   (main.rs:439-458)
+//
+// All arithmetic is integer; results are bit-exact by construction (scores are i32 sums).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tfbs.h"
+#include "tables.hpp"
+
+namespace tfbs {
+
+typedef unsigned long long u64;
+typedef long long i64;
+typedef unsigned int u32;
+typedef unsigned short u16;
+typedef unsigned char u8;
+
+// ------------------------------------------------------------------------------------------------
+// Device-side views
+// ------------------------------------------------------------------------------------------------
+
+// One output segment of a patched haplotype: bases [out_start, next.out_start) come either from the
+// reference window (kind 0: window index src, ref position region_start + relpos + k) or from an ALT
+// allele (kind 1: allele_codes[src + k], every base at region_start + relpos, haplotype.rs:130-132).
+struct Seg {
+    u32 out_start;
+    u32 src;
+    int relpos;
+    u32 kind;
+};
+
+struct DevBlock {
+    u32 R, S, H;
+    const i64* region_start;
+    const i64* region_end;
+    const u64* ref_off;
+    const u8* ref_codes;        // 0..4 per base of the concatenated windows
+    const u32* inner_off;
+    const tfbs_inner_region* inner;
+    const u32* var_off;
+    const tfbs_variant* variants;
+    const u8* allele_codes;
+    const u32* carriers;
+    u32 pitch;
+    // derived per variant
+    const u32* var_class;       // index (inside the region) of the first record with the same Diff
+    const u8* var_inwin;        // region_start <= pos <= region_end (haplotype.rs:95)
+};
+
+// Error / status word: the smallest key wins so that the reported failure is deterministic.
+// key = (sequence index << 32) | (relpos + 2^27) << 4 | code
+enum { DEV_OK = 0, DEV_REF_MISMATCH = 1, DEV_MISSING_CASE = 2, DEV_SIG_COLLISION = 3, DEV_SEQ_COLLISION = 4, DEV_MATCH_OVERFLOW = 5 };
+
+struct DevStatus {
+    u64 err_key;          // ~0 = none
+    u64 bad_ref_base;     // first offending index in ref_bases (~0 = none)
+    u64 bad_allele_base;  // same for allele_bases
+    u64 n_hits;
+    u64 executed_cells;
+    u64 nominal_cells;
+    u64 n_scanned;        // sequences scanned
+    u64 n_matches;        // cursor of the match buffer
+    u32 n_dropped;        // groups overwritten in the sequence-keyed map
+    u32 n_truncated;      // haplotypes truncated by an overlapping variant (haplotype.rs:144-149)
+    u32 sig_collision;
+    u32 seq_collision;
+    u32 work_counter;     // dynamic scheduler of k_scan
+    u32 pad;
+};
+
+__device__ __forceinline__ u64 mix64(u64 x) {
+    x ^= x >> 30;
+    x *= 0xbf58476d1ce4e5b9ULL;
+    x ^= x >> 27;
+    x *= 0x94d049bb133111ebULL;
+    x ^= x >> 31;
+    return x;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Input encoding: ASCII -> Nucleotide code (util.rs:4-16), unknown letters are reported
+// ------------------------------------------------------------------------------------------------
+__global__ void k_encode(const u8* __restrict__ ascii, u8* __restrict__ codes, u64 n, u64* bad_first) {
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) {
+        u8 l = ascii[i], c;
+        switch (l) {
+            case 65: case 97: c = 0; break;
+            case 67: case 99: c = 1; break;
+            case 71: case 103: c = 2; break;
+            case 84: case 116: c = 3; break;
+            case 78: case 110: c = 4; break;
+            default: c = 4; atomicMin(bad_first, i); break;
+        }
+        codes[i] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: grouping of haplotypes by their Vec<Diff> (haplotype.rs:65-75)
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ bool same_diff(const DevBlock& b, const tfbs_variant& x, const tfbs_variant& y) {
+    if (x.pos != y.pos || x.ref_len != y.ref_len || x.alt_len != y.alt_len) return false;
+    for (u32 i = 0; i < x.ref_len; ++i)
+        if (b.allele_codes[x.ref_off + i] != b.allele_codes[y.ref_off + i]) return false;
+    for (u32 i = 0; i < x.alt_len; ++i)
+        if (b.allele_codes[x.alt_off + i] != b.allele_codes[y.alt_off + i]) return false;
+    return true;
+}
+
+// One CTA per region.  Two records with equal (pos, reference, alternative) are the same Diff value
+// for Vec<Diff> equality, so they share a class.
+__global__ void k_variant_prep(DevBlock b, u32 r0, u32* var_class, u8* var_inwin) {
+    u32 r = r0 + blockIdx.x;
+    u32 v0 = b.var_off[r], v1 = b.var_off[r + 1];
+    i64 s = b.region_start[r], e = b.region_end[r];
+    for (u32 v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
+        tfbs_variant x = b.variants[v];
+        var_inwin[v] = (x.pos >= s && x.pos <= e) ? 1 : 0;
+        u32 cls = v - v0;
+        for (u32 u = v0; u < v; ++u)
+            if (same_diff(b, b.variants[u], x)) { cls = u - v0; break; }
+        var_class[v] = cls;
+    }
+}
+
+__device__ __forceinline__ bool carries(const DevBlock& b, u32 v, u32 h) {
+    return (b.carriers[(size_t)b.variants[v].carrier_row * b.pitch + (h >> 5)] >> (h & 31)) & 1u;
+}
+
+// Thread per (region, haplotype): hash of the ordered list of carried Diff classes; 0 = no diff
+// (such a haplotype stays in the reference set, main.rs:74-81,103-105).
+__global__ void k_signatures(DevBlock b, u32 r0, u32 nr, u64 seed, u64* sig, u32* nd_in) {
+    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (u64)nr * b.H) return;
+    u32 r = r0 + (u32)(idx / b.H), h = (u32)(idx % b.H);
+    u64 s = seed;
+    u32 carried = 0, inw = 0;
+    for (u32 v = b.var_off[r]; v < b.var_off[r + 1]; ++v)
+        if (carries(b, v, h)) {
+            s = mix64(s + b.var_class[v] + 1) * 0x9e3779b97f4a7c15ULL + carried;
+            ++carried;
+            inw += b.var_inwin[v];
+        }
+    sig[(size_t)r * b.H + h] = carried ? (mix64(s) | 1ULL) : 0ULL;
+    nd_in[(size_t)r * b.H + h] = inw;
+}
+
+__device__ __forceinline__ u32 table_find_or_insert(u64* keys, u32 mask, u64 key) {
+    u32 slot = (u32)(key >> 17) & mask;
+    for (;;) {
+        u64 prev = atomicCAS(&keys[slot], 0ULL, key);
+        if (prev == 0ULL || prev == key) return slot;
+        slot = (slot + 1) & mask;
+    }
+}
+__device__ __forceinline__ u32 table_find(const u64* keys, u32 mask, u64 key) {
+    u32 slot = (u32)(key >> 17) & mask;
+    for (;;) {
+        u64 k = keys[slot];
+        if (k == key) return slot;
+        if (k == 0ULL) return 0xffffffffu;
+        slot = (slot + 1) & mask;
+    }
+}
+
+__device__ __forceinline__ u64 region_key(u64 h, u32 r) { return mix64(h ^ ((u64)(r + 1) * 0xd6e8feb86659fd93ULL)) | 1ULL; }
+
+__global__ void k_group_insert(u32 H, u32 r0, u32 nr, const u64* sig, u64* keys, u32* vals, u32 mask) {
+    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (u64)nr * H) return;
+    u32 r = r0 + (u32)(idx / H), h = (u32)(idx % H);
+    u64 s = sig[(size_t)r * H + h];
+    if (!s) return;
+    u32 slot = table_find_or_insert(keys, mask, region_key(s, r));
+    atomicMin(&vals[slot], h);
+}
+
+// leader[r,h] = smallest haplotype with the same signature; the class lists are compared exactly so
+// that a hash collision is detected (and retried with another seed) instead of merging two groups.
+__global__ void k_group_lookup(DevBlock b, u32 r0, u32 nr, const u64* sig, const u64* keys, const u32* vals, u32 mask, u32* leader,
+                               DevStatus* st) {
+    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (u64)nr * b.H) return;
+    u32 r = r0 + (u32)(idx / b.H), h = (u32)(idx % b.H);
+    u64 s = sig[(size_t)r * b.H + h];
+    if (!s) { leader[(size_t)r * b.H + h] = 0xffffffffu; return; }
+    u32 slot = table_find(keys, mask, region_key(s, r));
+    u32 ld = vals[slot];
+    leader[(size_t)r * b.H + h] = ld;
+    if (ld == h) return;
+    bool ok = ld < b.H;
+    if (ok) {
+        u32 v1 = b.var_off[r + 1];
+        u32 i = b.var_off[r], j = i;
+        for (;;) {
+            while (i < v1 && !carries(b, i, h)) ++i;
+            while (j < v1 && !carries(b, j, ld)) ++j;
+            if (i == v1 || j == v1) { ok = (i == v1 && j == v1); break; }
+            if (b.var_class[i] != b.var_class[j]) { ok = false; break; }
+            ++i; ++j;
+        }
+    }
+    if (!ok) atomicAdd(&st->sig_collision, 1u);
+}
+
+// One CTA per region: groups are numbered 1.. in order of their smallest haplotype; 0 is the reference.
+__global__ void k_group_rank(u32 H, u32 r0, const u32* leader, const u32* nd_in, u32* hap_group, u32* ngroups, u32* sum_nd) {
+    __shared__ u32 s_warp[32];
+    __shared__ u32 s_base;
+    __shared__ u32 s_nd;
+    u32 r = r0 + blockIdx.x;
+    const u32* ld = leader + (size_t)r * H;
+    u32* hg = hap_group + (size_t)r * H;
+    if (threadIdx.x == 0) { s_base = 0; s_nd = 0; }
+    __syncthreads();
+    u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (u32 h0 = 0; h0 < H; h0 += blockDim.x) {
+        u32 h = h0 + threadIdx.x;
+        u32 flag = (h < H && ld[h] == h) ? 1u : 0u;
+        u32 bal = __ballot_sync(0xffffffffu, flag);
+        u32 pre = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        u32 woff = 0, tot = 0;
+        for (u32 w = 0; w < nw; ++w) { u32 c = s_warp[w]; if (w < wid) woff += c; tot += c; }
+        u32 base = s_base;
+        if (flag) {
+            hg[h] = 1 + base + woff + pre;
+            atomicAdd(&s_nd, nd_in[(size_t)r * H + h]);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_base = base + tot;
+        __syncthreads();
+    }
+    for (u32 h = threadIdx.x; h < H; h += blockDim.x) {
+        u32 l = ld[h];
+        if (l == 0xffffffffu) hg[h] = 0;
+        else if (l != h) hg[h] = hg[l < H ? l : h];  // leaders were written above
+    }
+    if (threadIdx.x == 0) { ngroups[r] = 1 + s_base; sum_nd[r] = s_nd; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic exclusive scan (u32 in -> u64 out), three launches; total in out[n]
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ u64 block_exclusive_scan(u64 v, u64* total) {
+    __shared__ u64 s_w[SCAN_THREADS / 32];
+    u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u64 x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u64 y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= (u32)o) x += y;
+    }
+    if (lane == 31) s_w[wid] = x;
+    __syncthreads();
+    u64 woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; ++w) { u64 c = s_w[w]; if (w < (int)wid) woff += c; tot += c; }
+    __syncthreads();
+    *total = tot;
+    return woff + x - v;
+}
+
+__global__ void k_scan_tiles(const u32* in, u64 n, u64* out, u64* tile_sums) {
+    u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    u32 v[SCAN_ITEMS];
+    u64 sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { v[k] = (base + k < n) ? in[base + k] : 0; sum += v[k]; }
+    u64 tot;
+    u64 ex = block_exclusive_scan(sum, &tot);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+__global__ void k_scan_sums(u64* tile_sums, u32 n_tiles, u64* total_out) {
+    __shared__ u64 s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (u32 t0 = 0; t0 < n_tiles; t0 += SCAN_THREADS) {
+        u32 t = t0 + threadIdx.x;
+        u64 v = t < n_tiles ? tile_sums[t] : 0;
+        u64 tot;
+        u64 ex = block_exclusive_scan(v, &tot);
+        u64 carry = s_carry;
+        if (t < n_tiles) tile_sums[t] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = s_carry;
+}
+__global__ void k_scan_add(u64* out, u64 n, const u64* tile_sums) {
+    u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
+    u64 add = tile_sums[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < n) out[base + k] += add;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: haplotype build
+// ------------------------------------------------------------------------------------------------
+
+// Sequence table of a batch: q = gbase[r] - gbase[r0] + g.
+struct DevSeqs {
+    u32 n_seq;
+    const u64* gbase;        // per region (block-wide index), first sequence of the region (batch-relative after -gbase0)
+    u64 gbase0;
+    u32* seq_region;         // [n_seq]
+    u32* seq_leader;         // [n_seq] haplotype whose diff list defines the sequence (0xffffffff for the reference)
+    u32* seq_nd;             // [n_seq] in-window diffs
+    u64* seq_doff;           // [n_seq+1] offset into dlist
+    u32* dlist;              // variant indices, sorted per sequence
+    Seg* segs;               // at 2*doff + 2*q, at most 2*nd + 2 entries
+    u32* seq_nseg;           // [n_seq] segments without the terminator
+    u32* seq_len;            // [n_seq] bases
+    u32* seq_units;          // [n_seq] ceil(len / 32)
+    u64* seq_uoff;           // [n_seq+1] offset into pk / nm
+    u64* pk;                 // 32 bases per word, 2 bits each
+    u32* nm;                 // N mask, bit b = base 32u+b is N
+    u64* seq_hash;           // [n_seq]
+    u8* seq_flags;           // bit0 truncated, bit1 dropped (overwritten in the sequence-keyed map)
+};
+
+__global__ void k_seq_init(u32 H, u32 r0, const u32* hap_group, const u32* leader, const u32* nd_in, DevSeqs sq) {
+    u32 r = r0 + blockIdx.x;
+    u64 qb = sq.gbase[r] - sq.gbase0;
+    if (threadIdx.x == 0) {
+        sq.seq_region[qb] = r;
+        sq.seq_leader[qb] = 0xffffffffu;
+        sq.seq_nd[qb] = 0;
+    }
+    for (u32 h = threadIdx.x; h < H; h += blockDim.x) {
+        if (leader[(size_t)r * H + h] == h) {
+            u64 q = qb + hap_group[(size_t)r * H + h];
+            sq.seq_region[q] = r;
+            sq.seq_leader[q] = h;
+            sq.seq_nd[q] = nd_in[(size_t)r * H + h];
+        }
+    }
+}
+
+// derived Ord of Diff: (pos, reference, alternative), vectors lexicographic, A<C<G<T<N (types.rs:5-8,39-44)
+__device__ __forceinline__ int cmp_codes(const u8* a, u32 na, const u8* b, u32 nb) {
+    u32 n = na < nb ? na : nb;
+    for (u32 i = 0; i < n; ++i)
+        if (a[i] != b[i]) return a[i] < b[i] ? -1 : 1;
+    return na == nb ? 0 : (na < nb ? -1 : 1);
+}
+__device__ __forceinline__ bool diff_less(const DevBlock& b, u32 x, u32 y) {
+    const tfbs_variant& vx = b.variants[x];
+    const tfbs_variant& vy = b.variants[y];
+    if (vx.pos != vy.pos) return vx.pos < vy.pos;
+    int c = cmp_codes(b.allele_codes + vx.ref_off, vx.ref_len, b.allele_codes + vy.ref_off, vy.ref_len);
+    if (c) return c < 0;
+    return cmp_codes(b.allele_codes + vx.alt_off, vx.alt_len, b.allele_codes + vy.alt_off, vy.alt_len) < 0;
+}
+
+__device__ __forceinline__ void report(DevStatus* st, u64 q, i64 relpos, u32 code) {
+    u64 key = (q << 32) | ((u64)((relpos + (1 << 27)) & 0xfffffff) << 4) | code;
+    atomicMin(&st->err_key, key);
+}
+
+// Thread per sequence: gathers the carried in-window diffs (haplotype.rs:95), sorts them (:96) and walks
+// them exactly like next_chunk (:98-153), emitting segments instead of bases.
+__global__ void k_walk(DevBlock b, DevSeqs sq, DevStatus* st) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= sq.n_seq) return;
+    u32 r = sq.seq_region[q];
+    u32 h = sq.seq_leader[q];
+    u64 doff = sq.seq_doff[q];
+    u32* dl = sq.dlist + doff;
+    Seg* sg = sq.segs + 2 * doff + 2 * (u64)q;
+    i64 start = b.region_start[r], end = b.region_end[r];
+    u64 ro = b.ref_off[r];
+    i64 n_ref = (i64)(b.ref_off[r + 1] - ro);
+    i64 avail_end = start + n_ref - 1;
+    u32 nd = 0;
+    if (h != 0xffffffffu) {
+        for (u32 v = b.var_off[r]; v < b.var_off[r + 1]; ++v)
+            if (b.var_inwin[v] && carries(b, v, h)) {
+                // insertion sort; records come sorted by position, so this is nearly linear
+                u32 k = nd++;
+                while (k > 0 && diff_less(b, v, dl[k - 1])) { dl[k] = dl[k - 1]; --k; }
+                dl[k] = v;
+            }
+    }
+    u32 out = 0, ns = 0;
+    bool trunc = false;
+    i64 rp = start;
+    auto emit_ref = [&](i64 a, i64 e2) {
+        if (a < start) a = start;
+        if (e2 > avail_end) e2 = avail_end;
+        if (e2 >= a) {
+            sg[ns++] = Seg{out, (u32)(a - start), (int)(a - start), 0u};
+            out += (u32)(e2 - a + 1);
+        }
+    };
+    u32 k = 0;
+    for (;;) {
+        if (k == nd) {  // haplotype.rs:100-108
+            if (rp <= end) emit_ref(rp, end);
+            break;
+        }
+        const tfbs_variant d = b.variants[dl[k]];
+        if (d.pos > rp) {  // :110-114
+            emit_ref(rp, d.pos - 1);
+            rp = d.pos;
+        } else if (d.pos == rp && d.ref_len == 1) {  // :115-135 SNV or insertion
+            u8 at = (rp >= start && rp <= avail_end) ? b.ref_codes[ro + (u64)(rp - start)] : (u8)4;
+            if (b.allele_codes[d.ref_off] != at) { report(st, q, rp - start, DEV_REF_MISMATCH); break; }
+            sg[ns++] = Seg{out, d.alt_off, (int)(rp - start), 1u};
+            out += d.alt_len;
+            rp += 1;
+            ++k;
+        } else if (d.pos == rp && d.alt_len == 1) {  // :136-140 deletion
+            sg[ns++] = Seg{out, d.alt_off, (int)(rp - start), 1u};
+            out += 1;
+            rp += d.ref_len;
+            ++k;
+        } else if (d.pos == rp) {  // :141-143
+            report(st, q, rp - start, DEV_MISSING_CASE);
+            break;
+        } else if (rp >= end) {  // :144-146
+            trunc = true;
+            emit_ref(rp, rp);
+            break;
+        } else {  // :147-149
+            trunc = true;
+            break;
+        }
+    }
+    sg[ns] = Seg{out, 0u, 0, 2u};  // terminator
+    sq.seq_nseg[q] = ns;
+    sq.seq_len[q] = out;
+    sq.seq_units[q] = (out + 31) / 32;
+    sq.seq_flags[q] = trunc ? 1 : 0;
+    sq.seq_hash[q] = 0;
+    if (trunc) atomicAdd(&st->n_truncated, 1u);
+}
+
+__device__ __forceinline__ u32 seg_find(const Seg* sg, u32 ns, u32 i) {  // last segment with out_start <= i
+    u32 lo = 0, hi = ns;  // sg[ns] is the terminator
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (sg[mid].out_start <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// One CTA per sequence, one thread per unit of 32 bases: gathers the bases through the segment list,
+// packs them 2 bits each (+ N mask) and accumulates the hash of the (nuc, pos) vector, which is the key
+// of the map in load_haplotypes (haplotype.rs:84).
+__global__ void k_emit(DevBlock b, DevSeqs sq) {
+    u32 q = blockIdx.x;
+    u32 len = sq.seq_len[q];
+    u32 nu = sq.seq_units[q];
+    u32 r = sq.seq_region[q];
+    u32 ns = sq.seq_nseg[q];
+    const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
+    const u8* refc = b.ref_codes + b.ref_off[r];
+    u64 uoff = sq.seq_uoff[q];
+    u64 hsum = 0;
+    for (u32 u = threadIdx.x; u < nu; u += blockDim.x) {
+        u32 i0 = u * 32;
+        u32 s = seg_find(sg, ns, i0);
+        Seg cur = sg[s];
+        u32 nxt = sg[s + 1].out_start;
+        u64 pk = 0;
+        u32 nm = 0;
+        u64 acc = 0;
+        for (u32 k = 0; k < 32; ++k) {
+            u32 i = i0 + k;
+            if (i >= len) break;
+            while (i >= nxt) { ++s; cur = sg[s]; nxt = sg[s + 1].out_start; }
+            u32 o = i - cur.out_start;
+            u8 c;
+            int rel;
+            if (cur.kind == 0) { c = refc[cur.src + o]; rel = cur.relpos + (int)o; }
+            else { c = b.allele_codes[cur.src + o]; rel = cur.relpos; }
+            pk |= (u64)(c & 3) << (2 * k);
+            nm |= (c == 4 ? 1u : 0u) << k;
+            acc = acc * 0x100000001b3ULL + (u64)((u32)rel * 8u + c + 1u);
+        }
+        sq.pk[uoff + u] = pk;
+        sq.nm[uoff + u] = nm;
+        hsum += mix64(acc ^ mix64((u64)u + 0x51ed27ULL));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
+    if ((threadIdx.x & 31) == 0 && hsum) atomicAdd(&sq.seq_hash[q], hsum);
+}
+
+__device__ __forceinline__ u32 seq_group(const DevSeqs& sq, u32 q) {  // group index of q inside its region
+    return (u32)((u64)q + sq.gbase0 - sq.gbase[sq.seq_region[q]]);
+}
+
+__global__ void k_seq_insert(DevSeqs sq, u64* keys, u32* vals, u32 mask) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= sq.n_seq) return;
+    u32 g = seq_group(sq, q);
+    if (g == 0) return;  // the reference haplotype is not in the map (main.rs:129-147)
+    u64 key = region_key(sq.seq_hash[q] + mix64(sq.seq_len[q]), sq.seq_region[q]);
+    u32 slot = table_find_or_insert(keys, mask, key);
+    atomicMin(&vals[slot], g);
+}
+
+__device__ __forceinline__ void base_at(const DevBlock& b, const DevSeqs& sq, u32 q, u32 i, u8* c, int* rel) {
+    const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
+    u32 s = seg_find(sg, sq.seq_nseg[q], i);
+    Seg cur = sg[s];
+    u32 o = i - cur.out_start;
+    if (cur.kind == 0) { *c = b.ref_codes[b.ref_off[sq.seq_region[q]] + cur.src + o]; *rel = cur.relpos + (int)o; }
+    else { *c = b.allele_codes[cur.src + o]; *rel = cur.relpos; }
+}
+
+// A later insert with an equal key overwrites the earlier one in the reference (haplotype.rs:84); the
+// winner there depends on HashMap order, here the group with the smallest first haplotype wins (same rule
+// as the oracle).  The losers are dropped: their haplotypes stay in the reference set (main.rs:103-105).
+__global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32* vals, u32 mask, DevStatus* st) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= sq.n_seq) return;
+    u32 g = seq_group(sq, q);
+    if (g == 0) return;
+    u64 key = region_key(sq.seq_hash[q] + mix64(sq.seq_len[q]), sq.seq_region[q]);
+    u32 slot = table_find(keys, mask, key);
+    u32 w = vals[slot];
+    if (w == g) return;
+    u32 qw = q - g + w;
+    bool same = sq.seq_len[qw] == sq.seq_len[q] && sq.seq_region[qw] == sq.seq_region[q];
+    for (u32 i = 0; same && i < sq.seq_len[q]; ++i) {
+        u8 c0, c1;
+        int p0, p1;
+        base_at(b, sq, q, i, &c0, &p0);
+        base_at(b, sq, qw, i, &c1, &p1);
+        same = c0 == c1 && p0 == p1;
+    }
+    if (same) {
+        sq.seq_flags[q] |= 2;
+        atomicAdd(&st->n_dropped, 1u);
+    } else {
+        atomicAdd(&st->seq_collision, 1u);
+    }
+}
+
+__global__ void k_redirect(u32 H, u32 r0, u32 nr, DevSeqs sq, u32* hap_group, u32* ref_used) {
+    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (u64)nr * H) return;
+    u32 r = r0 + (u32)(idx / H), h = (u32)(idx % H);
+    u32 g = hap_group[(size_t)r * H + h];
+    if (g && (sq.seq_flags[sq.gbase[r] - sq.gbase0 + g] & 2)) { g = 0; hap_group[(size_t)r * H + h] = 0; }
+    if (g == 0) ref_used[r] = 1;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: PWM scan
+// ------------------------------------------------------------------------------------------------
+
+struct DevPatterns {
+    const u64* table;
+    const ChunkDesc* chunks;
+    const RunDesc* runs;
+    const int* trip_pat;
+    const u32* pat_len;
+    const u32* pat_pid_index;
+    u32 n_chunks;
+    u32 n_pid;       // distinct pattern ids
+    u32 n_patterns;
+    u32 max_len;
+    u32 sum_len;
+    u64 sum_len_sq;
+};
+
+struct DevCounts {
+    u32* C;               // counts, [region][group][pid][inner]
+    const u64* cbase;     // per region (block-wide), offset into C relative to cbase0
+    u64 cbase0;
+};
+
+struct DevMatches {
+    u32 enabled;
+    u32 cap;
+    u32* region;
+    u32* pattern_index;
+    u32* group;
+    i64* start;
+};
+
+constexpr int SCAN_CTA = 256;
+constexpr int TILE_POS = 2048;                       // window starts staged per pass
+constexpr int PLANE_BYTES = TILE_POS / 2 + 64;       // pair codes of even / odd starts (+ halo, padded)
+constexpr int RAW_UNITS = TILE_POS / 32 + 2;
+constexpr int CNT_WORDS = 2048;                      // shared-memory count table (pid x inner)
+constexpr int SEG_CACHE = 64;
+
+struct ScanShared {
+    u64 raw_pk[RAW_UNITS];
+    u32 raw_nm[RAW_UNITS];
+    u32 cnt[CNT_WORDS];
+    Seg segs[SEG_CACHE + 1];
+    u8 plane[2][PLANE_BYTES];
+    u32 item;       // current work item
+    u32 cnt_dirty;
+};
+
+template <int G, int FIELDS>
+struct HitMask;
+template <int G>
+struct HitMask<G, 3> { static constexpr u64 value = (1ULL << 20) | (1ULL << 41) | (1ULL << 62); };
+template <int G>
+struct HitMask<G, 2> { static constexpr u64 value = (1ULL << 31) | (1ULL << 63); };
+
+struct ScanItem {
+    u32 q, r, g, len, nseg, nk, n_pid_chunk, pid_lo, use_smem_cnt;
+    i64 region_start;
+    const Seg* segs;          // global
+    const tfbs_inner_region* inner;
+    u32* Crow;                // C + offset of (region, group), row of n_pid_total * nk
+    u32 trip_off;
+    u32 fields;
+};
+
+// Rare path: a window scored above the threshold in at least one field.
+__device__ __noinline__ void scan_on_hit(u64 hit, u32 t, u32 i, const ScanItem& it, const DevPatterns& pt, ScanShared* sh,
+                                         const DevMatches& mt, DevStatus* st) {
+    const int bits = it.fields == 3 ? 21 : 32;
+    for (u32 f = 0; f < it.fields; ++f) {
+        if (!((hit >> (bits * f + bits - 1)) & 1ULL)) continue;
+        int pi = pt.trip_pat[(size_t)(it.trip_off + t) * 3 + f];
+        if (pi < 0) continue;
+        u32 L = pt.pat_len[pi];
+        if (i + L > it.len) continue;  // pattern.rs:147-149: only full windows
+        // pos of the first base of the window (pattern.rs:156)
+        const Seg* sg = it.nseg <= SEG_CACHE ? sh->segs : it.segs;
+        u32 s = seg_find(sg, it.nseg, i);
+        Seg cur = sg[s];
+        i64 hs = (i64)cur.relpos + (cur.kind == 0 ? (i64)(i - cur.out_start) : 0);
+        i64 he = hs + L - 1;
+        u32 pl = pt.pat_pid_index[pi];
+        atomicAdd(&st->n_hits, 1ULL);
+        for (u32 k = 0; k < it.nk; ++k) {
+            i64 is = it.inner[k].start - it.region_start, ie = it.inner[k].end - it.region_start;
+            bool ov = (hs >= is && hs <= ie) || (he >= is && he <= ie);  // inner.overlaps(match.range), range.rs:18-21
+            if (!ov) continue;
+            u32 m = it.inner[k].multiplicity;
+            if (it.use_smem_cnt) {
+                atomicAdd(&sh->cnt[(pl - it.pid_lo) * it.nk + k], m);
+                sh->cnt_dirty = 1;
+            } else {
+                atomicAdd(&it.Crow[(size_t)pl * it.nk + k], m);
+            }
+        }
+        if (mt.enabled) {
+            u64 slot = atomicAdd(&st->n_matches, 1ULL);
+            if (slot < mt.cap) {
+                mt.region[slot] = it.r;
+                mt.pattern_index[slot] = (u32)pi;
+                mt.group[slot] = it.g;
+                mt.start[slot] = it.region_start + hs;
+            }
+        }
+    }
+}
+
+// All triples of one run (same number of column pairs G): G LDS.64 + 64-bit adds per triple and lane.
+template <int G, int FIELDS>
+__device__ __forceinline__ void scan_run(const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i, const ScanItem& it,
+                                         const DevPatterns& pt, ScanShared* sh, const DevMatches& mt, DevStatus* st) {
+#pragma unroll 2
+    for (u32 t = 0; t < n_trip; ++t) {
+        u64 acc = 0;
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc += *reinterpret_cast<const u64*>(tb + g * (kPairEntries * 8) + idx[g]);
+        u64 hit = acc & HitMask<G, FIELDS>::value;
+        if (hit) scan_on_hit(hit, t0 + t, i, it, pt, sh, mt, st);
+        tb += G * (kPairEntries * 8);
+    }
+}
+
+template <int FIELDS>
+__device__ __forceinline__ void scan_dispatch(u32 G, const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i,
+                                              const ScanItem& it, const DevPatterns& pt, ScanShared* sh, const DevMatches& mt,
+                                              DevStatus* st) {
+    switch (G) {
+#define TFBS_CASE(N) case N: scan_run<N, FIELDS>(tb, n_trip, t0, idx, i, it, pt, sh, mt, st); break;
+        TFBS_CASE(1) TFBS_CASE(2) TFBS_CASE(3) TFBS_CASE(4) TFBS_CASE(5) TFBS_CASE(6) TFBS_CASE(7) TFBS_CASE(8)
+        TFBS_CASE(9) TFBS_CASE(10) TFBS_CASE(11) TFBS_CASE(12) TFBS_CASE(13) TFBS_CASE(14) TFBS_CASE(15) TFBS_CASE(16)
+#undef TFBS_CASE
+    }
+}
+
+__device__ __forceinline__ u32 pair_code_bytes(u32 a, u32 b) {  // pair_entry(a, b) * 8
+    u32 e = (a < 4 && b < 4) ? 4 * a + b : (a == 4 ? 16 + b : 21 + a);
+    return e * 8;
+}
+
+// Persistent CTAs.  Work item w = chunk * n_seq + q, handed out by an atomic counter; the tables of a
+// chunk stay in shared memory while consecutive items use the same chunk.
+__global__ void __launch_bounds__(SCAN_CTA) k_scan(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, DevMatches mt,
+                                                    const u32* ref_used, DevStatus* st, u32 n_items) {
+    extern __shared__ __align__(16) u8 smem_raw[];
+    ScanShared* sh = reinterpret_cast<ScanShared*>(smem_raw);
+    u8* tbl = smem_raw + ((sizeof(ScanShared) + 15) & ~size_t(15));
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = SCAN_CTA / 32;
+    u32 cur_chunk = 0xffffffffu;
+    for (u32 k = tid; k < CNT_WORDS; k += SCAN_CTA) sh->cnt[k] = 0;
+    if (tid == 0) sh->cnt_dirty = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) sh->item = atomicAdd(&st->work_counter, 1u);
+        __syncthreads();
+        u32 w = sh->item;
+        if (w >= n_items) break;
+        u32 c = w / sq.n_seq, q = w % sq.n_seq;
+        const ChunkDesc cd = pt.chunks[c];
+        if (c != cur_chunk) {  // (re)load the tables: 128-bit coalesced copies
+            const uint4* src = reinterpret_cast<const uint4*>(pt.table + cd.tbl_off);
+            uint4* dst = reinterpret_cast<uint4*>(tbl);
+            u32 n16 = (cd.tbl_words + 1) / 2;
+            for (u32 k = tid; k < n16; k += SCAN_CTA) dst[k] = src[k];
+            cur_chunk = c;
+        }
+        ScanItem it;
+        it.q = q;
+        it.r = sq.seq_region[q];
+        it.g = seq_group(sq, q);
+        if ((sq.seq_flags[q] & 2) || (it.g == 0 && !ref_used[it.r])) continue;  // dropped, or nobody has the reference haplotype
+        it.len = sq.seq_len[q];
+        it.nseg = sq.seq_nseg[q];
+        it.segs = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
+        it.region_start = b.region_start[it.r];
+        it.nk = b.inner_off[it.r + 1] - b.inner_off[it.r];
+        it.inner = b.inner + b.inner_off[it.r];
+        it.n_pid_chunk = cd.n_pid;
+        it.pid_lo = cd.pid_lo;
+        it.use_smem_cnt = (cd.n_pid * it.nk <= CNT_WORDS) ? 1u : 0u;
+        it.Crow = ct.C + (ct.cbase[it.r] - ct.cbase0) + (u64)it.g * pt.n_pid * it.nk;
+        it.trip_off = cd.trip_off;
+        it.fields = cd.fields;
+        if (it.nseg <= SEG_CACHE)
+            for (u32 k = tid; k <= it.nseg; k += SCAN_CTA) sh->segs[k] = it.segs[k];
+        if (tid == 0 && c == 0) {  // statistics, once per sequence
+            // executed cells = sum_p max(0, len - L + 1) * L (pattern.rs:147-150)
+            u64 cells = 0;
+            if (it.len >= pt.max_len) cells = (u64)(it.len + 1) * pt.sum_len - (pt.sum_len_sq + pt.sum_len);
+            else
+                for (u32 p = 0; p < pt.n_patterns; ++p) {
+                    u32 L = pt.pat_len[p];
+                    if (L && it.len >= L) cells += (u64)(it.len - L + 1) * L;
+                }
+            atomicAdd(&st->executed_cells, cells);
+            atomicAdd(&st->n_scanned, 1ULL);
+        }
+        if (it.nk == 0 && !mt.enabled) continue;  // no inner region can be hit: nothing to count (main.rs:503)
+
+        const u64* gpk = sq.pk + sq.seq_uoff[q];
+        const u32* gnm = sq.nm + sq.seq_uoff[q];
+        const u32 n_units = sq.seq_units[q];
+        for (u32 tile0 = 0; tile0 < it.len; tile0 += TILE_POS) {
+            __syncthreads();
+            // stage the packed bases of [tile0, tile0 + TILE_POS + 64)
+            u32 u0 = tile0 / 32;
+            for (u32 k = tid; k < RAW_UNITS; k += SCAN_CTA) {
+                bool in = u0 + k < n_units;
+                sh->raw_pk[k] = in ? gpk[u0 + k] : 0ULL;
+                sh->raw_nm[k] = in ? gnm[u0 + k] : 0xffffffffu;
+            }
+            __syncthreads();
+            // pair codes: plane[j & 1][j >> 1] = 8 * pair_entry(code[tile0 + j], code[tile0 + j + 1]); beyond the end: N
+            for (u32 j = tid; j < TILE_POS + 32; j += SCAN_CTA) {
+                u32 p0 = j, p1 = j + 1;
+                u32 a = (u32)(sh->raw_pk[p0 >> 5] >> (2 * (p0 & 31))) & 3u;
+                u32 bb = (u32)(sh->raw_pk[p1 >> 5] >> (2 * (p1 & 31))) & 3u;
+                if (((sh->raw_nm[p0 >> 5] >> (p0 & 31)) & 1u) || tile0 + p0 >= it.len) a = 4;
+                if (((sh->raw_nm[p1 >> 5] >> (p1 & 31)) & 1u) || tile0 + p1 >= it.len) bb = 4;
+                sh->plane[j & 1][j >> 1] = (u8)pair_code_bytes(a, bb);
+            }
+            __syncthreads();
+            u32 npos = it.len - tile0 < (u32)TILE_POS ? it.len - tile0 : (u32)TILE_POS;
+            for (u32 p = wid * 32; p < npos; p += nwarp * 32) {
+                u32 j = p + lane;
+                const u8* pl = &sh->plane[j & 1][j >> 1];
+                u32 idx[kMaxGroups];
+#pragma unroll
+                for (int g = 0; g < kMaxGroups; ++g) idx[g] = pl[g];
+                const u8* tb = tbl;
+                u32 t0 = 0;
+                for (u32 rn = 0; rn < cd.n_runs; ++rn) {
+                    RunDesc rd = pt.runs[cd.run_off + rn];
+                    if (cd.fields == 3) scan_dispatch<3>(rd.groups, tb, rd.n_triples, t0, idx, tile0 + j, it, pt, sh, mt, st);
+                    else scan_dispatch<2>(rd.groups, tb, rd.n_triples, t0, idx, tile0 + j, it, pt, sh, mt, st);
+                    tb += (size_t)rd.n_triples * rd.groups * (kPairEntries * 8);
+                    t0 += rd.n_triples;
+                }
+            }
+        }
+        __syncthreads();
+        // flush the shared count table of this (sequence, chunk): plain stores, this CTA owns the slice
+        if (it.use_smem_cnt && sh->cnt_dirty) {
+            u32 n = cd.n_pid * it.nk;
+            for (u32 k = tid; k < n; k += SCAN_CTA) {
+                u32 v = sh->cnt[k];
+                if (v) { it.Crow[(size_t)cd.pid_lo * it.nk + k] = v; sh->cnt[k] = 0; }
+            }
+            __syncthreads();
+            if (tid == 0) sh->cnt_dirty = 0;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: fan-out to samples, min/max filter, row compaction
+// ------------------------------------------------------------------------------------------------
+
+// One CTA per region, one thread per key (pid, inner): v[s] = C[group(left)] + C[group(right)]
+// (main.rs:441-448), min and max over samples (:450-451).  flag: 1 = row is emitted.
+__global__ void k_rows_minmax(DevBlock b, u32 r0, const u32* hap_group, DevCounts ct, const u64* gbase, u32 n_pid, const u64* kbase,
+                              u64 kbase0, int rows_mode, u32* vmin, u32* vmax, u32* flag) {
+    u32 r = r0 + blockIdx.x;
+    u32 nk = b.inner_off[r + 1] - b.inner_off[r];
+    u32 nkeys = n_pid * nk;
+    const u32* C = ct.C + (ct.cbase[r] - ct.cbase0);
+    const u32* hg = hap_group + (size_t)r * b.H;
+    u64 ko = kbase[r] - kbase0;
+    (void)gbase;
+    for (u32 key = threadIdx.x; key < nkeys; key += blockDim.x) {
+        u32 lo = 0xffffffffu, hi = 0;
+        for (u32 s = 0; s < b.S; ++s) {
+            u32 g0 = hg[2 * s], g1 = hg[2 * s + 1];
+            u32 v = C[(size_t)g0 * nkeys + key] + C[(size_t)g1 * nkeys + key];
+            lo = min(lo, v);
+            hi = max(hi, v);
+        }
+        vmin[ko + key] = lo;
+        vmax[ko + key] = hi;
+        // keys exist once a hit of any scanned haplotype touched the inner region (main.rs:517-528);
+        // every scanned group has at least one member, so that is hi > 0
+        flag[ko + key] = (rows_mode == TFBS_ROWS_VARYING) ? (lo != hi ? 1u : 0u) : (hi > 0 ? 1u : 0u);
+    }
+}
+
+struct DevRows {
+    u32* region;
+    u32* inner;
+    u16* pattern_id;
+    u32* vmin;
+    u32* vmax;
+    u32* left;
+    u32* right;
+};
+
+// One warp per emitted row.
+__global__ void k_rows_write(DevBlock b, u32 r0, u32 nr, const u32* hap_group, DevCounts ct, u32 n_pid, const u16* pid_list,
+                             const u64* kbase, u64 kbase0, u64 n_keys, const u32* vmin, const u32* vmax, const u32* flag,
+                             const u64* rowidx, DevRows rows, u64 row_base) {
+    u64 key = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    u32 lane = threadIdx.x & 31;
+    if (key >= n_keys || !flag[key]) return;
+    // region of the key: last r with kbase[r] - kbase0 <= key
+    u32 lo = r0, hi = r0 + nr;
+    while (hi - lo > 1) {
+        u32 mid = (lo + hi) >> 1;
+        if (kbase[mid] - kbase0 <= key) lo = mid; else hi = mid;
+    }
+    u32 r = lo;
+    u32 nk = b.inner_off[r + 1] - b.inner_off[r];
+    u32 nkeys = n_pid * nk;
+    u32 kk = (u32)(key - (kbase[r] - kbase0));
+    u32 pidx = kk / nk, k = kk % nk;
+    u64 row = row_base + rowidx[key];
+    if (lane == 0) {
+        rows.region[row] = r;
+        rows.inner[row] = b.inner_off[r] + k;
+        rows.pattern_id[row] = pid_list[pidx];
+        rows.vmin[row] = vmin[key];
+        rows.vmax[row] = vmax[key];
+    }
+    const u32* C = ct.C + (ct.cbase[r] - ct.cbase0);
+    const u32* hg = hap_group + (size_t)r * b.H;
+    for (u32 s = lane; s < b.S; s += 32) {
+        rows.left[row * b.S + s] = C[(size_t)hg[2 * s] * nkeys + kk];
+        rows.right[row * b.S + s] = C[(size_t)hg[2 * s + 1] * nkeys + kk];
+    }
+}
+
+// nominal cells: every haplotype of every sample scanned on its own sequence (BASELINE.md "Unit of work")
+__global__ void k_nominal(DevBlock b, u32 r0, u32 nr, const u32* hap_group, DevSeqs sq, DevPatterns pt, DevStatus* st) {
+    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 cells = 0;
+    if (idx < (u64)nr * b.H) {
+        u32 r = r0 + (u32)(idx / b.H), h = (u32)(idx % b.H);
+        u32 len = sq.seq_len[sq.gbase[r] - sq.gbase0 + hap_group[(size_t)r * b.H + h]];
+        if (len >= pt.max_len) cells = (u64)(len + 1) * pt.sum_len - (pt.sum_len_sq + pt.sum_len);
+        else
+            for (u32 p = 0; p < pt.n_patterns; ++p) {
+                u32 L = pt.pat_len[p];
+                if (L && len >= L) cells += (u64)(len - L + 1) * L;
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
+    if ((threadIdx.x & 31) == 0 && cells) atomicAdd(&st->nominal_cells, cells);
+}
+
+}  // namespace tfbs

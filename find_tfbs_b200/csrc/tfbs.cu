@@ -1,0 +1,819 @@
+// tfbs.cu -- C ABI (include/tfbs.h) over the sm_100a kernels in kernels.cuh.
+//
+// One context = one CUDA device + one stream.  A block of merged regions is processed in batches sized to a
+// scratch budget: phase 1 groups the haplotypes of every region (K0) and reports per-region group counts,
+// phase 2 builds (K1), scans (K2) and reduces (K3) one batch at a time.  There is no CPU fallback: every
+// entry point that computes fails with TFBS_ERR_CUDA when no device is usable.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+
+using namespace tfbs;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct HostBuf {  // pinned
+    void* p = nullptr;
+    size_t cap = 0;
+    ~HostBuf() { if (p) cudaFreeHost(p); }
+    cudaError_t reserve(size_t bytes, bool keep) {
+        if (bytes <= cap) return cudaSuccess;
+        void* np = nullptr;
+        size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMallocHost(&np, want);
+        if (e != cudaSuccess) return e;
+        if (keep && p && cap) memcpy(np, p, cap);
+        if (p) cudaFreeHost(p);
+        p = np;
+        cap = want;
+        return cudaSuccess;
+    }
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+}  // namespace
+
+struct tfbs_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    std::string err;
+
+    // options
+    int rows_mode = TFBS_ROWS_VARYING;
+    int record_matches = 0;
+    uint64_t max_matches = 1u << 22;
+    int verify_groups = 1;
+    int scan_format = 0;
+    uint64_t scratch_bytes = 24ull << 30;
+    uint32_t table_budget = 96 * 1024;
+    int scan_ctas_per_sm = 0;  // 0 = as many as fit
+
+    // patterns
+    bool have_patterns = false;
+    CompiledPatterns cp;
+    DevBuf d_table, d_chunks, d_runs, d_trip_pat, d_pat_len, d_pat_pid, d_pid_list;
+    DevPatterns dpat{};
+
+    // block inputs (device)
+    bool have_block = false;
+    uint32_t R = 0, S = 0, H = 0, pitch = 0;
+    uint64_t n_ref_bytes = 0, n_allele_bytes = 0, n_var = 0, n_inner = 0, n_carrier_rows = 0;
+    DevBuf d_region_start, d_region_end, d_ref_off, d_ref_ascii, d_ref_codes, d_inner_off, d_inner, d_var_off, d_variants,
+        d_allele_ascii, d_allele_codes, d_carriers, d_var_class, d_var_inwin;
+    // host copies of the small per-region arrays (batch planning, error messages)
+    std::vector<int64_t> h_region_start, h_region_end;
+    std::vector<uint64_t> h_ref_off;
+    std::vector<uint32_t> h_inner_off, h_var_off;
+    std::vector<uint64_t> h_ins_extra;  // per region: sum over variants of max(0, alt_len - 1)
+
+    // phase 1
+    DevBuf d_sig, d_nd_in, d_leader, d_hap_group, d_ngroups, d_sum_nd, d_ref_used;
+    DevBuf d_keys, d_vals;
+    std::vector<uint32_t> h_ngroups, h_sum_nd;
+    // per region prefix arrays (block-wide)
+    std::vector<uint64_t> h_gbase, h_cbase, h_kbase;
+    DevBuf d_gbase, d_cbase, d_kbase;
+
+    // phase 2 scratch
+    DevBuf d_seq_region, d_seq_leader, d_seq_nd, d_seq_doff, d_dlist, d_segs, d_seq_nseg, d_seq_len, d_seq_units, d_seq_uoff, d_pk,
+        d_nm, d_seq_hash, d_seq_flags, d_tile_sums, d_C, d_vmin, d_vmax, d_flag, d_rowidx;
+    DevBuf d_status;
+    DevBuf d_rows_region, d_rows_inner, d_rows_pid, d_rows_vmin, d_rows_vmax, d_rows_left, d_rows_right;
+    DevBuf d_m_region, d_m_pattern, d_m_group, d_m_start;
+
+    // results (host, pinned)
+    HostBuf h_rows_region, h_rows_inner, h_rows_pid, h_rows_vmin, h_rows_vmax, h_rows_left, h_rows_right;
+    HostBuf h_m_region, h_m_pattern, h_m_group, h_m_start, h_hap_group;
+    HostBuf h_status, h_totals;
+    uint64_t n_rows = 0, n_matches = 0;
+    bool matches_truncated = false;
+    bool ran = false;
+
+    tfbs_stats stats{};
+    cudaEvent_t ev[8]{};
+};
+
+namespace {
+
+#define CK(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e_ = (call);                                                                              \
+        if (e_ != cudaSuccess) {                                                                              \
+            ctx->err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #call;                   \
+            return TFBS_ERR_CUDA;                                                                             \
+        }                                                                                                     \
+    } while (0)
+
+int fail(tfbs_ctx* ctx, int code, const std::string& msg) {
+    ctx->err = msg;
+    return code;
+}
+
+template <class T>
+int upload(tfbs_ctx* ctx, DevBuf& buf, const T* src, size_t n) {
+    CK(buf.reserve(std::max<size_t>(1, n) * sizeof(T)));
+    if (n) CK(cudaMemcpyAsync(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->stats.h2d_bytes += n * sizeof(T);
+    return TFBS_OK;
+}
+
+inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)std::max<uint64_t>(1, (n + block - 1) / block); }
+
+// exclusive scan of d_in[0..n) into d_out[0..n], total into d_out[n]
+int device_scan(tfbs_ctx* ctx, const uint32_t* d_in, uint64_t n, u64* d_out) {
+    uint32_t tiles = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+    if (tiles == 0) {
+        CK(cudaMemsetAsync(d_out, 0, sizeof(u64), ctx->stream));
+        return TFBS_OK;
+    }
+    CK(ctx->d_tile_sums.reserve((size_t)tiles * 8));
+    k_scan_tiles<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, d_out, ctx->d_tile_sums.as<u64>());
+    k_scan_sums<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->d_tile_sums.as<u64>(), tiles, d_out + n);
+    k_scan_add<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(d_out, n, ctx->d_tile_sums.as<u64>());
+    ctx->stats.total_launches += 3;
+    CK(cudaGetLastError());
+    return TFBS_OK;
+}
+
+DevBlock dev_block(const tfbs_ctx* ctx) {
+    DevBlock b{};
+    b.R = ctx->R;
+    b.S = ctx->S;
+    b.H = ctx->H;
+    b.region_start = ctx->d_region_start.as<i64>();
+    b.region_end = ctx->d_region_end.as<i64>();
+    b.ref_off = ctx->d_ref_off.as<u64>();
+    b.ref_codes = ctx->d_ref_codes.as<u8>();
+    b.inner_off = ctx->d_inner_off.as<u32>();
+    b.inner = ctx->d_inner.as<tfbs_inner_region>();
+    b.var_off = ctx->d_var_off.as<u32>();
+    b.variants = ctx->d_variants.as<tfbs_variant>();
+    b.allele_codes = ctx->d_allele_codes.as<u8>();
+    b.carriers = ctx->d_carriers.as<u32>();
+    b.pitch = ctx->pitch;
+    b.var_class = ctx->d_var_class.as<u32>();
+    b.var_inwin = ctx->d_var_inwin.as<u8>();
+    return b;
+}
+
+int validate_block(tfbs_ctx* ctx, const tfbs_block* b) {
+    if (!b) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "block is NULL");
+    if (b->n_regions && (!b->region_start || !b->region_end || !b->ref_off || !b->inner_off || !b->var_off))
+        return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "block has NULL region arrays");
+    if ((uint64_t)b->n_samples * 2 > 0x7fffffffull) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "too many samples");
+    uint32_t H = 2 * b->n_samples;
+    if (b->n_carrier_rows && b->carrier_pitch < (H + 31) / 32) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "carrier_pitch is too small");
+    for (uint32_t r = 0; r < b->n_regions; ++r) {
+        if (b->region_start[r] < 0 || b->region_end[r] < b->region_start[r])
+            return fail(ctx, TFBS_ERR_INVALID_ARGUMENT,
+                        "region " + std::to_string(r) + " has an invalid extended window (main.rs:407 underflow)");
+        if (b->region_end[r] - b->region_start[r] >= (1ll << 26))
+            return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "region " + std::to_string(r) + " is longer than 2^26 bases");
+        if (b->ref_off[r + 1] < b->ref_off[r] ||
+            b->ref_off[r + 1] - b->ref_off[r] > (uint64_t)(b->region_end[r] - b->region_start[r] + 1))
+            return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "region " + std::to_string(r) + ": reference window longer than the region");
+        if (b->inner_off[r + 1] < b->inner_off[r] || b->var_off[r + 1] < b->var_off[r])
+            return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "offset arrays must be non-decreasing");
+    }
+    uint32_t nv = b->n_regions ? b->var_off[b->n_regions] : 0;
+    for (uint32_t v = 0; v < nv; ++v) {
+        const tfbs_variant& x = b->variants[v];
+        if (x.ref_len == 0 || x.alt_len == 0) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "variant " + std::to_string(v) + " has an empty allele");
+        if ((uint64_t)x.ref_off + x.ref_len > b->allele_bytes || (uint64_t)x.alt_off + x.alt_len > b->allele_bytes)
+            return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "variant " + std::to_string(v) + " points outside allele_bases");
+        if (x.carrier_row >= b->n_carrier_rows) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "variant " + std::to_string(v) + " has no carrier row");
+    }
+    return TFBS_OK;
+}
+
+int do_upload(tfbs_ctx* ctx, const tfbs_block* b) {
+    int rc = validate_block(ctx, b);
+    if (rc) return rc;
+    ctx->have_block = false;
+    ctx->R = b->n_regions;
+    ctx->S = b->n_samples;
+    ctx->H = 2 * b->n_samples;
+    ctx->pitch = b->carrier_pitch;
+    const uint32_t R = ctx->R;
+    ctx->n_ref_bytes = R ? b->ref_off[R] : 0;
+    ctx->n_inner = R ? b->inner_off[R] : 0;
+    ctx->n_var = R ? b->var_off[R] : 0;
+    ctx->n_allele_bytes = b->allele_bytes;
+    ctx->n_carrier_rows = b->n_carrier_rows;
+    ctx->h_region_start.assign(b->region_start, b->region_start + R);
+    ctx->h_region_end.assign(b->region_end, b->region_end + R);
+    if (R) {
+        ctx->h_ref_off.assign(b->ref_off, b->ref_off + R + 1);
+        ctx->h_inner_off.assign(b->inner_off, b->inner_off + R + 1);
+        ctx->h_var_off.assign(b->var_off, b->var_off + R + 1);
+    } else {
+        ctx->h_ref_off.assign(1, 0);
+        ctx->h_inner_off.assign(1, 0);
+        ctx->h_var_off.assign(1, 0);
+    }
+    ctx->h_ins_extra.assign(R, 0);
+    for (uint32_t r = 0; r < R; ++r)
+        for (uint32_t v = b->var_off[r]; v < b->var_off[r + 1]; ++v)
+            if (b->variants[v].alt_len > 1) ctx->h_ins_extra[r] += b->variants[v].alt_len - 1;
+
+    if ((rc = upload(ctx, ctx->d_region_start, b->region_start, R))) return rc;
+    if ((rc = upload(ctx, ctx->d_region_end, b->region_end, R))) return rc;
+    if ((rc = upload(ctx, ctx->d_ref_off, ctx->h_ref_off.data(), R + 1))) return rc;
+    if ((rc = upload(ctx, ctx->d_ref_ascii, b->ref_bases, ctx->n_ref_bytes))) return rc;
+    if ((rc = upload(ctx, ctx->d_inner_off, ctx->h_inner_off.data(), R + 1))) return rc;
+    if ((rc = upload(ctx, ctx->d_inner, b->inner, ctx->n_inner))) return rc;
+    if ((rc = upload(ctx, ctx->d_var_off, ctx->h_var_off.data(), R + 1))) return rc;
+    if ((rc = upload(ctx, ctx->d_variants, b->variants, ctx->n_var))) return rc;
+    if ((rc = upload(ctx, ctx->d_allele_ascii, b->allele_bases, ctx->n_allele_bytes))) return rc;
+    if ((rc = upload(ctx, ctx->d_carriers, b->carriers, (size_t)ctx->n_carrier_rows * ctx->pitch))) return rc;
+    CK(ctx->d_ref_codes.reserve(std::max<uint64_t>(1, ctx->n_ref_bytes)));
+    CK(ctx->d_allele_codes.reserve(std::max<uint64_t>(1, ctx->n_allele_bytes)));
+    CK(ctx->d_var_class.reserve(std::max<uint64_t>(1, ctx->n_var) * 4));
+    CK(ctx->d_var_inwin.reserve(std::max<uint64_t>(1, ctx->n_var)));
+    ctx->have_block = true;
+    return TFBS_OK;
+}
+
+std::string nuc_letter(unsigned c) { return std::string(1, "ACGTN"[c < 5 ? c : 4]); }
+
+// ---- the device pipeline on the resident block ---------------------------------------------------
+int run_pipeline(tfbs_ctx* ctx) {
+    if (!ctx->have_patterns) return fail(ctx, TFBS_ERR_STATE, "tfbs_set_patterns has not been called");
+    if (!ctx->have_block) return fail(ctx, TFBS_ERR_STATE, "no block has been uploaded");
+    cudaStream_t st = ctx->stream;
+    const uint32_t R = ctx->R, S = ctx->S, H = ctx->H;
+    uint64_t h2d_keep = ctx->stats.h2d_bytes;
+    memset(&ctx->stats, 0, sizeof ctx->stats);
+    ctx->stats.h2d_bytes = h2d_keep;
+    ctx->stats.sm_count = (uint32_t)ctx->prop.multiProcessorCount;
+    ctx->n_rows = 0;
+    ctx->n_matches = 0;
+    ctx->matches_truncated = false;
+    ctx->ran = false;
+    auto& launches = ctx->stats.total_launches;
+
+    CK(ctx->d_status.reserve(sizeof(DevStatus)));
+    CK(ctx->h_status.reserve(sizeof(DevStatus), false));
+    CK(ctx->h_totals.reserve(64, false));
+    DevStatus* dst = ctx->d_status.as<DevStatus>();
+    DevStatus init{};
+    init.err_key = ~0ull;
+    init.bad_ref_base = ~0ull;
+    init.bad_allele_base = ~0ull;
+    memcpy(ctx->h_status.p, &init, sizeof init);
+    CK(cudaMemcpyAsync(dst, ctx->h_status.p, sizeof init, cudaMemcpyHostToDevice, st));
+    CK(cudaEventRecord(ctx->ev[0], st));
+    if (R == 0 || S == 0) {
+        CK(cudaStreamSynchronize(st));
+        ctx->ran = true;
+        return TFBS_OK;
+    }
+
+    // ---- input encoding -----------------------------------------------------------------------
+    if (ctx->n_ref_bytes) {
+        k_encode<<<std::min<unsigned>(grid_for(ctx->n_ref_bytes, 256), 148 * 16), 256, 0, st>>>(ctx->d_ref_ascii.as<u8>(), ctx->d_ref_codes.as<u8>(),
+                                                                                                 ctx->n_ref_bytes, &dst->bad_ref_base);
+        ++launches;
+    }
+    if (ctx->n_allele_bytes) {
+        k_encode<<<std::min<unsigned>(grid_for(ctx->n_allele_bytes, 256), 148 * 16), 256, 0, st>>>(
+            ctx->d_allele_ascii.as<u8>(), ctx->d_allele_codes.as<u8>(), ctx->n_allele_bytes, &dst->bad_allele_base);
+        ++launches;
+    }
+    DevBlock db = dev_block(ctx);
+    k_variant_prep<<<R, 128, 0, st>>>(db, 0, ctx->d_var_class.as<u32>(), ctx->d_var_inwin.as<u8>());
+    ++launches;
+
+    // ---- phase 1: grouping (K0), over super-batches bounded by the hash table ---------------------
+    const uint64_t RH = (uint64_t)R * H;
+    CK(ctx->d_sig.reserve(RH * 8));
+    CK(ctx->d_nd_in.reserve(RH * 4));
+    CK(ctx->d_leader.reserve(RH * 4));
+    CK(ctx->d_hap_group.reserve(RH * 4));
+    CK(ctx->d_ngroups.reserve((size_t)R * 4));
+    CK(ctx->d_sum_nd.reserve((size_t)R * 4));
+    CK(ctx->d_ref_used.reserve((size_t)R * 4));
+    const uint64_t max_pairs = 1ull << 25;
+    uint32_t regions_per_super = (uint32_t)std::max<uint64_t>(1, max_pairs / std::max<uint32_t>(1, H));
+    uint64_t seed = 0x243f6a8885a308d3ull;
+    for (int attempt = 0;; ++attempt) {
+        for (uint32_t r0 = 0; r0 < R; r0 += regions_per_super) {
+            uint32_t nr = std::min(regions_per_super, R - r0);
+            uint64_t pairs = (uint64_t)nr * H;
+            uint32_t cap = 1024;
+            while (cap < 2 * pairs) cap <<= 1;
+            CK(ctx->d_keys.reserve((size_t)cap * 8));
+            CK(ctx->d_vals.reserve((size_t)cap * 4));
+            CK(cudaMemsetAsync(ctx->d_keys.p, 0, (size_t)cap * 8, st));
+            CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, (size_t)cap * 4, st));
+            k_signatures<<<grid_for(pairs, 256), 256, 0, st>>>(db, r0, nr, seed, ctx->d_sig.as<u64>(), ctx->d_nd_in.as<u32>());
+            k_group_insert<<<grid_for(pairs, 256), 256, 0, st>>>(H, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1);
+            k_group_lookup<<<grid_for(pairs, 256), 256, 0, st>>>(db, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1,
+                                                                 ctx->d_leader.as<u32>(), dst);
+            k_group_rank<<<nr, 256, 0, st>>>(H, r0, ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), ctx->d_hap_group.as<u32>(),
+                                             ctx->d_ngroups.as<u32>(), ctx->d_sum_nd.as<u32>());
+            launches += 4;
+        }
+        CK(cudaGetLastError());
+        ctx->h_ngroups.resize(R);
+        ctx->h_sum_nd.resize(R);
+        CK(cudaMemcpyAsync(ctx->h_ngroups.data(), ctx->d_ngroups.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_sum_nd.data(), ctx->d_sum_nd.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(ctx->h_status.p, dst, sizeof(DevStatus), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        DevStatus hs;
+        memcpy(&hs, ctx->h_status.p, sizeof hs);
+        if (hs.bad_ref_base != ~0ull || hs.bad_allele_base != ~0ull) {
+            // util.rs:15 panic!("Unknown nucleotide {}", l)
+            return fail(ctx, TFBS_ERR_UNKNOWN_NUCLEOTIDE,
+                        std::string("Unknown nucleotide at byte ") +
+                            std::to_string(hs.bad_ref_base != ~0ull ? hs.bad_ref_base : hs.bad_allele_base) +
+                            (hs.bad_ref_base != ~0ull ? " of ref_bases" : " of allele_bases"));
+        }
+        if (hs.sig_collision == 0 || !ctx->verify_groups) break;
+        if (attempt >= 3) return fail(ctx, TFBS_ERR_INTERNAL, "haplotype signature hash collision persisted over 4 seeds");
+        seed = seed * 0x9e3779b97f4a7c15ull + 0x7f4a7c15ull;
+        CK(cudaMemsetAsync(&dst->sig_collision, 0, 4, st));
+    }
+    CK(cudaEventRecord(ctx->ev[1], st));
+
+    // per region prefix arrays
+    const uint32_t n_pid = (uint32_t)ctx->cp.pid_list.size();
+    ctx->h_gbase.assign(R + 1, 0);
+    ctx->h_cbase.assign(R + 1, 0);
+    ctx->h_kbase.assign(R + 1, 0);
+    for (uint32_t r = 0; r < R; ++r) {
+        uint64_t nk = ctx->h_inner_off[r + 1] - ctx->h_inner_off[r];
+        ctx->h_gbase[r + 1] = ctx->h_gbase[r] + ctx->h_ngroups[r];
+        ctx->h_cbase[r + 1] = ctx->h_cbase[r] + (uint64_t)ctx->h_ngroups[r] * n_pid * nk;
+        ctx->h_kbase[r + 1] = ctx->h_kbase[r] + (uint64_t)n_pid * nk;
+    }
+    int rc;
+    if ((rc = upload(ctx, ctx->d_gbase, ctx->h_gbase.data(), R + 1))) return rc;
+    if ((rc = upload(ctx, ctx->d_cbase, ctx->h_cbase.data(), R + 1))) return rc;
+    if ((rc = upload(ctx, ctx->d_kbase, ctx->h_kbase.data(), R + 1))) return rc;
+    ctx->stats.h2d_bytes -= 3ull * (R + 1) * 8;  // internal traffic, not the caller's inputs
+
+    if (ctx->record_matches) {
+        CK(ctx->d_m_region.reserve(ctx->max_matches * 4));
+        CK(ctx->d_m_pattern.reserve(ctx->max_matches * 4));
+        CK(ctx->d_m_group.reserve(ctx->max_matches * 4));
+        CK(ctx->d_m_start.reserve(ctx->max_matches * 8));
+    }
+    DevMatches dm{};
+    dm.enabled = ctx->record_matches ? 1u : 0u;
+    dm.cap = (u32)std::min<uint64_t>(ctx->max_matches, 0xffffffffu);
+    dm.region = ctx->d_m_region.as<u32>();
+    dm.pattern_index = ctx->d_m_pattern.as<u32>();
+    dm.group = ctx->d_m_group.as<u32>();
+    dm.start = ctx->d_m_start.as<i64>();
+
+    // ---- phase 2: batches under the scratch budget ---------------------------------------------------
+    auto region_cost = [&](uint32_t r, uint64_t* n_seq, uint64_t* n_d, uint64_t* n_units, uint64_t* n_c, uint64_t* n_keys) {
+        uint64_t g = ctx->h_ngroups[r];
+        uint64_t W = (uint64_t)(ctx->h_region_end[r] - ctx->h_region_start[r] + 1) + ctx->h_ins_extra[r];
+        uint64_t nk = ctx->h_inner_off[r + 1] - ctx->h_inner_off[r];
+        *n_seq = g;
+        *n_d = ctx->h_sum_nd[r];
+        *n_units = g * ((W + 31) / 32 + 1);
+        *n_c = g * n_pid * nk;
+        *n_keys = (uint64_t)n_pid * nk;
+    };
+    auto bytes_of = [&](uint64_t n_seq, uint64_t n_d, uint64_t n_units, uint64_t n_c, uint64_t n_keys) {
+        return n_seq * (4 * 6 + 8 * 3 + 1 + 32) + n_d * (4 + 32) + n_units * 12 + n_c * 4 + n_keys * 24 + n_seq * 2 * 12 * 2;
+    };
+    int smem_bytes = (int)(((sizeof(ScanShared) + 15) & ~size_t(15)) + ((ctx->cp.max_chunk_bytes + 15) & ~15u));
+    CK(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    int occ = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, SCAN_CTA, smem_bytes));
+    if (occ < 1) return fail(ctx, TFBS_ERR_CUDA, "the scan kernel does not fit on this device");
+    if (ctx->scan_ctas_per_sm > 0) occ = std::min(occ, ctx->scan_ctas_per_sm);
+    const uint32_t scan_grid = (uint32_t)(ctx->prop.multiProcessorCount * occ);
+    ctx->stats.scan_ctas = scan_grid;
+
+    float ms_build = 0, ms_scan = 0, ms_count = 0;
+    uint32_t r0 = 0;
+    while (r0 < R) {
+        uint64_t n_seq = 0, n_d = 0, n_units = 0, n_c = 0, n_keys = 0;
+        uint32_t r1 = r0;
+        while (r1 < R) {
+            uint64_t a, b2, c2, d2, e2;
+            region_cost(r1, &a, &b2, &c2, &d2, &e2);
+            if (r1 > r0 && (bytes_of(n_seq + a, n_d + b2, n_units + c2, n_c + d2, n_keys + e2) > ctx->scratch_bytes || n_seq + a > 0x7fffffffull)) break;
+            n_seq += a; n_d += b2; n_units += c2; n_c += d2; n_keys += e2;
+            ++r1;
+        }
+        const uint32_t nr = r1 - r0;
+        if (n_seq > 0xfffffff0ull) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "a single region has more than 2^32 haplotype groups");
+
+        CK(ctx->d_seq_region.reserve(n_seq * 4));
+        CK(ctx->d_seq_leader.reserve(n_seq * 4));
+        CK(ctx->d_seq_nd.reserve(n_seq * 4));
+        CK(ctx->d_seq_doff.reserve((n_seq + 1) * 8));
+        CK(ctx->d_dlist.reserve(std::max<uint64_t>(1, n_d) * 4));
+        CK(ctx->d_segs.reserve((2 * n_d + 2 * n_seq) * sizeof(Seg)));
+        CK(ctx->d_seq_nseg.reserve(n_seq * 4));
+        CK(ctx->d_seq_len.reserve(n_seq * 4));
+        CK(ctx->d_seq_units.reserve(n_seq * 4));
+        CK(ctx->d_seq_uoff.reserve((n_seq + 1) * 8));
+        CK(ctx->d_pk.reserve(n_units * 8));
+        CK(ctx->d_nm.reserve(n_units * 4));
+        CK(ctx->d_seq_hash.reserve(n_seq * 8));
+        CK(ctx->d_seq_flags.reserve(n_seq));
+        CK(ctx->d_C.reserve(std::max<uint64_t>(1, n_c) * 4));
+        CK(ctx->d_vmin.reserve(std::max<uint64_t>(1, n_keys) * 4));
+        CK(ctx->d_vmax.reserve(std::max<uint64_t>(1, n_keys) * 4));
+        CK(ctx->d_flag.reserve(std::max<uint64_t>(1, n_keys) * 4));
+        CK(ctx->d_rowidx.reserve((n_keys + 1) * 8));
+
+        DevSeqs sq{};
+        sq.n_seq = (u32)n_seq;
+        sq.gbase = ctx->d_gbase.as<u64>();
+        sq.gbase0 = ctx->h_gbase[r0];
+        sq.seq_region = ctx->d_seq_region.as<u32>();
+        sq.seq_leader = ctx->d_seq_leader.as<u32>();
+        sq.seq_nd = ctx->d_seq_nd.as<u32>();
+        sq.seq_doff = ctx->d_seq_doff.as<u64>();
+        sq.dlist = ctx->d_dlist.as<u32>();
+        sq.segs = ctx->d_segs.as<Seg>();
+        sq.seq_nseg = ctx->d_seq_nseg.as<u32>();
+        sq.seq_len = ctx->d_seq_len.as<u32>();
+        sq.seq_units = ctx->d_seq_units.as<u32>();
+        sq.seq_uoff = ctx->d_seq_uoff.as<u64>();
+        sq.pk = ctx->d_pk.as<u64>();
+        sq.nm = ctx->d_nm.as<u32>();
+        sq.seq_hash = ctx->d_seq_hash.as<u64>();
+        sq.seq_flags = ctx->d_seq_flags.as<u8>();
+
+        CK(cudaEventRecord(ctx->ev[2], st));
+        // K1 build
+        k_seq_init<<<nr, 128, 0, st>>>(H, r0, ctx->d_hap_group.as<u32>(), ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), sq);
+        ++launches;
+        if ((rc = device_scan(ctx, sq.seq_nd, n_seq, sq.seq_doff))) return rc;
+        k_walk<<<grid_for(n_seq, 128), 128, 0, st>>>(db, sq, dst);
+        ++launches;
+        if ((rc = device_scan(ctx, sq.seq_units, n_seq, sq.seq_uoff))) return rc;
+        k_emit<<<(unsigned)n_seq, 64, 0, st>>>(db, sq);
+        ++launches;
+        // the sequence-keyed map of load_haplotypes
+        {
+            uint32_t cap = 1024;
+            while (cap < 2 * n_seq) cap <<= 1;
+            CK(ctx->d_keys.reserve((size_t)cap * 8));
+            CK(ctx->d_vals.reserve((size_t)cap * 4));
+            CK(cudaMemsetAsync(ctx->d_keys.p, 0, (size_t)cap * 8, st));
+            CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, (size_t)cap * 4, st));
+            CK(cudaMemsetAsync(ctx->d_ref_used.as<u32>() + r0, 0, (size_t)nr * 4, st));
+            k_seq_insert<<<grid_for(n_seq, 256), 256, 0, st>>>(sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1);
+            k_seq_resolve<<<grid_for(n_seq, 128), 128, 0, st>>>(db, sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1, dst);
+            k_redirect<<<grid_for((uint64_t)nr * H, 256), 256, 0, st>>>(H, r0, nr, sq, ctx->d_hap_group.as<u32>(), ctx->d_ref_used.as<u32>());
+            launches += 3;
+        }
+        CK(cudaEventRecord(ctx->ev[3], st));
+
+        // K2 scan
+        DevCounts dc{};
+        dc.C = ctx->d_C.as<u32>();
+        dc.cbase = ctx->d_cbase.as<u64>();
+        dc.cbase0 = ctx->h_cbase[r0];
+        if (n_c) CK(cudaMemsetAsync(ctx->d_C.p, 0, n_c * 4, st));
+        CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
+        uint64_t n_items64 = n_seq * ctx->cp.chunks.size();
+        if (n_items64 > 0xfffffff0ull) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "batch too large for the scan scheduler");
+        if (n_items64) {
+            k_scan<<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, ctx->d_ref_used.as<u32>(), dst, (u32)n_items64);
+            ++launches;
+            ++ctx->stats.scan_launches;
+        }
+        CK(cudaEventRecord(ctx->ev[4], st));
+
+        // K3 rows
+        k_nominal<<<grid_for((uint64_t)nr * H, 256), 256, 0, st>>>(db, r0, nr, ctx->d_hap_group.as<u32>(), sq, ctx->dpat, dst);
+        ++launches;
+        uint64_t batch_rows = 0;
+        if (n_keys) {
+            k_rows_minmax<<<nr, 128, 0, st>>>(db, r0, ctx->d_hap_group.as<u32>(), dc, ctx->d_gbase.as<u64>(), n_pid, ctx->d_kbase.as<u64>(),
+                                              ctx->h_kbase[r0], ctx->rows_mode, ctx->d_vmin.as<u32>(), ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>());
+            ++launches;
+            if ((rc = device_scan(ctx, ctx->d_flag.as<u32>(), n_keys, ctx->d_rowidx.as<u64>()))) return rc;
+            CK(cudaMemcpyAsync(ctx->h_totals.p, ctx->d_rowidx.as<u64>() + n_keys, 8, cudaMemcpyDeviceToHost, st));
+        }
+        CK(cudaMemcpyAsync(ctx->h_status.p, dst, sizeof(DevStatus), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        CK(cudaGetLastError());
+        DevStatus hs;
+        memcpy(&hs, ctx->h_status.p, sizeof hs);
+        if (hs.err_key != ~0ull) {
+            uint32_t q = (uint32_t)(hs.err_key >> 32);
+            int64_t rel = (int64_t)((hs.err_key >> 4) & 0xfffffff) - (1 << 27);
+            uint32_t code = (uint32_t)(hs.err_key & 15);
+            // region of sequence q: last r with gbase[r] - gbase[r0] <= q
+            uint32_t r = (uint32_t)(std::upper_bound(ctx->h_gbase.begin() + r0, ctx->h_gbase.begin() + r1, ctx->h_gbase[r0] + q) - ctx->h_gbase.begin() - 1);
+            int64_t pos = ctx->h_region_start[r] + rel;
+            if (code == DEV_REF_MISMATCH)
+                return fail(ctx, TFBS_ERR_REF_MISMATCH,
+                            "First reference nucleotide of variant doesn't match reference genome: ref_position=" + std::to_string(pos) +
+                                " region=" + std::to_string(r));
+            return fail(ctx, TFBS_ERR_MISSING_CASE, "Missing case in haplotype patcher (ref_position=" + std::to_string(pos) + " region=" + std::to_string(r) + ")");
+        }
+        if (hs.seq_collision) return fail(ctx, TFBS_ERR_INTERNAL, "sequence hash collision between distinct haplotypes");
+        if (n_keys) batch_rows = *ctx->h_totals.as<uint64_t>();
+
+        if (batch_rows) {
+            uint64_t tot = ctx->n_rows + batch_rows;
+            CK(ctx->d_rows_region.reserve(batch_rows * 4));
+            CK(ctx->d_rows_inner.reserve(batch_rows * 4));
+            CK(ctx->d_rows_pid.reserve(batch_rows * 2));
+            CK(ctx->d_rows_vmin.reserve(batch_rows * 4));
+            CK(ctx->d_rows_vmax.reserve(batch_rows * 4));
+            CK(ctx->d_rows_left.reserve(batch_rows * S * 4));
+            CK(ctx->d_rows_right.reserve(batch_rows * S * 4));
+            CK(ctx->h_rows_region.reserve(tot * 4, true));
+            CK(ctx->h_rows_inner.reserve(tot * 4, true));
+            CK(ctx->h_rows_pid.reserve(tot * 2, true));
+            CK(ctx->h_rows_vmin.reserve(tot * 4, true));
+            CK(ctx->h_rows_vmax.reserve(tot * 4, true));
+            CK(ctx->h_rows_left.reserve(tot * S * 4, true));
+            CK(ctx->h_rows_right.reserve(tot * S * 4, true));
+            DevRows dr{ctx->d_rows_region.as<u32>(), ctx->d_rows_inner.as<u32>(), ctx->d_rows_pid.as<u16>(), ctx->d_rows_vmin.as<u32>(),
+                       ctx->d_rows_vmax.as<u32>(), ctx->d_rows_left.as<u32>(), ctx->d_rows_right.as<u32>()};
+            k_rows_write<<<grid_for(n_keys * 32, 256), 256, 0, st>>>(db, r0, nr, ctx->d_hap_group.as<u32>(), dc, n_pid, ctx->d_pid_list.as<u16>(),
+                                                                     ctx->d_kbase.as<u64>(), ctx->h_kbase[r0], n_keys, ctx->d_vmin.as<u32>(),
+                                                                     ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(), ctx->d_rowidx.as<u64>(), dr, 0);
+            ++launches;
+            uint64_t o = ctx->n_rows;
+            CK(cudaMemcpyAsync(ctx->h_rows_region.as<u32>() + o, dr.region, batch_rows * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_rows_inner.as<u32>() + o, dr.inner, batch_rows * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_rows_pid.as<u16>() + o, dr.pattern_id, batch_rows * 2, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_rows_vmin.as<u32>() + o, dr.vmin, batch_rows * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_rows_vmax.as<u32>() + o, dr.vmax, batch_rows * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_rows_left.as<u32>() + o * S, dr.left, batch_rows * S * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_rows_right.as<u32>() + o * S, dr.right, batch_rows * S * 4, cudaMemcpyDeviceToHost, st));
+            ctx->stats.d2h_bytes += batch_rows * (4 * 4 + 2 + 8ull * S);
+            ctx->n_rows = tot;
+        }
+        CK(cudaEventRecord(ctx->ev[5], st));
+        CK(cudaStreamSynchronize(st));
+        float t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]));
+        ms_build += t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[3], ctx->ev[4]));
+        ms_scan += t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]));
+        ms_count += t;
+        r0 = r1;
+    }
+    CK(cudaEventRecord(ctx->ev[6], st));
+    CK(cudaMemcpyAsync(ctx->h_status.p, dst, sizeof(DevStatus), cudaMemcpyDeviceToHost, st));
+    if (ctx->record_matches) {
+        CK(ctx->h_hap_group.reserve(RH * 4, false));
+        CK(cudaMemcpyAsync(ctx->h_hap_group.p, ctx->d_hap_group.p, RH * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    DevStatus hs;
+    memcpy(&hs, ctx->h_status.p, sizeof hs);
+    if (ctx->record_matches) {
+        uint64_t n = std::min<uint64_t>(hs.n_matches, dm.cap);
+        ctx->matches_truncated = hs.n_matches > dm.cap;
+        CK(ctx->h_m_region.reserve(std::max<uint64_t>(1, n) * 4, false));
+        CK(ctx->h_m_pattern.reserve(std::max<uint64_t>(1, n) * 4, false));
+        CK(ctx->h_m_group.reserve(std::max<uint64_t>(1, n) * 4, false));
+        CK(ctx->h_m_start.reserve(std::max<uint64_t>(1, n) * 8, false));
+        if (n) {
+            CK(cudaMemcpyAsync(ctx->h_m_region.p, dm.region, n * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_m_pattern.p, dm.pattern_index, n * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_m_group.p, dm.group, n * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_m_start.p, dm.start, n * 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+        }
+        ctx->n_matches = n;
+    }
+    float t;
+    CK(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
+    ctx->stats.ms_group = t;
+    CK(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[6]));
+    ctx->stats.ms_total = t;
+    ctx->stats.ms_build = ms_build;
+    ctx->stats.ms_scan = ms_scan;
+    ctx->stats.ms_count = ms_count;
+    ctx->stats.n_regions = R;
+    ctx->stats.n_groups = hs.n_scanned;
+    ctx->stats.executed_cells = hs.executed_cells;
+    ctx->stats.nominal_cells = hs.nominal_cells;
+    ctx->stats.n_hits = hs.n_hits;
+    ctx->stats.n_keys = ctx->h_kbase[R];
+    ctx->stats.n_rows = ctx->n_rows;
+    ctx->ran = true;
+    return TFBS_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------------
+extern "C" {
+
+int tfbs_abi_version(void) { return TFBS_ABI_VERSION; }
+
+int tfbs_create(int device, tfbs_ctx** out) {
+    if (!out) return TFBS_ERR_INVALID_ARGUMENT;
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        g_create_error = std::string("no usable CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") +
+                         " (this library has no CPU fallback)";
+        return TFBS_ERR_CUDA;
+    }
+    if (device < 0 || device >= n) {
+        g_create_error = "device index out of range";
+        return TFBS_ERR_INVALID_ARGUMENT;
+    }
+    if ((e = cudaSetDevice(device)) != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice failed: ") + cudaGetErrorString(e);
+        return TFBS_ERR_CUDA;
+    }
+    tfbs_ctx* ctx = new tfbs_ctx();
+    ctx->device = device;
+    if ((e = cudaGetDeviceProperties(&ctx->prop, device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+        g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
+        delete ctx;
+        return TFBS_ERR_CUDA;
+    }
+    if (ctx->prop.major < 10) {
+        g_create_error = std::string("device ") + ctx->prop.name + " is not sm_100-class; this library carries sm_100a code only";
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return TFBS_ERR_CUDA;
+    }
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    *out = ctx;
+    return TFBS_OK;
+}
+
+void tfbs_destroy(tfbs_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& ev : ctx->ev)
+        if (ev) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* tfbs_last_error(const tfbs_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int tfbs_set_option(tfbs_ctx* ctx, const char* key, int64_t value) {
+    if (!ctx || !key) return TFBS_ERR_INVALID_ARGUMENT;
+    std::string k(key);
+    if (k == "rows_mode") {
+        if (value != TFBS_ROWS_VARYING && value != TFBS_ROWS_ALL_KEYS) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "rows_mode must be 0 or 1");
+        ctx->rows_mode = (int)value;
+    } else if (k == "record_matches") ctx->record_matches = value != 0;
+    else if (k == "max_matches") ctx->max_matches = (uint64_t)std::max<int64_t>(1, value);
+    else if (k == "verify_groups") ctx->verify_groups = value != 0;
+    else if (k == "scan_format") { ctx->scan_format = (int)value; ctx->have_patterns = false; }
+    else if (k == "scratch_mb") ctx->scratch_bytes = (uint64_t)std::max<int64_t>(64, value) << 20;
+    else if (k == "table_budget_kb") { ctx->table_budget = (uint32_t)std::max<int64_t>(8, value) * 1024; ctx->have_patterns = false; }
+    else if (k == "scan_ctas_per_sm") ctx->scan_ctas_per_sm = (int)value;
+    else return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "unknown option " + k);
+    return TFBS_OK;
+}
+
+int tfbs_set_patterns(tfbs_ctx* ctx, const tfbs_pattern* patterns, uint32_t n_patterns) {
+    if (!ctx || (!patterns && n_patterns)) return TFBS_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    ctx->have_patterns = false;
+    if (n_patterns == 0) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "assertion failed: pwm_list.len() > 0");  // main.rs:238
+    size_t max_smem = ctx->prop.sharedMemPerBlockOptin;
+    size_t fixed = ((sizeof(ScanShared) + 15) & ~size_t(15)) + 1024;
+    uint32_t budget = (uint32_t)std::min<size_t>(ctx->table_budget, max_smem > fixed ? max_smem - fixed : 0);
+    std::string err;
+    CompiledPatterns cp;
+    int rc = compile_patterns(patterns, n_patterns, budget, ctx->scan_format == 1, &cp, &err);
+    if (rc != TFBS_OK) return fail(ctx, rc, err);
+    ctx->cp = std::move(cp);
+    const CompiledPatterns& c = ctx->cp;
+    uint64_t keep = ctx->stats.h2d_bytes;
+    std::vector<uint64_t> table = c.table;
+    table.resize(table.size() + 2, 0);  // 128-bit loads may read one word past the end
+    if ((rc = upload(ctx, ctx->d_table, table.data(), table.size()))) return rc;
+    if ((rc = upload(ctx, ctx->d_chunks, c.chunks.data(), c.chunks.size()))) return rc;
+    if ((rc = upload(ctx, ctx->d_runs, c.runs.data(), c.runs.size()))) return rc;
+    if ((rc = upload(ctx, ctx->d_trip_pat, c.trip_pat.data(), c.trip_pat.size()))) return rc;
+    if ((rc = upload(ctx, ctx->d_pat_len, c.pat_len.data(), c.pat_len.size()))) return rc;
+    if ((rc = upload(ctx, ctx->d_pat_pid, c.pat_pid_index.data(), c.pat_pid_index.size()))) return rc;
+    if ((rc = upload(ctx, ctx->d_pid_list, c.pid_list.data(), c.pid_list.size()))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->stats.h2d_bytes = keep;
+    DevPatterns& d = ctx->dpat;
+    d.table = ctx->d_table.as<u64>();
+    d.chunks = ctx->d_chunks.as<ChunkDesc>();
+    d.runs = ctx->d_runs.as<RunDesc>();
+    d.trip_pat = ctx->d_trip_pat.as<int>();
+    d.pat_len = ctx->d_pat_len.as<u32>();
+    d.pat_pid_index = ctx->d_pat_pid.as<u32>();
+    d.n_chunks = (u32)c.chunks.size();
+    d.n_pid = (u32)c.pid_list.size();
+    d.n_patterns = (u32)c.patterns.size();
+    d.max_len = c.max_len;
+    d.sum_len = c.sum_len;
+    d.sum_len_sq = c.sum_len_sq;
+    ctx->have_patterns = true;
+    return TFBS_OK;
+}
+
+int tfbs_upload_block(tfbs_ctx* ctx, const tfbs_block* block) {
+    if (!ctx) return TFBS_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    ctx->stats.h2d_bytes = 0;
+    int rc = do_upload(ctx, block);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TFBS_OK;
+}
+
+int tfbs_run_resident(tfbs_ctx* ctx) {
+    if (!ctx) return TFBS_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    return run_pipeline(ctx);
+}
+
+int tfbs_submit_block(tfbs_ctx* ctx, const tfbs_block* block) {
+    if (!ctx) return TFBS_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->have_patterns) return fail(ctx, TFBS_ERR_STATE, "tfbs_set_patterns has not been called");
+    ctx->stats.h2d_bytes = 0;
+    int rc = do_upload(ctx, block);
+    if (rc) return rc;
+    return run_pipeline(ctx);
+}
+
+int tfbs_collect(tfbs_ctx* ctx, tfbs_rows* out) {
+    if (!ctx || !out) return TFBS_ERR_INVALID_ARGUMENT;
+    if (!ctx->ran) return fail(ctx, TFBS_ERR_STATE, "tfbs_collect called before a successful tfbs_submit_block / tfbs_run_resident");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    out->n_rows = ctx->n_rows;
+    out->n_samples = ctx->S;
+    out->reserved = 0;
+    out->region = ctx->h_rows_region.as<uint32_t>();
+    out->inner = ctx->h_rows_inner.as<uint32_t>();
+    out->pattern_id = ctx->h_rows_pid.as<uint16_t>();
+    out->vmin = ctx->h_rows_vmin.as<uint32_t>();
+    out->vmax = ctx->h_rows_vmax.as<uint32_t>();
+    out->left = ctx->h_rows_left.as<uint32_t>();
+    out->right = ctx->h_rows_right.as<uint32_t>();
+    return TFBS_OK;
+}
+
+int tfbs_get_matches(tfbs_ctx* ctx, tfbs_matches* out) {
+    if (!ctx || !out) return TFBS_ERR_INVALID_ARGUMENT;
+    if (!ctx->ran || !ctx->record_matches) return fail(ctx, TFBS_ERR_STATE, "matches were not recorded (set option record_matches before the run)");
+    out->n_matches = ctx->n_matches;
+    out->region = ctx->h_m_region.as<uint32_t>();
+    out->pattern_index = ctx->h_m_pattern.as<uint32_t>();
+    out->group = ctx->h_m_group.as<uint32_t>();
+    out->start = ctx->h_m_start.as<int64_t>();
+    out->hap_group = ctx->h_hap_group.as<uint32_t>();
+    out->n_samples = ctx->S;
+    out->truncated = ctx->matches_truncated ? 1 : 0;
+    return TFBS_OK;
+}
+
+int tfbs_get_stats(const tfbs_ctx* ctx, tfbs_stats* out) {
+    if (!ctx || !out) return TFBS_ERR_INVALID_ARGUMENT;
+    *out = ctx->stats;
+    return TFBS_OK;
+}
+
+void* tfbs_stream(const tfbs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+}  // extern "C"

@@ -611,9 +611,12 @@ void process_block_range(const std::vector<Pattern>& pwm_list, const tfbs_block&
 }
 
 // main.rs:333-382: `threads` workers, each pulling chunks of 50 merged regions from a shared queue.
+static std::atomic<uint32_t> g_chunk_size{50};
+void set_chunk_size(uint32_t n) { g_chunk_size = n ? n : 50; }
+
 void process_block(const std::vector<Pattern>& pwm_list, const tfbs_block& blk, int rows_mode, bool want_matches, int n_threads,
                    BlockResult* out) {
-    const uint32_t CHUNK = 50;
+    const uint32_t CHUNK = g_chunk_size;  // 50 in the reference (main.rs:378); bench.py shrinks it for bounded samples
     uint32_t n_chunks = (blk.n_regions + CHUNK - 1) / CHUNK;
     std::vector<BlockResult> partial(n_chunks);
     std::atomic<uint32_t> next{0};

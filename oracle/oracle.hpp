@@ -242,6 +242,8 @@ void process_block_range(const std::vector<Pattern>& pwm_list, const tfbs_block&
 // Multi-threaded like the reference: n_threads workers pull chunks of 50 regions (main.rs:333-382).
 void process_block(const std::vector<Pattern>& pwm_list, const tfbs_block& blk, int rows_mode, bool want_matches,
                    int n_threads, BlockResult* out);
+// Work-queue granularity (regions per chunk); the reference uses 50 because BCF is block-compressed (main.rs:375-378).
+void set_chunk_size(uint32_t n);
 
 // ---- whole program (run(), main.rs:234-393) ---------------------------------------------
 struct RunOptions {

@@ -42,6 +42,7 @@ extern "C" {
 
 const char* ora_last_error(void) { return g_err.c_str(); }
 void ora_free(void* p) { free(p); }
+void ora_set_chunk_size(uint32_t n) { set_chunk_size(n); }
 
 // ---- block level ------------------------------------------------------------------------------
 typedef struct ora_block_result {

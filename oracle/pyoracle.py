@@ -86,9 +86,11 @@ def _arr(ptr, n, dtype):
     return np.ctypeslib.as_array(ptr, shape=(n,)).astype(dtype, copy=True)
 
 
-def process_block(c_patterns, n_patterns, c_block, n_samples, rows_mode=0, want_matches=False, n_threads=1):
-    """c_patterns: (TfbsPattern * n) array; c_block: TfbsBlock.  Returns a dict of numpy arrays."""
+def process_block(c_patterns, n_patterns, c_block, n_samples, rows_mode=0, want_matches=False, n_threads=1, chunk=50):
+    """c_patterns: (TfbsPattern * n) array; c_block: TfbsBlock.  Returns a dict of numpy arrays.
+    chunk: regions per work-queue item (50 in the reference, main.rs:378)."""
     res = _BlockResult()
+    lib().ora_set_chunk_size(C.c_uint32(chunk))
     _check(lib().ora_process_block(c_patterns, C.c_uint32(n_patterns), C.byref(c_block), C.c_int(rows_mode),
                                    C.c_int(1 if want_matches else 0), C.c_int(n_threads), C.byref(res)))
     n = res.n_rows

@@ -1,0 +1,116 @@
+"""Shared helpers of the parity tests: run the same block through the CUDA path (C ABI) and through the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+
+from find_tfbs_b200 import binding
+from find_tfbs_b200.binding import Block, INNER_DTYPE, VARIANT_DTYPE
+from oracle import pyoracle as ora
+
+
+def run_oracle(pattern_set, block, rows_mode=0, want_matches=False, n_threads=4, chunk=50):
+    """The oracle takes the very same C structs (layouts are asserted equal in test_abi.py)."""
+    cp = C.cast(pattern_set.c, C.POINTER(ora.TfbsPattern))
+    cb = C.cast(C.pointer(block.c), C.POINTER(ora.TfbsBlock)).contents
+    return ora.process_block(cp, pattern_set.n, cb, block.n_samples, rows_mode, want_matches, n_threads, chunk)
+
+
+def run_gpu(pattern_set, block, rows_mode=0, record_matches=False, options=None, resident=False):
+    ctx = binding.Context(0)
+    try:
+        ctx.set_option("rows_mode", rows_mode)
+        ctx.set_option("record_matches", 1 if record_matches else 0)
+        for k, v in (options or {}).items():
+            ctx.set_option(k, v)
+        ctx.set_patterns(pattern_set)
+        if resident:
+            ctx.upload_block(block)
+            ctx.run_resident()
+        else:
+            ctx.submit_block(block)
+        rows = ctx.collect()
+        rows["stats"] = ctx.stats()
+        if record_matches:
+            rows["matches"] = ctx.matches(block.n_regions)
+        return rows
+    finally:
+        ctx.close()
+
+
+def assert_rows_equal(g, o):
+    assert len(g["region"]) == len(o["region"]), "row count: gpu %d oracle %d" % (len(g["region"]), len(o["region"]))
+    for k in ("region", "inner", "pattern_id", "vmin", "vmax", "left", "right"):
+        assert np.array_equal(g[k], o[k]), "rows differ in " + k
+
+
+def sorted_matches(region, pattern_index, group, start):
+    m = np.stack([region.astype(np.int64), pattern_index.astype(np.int64), group.astype(np.int64), start.astype(np.int64)], axis=1)
+    if len(m):
+        m = m[np.lexsort((m[:, 3], m[:, 2], m[:, 1], m[:, 0]))]
+    return m
+
+
+def assert_matches_equal(g, o):
+    gm = g["matches"]
+    assert not gm["truncated"]
+    a = sorted_matches(gm["region"], gm["pattern_index"], gm["group"], gm["start"])
+    b = sorted_matches(o["m_region"], o["m_pattern_index"], o["m_group"], o["m_start"])
+    assert a.shape == b.shape, "hit count: gpu %d oracle %d" % (len(a), len(b))
+    assert np.array_equal(a, b), "hit lists differ"
+    assert np.array_equal(gm["hap_group"], o["hap_group"]), "haplotype -> group maps differ"
+
+
+def check_parity(pattern_set, block, rows_mode=0, options=None, matches=True, resident=False):
+    o = run_oracle(pattern_set, block, rows_mode, matches)
+    g = run_gpu(pattern_set, block, rows_mode, matches, options, resident)
+    assert_rows_equal(g, o)
+    if matches:
+        assert_matches_equal(g, o)
+    st = g["stats"]
+    assert st["executed_cells"] == o["executed_cells"]
+    assert st["nominal_cells"] == o["nominal_cells"]
+    assert st["n_hits"] == o["n_hits"]
+    assert st["n_groups"] == o["n_groups"]
+    return g, o
+
+
+def hand_block(n_samples, regions, variants, carriers_by_variant, inner=None):
+    """Small explicit blocks.  regions: [(start, end, 'REFWINDOW')]; variants: [(region, pos, 'REF', 'ALT')] in record order;
+    carriers_by_variant: list of haplotype index lists; inner: per region list of (start, end, bed, multiplicity)."""
+    H = 2 * n_samples
+    pitch = max(1, (H + 31) // 32)
+    rs = np.array([r[0] for r in regions], dtype=np.int64)
+    re = np.array([r[1] for r in regions], dtype=np.int64)
+    ref = b"".join(r[2].encode() for r in regions)
+    ref_off = np.cumsum([0] + [len(r[2]) for r in regions]).astype(np.uint64)
+    var = np.zeros(len(variants), dtype=VARIANT_DTYPE)
+    allele = bytearray()
+    var_off = np.zeros(len(regions) + 1, dtype=np.uint32)
+    car = np.zeros((max(1, len(variants)), pitch), dtype=np.uint32)
+    order = sorted(range(len(variants)), key=lambda i: variants[i][0])  # stable: keeps record order inside a region
+    for k, i in enumerate(order):
+        r, pos, rf, al = variants[i]
+        var[k]["pos"] = pos
+        var[k]["ref_off"] = len(allele)
+        var[k]["ref_len"] = len(rf)
+        allele += rf.encode()
+        var[k]["alt_off"] = len(allele)
+        var[k]["alt_len"] = len(al)
+        allele += al.encode()
+        var[k]["carrier_row"] = k
+        for h in carriers_by_variant[i]:
+            car[k, h // 32] |= np.uint32(1 << (h % 32))
+        var_off[r + 1] += 1
+    var_off = np.cumsum(var_off).astype(np.uint32)
+    if inner is None:
+        inner = [[(int(rs[i]), int(re[i]), 0, 1)] for i in range(len(regions))]
+    inn = np.zeros(sum(len(x) for x in inner), dtype=INNER_DTYPE)
+    inner_off = np.zeros(len(regions) + 1, dtype=np.uint32)
+    k = 0
+    for r, lst in enumerate(inner):
+        for (s, e, b, m) in lst:
+            inn[k] = (s, e, b, m)
+            k += 1
+        inner_off[r + 1] = k
+    return Block(n_samples, rs, re, ref_off, np.frombuffer(ref, dtype=np.uint8) if ref else np.zeros(0, np.uint8), inner_off, inn, var_off, var,
+                 np.frombuffer(bytes(allele), dtype=np.uint8) if allele else np.zeros(0, np.uint8), car)

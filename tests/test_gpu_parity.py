@@ -1,0 +1,267 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle: rows, hit lists, haplotype grouping and work counters
+must be bit-identical (scores are exact i32 sums, src/pattern.rs:119-151 of the reference; no tolerance applies)."""
+import numpy as np
+import pytest
+
+from find_tfbs_b200 import binding, synth
+from find_tfbs_b200.binding import PatternSet
+import parity_helpers as hp
+
+pytestmark = pytest.mark.gpu
+
+ACGT = {"weights": np.eye(4, dtype=np.int32) * 1000, "min_score": 3999, "pattern_id": 0}
+
+
+def acgt_patterns():
+    return PatternSet([dict(ACGT, direction=0), dict(ACGT, direction=1)])
+
+
+def fixture_block(alt_carriers):
+    """The reference's integration fixture: chr1 = 250 x 'A' with ACGT at 100..103, regions1+regions2
+    merged, one SNV A->G at 100; 4 samples.  Windows are the merged regions extended by Lmax-1 = 3."""
+    genome = bytearray(b"A" * 250)
+    genome[100:104] = b"ACGT"
+    merged = [(100, 115), (118, 130), (150, 160), (161, 165), (180, 210)]
+    bed1 = [(100, 110), (120, 130), (150, 160), (180, 190), (200, 210)]
+    bed2 = [(110, 115), (118, 125), (161, 165), (190, 200)]
+    regions, inner = [], []
+    for m in merged:
+        s, e = m[0] - 3, m[1] + 3
+        regions.append((s, e, genome[s:e + 1].decode()))
+        inner.append([tuple(x) for x in synth.select_inner_peaks(m, [bed1, bed2])])
+    return hp.hand_block(4, regions, [(0, 100, "A", "G")], [alt_carriers], inner)
+
+
+def test_fixture_one_polymorphism():
+    """main.rs:559-568 / expected_output_2: INDIVIDUAL1 = 1|0 -> v = [2,4,4,4] for regions1.bed 100-110 only."""
+    blk = fixture_block([0])
+    g, o = hp.check_parity(acgt_patterns(), blk)
+    assert len(g["region"]) == 1
+    assert g["region"][0] == 0 and g["pattern_id"][0] == 0
+    assert blk.inner[g["inner"][0]]["start"] == 100 and blk.inner[g["inner"][0]]["end"] == 110 and blk.inner[g["inner"][0]]["bed_index"] == 0
+    assert (g["left"][0] + g["right"][0]).tolist() == [2, 4, 4, 4]
+    assert g["vmin"][0] == 2 and g["vmax"][0] == 4
+
+
+def test_fixture_no_polymorphism():
+    """main.rs:548-557 / expected_output_1: nobody carries the variant -> header only."""
+    blk = fixture_block([])
+    g, o = hp.check_parity(acgt_patterns(), blk)
+    assert len(g["region"]) == 0
+    g, o = hp.check_parity(acgt_patterns(), blk, rows_mode=binding.ROWS_ALL_KEYS)
+    assert len(g["region"]) == 1 and g["vmin"][0] == 4 and g["vmax"][0] == 4
+
+
+def test_gataa_strict_threshold_and_n():
+    """pattern.rs:285-301: N scores 0, score > min_score is strict."""
+    w = np.array([[0, 0, 100, 0], [100, 0, 0, 0], [0, 0, 0, 100], [100, 0, 0, 0], [100, 0, 0, 0]], dtype=np.int32)
+    blk = hp.hand_block(1, [(0, 6, "NGATAAN"), (10, 14, "GATAA")], [], [])
+    for ms, n in ((499, 2), (500, 0)):
+        ps = PatternSet([{"weights": w, "min_score": ms, "pattern_id": 123}])
+        g, o = hp.check_parity(ps, blk, rows_mode=binding.ROWS_ALL_KEYS)
+        assert len(g["matches"]["start"]) == n
+
+
+def test_patch_vectors_through_the_kernel():
+    """haplotype.rs:172-254 vectors pushed through K1 (the hit list pins every base and position of the patched sequence)."""
+    # single-column patterns that hit on one base each: a hit list is then the (nuc, pos) vector of the haplotype
+    pats = []
+    for b in range(4):
+        w = np.zeros((1, 4), dtype=np.int32)
+        w[0, b] = 10
+        pats.append({"weights": w, "min_score": 5, "pattern_id": b})
+    ps = PatternSet(pats)
+    ref = "ACGT"
+    cases = [
+        [(100, "A", "C")], [(1, "C", "N")], [(2, "G", "A")], [(1, "C", "N"), (2, "G", "A")], [(1, "C", "N"), (4, "G", "A")],
+        [(1, "C", "NN")], [(2, "G", "NN")], [(3, "T", "NN")], [(1, "CG", "C")], [(2, "GT", "G")], [(0, "AC", "A")],
+        [(1, "C", "CTT")], [(1, "C", "TAG"), (2, "G", "T")],
+    ]
+    regions, variants, carriers = [], [], []
+    for i, diffs in enumerate(cases):
+        regions.append((1, 2, "CG"))  # window [1,2] of the 4-base genome; haplotype 0 carries the diffs of its case
+        for d in diffs:
+            variants.append((i, d[0], d[1], d[2]))
+            carriers.append([0])
+    blk = hp.hand_block(1, regions, variants, carriers)
+    hp.check_parity(ps, blk, rows_mode=binding.ROWS_ALL_KEYS)
+    assert ref
+
+
+def test_truncation_and_same_position():
+    """haplotype.rs:144-149: a variant overlapped by a previous deletion, or a second variant at one position, truncates."""
+    g = "ACGTACGTACGTACGTACGTACGT"
+    blk = hp.hand_block(3, [(0, 23, g), (0, 4, g[:6])],
+                        [(0, 2, "GTA", "G"), (0, 3, "T", "A"), (0, 10, "G", "A"), (0, 10, "G", "T"), (0, 14, "G", "GAC"),
+                         (1, 3, "TA", "T"), (1, 4, "A", "C")],
+                        [[0, 1], [0, 2], [3], [3, 4], [1, 5], [0], [0]])
+    w = np.array([[1000, 0, 0, 0], [0, 1000, 0, 0]], dtype=np.int32)
+    ps = PatternSet([{"weights": w, "min_score": 1500, "pattern_id": 7}, {"weights": w[::-1, ::-1].copy(), "min_score": 1500, "pattern_id": 7, "direction": 1}])
+    g_, o = hp.check_parity(ps, blk, rows_mode=binding.ROWS_ALL_KEYS)
+    assert o["truncated_regions"] == 2
+
+
+def test_sequence_keyed_overwrite():
+    """haplotype.rs:84 / SURVEY A.6 Q4: two diff lists that patch to the same sequence: the later group is dropped and its
+    haplotypes count as reference.  Here hap 1 additionally carries a deletion that starts before the window (not applied)."""
+    g = "TTACGTTTTTTT"
+    blk = hp.hand_block(2, [(2, 9, g[2:10])], [(0, 1, "TA", "T"), (0, 4, "G", "C")], [[1], [0, 1]])
+    w = np.array([[1000, 0, 0, 0], [0, 1000, 0, 0], [0, 0, 1000, 0]], dtype=np.int32)  # ACG
+    ps = PatternSet([{"weights": w, "min_score": 2500, "pattern_id": 3}])
+    g_, o = hp.check_parity(ps, blk, rows_mode=binding.ROWS_ALL_KEYS)
+    assert o["collision_regions"] == 1
+    # hap 0 (ACC..) has no hit, hap 1 was dropped into the reference group and so counts the reference hit
+    assert (g_["left"][0].tolist(), g_["right"][0].tolist()) == ([0, 1], [1, 1])
+
+
+def test_errors_match_the_reference_panics():
+    w = np.eye(4, dtype=np.int32)
+    ps = PatternSet([{"weights": w, "min_score": 0, "pattern_id": 0}])
+    cases = [
+        (hp.hand_block(1, [(0, 7, "ACGTACGT")], [(0, 2, "A", "T")], [[0]]), binding.ERR_REF_MISMATCH, "doesn't match reference genome"),
+        (hp.hand_block(1, [(0, 7, "ACGTACGT")], [(0, 2, "GT", "AC")], [[1]]), binding.ERR_MISSING_CASE, "Missing case in haplotype patcher"),
+        (hp.hand_block(1, [(0, 7, "ACGTXCGT")], [], []), binding.ERR_UNKNOWN_NUCLEOTIDE, "Unknown nucleotide"),
+        (hp.hand_block(1, [(0, 7, "ACGTACGT")], [(0, 2, "G", "R")], [[]]), binding.ERR_UNKNOWN_NUCLEOTIDE, "Unknown nucleotide"),
+    ]
+    for blk, code, text in cases:
+        with pytest.raises(binding.TfbsError) as e:
+            hp.run_gpu(ps, blk)
+        assert e.value.code == code and text in e.value.message
+        with pytest.raises(hp.ora.OracleError) as e2:
+            hp.run_oracle(ps, blk)
+        assert e2.value.code == code
+    # a mismatching record nobody carries, or one hidden behind a deletion, does not panic in the reference either
+    ok = hp.hand_block(1, [(0, 7, "ACGTACGT")], [(0, 2, "A", "T"), (0, 4, "ACG", "A"), (0, 5, "T", "G")], [[], [0], [0]])
+    hp.check_parity(ps, ok, rows_mode=binding.ROWS_ALL_KEYS)
+
+
+def test_empty_and_degenerate_blocks():
+    ps = acgt_patterns()
+    empty = hp.hand_block(2, [], [], [])
+    g = hp.run_gpu(ps, empty)
+    assert len(g["region"]) == 0
+    # windows shorter than the pattern, an empty reference window, a region without inner regions
+    blk = hp.hand_block(2, [(5, 7, "ACG"), (20, 30, ""), (40, 50, "AAACGTACGTA")], [(2, 44, "G", "T")], [[1]],
+                        inner=[[(5, 7, 0, 1)], [(20, 30, 0, 1)], []])
+    hp.check_parity(ps, blk, rows_mode=binding.ROWS_ALL_KEYS)
+    # OtherPattern never matches (pattern.rs:166-168)
+    ps2 = PatternSet([dict(ACGT), {"kind": binding.PATTERN_OTHER, "pattern_id": 9}])
+    hp.check_parity(ps2, fixture_block([0]), rows_mode=binding.ROWS_ALL_KEYS)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_synthetic_small(seed):
+    pats = synth.make_pwms(6, seed=seed, lmin=4, lmax=30)
+    lmax = max(p["weights"].shape[0] for p in pats)
+    blk = synth.make_cohort(12, 40, seed=seed, lmax_pattern=lmax, region_len=(50, 600), variant_rate=1 / 20.0)
+    hp.check_parity(PatternSet(pats), blk)
+    hp.check_parity(PatternSet(pats), blk, rows_mode=binding.ROWS_ALL_KEYS, matches=False)
+
+
+def test_synthetic_two_beds_n_runs_lowercase_same_pos():
+    pats = synth.make_pwms(8, seed=11, lmin=6, lmax=24)
+    lmax = max(p["weights"].shape[0] for p in pats)
+    blk = synth.make_cohort(20, 60, seed=11, lmax_pattern=lmax, region_len=(80, 700), variant_rate=1 / 12.0, frac_ins=0.15, frac_del=0.15,
+                            n_runs=12, lowercase_frac=0.1, two_beds=True, same_pos_frac=0.08)
+    g, o = hp.check_parity(PatternSet(pats), blk, rows_mode=binding.ROWS_ALL_KEYS)
+    assert o["truncated_regions"] > 0
+
+
+def test_config5_long_pwm_dense_variants():
+    """BASELINE.json configs[4]: 30-bp PWMs, dense rare variants, >= 30% indels, overlapping / same-position records, N runs;
+    every window with score == min_score must NOT be a hit (strict >): the oracle enumerates hits, equality of the lists is the audit."""
+    pats = synth.make_pwms(5, seed=5, lmin=30, lmax=30, pvalue=1e-3)
+    blk = synth.make_cohort(30, 30, seed=5, lmax_pattern=30, region_len=(100, 500), variant_rate=1 / 8.0, frac_ins=0.2, frac_del=0.2,
+                            n_runs=4, same_pos_frac=0.1)
+    hp.check_parity(PatternSet(pats), blk, rows_mode=binding.ROWS_ALL_KEYS)
+
+
+def test_threshold_boundary_ties():
+    """A pattern whose min_score equals an attainable score: windows scoring exactly min_score are not hits, min_score-1 makes them hits."""
+    rng = np.random.default_rng(3)
+    w = rng.integers(-3, 4, size=(8, 4)).astype(np.int32) * 100
+    blk = synth.make_cohort(6, 20, seed=9, lmax_pattern=8, region_len=(200, 400))
+    best = int(w.max(axis=1).sum())
+    counts = []
+    for ms in (best - 401, best - 400, best - 301, best - 300):
+        ps = PatternSet([{"weights": w, "min_score": ms, "pattern_id": 1}])
+        g, o = hp.check_parity(ps, blk, rows_mode=binding.ROWS_ALL_KEYS)
+        counts.append(o["n_hits"])
+    assert counts[0] >= counts[1] >= counts[2] >= counts[3] and counts[0] > counts[3]
+
+
+def test_wide_fields_and_forced_format():
+    """Weights too large for the 21-bit packed fields use the two-32-bit-field tables; results must not change."""
+    pats = synth.make_pwms(4, seed=21, lmin=10, lmax=20)
+    for p in pats:
+        p["weights"] = (p["weights"].astype(np.int64) * 40).astype(np.int32)
+        p["min_score"] = int(p["min_score"]) * 40
+    blk = synth.make_cohort(8, 25, seed=21, lmax_pattern=20, region_len=(100, 500))
+    hp.check_parity(PatternSet(pats), blk, rows_mode=binding.ROWS_ALL_KEYS)
+    pats2 = synth.make_pwms(4, seed=22, lmin=10, lmax=20)
+    a = hp.run_gpu(PatternSet(pats2), blk, rows_mode=binding.ROWS_ALL_KEYS, options={"scan_format": 1})
+    b = hp.run_gpu(PatternSet(pats2), blk, rows_mode=binding.ROWS_ALL_KEYS)
+    hp.assert_rows_equal(a, b)
+    # always-hit and never-hit thresholds
+    pats3 = synth.make_pwms(2, seed=23, lmin=5, lmax=9)
+    pats3[0]["min_score"] = pats3[1]["min_score"] = -10 ** 9
+    pats3[2]["min_score"] = pats3[3]["min_score"] = 10 ** 9
+    hp.check_parity(PatternSet(pats3), synth.make_cohort(3, 6, seed=2, lmax_pattern=9, region_len=(30, 90)), rows_mode=binding.ROWS_ALL_KEYS)
+
+
+def test_pattern_chunks_and_region_batches():
+    """Small shared-memory budget -> several pattern chunks; small scratch budget -> several region batches."""
+    pats = synth.make_pwms(30, seed=31, lmin=8, lmax=30)
+    lmax = max(p["weights"].shape[0] for p in pats)
+    blk = synth.make_cohort(10, 80, seed=31, lmax_pattern=lmax, region_len=(100, 400), two_beds=True)
+    ps = PatternSet(pats)
+    base = hp.run_oracle(ps, blk, binding.ROWS_ALL_KEYS, True)
+    for opts in ({"table_budget_kb": 16}, {"scratch_mb": 64}, {"table_budget_kb": 24, "scratch_mb": 64, "scan_ctas_per_sm": 1}):
+        g = hp.run_gpu(ps, blk, binding.ROWS_ALL_KEYS, True, opts)
+        hp.assert_rows_equal(g, base)
+        hp.assert_matches_equal(g, base)
+
+
+def test_resident_path_and_rerun():
+    pats = synth.make_pwms(5, seed=41)
+    lmax = max(p["weights"].shape[0] for p in pats)
+    blk = synth.make_cohort(16, 30, seed=41, lmax_pattern=lmax, region_len=(100, 900))
+    ps = PatternSet(pats)
+    o = hp.run_oracle(ps, blk)
+    ctx = binding.Context(0)
+    ctx.set_patterns(ps)
+    ctx.upload_block(blk)
+    for _ in range(3):  # idempotent: same rows every run
+        ctx.run_resident()
+        hp.assert_rows_equal(ctx.collect(), o)
+    ctx.submit_block(blk)
+    hp.assert_rows_equal(ctx.collect(), o)
+    ctx.close()
+
+
+def test_many_samples_few_groups():
+    """Carriers drawn from founder classes: thousands of haplotypes collapse into a few groups per region."""
+    pats = synth.make_pwms(4, seed=51, lmin=8, lmax=16)
+    blk = synth.make_cohort(700, 12, seed=51, lmax_pattern=16, region_len=(200, 600), ld_blocks=12)
+    g, o = hp.check_parity(PatternSet(pats), blk)
+    assert o["n_groups"] < 12 * 14
+
+
+def test_config2_slice_properties():
+    """configs[1] at 3% size against the oracle, plus size-independent properties of the rows."""
+    pats, blk = synth.config2(scale=0.03)
+    ps = PatternSet(pats)
+    g, o = hp.check_parity(ps, blk, matches=False)
+    v = g["left"].astype(np.int64) + g["right"]
+    assert np.array_equal(v.min(axis=1), g["vmin"]) and np.array_equal(v.max(axis=1), g["vmax"])
+    assert np.all(g["vmin"] != g["vmax"])
+    key = g["region"].astype(np.int64) * (1 << 32) + g["pattern_id"].astype(np.int64) * (1 << 16)
+    assert np.all(np.diff(g["region"].astype(np.int64)) >= 0)
+    assert np.all(np.diff(key) >= 0)
+    # splitting the block into two halves of regions gives the same rows (regions are independent, main.rs:395-429)
+    h = blk.n_regions // 2
+    a = hp.run_gpu(ps, blk.slice(0, h))
+    b = hp.run_gpu(ps, blk.slice(h, blk.n_regions))
+    assert len(a["region"]) + len(b["region"]) == len(g["region"])
+    assert np.array_equal(np.concatenate([a["left"], b["left"]]), g["left"])
+    assert np.array_equal(np.concatenate([a["region"], b["region"] + h]), g["region"])
