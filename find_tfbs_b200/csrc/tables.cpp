@@ -169,6 +169,7 @@ int compile_patterns(const tfbs_pattern* patterns, uint32_t n, uint32_t table_bu
             }
         }
         cd.n_runs = (uint32_t)cp.runs.size() - cd.run_off;
+        if (cp.table.size() & 1) cp.table.push_back(0);  // chunks start 16-byte aligned (128-bit copies into shared memory)
         cp.chunks.push_back(cd);
         cp.max_chunk_bytes = std::max(cp.max_chunk_bytes, words * 8);
         return TFBS_OK;

@@ -50,14 +50,37 @@ def sorted_matches(region, pattern_index, group, start):
     return m
 
 
+def group_leaders(hap_group, n_regions):
+    """Group numbers are labels (0 = reference); what is comparable is the partition.  Returns per haplotype the smallest
+    haplotype of its group (-1 for the reference group) and a dict (region, group) -> that leader."""
+    hg = hap_group.reshape(n_regions, -1).astype(np.int64)
+    lead = np.full(hg.shape, -1, dtype=np.int64)
+    table = {}
+    for r in range(n_regions):
+        for h, g in enumerate(hg[r]):
+            if g == 0:
+                continue
+            if (r, g) not in table:
+                table[(r, g)] = h
+            lead[r, h] = table[(r, g)]
+    return lead, table
+
+
 def assert_matches_equal(g, o):
     gm = g["matches"]
     assert not gm["truncated"]
-    a = sorted_matches(gm["region"], gm["pattern_index"], gm["group"], gm["start"])
-    b = sorted_matches(o["m_region"], o["m_pattern_index"], o["m_group"], o["m_start"])
+    n_regions = int(max(gm["region"].astype(np.int64).max(initial=-1), o["m_region"].astype(np.int64).max(initial=-1))) + 1
+    H = 2 * g["left"].shape[1] if g["left"].ndim == 2 and g["left"].shape[1] else 0
+    n_regions = len(o["hap_group"]) // H if H else n_regions
+    gl, gt = group_leaders(gm["hap_group"], n_regions) if H else (np.zeros(0), {})
+    ol, ot = group_leaders(o["hap_group"], n_regions) if H else (np.zeros(0), {})
+    assert np.array_equal(gl, ol), "haplotype -> group partitions differ"
+    ga = np.array([gt.get((int(r), int(x)), -1) for r, x in zip(gm["region"], gm["group"])], dtype=np.int64)
+    oa = np.array([ot.get((int(r), int(x)), -1) for r, x in zip(o["m_region"], o["m_group"])], dtype=np.int64)
+    a = sorted_matches(gm["region"], gm["pattern_index"], ga, gm["start"])
+    b = sorted_matches(o["m_region"], o["m_pattern_index"], oa, o["m_start"])
     assert a.shape == b.shape, "hit count: gpu %d oracle %d" % (len(a), len(b))
     assert np.array_equal(a, b), "hit lists differ"
-    assert np.array_equal(gm["hap_group"], o["hap_group"]), "haplotype -> group maps differ"
 
 
 def check_parity(pattern_set, block, rows_mode=0, options=None, matches=True, resident=False):

@@ -91,7 +91,7 @@ def test_patch_vectors_through_the_kernel():
 def test_truncation_and_same_position():
     """haplotype.rs:144-149: a variant overlapped by a previous deletion, or a second variant at one position, truncates."""
     g = "ACGTACGTACGTACGTACGTACGT"
-    blk = hp.hand_block(3, [(0, 23, g), (0, 4, g[:6])],
+    blk = hp.hand_block(3, [(0, 23, g), (0, 4, g[:5])],
                         [(0, 2, "GTA", "G"), (0, 3, "T", "A"), (0, 10, "G", "A"), (0, 10, "G", "T"), (0, 14, "G", "GAC"),
                          (1, 3, "TA", "T"), (1, 4, "A", "C")],
                         [[0, 1], [0, 2], [3], [3, 4], [1, 5], [0], [0]])
