@@ -278,7 +278,7 @@ __device__ __forceinline__ u64 block_exclusive_scan(u64 v, u64* total) {
     return woff + x - v;
 }
 
-__global__ void k_scan_tiles(const u32* in, u64 n, u64* out, u64* tile_sums) {
+__global__ void k_prefix_tiles(const u32* in, u64 n, u64* out, u64* tile_sums) {
     u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
     u32 v[SCAN_ITEMS];
     u64 sum = 0;
@@ -290,7 +290,7 @@ __global__ void k_scan_tiles(const u32* in, u64 n, u64* out, u64* tile_sums) {
     for (int k = 0; k < SCAN_ITEMS; ++k) { if (base + k < n) out[base + k] = ex; ex += v[k]; }
     if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
 }
-__global__ void k_scan_sums(u64* tile_sums, u32 n_tiles, u64* total_out) {
+__global__ void k_prefix_sums(u64* tile_sums, u32 n_tiles, u64* total_out) {
     __shared__ u64 s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
@@ -307,7 +307,7 @@ __global__ void k_scan_sums(u64* tile_sums, u32 n_tiles, u64* total_out) {
     }
     if (threadIdx.x == 0) *total_out = s_carry;
 }
-__global__ void k_scan_add(u64* out, u64 n, const u64* tile_sums) {
+__global__ void k_prefix_add(u64* out, u64 n, const u64* tile_sums) {
     u64 base = (u64)blockIdx.x * SCAN_TILE + (u64)threadIdx.x * SCAN_ITEMS;
     u64 add = tile_sums[blockIdx.x];
 #pragma unroll

@@ -153,9 +153,9 @@ int device_scan(tfbs_ctx* ctx, const uint32_t* d_in, uint64_t n, u64* d_out) {
         return TFBS_OK;
     }
     CK(ctx->d_tile_sums.reserve((size_t)tiles * 8));
-    k_scan_tiles<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, d_out, ctx->d_tile_sums.as<u64>());
-    k_scan_sums<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->d_tile_sums.as<u64>(), tiles, d_out + n);
-    k_scan_add<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(d_out, n, ctx->d_tile_sums.as<u64>());
+    k_prefix_tiles<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, d_out, ctx->d_tile_sums.as<u64>());
+    k_prefix_sums<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->d_tile_sums.as<u64>(), tiles, d_out + n);
+    k_prefix_add<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(d_out, n, ctx->d_tile_sums.as<u64>());
     ctx->stats.total_launches += 3;
     CK(cudaGetLastError());
     return TFBS_OK;
