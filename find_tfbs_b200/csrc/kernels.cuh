@@ -604,103 +604,115 @@ struct DevMatches {
     i64* start;
 };
 
-constexpr int SCAN_CTA = 256;
-constexpr int TILE_POS = 2048;                       // window starts staged per pass
-constexpr int PLANE_BYTES = TILE_POS / 2 + 64;       // pair codes of even / odd starts (+ halo, padded)
+constexpr int SCAN_WARPS = 24;                       // warps per CTA; one CTA per SM shares one copy of the tables
+constexpr int SCAN_CTA = SCAN_WARPS * 32;
+constexpr int TILE_POS = 1024;                       // window starts staged per pass (per warp)
+constexpr int PLANE_BYTES = TILE_POS / 2 + 32;       // pair codes of even / odd starts (+ halo)
 constexpr int RAW_UNITS = TILE_POS / 32 + 2;
-constexpr int CNT_WORDS = 2048;                      // shared-memory count table (pid x inner)
-constexpr int SEG_CACHE = 64;
+constexpr int CNT_WORDS = 256;                       // per-warp shared-memory count table (pid x inner)
+constexpr int SEG_CACHE = 32;
+constexpr int MAX_RUNS = 16;
 
-struct ScanShared {
+// Private to one warp: a warp owns a whole sequence, so the scan needs no CTA-wide barrier.
+struct __align__(16) WarpShared {
     u64 raw_pk[RAW_UNITS];
+    Seg segs[SEG_CACHE + 1];
     u32 raw_nm[RAW_UNITS];
     u32 cnt[CNT_WORDS];
-    Seg segs[SEG_CACHE + 1];
     u8 plane[2][PLANE_BYTES];
-    u32 item;       // current work item
-    u32 cnt_dirty;
-};
-
-template <int G, int FIELDS>
-struct HitMask;
-template <int G>
-struct HitMask<G, 3> { static constexpr u64 value = (1ULL << 20) | (1ULL << 41) | (1ULL << 62); };
-template <int G>
-struct HitMask<G, 2> { static constexpr u64 value = (1ULL << 31) | (1ULL << 63); };
-
-struct ScanItem {
-    u32 q, r, g, len, nseg, nk, n_pid_chunk, pid_lo, use_smem_cnt;
+    // the sequence being scanned
     i64 region_start;
-    const Seg* segs;          // global
+    const Seg* gsegs;
     const tfbs_inner_region* inner;
-    u32* Crow;                // C + offset of (region, group), row of n_pid_total * nk
-    u32 trip_off;
-    u32 fields;
+    u32* Crow;                // C + offset of (region, group): row of n_pid_total * nk
+    u32 r, g, len, nseg, nk, use_smem_cnt, cnt_dirty, pad;
 };
+
+struct __align__(16) CtaShared {
+    RunDesc runs[MAX_RUNS];
+    u32 n_runs;
+    u32 pad[3];
+};
+
+template <int FIELDS>
+struct HitMask;
+template <>
+struct HitMask<3> { static constexpr u64 value = (1ULL << 20) | (1ULL << 41) | (1ULL << 62); };
+template <>
+struct HitMask<2> { static constexpr u64 value = (1ULL << 31) | (1ULL << 63); };
 
 // Rare path: a window scored above the threshold in at least one field.
-__device__ __noinline__ void scan_on_hit(u64 hit, u32 t, u32 i, const ScanItem& it, const DevPatterns& pt, ScanShared* sh,
-                                         const DevMatches& mt, DevStatus* st) {
-    const int bits = it.fields == 3 ? 21 : 32;
-    for (u32 f = 0; f < it.fields; ++f) {
+__device__ __noinline__ void scan_on_hit(u64 hit, u32 t, u32 i, WarpShared* ws, ChunkDesc cd, const DevPatterns* pt, const DevMatches* mt,
+                                         DevStatus* st) {
+    const int bits = cd.fields == 3 ? 21 : 32;
+    for (u32 f = 0; f < cd.fields; ++f) {
         if (!((hit >> (bits * f + bits - 1)) & 1ULL)) continue;
-        int pi = pt.trip_pat[(size_t)(it.trip_off + t) * 3 + f];
+        int pi = pt->trip_pat[(size_t)(cd.trip_off + t) * 3 + f];
         if (pi < 0) continue;
-        u32 L = pt.pat_len[pi];
-        if (i + L > it.len) continue;  // pattern.rs:147-149: only full windows
+        u32 L = pt->pat_len[pi];
+        if (i + L > ws->len) continue;  // pattern.rs:147-149: only complete windows
         // pos of the first base of the window (pattern.rs:156)
-        const Seg* sg = it.nseg <= SEG_CACHE ? sh->segs : it.segs;
-        u32 s = seg_find(sg, it.nseg, i);
+        const Seg* sg = ws->nseg <= SEG_CACHE ? ws->segs : ws->gsegs;
+        u32 s = seg_find(sg, ws->nseg, i);
         Seg cur = sg[s];
         i64 hs = (i64)cur.relpos + (cur.kind == 0 ? (i64)(i - cur.out_start) : 0);
         i64 he = hs + L - 1;
-        u32 pl = pt.pat_pid_index[pi];
+        u32 pl = pt->pat_pid_index[pi];
         atomicAdd(&st->n_hits, 1ULL);
-        for (u32 k = 0; k < it.nk; ++k) {
-            i64 is = it.inner[k].start - it.region_start, ie = it.inner[k].end - it.region_start;
+        for (u32 k = 0; k < ws->nk; ++k) {
+            i64 is = ws->inner[k].start - ws->region_start, ie = ws->inner[k].end - ws->region_start;
             bool ov = (hs >= is && hs <= ie) || (he >= is && he <= ie);  // inner.overlaps(match.range), range.rs:18-21
             if (!ov) continue;
-            u32 m = it.inner[k].multiplicity;
-            if (it.use_smem_cnt) {
-                atomicAdd(&sh->cnt[(pl - it.pid_lo) * it.nk + k], m);
-                sh->cnt_dirty = 1;
+            u32 m = ws->inner[k].multiplicity;
+            if (ws->use_smem_cnt) {
+                atomicAdd(&ws->cnt[(pl - cd.pid_lo) * ws->nk + k], m);
+                ws->cnt_dirty = 1;
             } else {
-                atomicAdd(&it.Crow[(size_t)pl * it.nk + k], m);
+                atomicAdd(&ws->Crow[(size_t)pl * ws->nk + k], m);
             }
         }
-        if (mt.enabled) {
+        if (mt->enabled) {
             u64 slot = atomicAdd(&st->n_matches, 1ULL);
-            if (slot < mt.cap) {
-                mt.region[slot] = it.r;
-                mt.pattern_index[slot] = (u32)pi;
-                mt.group[slot] = it.g;
-                mt.start[slot] = it.region_start + hs;
+            if (slot < mt->cap) {
+                mt->region[slot] = ws->r;
+                mt->pattern_index[slot] = (u32)pi;
+                mt->group[slot] = ws->g;
+                mt->start[slot] = ws->region_start + hs;
             }
         }
     }
 }
 
+// Sum of the G table words of one triple, as a balanced tree (short dependency chains).
+template <int LO, int HI>
+__device__ __forceinline__ u64 pair_sum(const u8* tb, const u32 (&idx)[kMaxGroups]) {
+    if constexpr (HI - LO == 1) {
+        return *reinterpret_cast<const u64*>(tb + LO * (kPairEntries * 8) + idx[LO]);
+    } else {
+        constexpr int MID = (LO + HI) / 2;
+        return pair_sum<LO, MID>(tb, idx) + pair_sum<MID, HI>(tb, idx);
+    }
+}
+
 // All triples of one run (same number of column pairs G): G LDS.64 + 64-bit adds per triple and lane.
 template <int G, int FIELDS>
-__device__ __forceinline__ void scan_run(const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i, const ScanItem& it,
-                                         const DevPatterns& pt, ScanShared* sh, const DevMatches& mt, DevStatus* st) {
+__device__ __forceinline__ void scan_run(const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i, WarpShared* ws,
+                                         const ChunkDesc& cd, const DevPatterns* pt, const DevMatches* mt, DevStatus* st) {
 #pragma unroll 2
     for (u32 t = 0; t < n_trip; ++t) {
-        u64 acc = 0;
-#pragma unroll
-        for (int g = 0; g < G; ++g) acc += *reinterpret_cast<const u64*>(tb + g * (kPairEntries * 8) + idx[g]);
-        u64 hit = acc & HitMask<G, FIELDS>::value;
-        if (hit) scan_on_hit(hit, t0 + t, i, it, pt, sh, mt, st);
+        u64 acc = pair_sum<0, G>(tb, idx);
+        u64 hit = acc & HitMask<FIELDS>::value;
+        if (hit) scan_on_hit(hit, t0 + t, i, ws, cd, pt, mt, st);
         tb += G * (kPairEntries * 8);
     }
 }
 
 template <int FIELDS>
 __device__ __forceinline__ void scan_dispatch(u32 G, const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i,
-                                              const ScanItem& it, const DevPatterns& pt, ScanShared* sh, const DevMatches& mt,
+                                              WarpShared* ws, const ChunkDesc& cd, const DevPatterns* pt, const DevMatches* mt,
                                               DevStatus* st) {
     switch (G) {
-#define TFBS_CASE(N) case N: scan_run<N, FIELDS>(tb, n_trip, t0, idx, i, it, pt, sh, mt, st); break;
+#define TFBS_CASE(N) case N: scan_run<N, FIELDS>(tb, n_trip, t0, idx, i, ws, cd, pt, mt, st); break;
         TFBS_CASE(1) TFBS_CASE(2) TFBS_CASE(3) TFBS_CASE(4) TFBS_CASE(5) TFBS_CASE(6) TFBS_CASE(7) TFBS_CASE(8)
         TFBS_CASE(9) TFBS_CASE(10) TFBS_CASE(11) TFBS_CASE(12) TFBS_CASE(13) TFBS_CASE(14) TFBS_CASE(15) TFBS_CASE(16)
 #undef TFBS_CASE
@@ -712,118 +724,144 @@ __device__ __forceinline__ u32 pair_code_bytes(u32 a, u32 b) {  // pair_entry(a,
     return e * 8;
 }
 
-// Persistent CTAs.  Work item w = chunk * n_seq + q, handed out by an atomic counter; the tables of a
-// chunk stay in shared memory while consecutive items use the same chunk.
-__global__ void __launch_bounds__(SCAN_CTA) k_scan(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, DevMatches mt,
-                                                    const u32* ref_used, DevStatus* st, u32 n_items) {
+__device__ __forceinline__ bool seq_is_scanned(const DevSeqs& sq, u32 q, const u32* ref_used) {
+    if (sq.seq_flags[q] & 2) return false;                               // overwritten in the sequence-keyed map
+    if (seq_group(sq, q) == 0 && !ref_used[sq.seq_region[q]]) return false;  // nobody has the reference haplotype (main.rs:129)
+    return true;
+}
+
+// One launch per pattern chunk.  Persistent CTAs (one per SM) hold the chunk's tables in shared memory; every WARP
+// takes whole sequences from an atomic counter, stages the packed bases into its private pair-code planes and scans
+// all triples of the chunk, 32 window starts at a time.
+template <int FIELDS>
+__global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, DevMatches mt,
+                                                       const u32* ref_used, DevStatus* st, u32 chunk) {
     extern __shared__ __align__(16) u8 smem_raw[];
-    ScanShared* sh = reinterpret_cast<ScanShared*>(smem_raw);
-    u8* tbl = smem_raw + ((sizeof(ScanShared) + 15) & ~size_t(15));
-    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nwarp = SCAN_CTA / 32;
-    u32 cur_chunk = 0xffffffffu;
-    for (u32 k = tid; k < CNT_WORDS; k += SCAN_CTA) sh->cnt[k] = 0;
-    if (tid == 0) sh->cnt_dirty = 0;
+    CtaShared* cs = reinterpret_cast<CtaShared*>(smem_raw);
+    WarpShared* ws = reinterpret_cast<WarpShared*>(smem_raw + sizeof(CtaShared)) + (threadIdx.x >> 5);
+    u8* tbl = smem_raw + sizeof(CtaShared) + SCAN_WARPS * sizeof(WarpShared);
+    const u32 tid = threadIdx.x, lane = tid & 31;
+    const ChunkDesc cd = pt.chunks[chunk];
+    {  // tables: 128-bit coalesced copies (chunks are 16-byte aligned and padded)
+        const uint4* src = reinterpret_cast<const uint4*>(pt.table + cd.tbl_off);
+        uint4* dst = reinterpret_cast<uint4*>(tbl);
+        u32 n16 = (cd.tbl_words + 1) / 2;
+        for (u32 k = tid; k < n16; k += SCAN_CTA) dst[k] = src[k];
+        if (tid < cd.n_runs && tid < MAX_RUNS) cs->runs[tid] = pt.runs[cd.run_off + tid];
+        if (tid == 0) cs->n_runs = cd.n_runs;
+        for (u32 k = lane; k < CNT_WORDS; k += 32) ws->cnt[k] = 0;
+        if (lane == 0) ws->cnt_dirty = 0;
+    }
+    __syncthreads();
+    const u32 n_runs = cs->n_runs;
 
     for (;;) {
-        __syncthreads();
-        if (tid == 0) sh->item = atomicAdd(&st->work_counter, 1u);
-        __syncthreads();
-        u32 w = sh->item;
-        if (w >= n_items) break;
-        u32 c = w / sq.n_seq, q = w % sq.n_seq;
-        const ChunkDesc cd = pt.chunks[c];
-        if (c != cur_chunk) {  // (re)load the tables: 128-bit coalesced copies
-            const uint4* src = reinterpret_cast<const uint4*>(pt.table + cd.tbl_off);
-            uint4* dst = reinterpret_cast<uint4*>(tbl);
-            u32 n16 = (cd.tbl_words + 1) / 2;
-            for (u32 k = tid; k < n16; k += SCAN_CTA) dst[k] = src[k];
-            cur_chunk = c;
+        u32 q = 0;
+        if (lane == 0) q = atomicAdd(&st->work_counter, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= sq.n_seq) break;
+        if (!seq_is_scanned(sq, q, ref_used)) continue;
+        const u32 r = sq.seq_region[q];
+        const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
+        if (nk == 0 && !mt.enabled) continue;  // no inner region can be hit: nothing to count (main.rs:503)
+        const u32 len = sq.seq_len[q];
+        const u32 nseg = sq.seq_nseg[q];
+        const Seg* gsegs = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
+        __syncwarp();
+        if (lane == 0) {
+            ws->r = r;
+            ws->g = seq_group(sq, q);
+            ws->len = len;
+            ws->nseg = nseg;
+            ws->gsegs = gsegs;
+            ws->region_start = b.region_start[r];
+            ws->nk = nk;
+            ws->inner = b.inner + b.inner_off[r];
+            ws->use_smem_cnt = (cd.n_pid * nk <= CNT_WORDS) ? 1u : 0u;
+            ws->Crow = ct.C + (ct.cbase[r] - ct.cbase0) + (u64)ws->g * pt.n_pid * nk;
         }
-        ScanItem it;
-        it.q = q;
-        it.r = sq.seq_region[q];
-        it.g = seq_group(sq, q);
-        if ((sq.seq_flags[q] & 2) || (it.g == 0 && !ref_used[it.r])) continue;  // dropped, or nobody has the reference haplotype
-        it.len = sq.seq_len[q];
-        it.nseg = sq.seq_nseg[q];
-        it.segs = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
-        it.region_start = b.region_start[it.r];
-        it.nk = b.inner_off[it.r + 1] - b.inner_off[it.r];
-        it.inner = b.inner + b.inner_off[it.r];
-        it.n_pid_chunk = cd.n_pid;
-        it.pid_lo = cd.pid_lo;
-        it.use_smem_cnt = (cd.n_pid * it.nk <= CNT_WORDS) ? 1u : 0u;
-        it.Crow = ct.C + (ct.cbase[it.r] - ct.cbase0) + (u64)it.g * pt.n_pid * it.nk;
-        it.trip_off = cd.trip_off;
-        it.fields = cd.fields;
-        if (it.nseg <= SEG_CACHE)
-            for (u32 k = tid; k <= it.nseg; k += SCAN_CTA) sh->segs[k] = it.segs[k];
-        if (tid == 0 && c == 0) {  // statistics, once per sequence
-            // executed cells = sum_p max(0, len - L + 1) * L (pattern.rs:147-150)
-            u64 cells = 0;
-            if (it.len >= pt.max_len) cells = (u64)(it.len + 1) * pt.sum_len - (pt.sum_len_sq + pt.sum_len);
-            else
-                for (u32 p = 0; p < pt.n_patterns; ++p) {
-                    u32 L = pt.pat_len[p];
-                    if (L && it.len >= L) cells += (u64)(it.len - L + 1) * L;
-                }
-            atomicAdd(&st->executed_cells, cells);
-            atomicAdd(&st->n_scanned, 1ULL);
-        }
-        if (it.nk == 0 && !mt.enabled) continue;  // no inner region can be hit: nothing to count (main.rs:503)
+        if (nseg <= SEG_CACHE)
+            for (u32 k = lane; k <= nseg; k += 32) ws->segs[k] = gsegs[k];
 
         const u64* gpk = sq.pk + sq.seq_uoff[q];
         const u32* gnm = sq.nm + sq.seq_uoff[q];
         const u32 n_units = sq.seq_units[q];
-        for (u32 tile0 = 0; tile0 < it.len; tile0 += TILE_POS) {
-            __syncthreads();
-            // stage the packed bases of [tile0, tile0 + TILE_POS + 64)
-            u32 u0 = tile0 / 32;
-            for (u32 k = tid; k < RAW_UNITS; k += SCAN_CTA) {
+        for (u32 tile0 = 0; tile0 < len; tile0 += TILE_POS) {
+            const u32 npos = len - tile0 < (u32)TILE_POS ? len - tile0 : (u32)TILE_POS;
+            __syncwarp();
+            // stage the packed bases of [tile0, tile0 + npos + 64)
+            const u32 u0 = tile0 / 32, nu = (npos + 31) / 32 + 2;
+            for (u32 k = lane; k < nu; k += 32) {
                 bool in = u0 + k < n_units;
-                sh->raw_pk[k] = in ? gpk[u0 + k] : 0ULL;
-                sh->raw_nm[k] = in ? gnm[u0 + k] : 0xffffffffu;
+                ws->raw_pk[k] = in ? gpk[u0 + k] : 0ULL;
+                ws->raw_nm[k] = in ? gnm[u0 + k] : 0xffffffffu;
             }
-            __syncthreads();
+            __syncwarp();
             // pair codes: plane[j & 1][j >> 1] = 8 * pair_entry(code[tile0 + j], code[tile0 + j + 1]); beyond the end: N
-            for (u32 j = tid; j < TILE_POS + 32; j += SCAN_CTA) {
-                u32 p0 = j, p1 = j + 1;
-                u32 a = (u32)(sh->raw_pk[p0 >> 5] >> (2 * (p0 & 31))) & 3u;
-                u32 bb = (u32)(sh->raw_pk[p1 >> 5] >> (2 * (p1 & 31))) & 3u;
-                if (((sh->raw_nm[p0 >> 5] >> (p0 & 31)) & 1u) || tile0 + p0 >= it.len) a = 4;
-                if (((sh->raw_nm[p1 >> 5] >> (p1 & 31)) & 1u) || tile0 + p1 >= it.len) bb = 4;
-                sh->plane[j & 1][j >> 1] = (u8)pair_code_bytes(a, bb);
+            const u32 nstage = ((npos + 31) & ~31u) + 32;
+            for (u32 j = lane; j < nstage; j += 32) {
+                u32 p1 = j + 1;
+                u32 a = (u32)(ws->raw_pk[j >> 5] >> (2 * (j & 31))) & 3u;
+                u32 bb = (u32)(ws->raw_pk[p1 >> 5] >> (2 * (p1 & 31))) & 3u;
+                if (((ws->raw_nm[j >> 5] >> (j & 31)) & 1u) || tile0 + j >= len) a = 4;
+                if (((ws->raw_nm[p1 >> 5] >> (p1 & 31)) & 1u) || tile0 + p1 >= len) bb = 4;
+                ws->plane[j & 1][j >> 1] = (u8)pair_code_bytes(a, bb);
             }
-            __syncthreads();
-            u32 npos = it.len - tile0 < (u32)TILE_POS ? it.len - tile0 : (u32)TILE_POS;
-            for (u32 p = wid * 32; p < npos; p += nwarp * 32) {
-                u32 j = p + lane;
-                const u8* pl = &sh->plane[j & 1][j >> 1];
+            __syncwarp();
+            for (u32 p = 0; p < npos; p += 32) {
+                const u32 j = p + lane;
+                const u8* pl = &ws->plane[j & 1][j >> 1];
                 u32 idx[kMaxGroups];
 #pragma unroll
                 for (int g = 0; g < kMaxGroups; ++g) idx[g] = pl[g];
                 const u8* tb = tbl;
                 u32 t0 = 0;
-                for (u32 rn = 0; rn < cd.n_runs; ++rn) {
-                    RunDesc rd = pt.runs[cd.run_off + rn];
-                    if (cd.fields == 3) scan_dispatch<3>(rd.groups, tb, rd.n_triples, t0, idx, tile0 + j, it, pt, sh, mt, st);
-                    else scan_dispatch<2>(rd.groups, tb, rd.n_triples, t0, idx, tile0 + j, it, pt, sh, mt, st);
+                for (u32 rn = 0; rn < n_runs; ++rn) {
+                    const RunDesc rd = cs->runs[rn];
+                    scan_dispatch<FIELDS>(rd.groups, tb, rd.n_triples, t0, idx, tile0 + j, ws, cd, &pt, &mt, st);
                     tb += (size_t)rd.n_triples * rd.groups * (kPairEntries * 8);
                     t0 += rd.n_triples;
                 }
             }
         }
-        __syncthreads();
-        // flush the shared count table of this (sequence, chunk): plain stores, this CTA owns the slice
-        if (it.use_smem_cnt && sh->cnt_dirty) {
-            u32 n = cd.n_pid * it.nk;
-            for (u32 k = tid; k < n; k += SCAN_CTA) {
-                u32 v = sh->cnt[k];
-                if (v) { it.Crow[(size_t)cd.pid_lo * it.nk + k] = v; sh->cnt[k] = 0; }
+        __syncwarp();
+        // flush this warp's count table: plain stores, the warp owns the (sequence, pid-range) slice of C
+        if (ws->cnt_dirty) {
+            u32 n = cd.n_pid * nk;
+            u32* crow = ws->Crow + (size_t)cd.pid_lo * nk;
+            for (u32 k = lane; k < n; k += 32) {
+                u32 v = ws->cnt[k];
+                if (v) { crow[k] = v; ws->cnt[k] = 0; }
             }
-            __syncthreads();
-            if (tid == 0) sh->cnt_dirty = 0;
+            __syncwarp();
+            if (lane == 0) ws->cnt_dirty = 0;
         }
+    }
+}
+
+// executed cells = sum over scanned sequences and patterns of max(0, len - L + 1) * L (pattern.rs:147-150)
+__global__ void k_scan_stats(DevSeqs sq, DevPatterns pt, const u32* ref_used, DevStatus* st) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    u64 cells = 0;
+    u32 scanned = 0;
+    if (q < sq.n_seq && seq_is_scanned(sq, q, ref_used)) {
+        scanned = 1;
+        u32 len = sq.seq_len[q];
+        if (len >= pt.max_len) cells = (u64)(len + 1) * pt.sum_len - (pt.sum_len_sq + pt.sum_len);
+        else
+            for (u32 p = 0; p < pt.n_patterns; ++p) {
+                u32 L = pt.pat_len[p];
+                if (L && len >= L) cells += (u64)(len - L + 1) * L;
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        cells += __shfl_xor_sync(0xffffffffu, cells, o);
+        scanned += __shfl_xor_sync(0xffffffffu, scanned, o);
+    }
+    if ((threadIdx.x & 31) == 0 && scanned) {
+        atomicAdd(&st->executed_cells, cells);
+        atomicAdd(&st->n_scanned, (u64)scanned);
     }
 }
 

@@ -184,6 +184,7 @@ int compile_patterns(const tfbs_pattern* patterns, uint32_t n, uint32_t table_bu
             if (p.kind == TFBS_PATTERN_PWM && !plan_field(p, 21, &fp)) fields = 2;
         }
 
+    cp.fields = (uint32_t)fields;
     uint32_t n_pid = (uint32_t)cp.pid_list.size();
     uint32_t lo = 0;
     while (lo < n_pid) {

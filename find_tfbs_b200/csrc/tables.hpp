@@ -73,6 +73,7 @@ struct CompiledPatterns {
     uint32_t sum_len = 0;                    // sum of L over PWM patterns
     uint64_t sum_len_sq = 0;                 // sum of L*(L-1)
     uint32_t max_chunk_bytes = 0;
+    uint32_t fields = 3;                     // 3 x 21-bit or 2 x 32-bit fields per table word (all chunks alike)
 };
 
 // Returns TFBS_OK or an error code with *err filled in.  table_budget_bytes bounds one chunk's tables.

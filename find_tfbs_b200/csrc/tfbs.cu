@@ -408,13 +408,12 @@ int run_pipeline(tfbs_ctx* ctx) {
     auto bytes_of = [&](uint64_t n_seq, uint64_t n_d, uint64_t n_units, uint64_t n_c, uint64_t n_keys) {
         return n_seq * (4 * 6 + 8 * 3 + 1 + 32) + n_d * (4 + 32) + n_units * 12 + n_c * 4 + n_keys * 24 + n_seq * 2 * 12 * 2;
     };
-    int smem_bytes = (int)(((sizeof(ScanShared) + 15) & ~size_t(15)) + ((ctx->cp.max_chunk_bytes + 15) & ~15u));
-    CK(cudaFuncSetAttribute(k_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    int occ = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_scan, SCAN_CTA, smem_bytes));
-    if (occ < 1) return fail(ctx, TFBS_ERR_CUDA, "the scan kernel does not fit on this device");
-    if (ctx->scan_ctas_per_sm > 0) occ = std::min(occ, ctx->scan_ctas_per_sm);
-    const uint32_t scan_grid = (uint32_t)(ctx->prop.multiProcessorCount * occ);
+    const int smem_bytes = (int)(sizeof(CtaShared) + SCAN_WARPS * sizeof(WarpShared) + ((ctx->cp.max_chunk_bytes + 15) & ~15u));
+    const bool wide = ctx->cp.fields == 2;
+    if (wide) CK(cudaFuncSetAttribute(k_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    else CK(cudaFuncSetAttribute(k_scan<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+    uint32_t scan_grid = (uint32_t)ctx->prop.multiProcessorCount;  // persistent: one CTA per SM shares one copy of the tables
+    if (ctx->scan_ctas_per_sm < 0) scan_grid = (uint32_t)std::max(1, -ctx->scan_ctas_per_sm);  // debugging: fixed grid size
     ctx->stats.scan_ctas = scan_grid;
 
     float ms_build = 0, ms_scan = 0, ms_count = 0;
@@ -503,11 +502,10 @@ int run_pipeline(tfbs_ctx* ctx) {
         dc.cbase = ctx->d_cbase.as<u64>();
         dc.cbase0 = ctx->h_cbase[r0];
         if (n_c) CK(cudaMemsetAsync(ctx->d_C.p, 0, n_c * 4, st));
-        CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
-        uint64_t n_items64 = n_seq * ctx->cp.chunks.size();
-        if (n_items64 > 0xfffffff0ull) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "batch too large for the scan scheduler");
-        if (n_items64) {
-            k_scan<<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, ctx->d_ref_used.as<u32>(), dst, (u32)n_items64);
+        for (uint32_t c = 0; c < ctx->cp.chunks.size() && n_seq; ++c) {
+            CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
+            if (wide) k_scan<2><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, ctx->d_ref_used.as<u32>(), dst, c);
+            else k_scan<3><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, ctx->d_ref_used.as<u32>(), dst, c);
             ++launches;
             ++ctx->stats.scan_launches;
         }
@@ -515,7 +513,8 @@ int run_pipeline(tfbs_ctx* ctx) {
 
         // K3 rows
         k_nominal<<<grid_for((uint64_t)nr * H, 256), 256, 0, st>>>(db, r0, nr, ctx->d_hap_group.as<u32>(), sq, ctx->dpat, dst);
-        ++launches;
+        k_scan_stats<<<grid_for(n_seq, 256), 256, 0, st>>>(sq, ctx->dpat, ctx->d_ref_used.as<u32>(), dst);
+        launches += 2;
         uint64_t batch_rows = 0;
         if (n_keys) {
             k_rows_minmax<<<nr, 128, 0, st>>>(db, r0, ctx->d_hap_group.as<u32>(), dc, ctx->d_gbase.as<u64>(), n_pid, ctx->d_kbase.as<u64>(),
@@ -713,7 +712,7 @@ int tfbs_set_patterns(tfbs_ctx* ctx, const tfbs_pattern* patterns, uint32_t n_pa
     ctx->have_patterns = false;
     if (n_patterns == 0) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "assertion failed: pwm_list.len() > 0");  // main.rs:238
     size_t max_smem = ctx->prop.sharedMemPerBlockOptin;
-    size_t fixed = ((sizeof(ScanShared) + 15) & ~size_t(15)) + 1024;
+    size_t fixed = sizeof(CtaShared) + SCAN_WARPS * sizeof(WarpShared) + 1024;
     uint32_t budget = (uint32_t)std::min<size_t>(ctx->table_budget, max_smem > fixed ? max_smem - fixed : 0);
     std::string err;
     CompiledPatterns cp;
