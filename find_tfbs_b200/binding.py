@@ -11,7 +11,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtfbs_b200.so")
+LIB_PATH = os.environ.get("TFBS_B200_LIB") or os.path.join(_HERE, "libtfbs_b200.so")  # the override is for kernel-variant experiments
 
 TFBS_OK = 0
 ERR_INVALID_ARGUMENT, ERR_CUDA, ERR_UNKNOWN_NUCLEOTIDE, ERR_REF_MISMATCH = -1, -2, -3, -4

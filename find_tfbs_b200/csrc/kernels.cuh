@@ -604,7 +604,14 @@ struct DevMatches {
     i64* start;
 };
 
-constexpr int SCAN_WARPS = 24;                       // warps per CTA; one CTA per SM shares one copy of the tables
+#ifndef TFBS_SCAN_WARPS
+#define TFBS_SCAN_WARPS 24
+#endif
+#ifndef TFBS_SCAN_UNROLL
+#define TFBS_SCAN_UNROLL 1   /* measured on B200: 1 -> 0.835 of the roof, 2 -> 0.775, 4 -> 0.61 (instruction cache) */
+#endif
+constexpr int SCAN_UNROLL = TFBS_SCAN_UNROLL;
+constexpr int SCAN_WARPS = TFBS_SCAN_WARPS;          // warps per CTA; one CTA per SM shares one copy of the tables
 constexpr int SCAN_CTA = SCAN_WARPS * 32;
 constexpr int TILE_POS = 1024;                       // window starts staged per pass (per warp)
 constexpr int PLANE_BYTES = TILE_POS / 2 + 32;       // pair codes of even / odd starts (+ halo)
@@ -698,7 +705,7 @@ __device__ __forceinline__ u64 pair_sum(const u8* tb, const u32 (&idx)[kMaxGroup
 template <int G, int FIELDS>
 __device__ __forceinline__ void scan_run(const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i, WarpShared* ws,
                                          const ChunkDesc& cd, const DevPatterns* pt, const DevMatches* mt, DevStatus* st) {
-#pragma unroll 2
+#pragma unroll SCAN_UNROLL
     for (u32 t = 0; t < n_trip; ++t) {
         u64 acc = pair_sum<0, G>(tb, idx);
         u64 hit = acc & HitMask<FIELDS>::value;
