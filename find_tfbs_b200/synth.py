@@ -248,7 +248,8 @@ def make_cohort(n_samples, n_regions, seed, lmax_pattern, region_len=(200, 2000)
             inner["start"], inner["end"], inner["bed_index"], inner["multiplicity"] = arr[:, 0], arr[:, 1], arr[:, 2], arr[:, 3]
 
     blk = Block(S, w_start, w_end, ref_off, ref_bases, inner_off, inner, var_off, variants, allele, carriers)
-    blk.meta = {"genome_len": glen, "n_variants_total": n_var, "merged": merged, "peak_map": peak_map, "halo": halo}
+    blk.meta = {"genome_len": glen, "n_variants_total": n_var, "merged": merged, "peak_map": peak_map, "halo": halo, "genome": genome,
+                "var_pos": pos, "var_ref_off": off, "var_ref_len": ref_len, "var_alt_off": aoff, "var_alt_len": alt_len, "allele": allele}
     return blk
 
 
