@@ -1,0 +1,58 @@
+"""Multi-GPU partitioning of the hot path: merged regions are independent (reference main.rs:395-429), so the block is cut
+into contiguous region ranges, one per rank, with no collective on the data path.  Rows come back in
+(region, pattern_id, inner) order per rank; concatenating the ranks in order gives the single-process result."""
+import numpy as np
+
+
+def region_ranges(costs, world):
+    """Contiguous ranges [r0, r1) per rank balancing sum(costs): costs[r] ~ window length x expected distinct haplotypes."""
+    costs = np.asarray(costs, dtype=np.float64)
+    n = len(costs)
+    if n == 0:
+        return [(0, 0)] * world
+    cum = np.concatenate([[0.0], np.cumsum(costs)])
+    total = cum[-1]
+    cuts = [0]
+    for k in range(1, world):
+        target = total * k / world
+        r = int(np.searchsorted(cum, target, side="left"))
+        # the boundary closest to the target, never before the previous cut
+        if r > 0 and abs(cum[r - 1] - target) <= abs(cum[min(r, n)] - target):
+            r -= 1
+        cuts.append(min(n, max(cuts[-1], r)))
+    cuts.append(n)
+    return [(cuts[k], cuts[k + 1]) for k in range(world)]
+
+
+def block_costs(block):
+    """Window length per region (the scan cost is ~ length x distinct haplotypes x sum of pattern lengths)."""
+    return (block.region_end - block.region_start + 1).astype(np.float64)
+
+
+def shard_block(block, world, rank):
+    r0, r1 = region_ranges(block_costs(block), world)[rank]
+    return block.slice(r0, r1), r0
+
+
+def merge_rows(parts, offsets):
+    """parts: per-rank row dicts (region indices relative to the shard), offsets: first region of each shard."""
+    out = {}
+    for k in ("region", "inner", "pattern_id", "vmin", "vmax", "left", "right"):
+        out[k] = np.concatenate([p[k] for p in parts]) if parts else np.zeros(0)
+    out["region"] = np.concatenate([p["region"].astype(np.int64) + o for p, o in zip(parts, offsets)]).astype(np.uint32) if parts else out["region"]
+    return out
+
+
+def gather_rows(rows, region_offset, inner_offset, group=None):
+    """torch.distributed gather of the per-rank rows to rank 0 (host tensors; gloo or nccl object collectives).  Returns the merged
+    rows on rank 0 and None elsewhere.  `inner` indices are made block-wide with inner_offset."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    payload = dict(rows)
+    payload["inner"] = (rows["inner"].astype(np.int64) + inner_offset).astype(np.uint32)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object((payload, region_offset), gathered, dst=0, group=group)
+    if rank != 0:
+        return None
+    return merge_rows([g[0] for g in gathered], [g[1] for g in gathered])

@@ -265,3 +265,21 @@ def test_config2_slice_properties():
     assert len(a["region"]) + len(b["region"]) == len(g["region"])
     assert np.array_equal(np.concatenate([a["left"], b["left"]]), g["left"])
     assert np.array_equal(np.concatenate([a["region"], b["region"] + h]), g["region"])
+
+
+def test_region_sharding_on_device():
+    """The multi-GPU partition (find_tfbs_b200/sharding.py) run shard by shard on one device equals the unsharded rows."""
+    from find_tfbs_b200 import sharding
+    pats = synth.make_pwms(6, seed=61, lmin=8, lmax=20)
+    blk = synth.make_cohort(10, 50, seed=61, lmax_pattern=20, region_len=(100, 500), two_beds=True)
+    ps = PatternSet(pats)
+    full = hp.run_gpu(ps, blk)
+    for world in (2, 4):
+        parts, offs = [], []
+        for rank in range(world):
+            shard, r0 = sharding.shard_block(blk, world, rank)
+            rows = hp.run_gpu(ps, shard)
+            rows["inner"] = (rows["inner"].astype(np.int64) + int(blk.inner_off[r0])).astype(np.uint32)
+            parts.append(rows)
+            offs.append(r0)
+        hp.assert_rows_equal(sharding.merge_rows(parts, offs), full)
