@@ -127,6 +127,16 @@ def cpu_reference_rate(ps, blk, seconds, threads):
 
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: anything libraries print there (e.g. the NCCL version banner) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(obj):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(obj), flush=True)
+        os.dup2(2, 1)
+
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -158,7 +168,7 @@ def main():
                "impl": "reference", "cpu_baseline": info,
                "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
                "note": "CPU restatement (oracle/) of the reference algorithm; the Rust reference cannot be compiled in this image (no cargo/rustc)"}
-        print(json.dumps(out))
+        emit(out)
         return
 
     import torch
@@ -280,7 +290,7 @@ def main():
            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference_rate(ps, blk, args.cpu_seconds, os.cpu_count() or 1)
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 

@@ -67,7 +67,8 @@ class TfbsStats(C.Structure):
                 ("n_hits", C.c_uint64), ("n_keys", C.c_uint64), ("n_rows", C.c_uint64), ("h2d_bytes", C.c_uint64),
                 ("d2h_bytes", C.c_uint64), ("scan_launches", C.c_uint32), ("total_launches", C.c_uint32),
                 ("ms_group", C.c_float), ("ms_build", C.c_float), ("ms_scan", C.c_float), ("ms_count", C.c_float),
-                ("ms_total", C.c_float), ("sm_count", C.c_uint32), ("scan_ctas", C.c_uint32)]
+                ("ms_total", C.c_float), ("sm_count", C.c_uint32), ("scan_ctas", C.c_uint32),
+                ("evaluated_cells", C.c_uint64), ("n_scan_items", C.c_uint64)]
 
 
 INNER_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("bed_index", "<u4"), ("multiplicity", "<u4")])

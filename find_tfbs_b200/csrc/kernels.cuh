@@ -74,6 +74,9 @@ struct DevStatus {
     u32 sig_collision;
     u32 seq_collision;
     u32 work_counter;     // dynamic scheduler of k_scan
+    u32 n_refhits;        // cursor of the reference-hit buffer (delta scoring)
+    u64 evaluated_cells;  // cells the scan kernel really scored
+    u32 refhit_overflow;
     u32 pad;
 };
 
@@ -319,6 +322,24 @@ __global__ void k_prefix_add(u64* out, u64 n, const u64* tile_sums) {
 // K1: haplotype build
 // ------------------------------------------------------------------------------------------------
 
+// Window starts [p0, p1] of sequence q.  With delta scoring only the windows that touch a variant are scored for a patched
+// haplotype; every other window is identical (bases and positions) to a window of the reference haplotype.
+struct ScanItem {
+    u32 q, p0, p1, pad;
+};
+
+// A hit of the reference haplotype, kept so that patched haplotypes can inherit or lose it.
+struct RefHit {
+    u32 region;
+    int relpos;   // window start relative to region_start
+    u32 len;      // pattern length
+    u32 pid;      // pid_index of the pattern
+};
+struct DevRefHits {
+    RefHit* buf;
+    u32 cap;
+};
+
 // Sequence table of a batch: q = gbase[r] - gbase[r0] + g.
 struct DevSeqs {
     u32 n_seq;
@@ -338,7 +359,13 @@ struct DevSeqs {
     u32* nm;                 // N mask, bit b = base 32u+b is N
     u64* seq_hash;           // [n_seq]
     u8* seq_flags;           // bit0 truncated, bit1 dropped (overwritten in the sequence-keyed map)
+    // scan work list: ranges of window starts that have to be scored
+    u32* seq_nitems;         // [n_seq]
+    u64* item_off;           // [n_seq+1]
+    ScanItem* items;         // flat, in sequence order
+    u32 n_items_cap;
 };
+
 
 __global__ void k_seq_init(u32 H, u32 r0, const u32* hap_group, const u32* leader, const u32* nd_in, DevSeqs sq) {
     u32 r = r0 + blockIdx.x;
@@ -615,24 +642,28 @@ constexpr int SCAN_WARPS = TFBS_SCAN_WARPS;          // warps per CTA; one CTA p
 constexpr int SCAN_CTA = SCAN_WARPS * 32;
 constexpr int TILE_POS = 1024;                       // window starts staged per pass (per warp)
 constexpr int PLANE_BYTES = TILE_POS / 2 + 32;       // pair codes of even / odd starts (+ halo)
-constexpr int RAW_UNITS = TILE_POS / 32 + 2;
+constexpr int RAW_UNITS = TILE_POS / 32 + 3;
 constexpr int CNT_WORDS = 256;                       // per-warp shared-memory count table (pid x inner)
 constexpr int SEG_CACHE = 32;
 constexpr int MAX_RUNS = 16;
+constexpr int MERGE_GAP = 24;                        // dirty ranges closer than this are scored as one item
 
-// Private to one warp: a warp owns a whole sequence, so the scan needs no CTA-wide barrier.
+// Private to one warp: a warp owns a whole work item, so the scan needs no CTA-wide barrier.
 struct __align__(16) WarpShared {
     u64 raw_pk[RAW_UNITS];
     Seg segs[SEG_CACHE + 1];
     u32 raw_nm[RAW_UNITS];
     u32 cnt[CNT_WORDS];
     u8 plane[2][PLANE_BYTES];
-    // the sequence being scanned
+    // the item being scanned
     i64 region_start;
     const Seg* gsegs;
     const tfbs_inner_region* inner;
     u32* Crow;                // C + offset of (region, group): row of n_pid_total * nk
-    u32 r, g, len, nseg, nk, use_smem_cnt, cnt_dirty, pad;
+    u32 r, g, len, nseg, nk, use_smem_cnt, cnt_dirty, p1;
+    u32 mode;                 // 0 count every hit; 1 reference haplotype under delta scoring (count + remember the hit);
+                              // 2 patched haplotype under delta scoring (count only windows that touch a variant)
+    u32 pad[3];
 };
 
 struct __align__(16) CtaShared {
@@ -650,7 +681,8 @@ struct HitMask<2> { static constexpr u64 value = (1ULL << 31) | (1ULL << 63); };
 
 // Rare path: a window scored above the threshold in at least one field.
 __device__ __noinline__ void scan_on_hit(u64 hit, u32 t, u32 i, WarpShared* ws, ChunkDesc cd, const DevPatterns* pt, const DevMatches* mt,
-                                         DevStatus* st) {
+                                         const DevRefHits* rh, DevStatus* st) {
+    if (i > ws->p1) return;  // lanes past the end of the item (the next item, if any, owns those starts)
     const int bits = cd.fields == 3 ? 21 : 32;
     for (u32 f = 0; f < cd.fields; ++f) {
         if (!((hit >> (bits * f + bits - 1)) & 1ULL)) continue;
@@ -662,10 +694,17 @@ __device__ __noinline__ void scan_on_hit(u64 hit, u32 t, u32 i, WarpShared* ws, 
         const Seg* sg = ws->nseg <= SEG_CACHE ? ws->segs : ws->gsegs;
         u32 s = seg_find(sg, ws->nseg, i);
         Seg cur = sg[s];
+        if (ws->mode == 2 && cur.kind == 0 && i + L <= sg[s + 1].out_start) continue;  // untouched window: inherited from the reference
         i64 hs = (i64)cur.relpos + (cur.kind == 0 ? (i64)(i - cur.out_start) : 0);
         i64 he = hs + L - 1;
         u32 pl = pt->pat_pid_index[pi];
-        atomicAdd(&st->n_hits, 1ULL);
+        if (ws->mode == 1) {
+            u32 slot = atomicAdd(&st->n_refhits, 1u);
+            if (slot < rh->cap) rh->buf[slot] = RefHit{ws->r, (int)hs, L, pl};
+            else st->refhit_overflow = 1;
+        } else {
+            atomicAdd(&st->n_hits, 1ULL);
+        }
         for (u32 k = 0; k < ws->nk; ++k) {
             i64 is = ws->inner[k].start - ws->region_start, ie = ws->inner[k].end - ws->region_start;
             bool ov = (hs >= is && hs <= ie) || (he >= is && he <= ie);  // inner.overlaps(match.range), range.rs:18-21
@@ -704,12 +743,13 @@ __device__ __forceinline__ u64 pair_sum(const u8* tb, const u32 (&idx)[kMaxGroup
 // All triples of one run (same number of column pairs G): G LDS.64 + 64-bit adds per triple and lane.
 template <int G, int FIELDS>
 __device__ __forceinline__ void scan_run(const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i, WarpShared* ws,
-                                         const ChunkDesc& cd, const DevPatterns* pt, const DevMatches* mt, DevStatus* st) {
+                                         const ChunkDesc& cd, const DevPatterns* pt, const DevMatches* mt, const DevRefHits* rh,
+                                         DevStatus* st) {
 #pragma unroll SCAN_UNROLL
     for (u32 t = 0; t < n_trip; ++t) {
         u64 acc = pair_sum<0, G>(tb, idx);
         u64 hit = acc & HitMask<FIELDS>::value;
-        if (hit) scan_on_hit(hit, t0 + t, i, ws, cd, pt, mt, st);
+        if (hit) scan_on_hit(hit, t0 + t, i, ws, cd, pt, mt, rh, st);
         tb += G * (kPairEntries * 8);
     }
 }
@@ -717,9 +757,9 @@ __device__ __forceinline__ void scan_run(const u8* tb, u32 n_trip, u32 t0, const
 template <int FIELDS>
 __device__ __forceinline__ void scan_dispatch(u32 G, const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i,
                                               WarpShared* ws, const ChunkDesc& cd, const DevPatterns* pt, const DevMatches* mt,
-                                              DevStatus* st) {
+                                              const DevRefHits* rh, DevStatus* st) {
     switch (G) {
-#define TFBS_CASE(N) case N: scan_run<N, FIELDS>(tb, n_trip, t0, idx, i, ws, cd, pt, mt, st); break;
+#define TFBS_CASE(N) case N: scan_run<N, FIELDS>(tb, n_trip, t0, idx, i, ws, cd, pt, mt, rh, st); break;
         TFBS_CASE(1) TFBS_CASE(2) TFBS_CASE(3) TFBS_CASE(4) TFBS_CASE(5) TFBS_CASE(6) TFBS_CASE(7) TFBS_CASE(8)
         TFBS_CASE(9) TFBS_CASE(10) TFBS_CASE(11) TFBS_CASE(12) TFBS_CASE(13) TFBS_CASE(14) TFBS_CASE(15) TFBS_CASE(16)
 #undef TFBS_CASE
@@ -737,12 +777,56 @@ __device__ __forceinline__ bool seq_is_scanned(const DevSeqs& sq, u32 q, const u
     return true;
 }
 
+// Work list of the scan.  Without delta scoring: one item per scanned sequence, all window starts.  With delta scoring the
+// reference haplotype of every region is scanned in full and a patched haplotype only where a window can differ from the
+// reference: a window is untouched iff it lies inside ONE reference-copy segment (then bases and positions equal the
+// reference window at the same position, so does the hit).  Touched starts: [a - Lmax + 1, e - 1] for every ALT segment
+// [a, e), and [b - Lmax + 1, b - 1] around a boundary b between two reference-copy segments.
+template <bool FILL>
+__global__ void k_items(DevSeqs sq, const u32* ref_used, u32 max_len, int delta) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= sq.n_seq) return;
+    const u32 g = seq_group(sq, q);
+    const u32 len = sq.seq_len[q];
+    u32 n = 0;
+    ScanItem* out = FILL ? sq.items + sq.item_off[q] : nullptr;
+    const bool dropped = sq.seq_flags[q] & 2;
+    if (len == 0 || dropped) {
+        n = 0;
+    } else if (!delta || g == 0) {
+        if (delta || seq_is_scanned(sq, q, ref_used)) {
+            if (FILL) out[0] = ScanItem{q, 0u, len - 1, 0u};
+            n = 1;
+        }
+    } else {
+        const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
+        const u32 ns = sq.seq_nseg[q];
+        bool open = false;
+        u32 a = 0, z = 0;
+        auto add = [&](long long lo, long long hi) {  // window starts [lo, hi], ascending lo
+            if (lo < 0) lo = 0;
+            if (hi > (long long)len - 1) hi = (long long)len - 1;
+            if (hi < lo) return;
+            if (open && (u32)lo <= z + MERGE_GAP) { if ((u32)hi > z) z = (u32)hi; return; }
+            if (open) { if (FILL) out[n] = ScanItem{q, a, z, 0u}; ++n; }
+            a = (u32)lo; z = (u32)hi; open = true;
+        };
+        for (u32 s = 0; s < ns; ++s) {
+            const long long b = sg[s].out_start, e = sg[s + 1].out_start;
+            if (sg[s].kind == 1) add(b - (long long)max_len + 1, e - 1);
+            else if (s > 0 && sg[s - 1].kind == 0) add(b - (long long)max_len + 1, b - 1);
+        }
+        if (open) { if (FILL) out[n] = ScanItem{q, a, z, 0u}; ++n; }
+    }
+    if (!FILL) sq.seq_nitems[q] = n;
+}
+
 // One launch per pattern chunk.  Persistent CTAs (one per SM) hold the chunk's tables in shared memory; every WARP
-// takes whole sequences from an atomic counter, stages the packed bases into its private pair-code planes and scans
-// all triples of the chunk, 32 window starts at a time.
+// takes items from an atomic counter, stages the packed bases into its private pair-code planes and scans all triples
+// of the chunk, 32 window starts at a time.
 template <int FIELDS>
-__global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, DevMatches mt,
-                                                       const u32* ref_used, DevStatus* st, u32 chunk) {
+__global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, DevMatches mt, DevRefHits rh,
+                                                       const u64* n_items_ptr, DevStatus* st, u32 chunk, int delta) {
     extern __shared__ __align__(16) u8 smem_raw[];
     CtaShared* cs = reinterpret_cast<CtaShared*>(smem_raw);
     WarpShared* ws = reinterpret_cast<WarpShared*>(smem_raw + sizeof(CtaShared)) + (threadIdx.x >> 5);
@@ -761,31 +845,36 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
     }
     __syncthreads();
     const u32 n_runs = cs->n_runs;
+    const u32 n_items = (u32)*n_items_ptr;
 
     for (;;) {
-        u32 q = 0;
-        if (lane == 0) q = atomicAdd(&st->work_counter, 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= sq.n_seq) break;
-        if (!seq_is_scanned(sq, q, ref_used)) continue;
+        u32 w = 0;
+        if (lane == 0) w = atomicAdd(&st->work_counter, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        if (w >= n_items) break;
+        const ScanItem item = sq.items[w];
+        const u32 q = item.q;
         const u32 r = sq.seq_region[q];
         const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
-        if (nk == 0 && !mt.enabled) continue;  // no inner region can be hit: nothing to count (main.rs:503)
         const u32 len = sq.seq_len[q];
         const u32 nseg = sq.seq_nseg[q];
+        const u32 g = seq_group(sq, q);
         const Seg* gsegs = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
         __syncwarp();
         if (lane == 0) {
             ws->r = r;
-            ws->g = seq_group(sq, q);
+            ws->g = g;
             ws->len = len;
             ws->nseg = nseg;
             ws->gsegs = gsegs;
             ws->region_start = b.region_start[r];
             ws->nk = nk;
             ws->inner = b.inner + b.inner_off[r];
-            ws->use_smem_cnt = (cd.n_pid * nk <= CNT_WORDS) ? 1u : 0u;
-            ws->Crow = ct.C + (ct.cbase[r] - ct.cbase0) + (u64)ws->g * pt.n_pid * nk;
+            ws->mode = delta ? (g == 0 ? 1u : 2u) : 0u;
+            // patched haplotypes under delta scoring share their count row between items: global atomics (hits are rare)
+            ws->use_smem_cnt = (cd.n_pid * nk <= CNT_WORDS && !(delta && g != 0)) ? 1u : 0u;
+            ws->Crow = ct.C + (ct.cbase[r] - ct.cbase0) + (u64)g * pt.n_pid * nk;
+            ws->p1 = item.p1;
         }
         if (nseg <= SEG_CACHE)
             for (u32 k = lane; k <= nseg; k += 32) ws->segs[k] = gsegs[k];
@@ -793,11 +882,13 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
         const u64* gpk = sq.pk + sq.seq_uoff[q];
         const u32* gnm = sq.nm + sq.seq_uoff[q];
         const u32 n_units = sq.seq_units[q];
-        for (u32 tile0 = 0; tile0 < len; tile0 += TILE_POS) {
-            const u32 npos = len - tile0 < (u32)TILE_POS ? len - tile0 : (u32)TILE_POS;
+        for (u32 tile0 = item.p0; tile0 <= item.p1; tile0 += TILE_POS) {
+            const u32 npos = item.p1 - tile0 + 1 < (u32)TILE_POS ? item.p1 - tile0 + 1 : (u32)TILE_POS;
             __syncwarp();
             // stage the packed bases of [tile0, tile0 + npos + 64)
-            const u32 u0 = tile0 / 32, nu = (npos + 31) / 32 + 2;
+            const u32 u0 = tile0 / 32, o = tile0 & 31;
+            const u32 nstage = ((npos + 31) & ~31u) + 32;
+            const u32 nu = (o + nstage + 1) / 32 + 1;
             for (u32 k = lane; k < nu; k += 32) {
                 bool in = u0 + k < n_units;
                 ws->raw_pk[k] = in ? gpk[u0 + k] : 0ULL;
@@ -805,13 +896,12 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
             }
             __syncwarp();
             // pair codes: plane[j & 1][j >> 1] = 8 * pair_entry(code[tile0 + j], code[tile0 + j + 1]); beyond the end: N
-            const u32 nstage = ((npos + 31) & ~31u) + 32;
             for (u32 j = lane; j < nstage; j += 32) {
-                u32 p1 = j + 1;
-                u32 a = (u32)(ws->raw_pk[j >> 5] >> (2 * (j & 31))) & 3u;
-                u32 bb = (u32)(ws->raw_pk[p1 >> 5] >> (2 * (p1 & 31))) & 3u;
-                if (((ws->raw_nm[j >> 5] >> (j & 31)) & 1u) || tile0 + j >= len) a = 4;
-                if (((ws->raw_nm[p1 >> 5] >> (p1 & 31)) & 1u) || tile0 + p1 >= len) bb = 4;
+                u32 x0 = o + j, x1 = x0 + 1;
+                u32 a = (u32)(ws->raw_pk[x0 >> 5] >> (2 * (x0 & 31))) & 3u;
+                u32 bb = (u32)(ws->raw_pk[x1 >> 5] >> (2 * (x1 & 31))) & 3u;
+                if (((ws->raw_nm[x0 >> 5] >> (x0 & 31)) & 1u) || tile0 + j >= len) a = 4;
+                if (((ws->raw_nm[x1 >> 5] >> (x1 & 31)) & 1u) || tile0 + j + 1 >= len) bb = 4;
                 ws->plane[j & 1][j >> 1] = (u8)pair_code_bytes(a, bb);
             }
             __syncwarp();
@@ -820,12 +910,12 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
                 const u8* pl = &ws->plane[j & 1][j >> 1];
                 u32 idx[kMaxGroups];
 #pragma unroll
-                for (int g = 0; g < kMaxGroups; ++g) idx[g] = pl[g];
+                for (int gg = 0; gg < kMaxGroups; ++gg) idx[gg] = pl[gg];
                 const u8* tb = tbl;
                 u32 t0 = 0;
                 for (u32 rn = 0; rn < n_runs; ++rn) {
                     const RunDesc rd = cs->runs[rn];
-                    scan_dispatch<FIELDS>(rd.groups, tb, rd.n_triples, t0, idx, tile0 + j, ws, cd, &pt, &mt, st);
+                    scan_dispatch<FIELDS>(rd.groups, tb, rd.n_triples, t0, idx, tile0 + j, ws, cd, &pt, &mt, &rh, st);
                     tb += (size_t)rd.n_triples * rd.groups * (kPairEntries * 8);
                     t0 += rd.n_triples;
                 }
@@ -843,6 +933,49 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
             __syncwarp();
             if (lane == 0) ws->cnt_dirty = 0;
         }
+    }
+}
+
+// Delta scoring, second half: a hit of the reference haplotype is inherited by a patched haplotype iff the hit's window lies
+// inside one of its reference-copy segments; otherwise it is taken back from that haplotype's count row (the rows hold
+// differences to the reference row, in wrapping u32 arithmetic).  One CTA per reference hit, threads over the groups.
+__global__ void k_lost(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, DevRefHits rh, const u32* ngroups, const u32* ref_used,
+                       DevStatus* st) {
+    __shared__ u32 s_kept;
+    const u32 n = st->n_refhits < rh.cap ? st->n_refhits : rh.cap;
+    for (u32 j = blockIdx.x; j < n; j += gridDim.x) {
+        const RefHit h = rh.buf[j];
+        const u32 r = h.region;
+        const u32 ng = ngroups[r];
+        const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
+        const tfbs_inner_region* inner = b.inner + b.inner_off[r];
+        const i64 rs = b.region_start[r];
+        const u64 qb = sq.gbase[r] - sq.gbase0;
+        u32* Cr = ct.C + (ct.cbase[r] - ct.cbase0);
+        if (threadIdx.x == 0) s_kept = ref_used[r] ? 1u : 0u;
+        __syncthreads();
+        u32 kept = 0;
+        for (u32 g = 1 + threadIdx.x; g < ng; g += blockDim.x) {
+            const u64 q = qb + g;
+            if (sq.seq_flags[q] & 2) continue;
+            const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * q;
+            const u32 ns = sq.seq_nseg[q];
+            bool inside = false;
+            for (u32 s = 0; s < ns && !inside; ++s)
+                inside = sg[s].kind == 0 && sg[s].relpos <= h.relpos &&
+                         (i64)h.relpos + h.len <= (i64)sg[s].relpos + (i64)(sg[s + 1].out_start - sg[s].out_start);
+            if (inside) { ++kept; continue; }
+            const i64 hs = h.relpos, he = hs + h.len - 1;
+            for (u32 k = 0; k < nk; ++k) {
+                i64 is = inner[k].start - rs, ie = inner[k].end - rs;
+                if ((hs >= is && hs <= ie) || (he >= is && he <= ie))
+                    atomicSub(&Cr[(u64)g * pt.n_pid * nk + (u64)h.pid * nk + k], inner[k].multiplicity);
+            }
+        }
+        if (kept) atomicAdd(&s_kept, kept);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_kept) atomicAdd(&st->n_hits, (u64)s_kept);
+        __syncthreads();
     }
 }
 
@@ -872,6 +1005,27 @@ __global__ void k_scan_stats(DevSeqs sq, DevPatterns pt, const u32* ref_used, De
     }
 }
 
+// evaluated cells = what k_scan really scored: complete windows starting inside the items
+__global__ void k_item_stats(DevSeqs sq, DevPatterns pt, const u64* n_items_ptr, DevStatus* st) {
+    u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 cells = 0;
+    if (w < *n_items_ptr) {
+        const ScanItem it = sq.items[w];
+        const u32 len = sq.seq_len[it.q];
+        if (it.p1 + pt.max_len <= len) cells = (u64)(it.p1 - it.p0 + 1) * pt.sum_len;
+        else
+            for (u32 p = 0; p < pt.n_patterns; ++p) {
+                u32 L = pt.pat_len[p];
+                if (!L || len < L) continue;
+                u32 last = len - L < it.p1 ? len - L : it.p1;
+                if (last >= it.p0) cells += (u64)(last - it.p0 + 1) * L;
+            }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
+    if ((threadIdx.x & 31) == 0 && cells) atomicAdd(&st->evaluated_cells, cells);
+}
+
 // ------------------------------------------------------------------------------------------------
 // K3: fan-out to samples, min/max filter, row compaction
 // ------------------------------------------------------------------------------------------------
@@ -879,7 +1033,7 @@ __global__ void k_scan_stats(DevSeqs sq, DevPatterns pt, const u32* ref_used, De
 // One CTA per region, one thread per key (pid, inner): v[s] = C[group(left)] + C[group(right)]
 // (main.rs:441-448), min and max over samples (:450-451).  flag: 1 = row is emitted.
 __global__ void k_rows_minmax(DevBlock b, u32 r0, const u32* hap_group, DevCounts ct, const u64* gbase, u32 n_pid, const u64* kbase,
-                              u64 kbase0, int rows_mode, u32* vmin, u32* vmax, u32* flag) {
+                              u64 kbase0, int rows_mode, int delta, u32* vmin, u32* vmax, u32* flag) {
     u32 r = r0 + blockIdx.x;
     u32 nk = b.inner_off[r + 1] - b.inner_off[r];
     u32 nkeys = n_pid * nk;
@@ -889,9 +1043,11 @@ __global__ void k_rows_minmax(DevBlock b, u32 r0, const u32* hap_group, DevCount
     (void)gbase;
     for (u32 key = threadIdx.x; key < nkeys; key += blockDim.x) {
         u32 lo = 0xffffffffu, hi = 0;
+        // under delta scoring the rows of patched haplotypes hold differences to the reference row (wrapping u32)
+        const u32 base = delta ? C[key] : 0u;
         for (u32 s = 0; s < b.S; ++s) {
             u32 g0 = hg[2 * s], g1 = hg[2 * s + 1];
-            u32 v = C[(size_t)g0 * nkeys + key] + C[(size_t)g1 * nkeys + key];
+            u32 v = C[(size_t)g0 * nkeys + key] + C[(size_t)g1 * nkeys + key] + (g0 ? base : 0u) + (g1 ? base : 0u);
             lo = min(lo, v);
             hi = max(hi, v);
         }
@@ -916,7 +1072,7 @@ struct DevRows {
 // One warp per emitted row.
 __global__ void k_rows_write(DevBlock b, u32 r0, u32 nr, const u32* hap_group, DevCounts ct, u32 n_pid, const u16* pid_list,
                              const u64* kbase, u64 kbase0, u64 n_keys, const u32* vmin, const u32* vmax, const u32* flag,
-                             const u64* rowidx, DevRows rows, u64 row_base) {
+                             const u64* rowidx, DevRows rows, u64 row_base, int delta) {
     u64 key = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     u32 lane = threadIdx.x & 31;
     if (key >= n_keys || !flag[key]) return;
@@ -941,9 +1097,11 @@ __global__ void k_rows_write(DevBlock b, u32 r0, u32 nr, const u32* hap_group, D
     }
     const u32* C = ct.C + (ct.cbase[r] - ct.cbase0);
     const u32* hg = hap_group + (size_t)r * b.H;
+    const u32 base = delta ? C[kk] : 0u;
     for (u32 s = lane; s < b.S; s += 32) {
-        rows.left[row * b.S + s] = C[(size_t)hg[2 * s] * nkeys + kk];
-        rows.right[row * b.S + s] = C[(size_t)hg[2 * s + 1] * nkeys + kk];
+        u32 g0 = hg[2 * s], g1 = hg[2 * s + 1];
+        rows.left[row * b.S + s] = C[(size_t)g0 * nkeys + kk] + (g0 ? base : 0u);
+        rows.right[row * b.S + s] = C[(size_t)g1 * nkeys + kk] + (g1 ? base : 0u);
     }
 }
 

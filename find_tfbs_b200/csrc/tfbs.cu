@@ -72,7 +72,8 @@ struct tfbs_ctx {
     int scan_format = 0;
     uint64_t scratch_bytes = 24ull << 30;
     uint32_t table_budget = 96 * 1024;
-    int scan_ctas_per_sm = 0;  // 0 = as many as fit
+    int scan_ctas_per_sm = 0;  // < 0: fixed grid size (debugging)
+    int delta = 1;             // delta scoring of patched haplotypes
 
     // patterns
     bool have_patterns = false;
@@ -102,7 +103,7 @@ struct tfbs_ctx {
 
     // phase 2 scratch
     DevBuf d_seq_region, d_seq_leader, d_seq_nd, d_seq_doff, d_dlist, d_segs, d_seq_nseg, d_seq_len, d_seq_units, d_seq_uoff, d_pk,
-        d_nm, d_seq_hash, d_seq_flags, d_tile_sums, d_C, d_vmin, d_vmax, d_flag, d_rowidx;
+        d_nm, d_seq_hash, d_seq_flags, d_tile_sums, d_C, d_vmin, d_vmax, d_flag, d_rowidx, d_seq_nitems, d_item_off, d_items, d_refhits;
     DevBuf d_status;
     DevBuf d_rows_region, d_rows_inner, d_rows_pid, d_rows_vmin, d_rows_vmax, d_rows_left, d_rows_right;
     DevBuf d_m_region, d_m_pattern, d_m_group, d_m_start;
@@ -417,6 +418,7 @@ int run_pipeline(tfbs_ctx* ctx) {
     ctx->stats.scan_ctas = scan_grid;
 
     float ms_build = 0, ms_scan = 0, ms_count = 0;
+    uint64_t n_items_total = 0, n_hits_before = 0;
     uint32_t r0 = 0;
     while (r0 < R) {
         uint64_t n_seq = 0, n_d = 0, n_units = 0, n_c = 0, n_keys = 0;
@@ -450,6 +452,12 @@ int run_pipeline(tfbs_ctx* ctx) {
         CK(ctx->d_vmax.reserve(std::max<uint64_t>(1, n_keys) * 4));
         CK(ctx->d_flag.reserve(std::max<uint64_t>(1, n_keys) * 4));
         CK(ctx->d_rowidx.reserve((n_keys + 1) * 8));
+        const uint64_t items_cap = n_d + n_seq;
+        const uint32_t refhit_cap = (uint32_t)std::min<uint64_t>(256ull * nr + 4096, 1u << 26);
+        CK(ctx->d_seq_nitems.reserve(n_seq * 4));
+        CK(ctx->d_item_off.reserve((n_seq + 1) * 8));
+        CK(ctx->d_items.reserve(std::max<uint64_t>(1, items_cap) * sizeof(ScanItem)));
+        CK(ctx->d_refhits.reserve((size_t)refhit_cap * sizeof(RefHit)));
 
         DevSeqs sq{};
         sq.n_seq = (u32)n_seq;
@@ -469,7 +477,20 @@ int run_pipeline(tfbs_ctx* ctx) {
         sq.nm = ctx->d_nm.as<u32>();
         sq.seq_hash = ctx->d_seq_hash.as<u64>();
         sq.seq_flags = ctx->d_seq_flags.as<u8>();
+        sq.seq_nitems = ctx->d_seq_nitems.as<u32>();
+        sq.item_off = ctx->d_item_off.as<u64>();
+        sq.items = ctx->d_items.as<ScanItem>();
+        sq.n_items_cap = (u32)std::min<uint64_t>(items_cap, 0xffffffffu);
+        DevRefHits drh{ctx->d_refhits.as<RefHit>(), refhit_cap};
 
+        {   // hits so far, in case this batch has to be re-scored without delta scoring
+            CK(cudaMemcpyAsync(ctx->h_status.p, dst, sizeof(DevStatus), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            DevStatus cur;
+            memcpy(&cur, ctx->h_status.p, sizeof cur);
+            n_hits_before = cur.n_hits;
+            CK(cudaMemsetAsync(&dst->n_refhits, 0, 4, st));
+        }
         CK(cudaEventRecord(ctx->ev[2], st));
         // K1 build
         k_seq_init<<<nr, 128, 0, st>>>(H, r0, ctx->d_hap_group.as<u32>(), ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), sq);
@@ -496,33 +517,58 @@ int run_pipeline(tfbs_ctx* ctx) {
         }
         CK(cudaEventRecord(ctx->ev[3], st));
 
-        // K2 scan
+        // K2 scan (+ the inherit / lose pass of delta scoring)
         DevCounts dc{};
         dc.C = ctx->d_C.as<u32>();
         dc.cbase = ctx->d_cbase.as<u64>();
         dc.cbase0 = ctx->h_cbase[r0];
-        if (n_c) CK(cudaMemsetAsync(ctx->d_C.p, 0, n_c * 4, st));
-        for (uint32_t c = 0; c < ctx->cp.chunks.size() && n_seq; ++c) {
-            CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
-            if (wide) k_scan<2><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, ctx->d_ref_used.as<u32>(), dst, c);
-            else k_scan<3><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, ctx->d_ref_used.as<u32>(), dst, c);
+        if (items_cap > 0xfffffff0ull) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "batch too large for the scan scheduler");
+        const u64* d_n_items = sq.item_off + n_seq;
+        auto scan_pass = [&](int delta) -> int {
+            int rc2;
+            if (n_c) CK(cudaMemsetAsync(ctx->d_C.p, 0, n_c * 4, st));
+            k_items<false><<<grid_for(n_seq, 128), 128, 0, st>>>(sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta);
             ++launches;
-            ++ctx->stats.scan_launches;
-        }
+            if ((rc2 = device_scan(ctx, sq.seq_nitems, n_seq, sq.item_off))) return rc2;
+            k_items<true><<<grid_for(n_seq, 128), 128, 0, st>>>(sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta);
+            k_item_stats<<<grid_for(items_cap, 256), 256, 0, st>>>(sq, ctx->dpat, d_n_items, dst);
+            launches += 2;
+            for (uint32_t c = 0; c < ctx->cp.chunks.size() && n_seq; ++c) {
+                CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
+                if (wide) k_scan<2><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, drh, d_n_items, dst, c, delta);
+                else k_scan<3><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, drh, d_n_items, dst, c, delta);
+                ++launches;
+                ++ctx->stats.scan_launches;
+            }
+            if (delta) {
+                k_lost<<<(unsigned)std::min<uint64_t>(refhit_cap, (uint64_t)ctx->prop.multiProcessorCount * 16), 128, 0, st>>>(
+                    db, sq, ctx->dpat, dc, drh, ctx->d_ngroups.as<u32>(), ctx->d_ref_used.as<u32>(), dst);
+                ++launches;
+            }
+            CK(cudaGetLastError());
+            return TFBS_OK;
+        };
+        int use_delta = (ctx->delta && !ctx->record_matches) ? 1 : 0;
+        if ((rc = scan_pass(use_delta))) return rc;
         CK(cudaEventRecord(ctx->ev[4], st));
 
         // K3 rows
         k_nominal<<<grid_for((uint64_t)nr * H, 256), 256, 0, st>>>(db, r0, nr, ctx->d_hap_group.as<u32>(), sq, ctx->dpat, dst);
         k_scan_stats<<<grid_for(n_seq, 256), 256, 0, st>>>(sq, ctx->dpat, ctx->d_ref_used.as<u32>(), dst);
         launches += 2;
-        uint64_t batch_rows = 0;
-        if (n_keys) {
+        auto rows_pass = [&](int delta) -> int {
+            if (!n_keys) return TFBS_OK;
+            int rc2;
             k_rows_minmax<<<nr, 128, 0, st>>>(db, r0, ctx->d_hap_group.as<u32>(), dc, ctx->d_gbase.as<u64>(), n_pid, ctx->d_kbase.as<u64>(),
-                                              ctx->h_kbase[r0], ctx->rows_mode, ctx->d_vmin.as<u32>(), ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>());
+                                              ctx->h_kbase[r0], ctx->rows_mode, delta, ctx->d_vmin.as<u32>(), ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>());
             ++launches;
-            if ((rc = device_scan(ctx, ctx->d_flag.as<u32>(), n_keys, ctx->d_rowidx.as<u64>()))) return rc;
+            if ((rc2 = device_scan(ctx, ctx->d_flag.as<u32>(), n_keys, ctx->d_rowidx.as<u64>()))) return rc2;
             CK(cudaMemcpyAsync(ctx->h_totals.p, ctx->d_rowidx.as<u64>() + n_keys, 8, cudaMemcpyDeviceToHost, st));
-        }
+            return TFBS_OK;
+        };
+        uint64_t batch_rows = 0;
+        if ((rc = rows_pass(use_delta))) return rc;
+        CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 8, d_n_items, 8, cudaMemcpyDeviceToHost, st));
         CK(cudaMemcpyAsync(ctx->h_status.p, dst, sizeof(DevStatus), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         CK(cudaGetLastError());
@@ -542,6 +588,22 @@ int run_pipeline(tfbs_ctx* ctx) {
             return fail(ctx, TFBS_ERR_MISSING_CASE, "Missing case in haplotype patcher (ref_position=" + std::to_string(pos) + " region=" + std::to_string(r) + ")");
         }
         if (hs.seq_collision) return fail(ctx, TFBS_ERR_INTERNAL, "sequence hash collision between distinct haplotypes");
+        if (use_delta && hs.refhit_overflow) {
+            // more reference hits than the buffer holds (very permissive thresholds): score this batch in full instead
+            DevStatus fix = hs;
+            fix.refhit_overflow = 0;
+            fix.n_refhits = 0;
+            fix.n_hits = n_hits_before;
+            memcpy(ctx->h_status.p, &fix, sizeof fix);
+            CK(cudaMemcpyAsync(dst, ctx->h_status.p, sizeof fix, cudaMemcpyHostToDevice, st));
+            use_delta = 0;
+            if ((rc = scan_pass(0))) return rc;
+            if ((rc = rows_pass(0))) return rc;
+            CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 8, d_n_items, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            CK(cudaGetLastError());
+        }
+        n_items_total += ctx->h_totals.as<uint64_t>()[1];
         if (n_keys) batch_rows = *ctx->h_totals.as<uint64_t>();
 
         if (batch_rows) {
@@ -564,7 +626,7 @@ int run_pipeline(tfbs_ctx* ctx) {
                        ctx->d_rows_vmax.as<u32>(), ctx->d_rows_left.as<u32>(), ctx->d_rows_right.as<u32>()};
             k_rows_write<<<grid_for(n_keys * 32, 256), 256, 0, st>>>(db, r0, nr, ctx->d_hap_group.as<u32>(), dc, n_pid, ctx->d_pid_list.as<u16>(),
                                                                      ctx->d_kbase.as<u64>(), ctx->h_kbase[r0], n_keys, ctx->d_vmin.as<u32>(),
-                                                                     ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(), ctx->d_rowidx.as<u64>(), dr, 0);
+                                                                     ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(), ctx->d_rowidx.as<u64>(), dr, 0, use_delta);
             ++launches;
             uint64_t o = ctx->n_rows;
             CK(cudaMemcpyAsync(ctx->h_rows_region.as<u32>() + o, dr.region, batch_rows * 4, cudaMemcpyDeviceToHost, st));
@@ -628,6 +690,8 @@ int run_pipeline(tfbs_ctx* ctx) {
     ctx->stats.n_hits = hs.n_hits;
     ctx->stats.n_keys = ctx->h_kbase[R];
     ctx->stats.n_rows = ctx->n_rows;
+    ctx->stats.evaluated_cells = hs.evaluated_cells;
+    ctx->stats.n_scan_items = n_items_total;
     ctx->ran = true;
     return TFBS_OK;
 }
@@ -702,6 +766,7 @@ int tfbs_set_option(tfbs_ctx* ctx, const char* key, int64_t value) {
     else if (k == "scratch_mb") ctx->scratch_bytes = (uint64_t)std::max<int64_t>(64, value) << 20;
     else if (k == "table_budget_kb") { ctx->table_budget = (uint32_t)std::max<int64_t>(8, value) * 1024; ctx->have_patterns = false; }
     else if (k == "scan_ctas_per_sm") ctx->scan_ctas_per_sm = (int)value;
+    else if (k == "delta") ctx->delta = value != 0;
     else return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "unknown option " + k);
     return TFBS_OK;
 }

@@ -183,6 +183,8 @@ typedef struct tfbs_stats {
     float ms_total;             /* first launch to last, device time */
     uint32_t sm_count;
     uint32_t scan_ctas;
+    uint64_t evaluated_cells;   /* cells the scan kernel really scored: == executed_cells without delta scoring, less with it */
+    uint64_t n_scan_items;      /* ranges of window starts handed to the scan kernel */
 } tfbs_stats;
 
 typedef struct tfbs_ctx tfbs_ctx;
@@ -201,7 +203,10 @@ const char* tfbs_last_error(const tfbs_ctx* ctx);
 
 /* Options: "rows_mode" (TFBS_ROWS_*), "record_matches" (0/1), "max_matches" (capacity of the
  * match buffer), "verify_groups" (0/1, exact check of hash-grouped haplotypes, default 1),
- * "scan_format" (0 auto, 1 force 32-bit tables). */
+ * "scan_format" (0 auto, 1 force 32-bit tables), "delta" (default 1: score a patched haplotype only where its windows
+ * touch a variant and inherit every other hit from the region's reference haplotype -- exact, scores are integers; 0: score
+ * every distinct haplotype in full like the reference does; forced to 0 while "record_matches" is on), "scratch_mb",
+ * "table_budget_kb". */
 int tfbs_set_option(tfbs_ctx* ctx, const char* key, int64_t value);
 
 /* Replace the pattern list (the reference's pwm_list, src/main.rs:237). */

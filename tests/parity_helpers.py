@@ -83,17 +83,28 @@ def assert_matches_equal(g, o):
     assert np.array_equal(a, b), "hit lists differ"
 
 
-def check_parity(pattern_set, block, rows_mode=0, options=None, matches=True, resident=False):
-    o = run_oracle(pattern_set, block, rows_mode, matches)
-    g = run_gpu(pattern_set, block, rows_mode, matches, options, resident)
-    assert_rows_equal(g, o)
-    if matches:
-        assert_matches_equal(g, o)
-    st = g["stats"]
+def check_stats(st, o):
     assert st["executed_cells"] == o["executed_cells"]
     assert st["nominal_cells"] == o["nominal_cells"]
     assert st["n_hits"] == o["n_hits"]
     assert st["n_groups"] == o["n_groups"]
+
+
+def check_parity(pattern_set, block, rows_mode=0, options=None, matches=True, resident=False):
+    """Oracle vs the CUDA path in both scan modes: full scan of every distinct haplotype (with the hit list when `matches`)
+    and delta scoring (the default; patched haplotypes are scored only where a window touches a variant)."""
+    o = run_oracle(pattern_set, block, rows_mode, matches)
+    full = dict(options or {})
+    full["delta"] = 0
+    g = run_gpu(pattern_set, block, rows_mode, matches, full, resident)
+    assert_rows_equal(g, o)
+    if matches:
+        assert_matches_equal(g, o)
+    check_stats(g["stats"], o)
+    assert g["stats"]["evaluated_cells"] == o["executed_cells"]
+    d = run_gpu(pattern_set, block, rows_mode, False, options, resident)
+    assert_rows_equal(d, o)
+    check_stats(d["stats"], o)
     return g, o
 
 
