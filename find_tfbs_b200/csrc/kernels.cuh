@@ -573,12 +573,27 @@ __global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32
     if (w == g) return;
     u32 qw = q - g + w;
     bool same = sq.seq_len[qw] == sq.seq_len[q] && sq.seq_region[qw] == sq.seq_region[q];
-    for (u32 i = 0; same && i < sq.seq_len[q]; ++i) {
-        u8 c0, c1;
-        int p0, p1;
-        base_at(b, sq, q, i, &c0, &p0);
-        base_at(b, sq, qw, i, &c1, &p1);
-        same = c0 == c1 && p0 == p1;
+    // bases: the packed words; positions: the two piecewise-linear position maps, walked over the union of their breakpoints
+    if (same) {
+        const u64 ua = sq.seq_uoff[q], ub = sq.seq_uoff[qw];
+        const u32 nu = sq.seq_units[q];
+        for (u32 u = 0; same && u < nu; ++u) same = sq.pk[ua + u] == sq.pk[ub + u] && sq.nm[ua + u] == sq.nm[ub + u];
+    }
+    if (same) {
+        const Seg* sa = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
+        const Seg* sb = sq.segs + 2 * sq.seq_doff[qw] + 2 * (u64)qw;
+        const u32 len = sq.seq_len[q];
+        u32 ia = 0, ib = 0, i = 0;
+        while (same && i < len) {
+            while (sa[ia + 1].out_start <= i) ++ia;
+            while (sb[ib + 1].out_start <= i) ++ib;
+            const u32 ea = sa[ia + 1].out_start, eb = sb[ib + 1].out_start;
+            const u32 e = ea < eb ? ea : eb;
+            const int pa = sa[ia].relpos + (sa[ia].kind == 0 ? (int)(i - sa[ia].out_start) : 0);
+            const int pb = sb[ib].relpos + (sb[ib].kind == 0 ? (int)(i - sb[ib].out_start) : 0);
+            same = pa == pb && (e - i == 1 || sa[ia].kind == sb[ib].kind);
+            i = e;
+        }
     }
     if (same) {
         sq.seq_flags[q] |= 2;
@@ -646,6 +661,7 @@ constexpr int RAW_UNITS = TILE_POS / 32 + 3;
 constexpr int CNT_WORDS = 256;                       // per-warp shared-memory count table (pid x inner)
 constexpr int SEG_CACHE = 32;
 constexpr int MAX_RUNS = 16;
+constexpr int MAX_PIECES = 16;                       // items (or tiles of a long item) scanned together by one warp
 constexpr int MERGE_GAP = 24;                        // dirty ranges closer than this are scored as one item
 
 // Private to one warp: a warp owns a whole work item, so the scan needs no CTA-wide barrier.
@@ -660,10 +676,12 @@ struct __align__(16) WarpShared {
     const Seg* gsegs;
     const tfbs_inner_region* inner;
     u32* Crow;                // C + offset of (region, group): row of n_pid_total * nk
-    u32 r, g, len, nseg, nk, use_smem_cnt, cnt_dirty, p1;
+    u32 r, g, len, nseg, nk, use_smem_cnt, cnt_dirty, n_pieces;
     u32 mode;                 // 0 count every hit; 1 reference haplotype under delta scoring (count + remember the hit);
                               // 2 patched haplotype under delta scoring (count only windows that touch a variant)
     u32 pad[3];
+    // pieces of this round: window starts [p0, p0 + n) staged at plane position pbase; vstart = starts before the piece
+    u32 piece_p0[MAX_PIECES], piece_vstart[MAX_PIECES + 1], piece_pbase[MAX_PIECES];
 };
 
 struct __align__(16) CtaShared {
@@ -682,7 +700,7 @@ struct HitMask<2> { static constexpr u64 value = (1ULL << 31) | (1ULL << 63); };
 // Rare path: a window scored above the threshold in at least one field.
 __device__ __noinline__ void scan_on_hit(u64 hit, u32 t, u32 i, WarpShared* ws, ChunkDesc cd, const DevPatterns* pt, const DevMatches* mt,
                                          const DevRefHits* rh, DevStatus* st) {
-    if (i > ws->p1) return;  // lanes past the end of the item (the next item, if any, owns those starts)
+    if (i == 0xffffffffu) return;  // lane without a window start in this round
     const int bits = cd.fields == 3 ? 21 : 32;
     for (u32 f = 0; f < cd.fields; ++f) {
         if (!((hit >> (bits * f + bits - 1)) & 1ULL)) continue;
@@ -845,15 +863,15 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
     }
     __syncthreads();
     const u32 n_runs = cs->n_runs;
-    const u32 n_items = (u32)*n_items_ptr;
+    (void)n_items_ptr;
 
     for (;;) {
-        u32 w = 0;
-        if (lane == 0) w = atomicAdd(&st->work_counter, 1u);
-        w = __shfl_sync(0xffffffffu, w, 0);
-        if (w >= n_items) break;
-        const ScanItem item = sq.items[w];
-        const u32 q = item.q;
+        u32 q = 0;
+        if (lane == 0) q = atomicAdd(&st->work_counter, 1u);
+        q = __shfl_sync(0xffffffffu, q, 0);
+        if (q >= sq.n_seq) break;
+        const u64 it0 = sq.item_off[q], it1 = sq.item_off[q + 1];
+        if (it0 == it1) continue;  // nothing to score for this sequence
         const u32 r = sq.seq_region[q];
         const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
         const u32 len = sq.seq_len[q];
@@ -871,10 +889,10 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
             ws->nk = nk;
             ws->inner = b.inner + b.inner_off[r];
             ws->mode = delta ? (g == 0 ? 1u : 2u) : 0u;
-            // patched haplotypes under delta scoring share their count row between items: global atomics (hits are rare)
+            // a sequence scored in full is owned by this warp: shared-memory counts, flushed with plain stores; patched
+            // haplotypes under delta scoring have few hits: global atomics
             ws->use_smem_cnt = (cd.n_pid * nk <= CNT_WORDS && !(delta && g != 0)) ? 1u : 0u;
             ws->Crow = ct.C + (ct.cbase[r] - ct.cbase0) + (u64)g * pt.n_pid * nk;
-            ws->p1 = item.p1;
         }
         if (nseg <= SEG_CACHE)
             for (u32 k = lane; k <= nseg; k += 32) ws->segs[k] = gsegs[k];
@@ -882,31 +900,60 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
         const u64* gpk = sq.pk + sq.seq_uoff[q];
         const u32* gnm = sq.nm + sq.seq_uoff[q];
         const u32 n_units = sq.seq_units[q];
-        for (u32 tile0 = item.p0; tile0 <= item.p1; tile0 += TILE_POS) {
-            const u32 npos = item.p1 - tile0 + 1 < (u32)TILE_POS ? item.p1 - tile0 + 1 : (u32)TILE_POS;
+        // rounds: pack items (long items in tiles of TILE_POS starts) into the planes until they are full
+        u64 it = it0;
+        u32 done_in_item = 0;  // starts of item `it` already scored
+        while (it < it1) {
             __syncwarp();
-            // stage the packed bases of [tile0, tile0 + npos + 64)
-            const u32 u0 = tile0 / 32, o = tile0 & 31;
-            const u32 nstage = ((npos + 31) & ~31u) + 32;
-            const u32 nu = (o + nstage + 1) / 32 + 1;
-            for (u32 k = lane; k < nu; k += 32) {
-                bool in = u0 + k < n_units;
-                ws->raw_pk[k] = in ? gpk[u0 + k] : 0ULL;
-                ws->raw_nm[k] = in ? gnm[u0 + k] : 0xffffffffu;
+            u32 np = 0, pos_used = 0, vtot = 0;
+            while (it < it1 && np < MAX_PIECES) {
+                const ScanItem item = sq.items[it];
+                const u32 left = item.p1 - item.p0 + 1 - done_in_item;
+                u32 n = left < (u32)TILE_POS ? left : (u32)TILE_POS;
+                const u32 blk = (n + 32 + 31) & ~31u;
+                if (pos_used + blk > 2 * (PLANE_BYTES - 16)) {
+                    if (np > 0) break;
+                    n = 2 * (PLANE_BYTES - 16) - 64;  // cannot happen with TILE_POS <= 2 * PLANE_BYTES - 96; kept for safety
+                }
+                const u32 p0 = item.p0 + done_in_item;
+                if (lane == 0) { ws->piece_p0[np] = p0; ws->piece_vstart[np] = vtot; ws->piece_pbase[np] = pos_used; }
+                // stage this piece: packed bases of [p0, p0 + blk + 1) -> pair codes at plane positions pos_used ..
+                {
+                    const u32 u0 = p0 / 32, o = p0 & 31;
+                    const u32 nu = (o + blk + 1) / 32 + 1;
+                    __syncwarp();
+                    for (u32 k = lane; k < nu; k += 32) {
+                        bool in = u0 + k < n_units;
+                        ws->raw_pk[k] = in ? gpk[u0 + k] : 0ULL;
+                        ws->raw_nm[k] = in ? gnm[u0 + k] : 0xffffffffu;
+                    }
+                    __syncwarp();
+                    for (u32 j = lane; j < blk; j += 32) {
+                        u32 x0 = o + j, x1 = x0 + 1;
+                        u32 a = (u32)(ws->raw_pk[x0 >> 5] >> (2 * (x0 & 31))) & 3u;
+                        u32 bb = (u32)(ws->raw_pk[x1 >> 5] >> (2 * (x1 & 31))) & 3u;
+                        if (((ws->raw_nm[x0 >> 5] >> (x0 & 31)) & 1u) || p0 + j >= len) a = 4;
+                        if (((ws->raw_nm[x1 >> 5] >> (x1 & 31)) & 1u) || p0 + j + 1 >= len) bb = 4;
+                        const u32 jj = pos_used + j;
+                        ws->plane[jj & 1][jj >> 1] = (u8)pair_code_bytes(a, bb);
+                    }
+                }
+                pos_used += blk;
+                vtot += n;
+                ++np;
+                done_in_item += n;
+                if (done_in_item == item.p1 - item.p0 + 1) { ++it; done_in_item = 0; }
             }
+            if (lane == 0) { ws->piece_vstart[np] = vtot; ws->n_pieces = np; }
             __syncwarp();
-            // pair codes: plane[j & 1][j >> 1] = 8 * pair_entry(code[tile0 + j], code[tile0 + j + 1]); beyond the end: N
-            for (u32 j = lane; j < nstage; j += 32) {
-                u32 x0 = o + j, x1 = x0 + 1;
-                u32 a = (u32)(ws->raw_pk[x0 >> 5] >> (2 * (x0 & 31))) & 3u;
-                u32 bb = (u32)(ws->raw_pk[x1 >> 5] >> (2 * (x1 & 31))) & 3u;
-                if (((ws->raw_nm[x0 >> 5] >> (x0 & 31)) & 1u) || tile0 + j >= len) a = 4;
-                if (((ws->raw_nm[x1 >> 5] >> (x1 & 31)) & 1u) || tile0 + j + 1 >= len) bb = 4;
-                ws->plane[j & 1][j >> 1] = (u8)pair_code_bytes(a, bb);
-            }
-            __syncwarp();
-            for (u32 p = 0; p < npos; p += 32) {
-                const u32 j = p + lane;
+            for (u32 v0 = 0; v0 < vtot; v0 += 32) {
+                const u32 v = v0 + lane;
+                u32 k = 0;
+                while (k + 1 < np && v >= ws->piece_vstart[k + 1]) ++k;
+                const bool valid = v < vtot;
+                const u32 off = valid ? v - ws->piece_vstart[k] : 0u;
+                const u32 j = ws->piece_pbase[k] + off;
+                const u32 i = valid ? ws->piece_p0[k] + off : 0xffffffffu;
                 const u8* pl = &ws->plane[j & 1][j >> 1];
                 u32 idx[kMaxGroups];
 #pragma unroll
@@ -915,7 +962,7 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
                 u32 t0 = 0;
                 for (u32 rn = 0; rn < n_runs; ++rn) {
                     const RunDesc rd = cs->runs[rn];
-                    scan_dispatch<FIELDS>(rd.groups, tb, rd.n_triples, t0, idx, tile0 + j, ws, cd, &pt, &mt, &rh, st);
+                    scan_dispatch<FIELDS>(rd.groups, tb, rd.n_triples, t0, idx, i, ws, cd, &pt, &mt, &rh, st);
                     tb += (size_t)rd.n_triples * rd.groups * (kPairEntries * 8);
                     t0 += rd.n_triples;
                 }
