@@ -56,3 +56,53 @@ def gather_rows(rows, region_offset, inner_offset, group=None):
     if rank != 0:
         return None
     return merge_rows([g[0] for g in gathered], [g[1] for g in gathered])
+
+
+# ---- sample-block sharding (BASELINE.json configs[3]: biobank-scale cohorts) -------------------------------------------
+def sample_block(block, s0, s1):
+    """The same regions and records restricted to samples [s0, s1) (carrier bits re-packed)."""
+    from .binding import Block
+    H = 2 * block.n_samples
+    bits = np.unpackbits(block.carriers.view(np.uint8), axis=1, bitorder="little")[:, :H]
+    sub = bits[:, 2 * s0:2 * s1]
+    pitch = max(1, (2 * (s1 - s0) + 31) // 32)
+    padded = np.zeros((sub.shape[0], pitch * 32), dtype=np.uint8)
+    padded[:, :sub.shape[1]] = sub
+    carriers = np.packbits(padded, axis=1, bitorder="little").view(np.uint32)
+    return Block(s1 - s0, block.region_start, block.region_end, block.ref_off, block.ref_bases, block.inner_off, block.inner,
+                 block.var_off, block.variants, block.allele_bases, carriers)
+
+
+def merge_sample_shards(parts):
+    """parts: rows of every sample shard in ROWS_ALL_KEYS mode (same regions, disjoint sample ranges, in sample order).
+    Counts are per sample, so shards concatenate along the sample axis; a key missing in a shard had no hit there (all zero).
+    The min == max filter of counts_as_genotypes (reference main.rs:450-458) needs ALL samples, so it is applied here, after the
+    gather.  Exact whenever no region has a sequence-keyed overwrite (the reference's own outcome is undefined there,
+    and the deterministic winner is chosen per shard)."""
+    keys = {}
+    for p in parts:
+        for i in range(len(p["region"])):
+            keys.setdefault((int(p["region"][i]), int(p["pattern_id"][i]), int(p["inner"][i])), None)
+    order = sorted(keys)
+    index = {k: i for i, k in enumerate(order)}
+    n = len(order)
+    lefts, rights = [], []
+    for p in parts:
+        S = p["left"].shape[1]
+        left = np.zeros((n, S), dtype=np.uint32)
+        right = np.zeros((n, S), dtype=np.uint32)
+        for i in range(len(p["region"])):
+            j = index[(int(p["region"][i]), int(p["pattern_id"][i]), int(p["inner"][i]))]
+            left[j] = p["left"][i]
+            right[j] = p["right"][i]
+        lefts.append(left)
+        rights.append(right)
+    left = np.concatenate(lefts, axis=1) if lefts else np.zeros((0, 0), np.uint32)
+    right = np.concatenate(rights, axis=1) if rights else np.zeros((0, 0), np.uint32)
+    v = left.astype(np.int64) + right
+    vmin = v.min(axis=1) if n else np.zeros(0, np.int64)
+    vmax = v.max(axis=1) if n else np.zeros(0, np.int64)
+    keep = vmin != vmax
+    arr = np.array(order, dtype=np.int64).reshape(-1, 3)
+    return {"region": arr[keep, 0].astype(np.uint32), "pattern_id": arr[keep, 1].astype(np.uint16), "inner": arr[keep, 2].astype(np.uint32),
+            "vmin": vmin[keep].astype(np.uint32), "vmax": vmax[keep].astype(np.uint32), "left": left[keep], "right": right[keep]}

@@ -283,3 +283,39 @@ def test_region_sharding_on_device():
             parts.append(rows)
             offs.append(r0)
         hp.assert_rows_equal(sharding.merge_rows(parts, offs), full)
+
+
+def test_sample_block_sharding_on_device():
+    """configs[3] semantics at small scale: sample blocks are scored independently (ALL_KEYS rows), concatenated along the sample
+    axis and filtered for min != max after the gather (main.rs:450-458 needs every sample)."""
+    from find_tfbs_b200 import sharding
+    pats = synth.make_pwms(5, seed=71, lmin=8, lmax=18)
+    blk = synth.make_cohort(24, 30, seed=71, lmax_pattern=18, region_len=(100, 400), frac_del=0.0, variant_rate=1 / 25.0)
+    ps = PatternSet(pats)
+    o = hp.run_oracle(ps, blk)
+    assert o["collision_regions"] == 0
+    full = hp.run_gpu(ps, blk)
+    hp.assert_rows_equal(full, o)
+    parts = [hp.run_gpu(ps, sharding.sample_block(blk, a, b), rows_mode=binding.ROWS_ALL_KEYS) for a, b in ((0, 7), (7, 16), (16, 24))]
+    hp.assert_rows_equal(sharding.merge_sample_shards(parts), full)
+
+
+def test_config3_like_many_samples_many_pwms():
+    """configs[2] shape at reduced size: 2,504 samples, several hundred patterns (several shared-memory table chunks), two BED sets.
+    Oracle parity on a few regions; size-independent properties on more."""
+    pats = synth.make_pwms(150, seed=81, lmin=8, lmax=24)
+    lmax = max(p["weights"].shape[0] for p in pats)
+    ps = PatternSet(pats)
+    for kw in ({"ld_blocks": 40, "two_beds": True}, {"variant_rate": 1 / 60.0}):  # few groups per region / nearly every haplotype distinct
+        blk = synth.make_cohort(2504, 4, seed=81, lmax_pattern=lmax, region_len=(150, 300), **kw)
+        o = hp.run_oracle(ps, blk, 0, False, 16, 1)
+        g = hp.run_gpu(ps, blk)
+        hp.assert_rows_equal(g, o)
+        hp.check_stats(g["stats"], o)
+        assert g["stats"]["scan_launches"] >= 2  # more than one pattern chunk
+    big = synth.make_cohort(2504, 40, seed=82, lmax_pattern=lmax, region_len=(200, 1200), two_beds=True)
+    a = hp.run_gpu(ps, big)
+    b = hp.run_gpu(ps, big, options={"delta": 0, "scratch_mb": 2048})
+    hp.assert_rows_equal(a, b)
+    v = a["left"].astype(np.int64) + a["right"]
+    assert np.array_equal(v.min(axis=1), a["vmin"]) and np.array_equal(v.max(axis=1), a["vmax"]) and np.all(a["vmin"] != a["vmax"])
