@@ -35,7 +35,7 @@ LDS64_PER_CLK_PER_SM = 16    # 128 B/clk/SM of shared-memory bandwidth
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the 10k regions of configs[1] (debugging only)")
@@ -224,11 +224,11 @@ def main():
         ctx.run_resident()
         ctx.collect(copy=False)
 
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()  # sampled from the warm-up on: a step is tens of milliseconds, nvidia-smi reports every 200 ms
+    for _ in range(args.warmup):
+        step_resident()
     scan_ms, launches = [], 0
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

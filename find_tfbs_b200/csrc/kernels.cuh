@@ -1027,7 +1027,7 @@ __global__ void k_lost(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, Dev
 }
 
 // executed cells = sum over scanned sequences and patterns of max(0, len - L + 1) * L (pattern.rs:147-150)
-__global__ void k_scan_stats(DevSeqs sq, DevPatterns pt, const u32* ref_used, DevStatus* st) {
+__global__ void k_seq_stats(DevSeqs sq, DevPatterns pt, const u32* ref_used, DevStatus* st) {
     u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     u64 cells = 0;
     u32 scanned = 0;

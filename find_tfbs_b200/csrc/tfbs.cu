@@ -554,7 +554,7 @@ int run_pipeline(tfbs_ctx* ctx) {
 
         // K3 rows
         k_nominal<<<grid_for((uint64_t)nr * H, 256), 256, 0, st>>>(db, r0, nr, ctx->d_hap_group.as<u32>(), sq, ctx->dpat, dst);
-        k_scan_stats<<<grid_for(n_seq, 256), 256, 0, st>>>(sq, ctx->dpat, ctx->d_ref_used.as<u32>(), dst);
+        k_seq_stats<<<grid_for(n_seq, 256), 256, 0, st>>>(sq, ctx->dpat, ctx->d_ref_used.as<u32>(), dst);
         launches += 2;
         auto rows_pass = [&](int delta) -> int {
             if (!n_keys) return TFBS_OK;
