@@ -325,7 +325,8 @@ __global__ void k_prefix_add(u64* out, u64 n, const u64* tile_sums) {
 // Window starts [p0, p1] of sequence q.  With delta scoring only the windows that touch a variant are scored for a patched
 // haplotype; every other window is identical (bases and positions) to a window of the reference haplotype.
 struct ScanItem {
-    u32 q, p0, p1, pad;
+    u32 q, p0, p1;
+    u32 owner;   // index of the item whose count vector this one shares (itself if it is scored)
 };
 
 // A hit of the reference haplotype, kept so that patched haplotypes can inherit or lose it.
@@ -364,6 +365,10 @@ struct DevSeqs {
     u64* item_off;           // [n_seq+1]
     ScanItem* items;         // flat, in sequence order
     u32 n_items_cap;
+    u64* item_key;           // [items] signature of the item (delta scoring, patched haplotypes)
+    u32* item_hits;          // [items] hits found in the item (owners only)
+    u64* item_coff;          // [items+1] offset of the owner's count vector in item_cnt
+    u32* item_cnt;           // count vectors [pid][inner] of the owners
 };
 
 
@@ -658,30 +663,18 @@ constexpr int SCAN_CTA = SCAN_WARPS * 32;
 constexpr int TILE_POS = 1024;                       // window starts staged per pass (per warp)
 constexpr int PLANE_BYTES = TILE_POS / 2 + 32;       // pair codes of even / odd starts (+ halo)
 constexpr int RAW_UNITS = TILE_POS / 32 + 3;
-constexpr int CNT_WORDS = 256;                       // per-warp shared-memory count table (pid x inner)
-constexpr int SEG_CACHE = 32;
 constexpr int MAX_RUNS = 16;
 constexpr int MAX_PIECES = 16;                       // items (or tiles of a long item) scanned together by one warp
 constexpr int MERGE_GAP = 24;                        // dirty ranges closer than this are scored as one item
 
-// Private to one warp: a warp owns a whole work item, so the scan needs no CTA-wide barrier.
+// Private to one warp: a warp owns the pieces of a round, so the scan needs no CTA-wide barrier.
 struct __align__(16) WarpShared {
     u64 raw_pk[RAW_UNITS];
-    Seg segs[SEG_CACHE + 1];
     u32 raw_nm[RAW_UNITS];
-    u32 cnt[CNT_WORDS];
     u8 plane[2][PLANE_BYTES];
-    // the item being scanned
-    i64 region_start;
-    const Seg* gsegs;
-    const tfbs_inner_region* inner;
-    u32* Crow;                // C + offset of (region, group): row of n_pid_total * nk
-    u32 r, g, len, nseg, nk, use_smem_cnt, cnt_dirty, n_pieces;
-    u32 mode;                 // 0 count every hit; 1 reference haplotype under delta scoring (count + remember the hit);
-                              // 2 patched haplotype under delta scoring (count only windows that touch a variant)
-    u32 pad[3];
-    // pieces of this round: window starts [p0, p0 + n) staged at plane position pbase; vstart = starts before the piece
-    u32 piece_p0[MAX_PIECES], piece_vstart[MAX_PIECES + 1], piece_pbase[MAX_PIECES];
+    // pieces of this round: window starts [p0, p0 + n) of item piece_item, staged at plane position pbase; vstart = starts before
+    u32 piece_p0[MAX_PIECES], piece_vstart[MAX_PIECES + 1], piece_pbase[MAX_PIECES], piece_item[MAX_PIECES];
+    u32 n_pieces, pad[3];
 };
 
 struct __align__(16) CtaShared {
@@ -697,51 +690,77 @@ struct HitMask<3> { static constexpr u64 value = (1ULL << 20) | (1ULL << 41) | (
 template <>
 struct HitMask<2> { static constexpr u64 value = (1ULL << 31) | (1ULL << 63); };
 
+// Everything the rare path needs, passed by pointer (the structs are __grid_constant__ kernel parameters).
+struct ScanEnv {
+    const DevBlock* b;
+    const DevSeqs* sq;
+    const DevPatterns* pt;
+    const DevCounts* ct;
+    const DevMatches* mt;
+    const DevRefHits* rh;
+    DevStatus* st;
+    int delta;
+};
+
 // Rare path: a window scored above the threshold in at least one field.
-__device__ __noinline__ void scan_on_hit(u64 hit, u32 t, u32 i, WarpShared* ws, ChunkDesc cd, const DevPatterns* pt, const DevMatches* mt,
-                                         const DevRefHits* rh, DevStatus* st) {
-    if (i == 0xffffffffu) return;  // lane without a window start in this round
+__device__ __noinline__ void scan_on_hit(u64 hit, u32 t, u32 i, u32 item_index, ChunkDesc cd, const ScanEnv* env) {
+    const DevSeqs& sq = *env->sq;
+    const DevBlock& b = *env->b;
+    const DevPatterns& pt = *env->pt;
+    DevStatus* st = env->st;
+    const ScanItem item = sq.items[item_index];
+    const u32 q = item.q;
+    const u32 len = sq.seq_len[q];
+    const u32 nseg = sq.seq_nseg[q];
+    const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
+    const u32 r = sq.seq_region[q];
+    const u32 g = seq_group(sq, q);
+    // 0 count every hit; 1 reference haplotype under delta scoring (count + remember the hit); 2 patched haplotype under delta
+    // scoring: count only windows that touch a variant, into the count vector of the (shared) item
+    const u32 mode = env->delta ? (g == 0 ? 1u : 2u) : 0u;
+    const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
+    const tfbs_inner_region* inner = b.inner + b.inner_off[r];
+    const i64 region_start = b.region_start[r];
     const int bits = cd.fields == 3 ? 21 : 32;
     for (u32 f = 0; f < cd.fields; ++f) {
         if (!((hit >> (bits * f + bits - 1)) & 1ULL)) continue;
-        int pi = pt->trip_pat[(size_t)(cd.trip_off + t) * 3 + f];
+        int pi = pt.trip_pat[(size_t)(cd.trip_off + t) * 3 + f];
         if (pi < 0) continue;
-        u32 L = pt->pat_len[pi];
-        if (i + L > ws->len) continue;  // pattern.rs:147-149: only complete windows
+        u32 L = pt.pat_len[pi];
+        if (i + L > len) continue;  // pattern.rs:147-149: only complete windows
         // pos of the first base of the window (pattern.rs:156)
-        const Seg* sg = ws->nseg <= SEG_CACHE ? ws->segs : ws->gsegs;
-        u32 s = seg_find(sg, ws->nseg, i);
+        u32 s = seg_find(sg, nseg, i);
         Seg cur = sg[s];
-        if (ws->mode == 2 && cur.kind == 0 && i + L <= sg[s + 1].out_start) continue;  // untouched window: inherited from the reference
+        if (mode == 2 && cur.kind == 0 && i + L <= sg[s + 1].out_start) continue;  // untouched window: inherited from the reference
         i64 hs = (i64)cur.relpos + (cur.kind == 0 ? (i64)(i - cur.out_start) : 0);
         i64 he = hs + L - 1;
-        u32 pl = pt->pat_pid_index[pi];
-        if (ws->mode == 1) {
-            u32 slot = atomicAdd(&st->n_refhits, 1u);
-            if (slot < rh->cap) rh->buf[slot] = RefHit{ws->r, (int)hs, L, pl};
-            else st->refhit_overflow = 1;
+        u32 pl = pt.pat_pid_index[pi];
+        u32* crow;
+        if (mode == 2) {
+            crow = sq.item_cnt + sq.item_coff[item_index];
+            atomicAdd(&sq.item_hits[item_index], 1u);
         } else {
-            atomicAdd(&st->n_hits, 1ULL);
-        }
-        for (u32 k = 0; k < ws->nk; ++k) {
-            i64 is = ws->inner[k].start - ws->region_start, ie = ws->inner[k].end - ws->region_start;
-            bool ov = (hs >= is && hs <= ie) || (he >= is && he <= ie);  // inner.overlaps(match.range), range.rs:18-21
-            if (!ov) continue;
-            u32 m = ws->inner[k].multiplicity;
-            if (ws->use_smem_cnt) {
-                atomicAdd(&ws->cnt[(pl - cd.pid_lo) * ws->nk + k], m);
-                ws->cnt_dirty = 1;
+            crow = env->ct->C + (env->ct->cbase[r] - env->ct->cbase0) + (u64)g * pt.n_pid * nk;
+            if (mode == 1) {
+                u32 slot = atomicAdd(&st->n_refhits, 1u);
+                if (slot < env->rh->cap) env->rh->buf[slot] = RefHit{r, (int)hs, L, pl};
+                else st->refhit_overflow = 1;
             } else {
-                atomicAdd(&ws->Crow[(size_t)pl * ws->nk + k], m);
+                atomicAdd(&st->n_hits, 1ULL);
             }
         }
-        if (mt->enabled) {
+        for (u32 k = 0; k < nk; ++k) {
+            i64 is = inner[k].start - region_start, ie = inner[k].end - region_start;
+            bool ov = (hs >= is && hs <= ie) || (he >= is && he <= ie);  // inner.overlaps(match.range), range.rs:18-21
+            if (ov) atomicAdd(&crow[(size_t)pl * nk + k], inner[k].multiplicity);
+        }
+        if (env->mt->enabled) {
             u64 slot = atomicAdd(&st->n_matches, 1ULL);
-            if (slot < mt->cap) {
-                mt->region[slot] = ws->r;
-                mt->pattern_index[slot] = (u32)pi;
-                mt->group[slot] = ws->g;
-                mt->start[slot] = ws->region_start + hs;
+            if (slot < env->mt->cap) {
+                env->mt->region[slot] = r;
+                env->mt->pattern_index[slot] = (u32)pi;
+                env->mt->group[slot] = g;
+                env->mt->start[slot] = region_start + hs;
             }
         }
     }
@@ -760,24 +779,22 @@ __device__ __forceinline__ u64 pair_sum(const u8* tb, const u32 (&idx)[kMaxGroup
 
 // All triples of one run (same number of column pairs G): G LDS.64 + 64-bit adds per triple and lane.
 template <int G, int FIELDS>
-__device__ __forceinline__ void scan_run(const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i, WarpShared* ws,
-                                         const ChunkDesc& cd, const DevPatterns* pt, const DevMatches* mt, const DevRefHits* rh,
-                                         DevStatus* st) {
+__device__ __forceinline__ void scan_run(const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i, u32 item_index,
+                                         const ChunkDesc& cd, const ScanEnv* env) {
 #pragma unroll SCAN_UNROLL
     for (u32 t = 0; t < n_trip; ++t) {
         u64 acc = pair_sum<0, G>(tb, idx);
         u64 hit = acc & HitMask<FIELDS>::value;
-        if (hit) scan_on_hit(hit, t0 + t, i, ws, cd, pt, mt, rh, st);
+        if (hit && i != 0xffffffffu) scan_on_hit(hit, t0 + t, i, item_index, cd, env);
         tb += G * (kPairEntries * 8);
     }
 }
 
 template <int FIELDS>
-__device__ __forceinline__ void scan_dispatch(u32 G, const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i,
-                                              WarpShared* ws, const ChunkDesc& cd, const DevPatterns* pt, const DevMatches* mt,
-                                              const DevRefHits* rh, DevStatus* st) {
+__device__ __forceinline__ void scan_dispatch(u32 G, const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i, u32 item_index,
+                                              const ChunkDesc& cd, const ScanEnv* env) {
     switch (G) {
-#define TFBS_CASE(N) case N: scan_run<N, FIELDS>(tb, n_trip, t0, idx, i, ws, cd, pt, mt, rh, st); break;
+#define TFBS_CASE(N) case N: scan_run<N, FIELDS>(tb, n_trip, t0, idx, i, item_index, cd, env); break;
         TFBS_CASE(1) TFBS_CASE(2) TFBS_CASE(3) TFBS_CASE(4) TFBS_CASE(5) TFBS_CASE(6) TFBS_CASE(7) TFBS_CASE(8)
         TFBS_CASE(9) TFBS_CASE(10) TFBS_CASE(11) TFBS_CASE(12) TFBS_CASE(13) TFBS_CASE(14) TFBS_CASE(15) TFBS_CASE(16)
 #undef TFBS_CASE
@@ -795,27 +812,84 @@ __device__ __forceinline__ bool seq_is_scanned(const DevSeqs& sq, u32 q, const u
     return true;
 }
 
+// Hash of everything that decides the hits of an item: the segments (kind, source, position) that cover the bases
+// [p0, p1 + Lmax) relative to p0, the ALT bases among them, and where the sequence ends.  Two items of one region with equal
+// descriptions score identically, window by window, so one of them is scored and the other shares its count vector.
+__device__ __forceinline__ u64 item_signature(const DevBlock& b, const DevSeqs& sq, u32 q, u32 p0, u32 p1, u32 max_len) {
+    const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
+    const u32 ns = sq.seq_nseg[q];
+    const u32 len = sq.seq_len[q];
+    const u32 bend = p1 + max_len < len ? p1 + max_len : len;
+    u64 h = mix64(((u64)(p1 - p0) << 32) ^ (bend - p0));
+    for (u32 s = seg_find(sg, ns, p0); s < ns && sg[s].out_start < bend; ++s) {
+        const u32 a = sg[s].out_start > p0 ? sg[s].out_start : p0;
+        const u32 e = sg[s + 1].out_start < bend ? sg[s + 1].out_start : bend;
+        const u32 d = a - sg[s].out_start;
+        h = mix64(h ^ (((u64)(a - p0) << 40) | ((u64)sg[s].kind << 32) | (u32)(sg[s].relpos + (sg[s].kind == 0 ? (int)d : 0))));
+        if (sg[s].kind == 1)
+            for (u32 k = a; k < e; ++k) h = h * 0x100000001b3ULL + b.allele_codes[sg[s].src + (k - sg[s].out_start)] + 1;
+    }
+    return h;
+}
+
+__device__ __forceinline__ bool items_equal(const DevBlock& b, const DevSeqs& sq, const ScanItem& x, const ScanItem& y, u32 max_len) {
+    if (x.p1 - x.p0 != y.p1 - y.p0) return false;
+    const Seg* sa = sq.segs + 2 * sq.seq_doff[x.q] + 2 * (u64)x.q;
+    const Seg* sb = sq.segs + 2 * sq.seq_doff[y.q] + 2 * (u64)y.q;
+    const u32 la = sq.seq_len[x.q], lb = sq.seq_len[y.q];
+    const u32 ea = x.p1 + max_len < la ? x.p1 + max_len : la, eb = y.p1 + max_len < lb ? y.p1 + max_len : lb;
+    if (ea - x.p0 != eb - y.p0) return false;
+    u32 ia = seg_find(sa, sq.seq_nseg[x.q], x.p0), ib = seg_find(sb, sq.seq_nseg[y.q], y.p0);
+    for (u32 o = 0; o < ea - x.p0;) {  // o = offset from p0
+        const u32 pa = x.p0 + o, pb = y.p0 + o;
+        while (sa[ia + 1].out_start <= pa) ++ia;
+        while (sb[ib + 1].out_start <= pb) ++ib;
+        // both must sit at the same place of the same kind of segment
+        if (sa[ia].kind != sb[ib].kind) return false;
+        const u32 da = pa - sa[ia].out_start, db = pb - sb[ib].out_start;
+        if ((da == 0) != (db == 0) && o != 0) return false;  // a boundary in one, not in the other
+        if (sa[ia].relpos + (sa[ia].kind == 0 ? (int)da : 0) != sb[ib].relpos + (sb[ib].kind == 0 ? (int)db : 0)) return false;
+        const u32 na = (sa[ia + 1].out_start < ea ? sa[ia + 1].out_start : ea) - pa;
+        const u32 nb = (sb[ib + 1].out_start < eb ? sb[ib + 1].out_start : eb) - pb;
+        if (na != nb) return false;
+        if (sa[ia].kind == 1)
+            for (u32 k = 0; k < na; ++k)
+                if (b.allele_codes[sa[ia].src + da + k] != b.allele_codes[sb[ib].src + db + k]) return false;
+        o += na;
+    }
+    return true;
+}
+
 // Work list of the scan.  Without delta scoring: one item per scanned sequence, all window starts.  With delta scoring the
 // reference haplotype of every region is scanned in full and a patched haplotype only where a window can differ from the
 // reference: a window is untouched iff it lies inside ONE reference-copy segment (then bases and positions equal the
 // reference window at the same position, so does the hit).  Touched starts: [a - Lmax + 1, e - 1] for every ALT segment
 // [a, e), and [b - Lmax + 1, b - 1] around a boundary b between two reference-copy segments.
 template <bool FILL>
-__global__ void k_items(DevSeqs sq, const u32* ref_used, u32 max_len, int delta) {
+__global__ void k_items(DevBlock b, DevSeqs sq, const u32* ref_used, u32 max_len, int delta, u64* keys, u32* vals, u32 mask) {
     u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= sq.n_seq) return;
     const u32 g = seq_group(sq, q);
     const u32 len = sq.seq_len[q];
     u32 n = 0;
-    ScanItem* out = FILL ? sq.items + sq.item_off[q] : nullptr;
+    const u64 base = FILL ? sq.item_off[q] : 0;
+    ScanItem* out = FILL ? sq.items + base : nullptr;
     const bool dropped = sq.seq_flags[q] & 2;
+    auto put = [&](u32 a, u32 z) {
+        if (FILL) {
+            out[n] = ScanItem{q, a, z, (u32)(base + n)};
+            if (delta && g != 0) {  // candidates for sharing: the smallest item index with this signature becomes the owner
+                u64 key = region_key(item_signature(b, sq, q, a, z, max_len), sq.seq_region[q]);
+                sq.item_key[base + n] = key;
+                atomicMin(&vals[table_find_or_insert(keys, mask, key)], (u32)(base + n));
+            }
+        }
+        ++n;
+    };
     if (len == 0 || dropped) {
         n = 0;
     } else if (!delta || g == 0) {
-        if (delta || seq_is_scanned(sq, q, ref_used)) {
-            if (FILL) out[0] = ScanItem{q, 0u, len - 1, 0u};
-            n = 1;
-        }
+        if (delta || seq_is_scanned(sq, q, ref_used)) put(0u, len - 1);
     } else {
         const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
         const u32 ns = sq.seq_nseg[q];
@@ -826,25 +900,56 @@ __global__ void k_items(DevSeqs sq, const u32* ref_used, u32 max_len, int delta)
             if (hi > (long long)len - 1) hi = (long long)len - 1;
             if (hi < lo) return;
             if (open && (u32)lo <= z + MERGE_GAP) { if ((u32)hi > z) z = (u32)hi; return; }
-            if (open) { if (FILL) out[n] = ScanItem{q, a, z, 0u}; ++n; }
+            if (open) put(a, z);
             a = (u32)lo; z = (u32)hi; open = true;
         };
         for (u32 s = 0; s < ns; ++s) {
-            const long long b = sg[s].out_start, e = sg[s + 1].out_start;
-            if (sg[s].kind == 1) add(b - (long long)max_len + 1, e - 1);
-            else if (s > 0 && sg[s - 1].kind == 0) add(b - (long long)max_len + 1, b - 1);
+            const long long bb = sg[s].out_start, e = sg[s + 1].out_start;
+            if (sg[s].kind == 1) add(bb - (long long)max_len + 1, e - 1);
+            else if (s > 0 && sg[s - 1].kind == 0) add(bb - (long long)max_len + 1, bb - 1);
         }
-        if (open) { if (FILL) out[n] = ScanItem{q, a, z, 0u}; ++n; }
+        if (open) put(a, z);
     }
     if (!FILL) sq.seq_nitems[q] = n;
 }
 
+// Decide the owner of every item (exact comparison with the candidate) and mark what has to be scored:
+// score_flag[w] = 1 for reference / full items and for owners.  count_size[w] = length of the owner's count vector.
+__global__ void k_item_resolve(DevBlock b, DevSeqs sq, DevPatterns pt, const u64* n_items_ptr, int delta, u32 max_len, const u64* keys,
+                               const u32* vals, u32 mask, u32* score_flag, u32* count_size) {
+    u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= *n_items_ptr) return;
+    ScanItem it = sq.items[w];
+    const u32 g = seq_group(sq, it.q);
+    u32 owner = (u32)w;
+    if (delta && g != 0) {
+        u32 cand = vals[table_find(keys, mask, sq.item_key[w])];
+        if (cand != (u32)w && items_equal(b, sq, it, sq.items[cand], max_len)) owner = cand;
+    }
+    sq.items[w].owner = owner;
+    const u32 r = sq.seq_region[it.q];
+    const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
+    score_flag[w] = owner == (u32)w ? 1u : 0u;
+    count_size[w] = (delta && g != 0 && owner == (u32)w) ? pt.n_pid * nk : 0u;
+    sq.item_hits[w] = 0;
+}
+
+// Compact list of the items to score: first the long ones (reference haplotypes / full scans), then the shared short ones.
+__global__ void k_item_lists(DevSeqs sq, const u64* n_items_ptr, const u32* score_flag, const u64* score_idx, u32* list) {
+    u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= *n_items_ptr || !score_flag[w]) return;
+    list[score_idx[w]] = (u32)w;
+}
+
 // One launch per pattern chunk.  Persistent CTAs (one per SM) hold the chunk's tables in shared memory; every WARP
-// takes items from an atomic counter, stages the packed bases into its private pair-code planes and scans all triples
-// of the chunk, 32 window starts at a time.
+// takes `per_grab` consecutive entries of the list from an atomic counter, stages their packed bases into its private
+// pair-code planes (several short items side by side, long items in tiles) and scans all triples of the chunk, 32 window
+// starts at a time.
 template <int FIELDS>
-__global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, DevMatches mt, DevRefHits rh,
-                                                       const u64* n_items_ptr, DevStatus* st, u32 chunk, int delta) {
+__global__ void __launch_bounds__(SCAN_CTA, 1)
+    k_scan(const __grid_constant__ DevBlock b, const __grid_constant__ DevSeqs sq, const __grid_constant__ DevPatterns pt,
+           const __grid_constant__ DevCounts ct, const __grid_constant__ DevMatches mt, const __grid_constant__ DevRefHits rh,
+           const u32* list, const u64* n_list_ptr, u32 per_grab, DevStatus* st, u32 chunk, int delta) {
     extern __shared__ __align__(16) u8 smem_raw[];
     CtaShared* cs = reinterpret_cast<CtaShared*>(smem_raw);
     WarpShared* ws = reinterpret_cast<WarpShared*>(smem_raw + sizeof(CtaShared)) + (threadIdx.x >> 5);
@@ -858,67 +963,39 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
         for (u32 k = tid; k < n16; k += SCAN_CTA) dst[k] = src[k];
         if (tid < cd.n_runs && tid < MAX_RUNS) cs->runs[tid] = pt.runs[cd.run_off + tid];
         if (tid == 0) cs->n_runs = cd.n_runs;
-        for (u32 k = lane; k < CNT_WORDS; k += 32) ws->cnt[k] = 0;
-        if (lane == 0) ws->cnt_dirty = 0;
     }
     __syncthreads();
     const u32 n_runs = cs->n_runs;
-    (void)n_items_ptr;
+    const u64 n_list = *n_list_ptr;
+    const ScanEnv env{&b, &sq, &pt, &ct, &mt, &rh, st, delta};
 
     for (;;) {
-        u32 q = 0;
-        if (lane == 0) q = atomicAdd(&st->work_counter, 1u);
-        q = __shfl_sync(0xffffffffu, q, 0);
-        if (q >= sq.n_seq) break;
-        const u64 it0 = sq.item_off[q], it1 = sq.item_off[q + 1];
-        if (it0 == it1) continue;  // nothing to score for this sequence
-        const u32 r = sq.seq_region[q];
-        const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
-        const u32 len = sq.seq_len[q];
-        const u32 nseg = sq.seq_nseg[q];
-        const u32 g = seq_group(sq, q);
-        const Seg* gsegs = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
-        __syncwarp();
-        if (lane == 0) {
-            ws->r = r;
-            ws->g = g;
-            ws->len = len;
-            ws->nseg = nseg;
-            ws->gsegs = gsegs;
-            ws->region_start = b.region_start[r];
-            ws->nk = nk;
-            ws->inner = b.inner + b.inner_off[r];
-            ws->mode = delta ? (g == 0 ? 1u : 2u) : 0u;
-            // a sequence scored in full is owned by this warp: shared-memory counts, flushed with plain stores; patched
-            // haplotypes under delta scoring have few hits: global atomics
-            ws->use_smem_cnt = (cd.n_pid * nk <= CNT_WORDS && !(delta && g != 0)) ? 1u : 0u;
-            ws->Crow = ct.C + (ct.cbase[r] - ct.cbase0) + (u64)g * pt.n_pid * nk;
-        }
-        if (nseg <= SEG_CACHE)
-            for (u32 k = lane; k <= nseg; k += 32) ws->segs[k] = gsegs[k];
-
-        const u64* gpk = sq.pk + sq.seq_uoff[q];
-        const u32* gnm = sq.nm + sq.seq_uoff[q];
-        const u32 n_units = sq.seq_units[q];
-        // rounds: pack items (long items in tiles of TILE_POS starts) into the planes until they are full
-        u64 it = it0;
-        u32 done_in_item = 0;  // starts of item `it` already scored
-        while (it < it1) {
+        u32 w = 0;
+        if (lane == 0) w = atomicAdd(&st->work_counter, 1u);
+        w = __shfl_sync(0xffffffffu, w, 0);
+        u64 li = (u64)w * per_grab;
+        if (li >= n_list) break;
+        const u64 lend = li + per_grab < n_list ? li + per_grab : n_list;
+        u32 done_in_item = 0;  // starts of entry li already scored
+        while (li < lend) {
             __syncwarp();
+            // a round: pack entries (long items in tiles of TILE_POS starts) into the planes until they are full
             u32 np = 0, pos_used = 0, vtot = 0;
-            while (it < it1 && np < MAX_PIECES) {
-                const ScanItem item = sq.items[it];
+            while (li < lend && np < MAX_PIECES) {
+                const u32 item_index = list[li];
+                const ScanItem item = sq.items[item_index];
+                const u32 q = item.q;
+                const u32 len = sq.seq_len[q];
                 const u32 left = item.p1 - item.p0 + 1 - done_in_item;
-                u32 n = left < (u32)TILE_POS ? left : (u32)TILE_POS;
+                const u32 n = left < (u32)TILE_POS ? left : (u32)TILE_POS;
                 const u32 blk = (n + 32 + 31) & ~31u;
-                if (pos_used + blk > 2 * (PLANE_BYTES - 16)) {
-                    if (np > 0) break;
-                    n = 2 * (PLANE_BYTES - 16) - 64;  // cannot happen with TILE_POS <= 2 * PLANE_BYTES - 96; kept for safety
-                }
+                if (pos_used + blk > 2 * (PLANE_BYTES - 16) && np > 0) break;
                 const u32 p0 = item.p0 + done_in_item;
-                if (lane == 0) { ws->piece_p0[np] = p0; ws->piece_vstart[np] = vtot; ws->piece_pbase[np] = pos_used; }
-                // stage this piece: packed bases of [p0, p0 + blk + 1) -> pair codes at plane positions pos_used ..
-                {
+                if (lane == 0) { ws->piece_p0[np] = p0; ws->piece_vstart[np] = vtot; ws->piece_pbase[np] = pos_used; ws->piece_item[np] = item_index; }
+                {   // stage this piece: packed bases of [p0, p0 + blk + 1) -> pair codes at plane positions pos_used ..
+                    const u64* gpk = sq.pk + sq.seq_uoff[q];
+                    const u32* gnm = sq.nm + sq.seq_uoff[q];
+                    const u32 n_units = sq.seq_units[q];
                     const u32 u0 = p0 / 32, o = p0 & 31;
                     const u32 nu = (o + blk + 1) / 32 + 1;
                     __syncwarp();
@@ -942,7 +1019,7 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
                 vtot += n;
                 ++np;
                 done_in_item += n;
-                if (done_in_item == item.p1 - item.p0 + 1) { ++it; done_in_item = 0; }
+                if (done_in_item == item.p1 - item.p0 + 1) { ++li; done_in_item = 0; }
             }
             if (lane == 0) { ws->piece_vstart[np] = vtot; ws->n_pieces = np; }
             __syncwarp();
@@ -954,6 +1031,7 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
                 const u32 off = valid ? v - ws->piece_vstart[k] : 0u;
                 const u32 j = ws->piece_pbase[k] + off;
                 const u32 i = valid ? ws->piece_p0[k] + off : 0xffffffffu;
+                const u32 item_index = ws->piece_item[k];
                 const u8* pl = &ws->plane[j & 1][j >> 1];
                 u32 idx[kMaxGroups];
 #pragma unroll
@@ -962,23 +1040,11 @@ __global__ void __launch_bounds__(SCAN_CTA, 1) k_scan(DevBlock b, DevSeqs sq, De
                 u32 t0 = 0;
                 for (u32 rn = 0; rn < n_runs; ++rn) {
                     const RunDesc rd = cs->runs[rn];
-                    scan_dispatch<FIELDS>(rd.groups, tb, rd.n_triples, t0, idx, i, ws, cd, &pt, &mt, &rh, st);
+                    scan_dispatch<FIELDS>(rd.groups, tb, rd.n_triples, t0, idx, i, item_index, cd, &env);
                     tb += (size_t)rd.n_triples * rd.groups * (kPairEntries * 8);
                     t0 += rd.n_triples;
                 }
             }
-        }
-        __syncwarp();
-        // flush this warp's count table: plain stores, the warp owns the (sequence, pid-range) slice of C
-        if (ws->cnt_dirty) {
-            u32 n = cd.n_pid * nk;
-            u32* crow = ws->Crow + (size_t)cd.pid_lo * nk;
-            for (u32 k = lane; k < n; k += 32) {
-                u32 v = ws->cnt[k];
-                if (v) { crow[k] = v; ws->cnt[k] = 0; }
-            }
-            __syncwarp();
-            if (lane == 0) ws->cnt_dirty = 0;
         }
     }
 }
@@ -1026,6 +1092,34 @@ __global__ void k_lost(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, Dev
     }
 }
 
+// Delta scoring, third half: every patched haplotype adds the count vectors of the (shared) items it is made of to its row.
+// One warp per sequence; lanes over the keys of the region.
+__global__ void k_item_gather(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, DevStatus* st) {
+    const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
+    if (q >= sq.n_seq) return;
+    const u32 g = seq_group(sq, q);
+    const u64 i0 = sq.item_off[q], i1 = sq.item_off[q + 1];
+    if (g == 0 || i0 == i1) return;
+    const u32 r = sq.seq_region[q];
+    const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
+    const u32 nkeys = pt.n_pid * nk;
+    u32* crow = ct.C + (ct.cbase[r] - ct.cbase0) + (u64)g * nkeys;
+    u32 hits = 0;
+    for (u64 w = i0; w < i1; ++w) {
+        const u32 owner = sq.items[w].owner;
+        const u32 nh = sq.item_hits[owner];
+        if (!nh) continue;
+        hits += nh;
+        const u32* src = sq.item_cnt + sq.item_coff[owner];
+        for (u32 k = lane; k < nkeys; k += 32) {
+            u32 v = src[k];
+            if (v) crow[k] += v;  // this warp owns the row here (k_lost ran before)
+        }
+    }
+    if (lane == 0 && hits) atomicAdd(&st->n_hits, (u64)hits);
+}
+
 // executed cells = sum over scanned sequences and patterns of max(0, len - L + 1) * L (pattern.rs:147-150)
 __global__ void k_seq_stats(DevSeqs sq, DevPatterns pt, const u32* ref_used, DevStatus* st) {
     u32 q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1052,12 +1146,12 @@ __global__ void k_seq_stats(DevSeqs sq, DevPatterns pt, const u32* ref_used, Dev
     }
 }
 
-// evaluated cells = what k_scan really scored: complete windows starting inside the items
-__global__ void k_item_stats(DevSeqs sq, DevPatterns pt, const u64* n_items_ptr, DevStatus* st) {
+// evaluated cells = what k_scan really scored: complete windows starting inside the scored items
+__global__ void k_item_stats(DevSeqs sq, DevPatterns pt, const u32* list, const u64* n_list_ptr, DevStatus* st) {
     u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u64 cells = 0;
-    if (w < *n_items_ptr) {
-        const ScanItem it = sq.items[w];
+    if (w < *n_list_ptr) {
+        const ScanItem it = sq.items[list[w]];
         const u32 len = sq.seq_len[it.q];
         if (it.p1 + pt.max_len <= len) cells = (u64)(it.p1 - it.p0 + 1) * pt.sum_len;
         else

@@ -103,7 +103,8 @@ struct tfbs_ctx {
 
     // phase 2 scratch
     DevBuf d_seq_region, d_seq_leader, d_seq_nd, d_seq_doff, d_dlist, d_segs, d_seq_nseg, d_seq_len, d_seq_units, d_seq_uoff, d_pk,
-        d_nm, d_seq_hash, d_seq_flags, d_tile_sums, d_C, d_vmin, d_vmax, d_flag, d_rowidx, d_seq_nitems, d_item_off, d_items, d_refhits;
+        d_nm, d_seq_hash, d_seq_flags, d_tile_sums, d_C, d_vmin, d_vmax, d_flag, d_rowidx, d_seq_nitems, d_item_off, d_items, d_refhits,
+        d_item_key, d_item_hits, d_item_coff, d_item_cnt, d_score_flag, d_count_size, d_score_idx, d_list;
     DevBuf d_status;
     DevBuf d_rows_region, d_rows_inner, d_rows_pid, d_rows_vmin, d_rows_vmax, d_rows_left, d_rows_right;
     DevBuf d_m_region, d_m_pattern, d_m_group, d_m_start;
@@ -458,6 +459,14 @@ int run_pipeline(tfbs_ctx* ctx) {
         CK(ctx->d_item_off.reserve((n_seq + 1) * 8));
         CK(ctx->d_items.reserve(std::max<uint64_t>(1, items_cap) * sizeof(ScanItem)));
         CK(ctx->d_refhits.reserve((size_t)refhit_cap * sizeof(RefHit)));
+        const uint64_t ic = std::max<uint64_t>(1, items_cap);
+        CK(ctx->d_item_key.reserve(ic * 8));
+        CK(ctx->d_item_hits.reserve(ic * 4));
+        CK(ctx->d_item_coff.reserve((ic + 1) * 8));
+        CK(ctx->d_score_flag.reserve(ic * 4));
+        CK(ctx->d_count_size.reserve(ic * 4));
+        CK(ctx->d_score_idx.reserve((ic + 1) * 8));
+        CK(ctx->d_list.reserve(ic * 4));
 
         DevSeqs sq{};
         sq.n_seq = (u32)n_seq;
@@ -481,6 +490,10 @@ int run_pipeline(tfbs_ctx* ctx) {
         sq.item_off = ctx->d_item_off.as<u64>();
         sq.items = ctx->d_items.as<ScanItem>();
         sq.n_items_cap = (u32)std::min<uint64_t>(items_cap, 0xffffffffu);
+        sq.item_key = ctx->d_item_key.as<u64>();
+        sq.item_hits = ctx->d_item_hits.as<u32>();
+        sq.item_coff = ctx->d_item_coff.as<u64>();
+        sq.item_cnt = nullptr;  // sized once the owners are known
         DevRefHits drh{ctx->d_refhits.as<RefHit>(), refhit_cap};
 
         {   // hits so far, in case this batch has to be re-scored without delta scoring
@@ -524,26 +537,60 @@ int run_pipeline(tfbs_ctx* ctx) {
         dc.cbase0 = ctx->h_cbase[r0];
         if (items_cap > 0xfffffff0ull) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "batch too large for the scan scheduler");
         const u64* d_n_items = sq.item_off + n_seq;
+        const u64* d_n_list = ctx->d_score_idx.as<u64>() + items_cap;
+        uint64_t n_list_host = 0;
         auto scan_pass = [&](int delta) -> int {
             int rc2;
             if (n_c) CK(cudaMemsetAsync(ctx->d_C.p, 0, n_c * 4, st));
-            k_items<false><<<grid_for(n_seq, 128), 128, 0, st>>>(sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta);
+            uint32_t tcap = 1024;
+            if (delta) {
+                while (tcap < 2 * items_cap) tcap <<= 1;
+                CK(ctx->d_keys.reserve((size_t)tcap * 8));
+                CK(ctx->d_vals.reserve((size_t)tcap * 4));
+                CK(cudaMemsetAsync(ctx->d_keys.p, 0, (size_t)tcap * 8, st));
+                CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, (size_t)tcap * 4, st));
+            }
+            CK(cudaMemsetAsync(ctx->d_score_flag.p, 0, ic * 4, st));
+            CK(cudaMemsetAsync(ctx->d_count_size.p, 0, ic * 4, st));
+            k_items<false><<<grid_for(n_seq, 128), 128, 0, st>>>(db, sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta, ctx->d_keys.as<u64>(),
+                                                                ctx->d_vals.as<u32>(), tcap - 1);
             ++launches;
             if ((rc2 = device_scan(ctx, sq.seq_nitems, n_seq, sq.item_off))) return rc2;
-            k_items<true><<<grid_for(n_seq, 128), 128, 0, st>>>(sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta);
-            k_item_stats<<<grid_for(items_cap, 256), 256, 0, st>>>(sq, ctx->dpat, d_n_items, dst);
+            k_items<true><<<grid_for(n_seq, 128), 128, 0, st>>>(db, sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta, ctx->d_keys.as<u64>(),
+                                                               ctx->d_vals.as<u32>(), tcap - 1);
+            k_item_resolve<<<grid_for(items_cap, 128), 128, 0, st>>>(db, sq, ctx->dpat, d_n_items, delta, ctx->cp.max_len, ctx->d_keys.as<u64>(),
+                                                                    ctx->d_vals.as<u32>(), tcap - 1, ctx->d_score_flag.as<u32>(),
+                                                                    ctx->d_count_size.as<u32>());
             launches += 2;
-            for (uint32_t c = 0; c < ctx->cp.chunks.size() && n_seq; ++c) {
+            if ((rc2 = device_scan(ctx, ctx->d_score_flag.as<u32>(), items_cap, ctx->d_score_idx.as<u64>()))) return rc2;
+            if ((rc2 = device_scan(ctx, ctx->d_count_size.as<u32>(), items_cap, sq.item_coff))) return rc2;
+            CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 16, sq.item_coff + items_cap, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 24, d_n_list, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const uint64_t cnt_words = ctx->h_totals.as<uint64_t>()[2];
+            n_list_host = ctx->h_totals.as<uint64_t>()[3];
+            CK(ctx->d_item_cnt.reserve(std::max<uint64_t>(1, cnt_words) * 4));
+            if (cnt_words) CK(cudaMemsetAsync(ctx->d_item_cnt.p, 0, cnt_words * 4, st));
+            sq.item_cnt = ctx->d_item_cnt.as<u32>();
+            if (n_list_host) {
+                k_item_lists<<<grid_for(items_cap, 256), 256, 0, st>>>(sq, d_n_items, ctx->d_score_flag.as<u32>(), ctx->d_score_idx.as<u64>(),
+                                                                      ctx->d_list.as<u32>());
+                k_item_stats<<<grid_for(n_list_host, 256), 256, 0, st>>>(sq, ctx->dpat, ctx->d_list.as<u32>(), d_n_list, dst);
+                launches += 2;
+            }
+            const u32 per_grab = delta ? 8u : 1u;
+            for (uint32_t c = 0; c < ctx->cp.chunks.size() && n_list_host; ++c) {
                 CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
-                if (wide) k_scan<2><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, drh, d_n_items, dst, c, delta);
-                else k_scan<3><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, drh, d_n_items, dst, c, delta);
+                if (wide) k_scan<2><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, drh, ctx->d_list.as<u32>(), d_n_list, per_grab, dst, c, delta);
+                else k_scan<3><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, drh, ctx->d_list.as<u32>(), d_n_list, per_grab, dst, c, delta);
                 ++launches;
                 ++ctx->stats.scan_launches;
             }
             if (delta) {
                 k_lost<<<(unsigned)std::min<uint64_t>(refhit_cap, (uint64_t)ctx->prop.multiProcessorCount * 16), 128, 0, st>>>(
                     db, sq, ctx->dpat, dc, drh, ctx->d_ngroups.as<u32>(), ctx->d_ref_used.as<u32>(), dst);
-                ++launches;
+                k_item_gather<<<grid_for(n_seq * 32, 256), 256, 0, st>>>(db, sq, ctx->dpat, dc, dst);
+                launches += 2;
             }
             CK(cudaGetLastError());
             return TFBS_OK;
@@ -603,7 +650,7 @@ int run_pipeline(tfbs_ctx* ctx) {
             CK(cudaStreamSynchronize(st));
             CK(cudaGetLastError());
         }
-        n_items_total += ctx->h_totals.as<uint64_t>()[1];
+        n_items_total += n_list_host;
         if (n_keys) batch_rows = *ctx->h_totals.as<uint64_t>();
 
         if (batch_rows) {
