@@ -54,6 +54,7 @@ struct DevBlock {
     // derived per variant
     const u32* var_class;       // index (inside the region) of the first record with the same Diff
     const u8* var_inwin;        // region_start <= pos <= region_end (haplotype.rs:95)
+    const u64* ref_prefix;      // polynomial prefix hash of every window: entry ref_off[r] + r + j = sum_{t<j} val(code_t, t) * B^t
 };
 
 // Error / status word: the smallest key wins so that the reported failure is deterministic.
@@ -87,6 +88,23 @@ __device__ __forceinline__ u64 mix64(u64 x) {
     x *= 0x94d049bb133111ebULL;
     x ^= x >> 31;
     return x;
+}
+
+// Hash of a haplotype = sum_i val(nuc_i, pos_i) * B^i (mod 2^64): the key of the map in load_haplotypes (haplotype.rs:84) is the
+// (nuc, pos) vector.  A reference-copy segment contributes B^(out - src) * (P[src + n] - P[src]) with P the prefix sums over the
+// region's window, so the hash of a patched haplotype costs O(segments), not O(bases).  Equal hashes are verified exactly.
+constexpr u64 HASH_B = 0x9e3779b97f4a7c15ULL;      // odd => invertible mod 2^64
+constexpr u64 HASH_BINV = 0xf1de83e19937733dULL;   // HASH_B * HASH_BINV == 1 (mod 2^64), checked at start-up
+__device__ __forceinline__ u64 hash_val(u32 code, int rel) { return mix64(((u64)(u32)rel << 3) | code) | 1ULL; }
+__device__ __forceinline__ u64 hash_pow(long long e) {  // HASH_B ^ e, negative exponents through the inverse
+    u64 base = e < 0 ? HASH_BINV : HASH_B;
+    u64 n = (u64)(e < 0 ? -e : e), r = 1;
+    while (n) {
+        if (n & 1) r *= base;
+        base *= base;
+        n >>= 1;
+    }
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -354,8 +372,8 @@ struct DevSeqs {
     Seg* segs;               // at 2*doff + 2*q, at most 2*nd + 2 entries
     u32* seq_nseg;           // [n_seq] segments without the terminator
     u32* seq_len;            // [n_seq] bases
-    u32* seq_units;          // [n_seq] ceil(len / 32)
-    u64* seq_uoff;           // [n_seq+1] offset into pk / nm
+    u32* ent_units;          // [list] packed units of a scored list entry: bases [p0 & ~31, p1 + 64]
+    u64* ent_uoff;           // [list+1] offset into pk / nm
     u64* pk;                 // 32 bases per word, 2 bits each
     u32* nm;                 // N mask, bit b = base 32u+b is N
     u64* seq_hash;           // [n_seq]
@@ -483,9 +501,20 @@ __global__ void k_walk(DevBlock b, DevSeqs sq, DevStatus* st) {
     sg[ns] = Seg{out, 0u, 0, 2u};  // terminator
     sq.seq_nseg[q] = ns;
     sq.seq_len[q] = out;
-    sq.seq_units[q] = (out + 31) / 32;
     sq.seq_flags[q] = trunc ? 1 : 0;
-    sq.seq_hash[q] = 0;
+    {   // hash of the (nuc, pos) vector from the segments
+        const u64* P = b.ref_prefix + ro + r;
+        u64 hsh = 0;
+        for (u32 s = 0; s < ns; ++s) {
+            const u32 n = sg[s + 1].out_start - sg[s].out_start;
+            if (sg[s].kind == 0) hsh += hash_pow((long long)sg[s].out_start - (long long)sg[s].src) * (P[sg[s].src + n] - P[sg[s].src]);
+            else {
+                u64 pw = hash_pow(sg[s].out_start);
+                for (u32 x = 0; x < n; ++x) { hsh += hash_val(b.allele_codes[sg[s].src + x], sg[s].relpos) * pw; pw *= HASH_B; }
+            }
+        }
+        sq.seq_hash[q] = hsh;
+    }
     if (trunc) atomicAdd(&st->n_truncated, 1u);
 }
 
@@ -498,47 +527,26 @@ __device__ __forceinline__ u32 seg_find(const Seg* sg, u32 ns, u32 i) {  // last
     return lo;
 }
 
-// One CTA per sequence, one thread per unit of 32 bases: gathers the bases through the segment list,
-// packs them 2 bits each (+ N mask) and accumulates the hash of the (nuc, pos) vector, which is the key
-// of the map in load_haplotypes (haplotype.rs:84).
-__global__ void k_emit(DevBlock b, DevSeqs sq) {
-    u32 q = blockIdx.x;
-    u32 len = sq.seq_len[q];
-    u32 nu = sq.seq_units[q];
-    u32 r = sq.seq_region[q];
-    u32 ns = sq.seq_nseg[q];
-    const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
-    const u8* refc = b.ref_codes + b.ref_off[r];
-    u64 uoff = sq.seq_uoff[q];
-    u64 hsum = 0;
-    for (u32 u = threadIdx.x; u < nu; u += blockDim.x) {
-        u32 i0 = u * 32;
-        u32 s = seg_find(sg, ns, i0);
-        Seg cur = sg[s];
-        u32 nxt = sg[s + 1].out_start;
-        u64 pk = 0;
-        u32 nm = 0;
-        u64 acc = 0;
-        for (u32 k = 0; k < 32; ++k) {
-            u32 i = i0 + k;
-            if (i >= len) break;
-            while (i >= nxt) { ++s; cur = sg[s]; nxt = sg[s + 1].out_start; }
-            u32 o = i - cur.out_start;
-            u8 c;
-            int rel;
-            if (cur.kind == 0) { c = refc[cur.src + o]; rel = cur.relpos + (int)o; }
-            else { c = b.allele_codes[cur.src + o]; rel = cur.relpos; }
-            pk |= (u64)(c & 3) << (2 * k);
-            nm |= (c == 4 ? 1u : 0u) << k;
-            acc = acc * 0x100000001b3ULL + (u64)((u32)rel * 8u + c + 1u);
-        }
-        sq.pk[uoff + u] = pk;
-        sq.nm[uoff + u] = nm;
-        hsum += mix64(acc ^ mix64((u64)u + 0x51ed27ULL));
+// Prefix sums of val(code_t, t) * B^t over the window of every region (one CTA per region).
+__global__ void k_ref_prefix(DevBlock b, u32 r0, u64* prefix) {
+    __shared__ u64 s_carry;
+    const u32 r = r0 + blockIdx.x;
+    const u64 ro = b.ref_off[r];
+    const u32 n = (u32)(b.ref_off[r + 1] - ro);
+    u64* P = prefix + ro + r;
+    if (threadIdx.x == 0) { s_carry = 0; P[0] = 0; }
+    __syncthreads();
+    for (u32 t0 = 0; t0 < n; t0 += SCAN_THREADS) {
+        const u32 t = t0 + threadIdx.x;
+        u64 term = t < n ? hash_val(b.ref_codes[ro + t], (int)t) * hash_pow(t) : 0ULL;
+        u64 tot;
+        u64 ex = block_exclusive_scan(term, &tot);
+        const u64 carry = s_carry;
+        if (t < n) P[t + 1] = carry + ex + term;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + tot;
+        __syncthreads();
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
-    if ((threadIdx.x & 31) == 0 && hsum) atomicAdd(&sq.seq_hash[q], hsum);
 }
 
 __device__ __forceinline__ u32 seq_group(const DevSeqs& sq, u32 q) {  // group index of q inside its region
@@ -578,15 +586,12 @@ __global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32
     if (w == g) return;
     u32 qw = q - g + w;
     bool same = sq.seq_len[qw] == sq.seq_len[q] && sq.seq_region[qw] == sq.seq_region[q];
-    // bases: the packed words; positions: the two piecewise-linear position maps, walked over the union of their breakpoints
-    if (same) {
-        const u64 ua = sq.seq_uoff[q], ub = sq.seq_uoff[qw];
-        const u32 nu = sq.seq_units[q];
-        for (u32 u = 0; same && u < nu; ++u) same = sq.pk[ua + u] == sq.pk[ub + u] && sq.nm[ua + u] == sq.nm[ub + u];
-    }
+    // walk the two segment lists over the union of their breakpoints: two reference-copy pieces at the same position are equal by
+    // construction, anything else is compared base by base (nuc and pos)
     if (same) {
         const Seg* sa = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
         const Seg* sb = sq.segs + 2 * sq.seq_doff[qw] + 2 * (u64)qw;
+        const u8* refc = b.ref_codes + b.ref_off[sq.seq_region[q]];
         const u32 len = sq.seq_len[q];
         u32 ia = 0, ib = 0, i = 0;
         while (same && i < len) {
@@ -594,9 +599,18 @@ __global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32
             while (sb[ib + 1].out_start <= i) ++ib;
             const u32 ea = sa[ia + 1].out_start, eb = sb[ib + 1].out_start;
             const u32 e = ea < eb ? ea : eb;
-            const int pa = sa[ia].relpos + (sa[ia].kind == 0 ? (int)(i - sa[ia].out_start) : 0);
-            const int pb = sb[ib].relpos + (sb[ib].kind == 0 ? (int)(i - sb[ib].out_start) : 0);
-            same = pa == pb && (e - i == 1 || sa[ia].kind == sb[ib].kind);
+            const u32 da = i - sa[ia].out_start, db = i - sb[ib].out_start;
+            if (sa[ia].kind == 0 && sb[ib].kind == 0) {
+                same = sa[ia].relpos + (int)da == sb[ib].relpos + (int)db;
+            } else {
+                for (u32 x = 0; same && x < e - i; ++x) {
+                    const u8 ca = sa[ia].kind == 0 ? refc[sa[ia].src + da + x] : b.allele_codes[sa[ia].src + da + x];
+                    const u8 cb = sb[ib].kind == 0 ? refc[sb[ib].src + db + x] : b.allele_codes[sb[ib].src + db + x];
+                    const int pa = sa[ia].relpos + (sa[ia].kind == 0 ? (int)(da + x) : 0);
+                    const int pb = sb[ib].relpos + (sb[ib].kind == 0 ? (int)(db + x) : 0);
+                    same = ca == cb && pa == pb;
+                }
+            }
             i = e;
         }
     }
@@ -938,7 +952,47 @@ __global__ void k_item_resolve(DevBlock b, DevSeqs sq, DevPatterns pt, const u64
 __global__ void k_item_lists(DevSeqs sq, const u64* n_items_ptr, const u32* score_flag, const u64* score_idx, u32* list) {
     u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= *n_items_ptr || !score_flag[w]) return;
-    list[score_idx[w]] = (u32)w;
+    const u64 e = score_idx[w];
+    list[e] = (u32)w;
+    const ScanItem it = sq.items[w];
+    sq.ent_units[e] = ((it.p1 + 64) >> 5) - (it.p0 >> 5) + 1;
+}
+
+// K1, second half: pack the bases the scored entries need (2 bits per base + N mask), gathered through the segment lists.
+// One warp per list entry, one lane per unit of 32 bases.
+__global__ void k_emit_list(DevBlock b, DevSeqs sq, const u32* list, const u64* n_list_ptr) {
+    const u64 e = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u32 lane = threadIdx.x & 31;
+    if (e >= *n_list_ptr) return;
+    const ScanItem it = sq.items[list[e]];
+    const u32 q = it.q;
+    const u32 len = sq.seq_len[q];
+    const u32 ns = sq.seq_nseg[q];
+    const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
+    const u8* refc = b.ref_codes + b.ref_off[sq.seq_region[q]];
+    const u32 ubase = it.p0 >> 5, nu = sq.ent_units[e];
+    const u64 uoff = sq.ent_uoff[e];
+    for (u32 u = lane; u < nu; u += 32) {
+        const u32 i0 = (ubase + u) * 32;
+        u64 pk = 0;
+        u32 nm = 0;
+        if (i0 < len) {
+            u32 s = seg_find(sg, ns, i0);
+            Seg cur = sg[s];
+            u32 nxt = sg[s + 1].out_start;
+            for (u32 k = 0; k < 32; ++k) {
+                const u32 i = i0 + k;
+                if (i >= len) break;
+                while (i >= nxt) { ++s; cur = sg[s]; nxt = sg[s + 1].out_start; }
+                const u32 o = i - cur.out_start;
+                const u8 c = cur.kind == 0 ? refc[cur.src + o] : b.allele_codes[cur.src + o];
+                pk |= (u64)(c & 3) << (2 * k);
+                nm |= (c == 4 ? 1u : 0u) << k;
+            }
+        }
+        sq.pk[uoff + u] = pk;
+        sq.nm[uoff + u] = nm;
+    }
 }
 
 // One launch per pattern chunk.  Persistent CTAs (one per SM) hold the chunk's tables in shared memory; every WARP
@@ -993,10 +1047,10 @@ __global__ void __launch_bounds__(SCAN_CTA, 1)
                 const u32 p0 = item.p0 + done_in_item;
                 if (lane == 0) { ws->piece_p0[np] = p0; ws->piece_vstart[np] = vtot; ws->piece_pbase[np] = pos_used; ws->piece_item[np] = item_index; }
                 {   // stage this piece: packed bases of [p0, p0 + blk + 1) -> pair codes at plane positions pos_used ..
-                    const u64* gpk = sq.pk + sq.seq_uoff[q];
-                    const u32* gnm = sq.nm + sq.seq_uoff[q];
-                    const u32 n_units = sq.seq_units[q];
-                    const u32 u0 = p0 / 32, o = p0 & 31;
+                    const u64* gpk = sq.pk + sq.ent_uoff[li];
+                    const u32* gnm = sq.nm + sq.ent_uoff[li];
+                    const u32 n_units = sq.ent_units[li];
+                    const u32 u0 = p0 / 32 - item.p0 / 32, o = p0 & 31;
                     const u32 nu = (o + blk + 1) / 32 + 1;
                     __syncwarp();
                     for (u32 k = lane; k < nu; k += 32) {

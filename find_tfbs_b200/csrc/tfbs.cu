@@ -86,7 +86,7 @@ struct tfbs_ctx {
     uint32_t R = 0, S = 0, H = 0, pitch = 0;
     uint64_t n_ref_bytes = 0, n_allele_bytes = 0, n_var = 0, n_inner = 0, n_carrier_rows = 0;
     DevBuf d_region_start, d_region_end, d_ref_off, d_ref_ascii, d_ref_codes, d_inner_off, d_inner, d_var_off, d_variants,
-        d_allele_ascii, d_allele_codes, d_carriers, d_var_class, d_var_inwin;
+        d_allele_ascii, d_allele_codes, d_carriers, d_var_class, d_var_inwin, d_ref_prefix;
     // host copies of the small per-region arrays (batch planning, error messages)
     std::vector<int64_t> h_region_start, h_region_end;
     std::vector<uint64_t> h_ref_off;
@@ -102,7 +102,7 @@ struct tfbs_ctx {
     DevBuf d_gbase, d_cbase, d_kbase;
 
     // phase 2 scratch
-    DevBuf d_seq_region, d_seq_leader, d_seq_nd, d_seq_doff, d_dlist, d_segs, d_seq_nseg, d_seq_len, d_seq_units, d_seq_uoff, d_pk,
+    DevBuf d_seq_region, d_seq_leader, d_seq_nd, d_seq_doff, d_dlist, d_segs, d_seq_nseg, d_seq_len, d_ent_units, d_ent_uoff, d_pk,
         d_nm, d_seq_hash, d_seq_flags, d_tile_sums, d_C, d_vmin, d_vmax, d_flag, d_rowidx, d_seq_nitems, d_item_off, d_items, d_refhits,
         d_item_key, d_item_hits, d_item_coff, d_item_cnt, d_score_flag, d_count_size, d_score_idx, d_list;
     DevBuf d_status;
@@ -181,6 +181,7 @@ DevBlock dev_block(const tfbs_ctx* ctx) {
     b.pitch = ctx->pitch;
     b.var_class = ctx->d_var_class.as<u32>();
     b.var_inwin = ctx->d_var_inwin.as<u8>();
+    b.ref_prefix = ctx->d_ref_prefix.as<u64>();
     return b;
 }
 
@@ -258,6 +259,7 @@ int do_upload(tfbs_ctx* ctx, const tfbs_block* b) {
     CK(ctx->d_allele_codes.reserve(std::max<uint64_t>(1, ctx->n_allele_bytes)));
     CK(ctx->d_var_class.reserve(std::max<uint64_t>(1, ctx->n_var) * 4));
     CK(ctx->d_var_inwin.reserve(std::max<uint64_t>(1, ctx->n_var)));
+    CK(ctx->d_ref_prefix.reserve((ctx->n_ref_bytes + R + 1) * 8));
     ctx->have_block = true;
     return TFBS_OK;
 }
@@ -310,7 +312,8 @@ int run_pipeline(tfbs_ctx* ctx) {
     }
     DevBlock db = dev_block(ctx);
     k_variant_prep<<<R, 128, 0, st>>>(db, 0, ctx->d_var_class.as<u32>(), ctx->d_var_inwin.as<u8>());
-    ++launches;
+    k_ref_prefix<<<R, SCAN_THREADS, 0, st>>>(db, 0, ctx->d_ref_prefix.as<u64>());
+    launches += 2;
 
     // ---- phase 1: grouping (K0), over super-batches bounded by the hash table ---------------------
     const uint64_t RH = (uint64_t)R * H;
@@ -442,10 +445,6 @@ int run_pipeline(tfbs_ctx* ctx) {
         CK(ctx->d_segs.reserve((2 * n_d + 2 * n_seq) * sizeof(Seg)));
         CK(ctx->d_seq_nseg.reserve(n_seq * 4));
         CK(ctx->d_seq_len.reserve(n_seq * 4));
-        CK(ctx->d_seq_units.reserve(n_seq * 4));
-        CK(ctx->d_seq_uoff.reserve((n_seq + 1) * 8));
-        CK(ctx->d_pk.reserve(n_units * 8));
-        CK(ctx->d_nm.reserve(n_units * 4));
         CK(ctx->d_seq_hash.reserve(n_seq * 8));
         CK(ctx->d_seq_flags.reserve(n_seq));
         CK(ctx->d_C.reserve(std::max<uint64_t>(1, n_c) * 4));
@@ -467,6 +466,8 @@ int run_pipeline(tfbs_ctx* ctx) {
         CK(ctx->d_count_size.reserve(ic * 4));
         CK(ctx->d_score_idx.reserve((ic + 1) * 8));
         CK(ctx->d_list.reserve(ic * 4));
+        CK(ctx->d_ent_units.reserve(ic * 4));
+        CK(ctx->d_ent_uoff.reserve((ic + 1) * 8));
 
         DevSeqs sq{};
         sq.n_seq = (u32)n_seq;
@@ -480,10 +481,10 @@ int run_pipeline(tfbs_ctx* ctx) {
         sq.segs = ctx->d_segs.as<Seg>();
         sq.seq_nseg = ctx->d_seq_nseg.as<u32>();
         sq.seq_len = ctx->d_seq_len.as<u32>();
-        sq.seq_units = ctx->d_seq_units.as<u32>();
-        sq.seq_uoff = ctx->d_seq_uoff.as<u64>();
-        sq.pk = ctx->d_pk.as<u64>();
-        sq.nm = ctx->d_nm.as<u32>();
+        sq.ent_units = ctx->d_ent_units.as<u32>();
+        sq.ent_uoff = ctx->d_ent_uoff.as<u64>();
+        sq.pk = nullptr;  // sized once the scored entries are known
+        sq.nm = nullptr;
         sq.seq_hash = ctx->d_seq_hash.as<u64>();
         sq.seq_flags = ctx->d_seq_flags.as<u8>();
         sq.seq_nitems = ctx->d_seq_nitems.as<u32>();
@@ -510,9 +511,6 @@ int run_pipeline(tfbs_ctx* ctx) {
         ++launches;
         if ((rc = device_scan(ctx, sq.seq_nd, n_seq, sq.seq_doff))) return rc;
         k_walk<<<grid_for(n_seq, 128), 128, 0, st>>>(db, sq, dst);
-        ++launches;
-        if ((rc = device_scan(ctx, sq.seq_units, n_seq, sq.seq_uoff))) return rc;
-        k_emit<<<(unsigned)n_seq, 64, 0, st>>>(db, sq);
         ++launches;
         // the sequence-keyed map of load_haplotypes
         {
@@ -552,6 +550,7 @@ int run_pipeline(tfbs_ctx* ctx) {
             }
             CK(cudaMemsetAsync(ctx->d_score_flag.p, 0, ic * 4, st));
             CK(cudaMemsetAsync(ctx->d_count_size.p, 0, ic * 4, st));
+            CK(cudaMemsetAsync(ctx->d_ent_units.p, 0, ic * 4, st));
             k_items<false><<<grid_for(n_seq, 128), 128, 0, st>>>(db, sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta, ctx->d_keys.as<u64>(),
                                                                 ctx->d_vals.as<u32>(), tcap - 1);
             ++launches;
@@ -564,17 +563,26 @@ int run_pipeline(tfbs_ctx* ctx) {
             launches += 2;
             if ((rc2 = device_scan(ctx, ctx->d_score_flag.as<u32>(), items_cap, ctx->d_score_idx.as<u64>()))) return rc2;
             if ((rc2 = device_scan(ctx, ctx->d_count_size.as<u32>(), items_cap, sq.item_coff))) return rc2;
+            k_item_lists<<<grid_for(items_cap, 256), 256, 0, st>>>(sq, d_n_items, ctx->d_score_flag.as<u32>(), ctx->d_score_idx.as<u64>(),
+                                                                  ctx->d_list.as<u32>());
+            ++launches;
+            if ((rc2 = device_scan(ctx, sq.ent_units, items_cap, sq.ent_uoff))) return rc2;
             CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 16, sq.item_coff + items_cap, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 24, d_n_list, 8, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 32, sq.ent_uoff + items_cap, 8, cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             const uint64_t cnt_words = ctx->h_totals.as<uint64_t>()[2];
             n_list_host = ctx->h_totals.as<uint64_t>()[3];
+            const uint64_t ent_units_total = ctx->h_totals.as<uint64_t>()[4];
             CK(ctx->d_item_cnt.reserve(std::max<uint64_t>(1, cnt_words) * 4));
             if (cnt_words) CK(cudaMemsetAsync(ctx->d_item_cnt.p, 0, cnt_words * 4, st));
             sq.item_cnt = ctx->d_item_cnt.as<u32>();
+            CK(ctx->d_pk.reserve(std::max<uint64_t>(1, ent_units_total) * 8));
+            CK(ctx->d_nm.reserve(std::max<uint64_t>(1, ent_units_total) * 4));
+            sq.pk = ctx->d_pk.as<u64>();
+            sq.nm = ctx->d_nm.as<u32>();
             if (n_list_host) {
-                k_item_lists<<<grid_for(items_cap, 256), 256, 0, st>>>(sq, d_n_items, ctx->d_score_flag.as<u32>(), ctx->d_score_idx.as<u64>(),
-                                                                      ctx->d_list.as<u32>());
+                k_emit_list<<<grid_for(n_list_host * 32, 256), 256, 0, st>>>(db, sq, ctx->d_list.as<u32>(), d_n_list);
                 k_item_stats<<<grid_for(n_list_host, 256), 256, 0, st>>>(sq, ctx->dpat, ctx->d_list.as<u32>(), d_n_list, dst);
                 launches += 2;
             }
