@@ -22,7 +22,7 @@ DIR_P, DIR_N = 0, 1
 
 EXPORTS = ["tfbs_abi_version", "tfbs_create", "tfbs_destroy", "tfbs_last_error", "tfbs_set_option", "tfbs_set_patterns",
            "tfbs_submit_block", "tfbs_collect", "tfbs_get_matches", "tfbs_upload_block", "tfbs_run_resident", "tfbs_get_stats",
-           "tfbs_stream"]
+           "tfbs_stream", "tfbs_host_register", "tfbs_host_unregister"]
 
 
 class TfbsPattern(C.Structure):
@@ -112,6 +112,8 @@ def lib():
         L.tfbs_get_stats.argtypes = [C.c_void_p, C.POINTER(TfbsStats)]
         L.tfbs_stream.argtypes = [C.c_void_p]
         L.tfbs_stream.restype = C.c_void_p
+        L.tfbs_host_register.argtypes = [C.c_void_p, C.c_size_t]
+        L.tfbs_host_unregister.argtypes = [C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -189,6 +191,24 @@ class Block:
         b.n_carrier_rows = self.carriers.shape[0]
         b.carrier_pitch = self.carriers.shape[1]
         self.c = b
+
+    def _arrays(self):
+        return (self.region_start, self.region_end, self.ref_off, self.ref_bases, self.inner_off, self.inner, self.var_off, self.variants,
+                self.allele_bases, self.carriers)
+
+    def pin(self):
+        """Page-lock the input arrays (tfbs_host_register) so that H2D copies run at PCIe speed."""
+        for a in self._arrays():
+            if a.nbytes and lib().tfbs_host_register(a.ctypes.data, a.nbytes) != TFBS_OK:
+                raise TfbsError(ERR_CUDA, "cudaHostRegister failed")
+        self._pinned = True
+
+    def unpin(self):
+        if getattr(self, "_pinned", False):
+            for a in self._arrays():
+                if a.nbytes:
+                    lib().tfbs_host_unregister(a.ctypes.data)
+            self._pinned = False
 
     def input_bytes(self):
         return sum(a.nbytes for a in (self.region_start, self.region_end, self.ref_off, self.ref_bases, self.inner_off, self.inner,

@@ -933,6 +933,15 @@ int tfbs_get_stats(const tfbs_ctx* ctx, tfbs_stats* out) {
     return TFBS_OK;
 }
 
+int tfbs_host_register(void* ptr, size_t bytes) {
+    if (!ptr || !bytes) return TFBS_OK;
+    return cudaHostRegister(ptr, bytes, cudaHostRegisterDefault) == cudaSuccess ? TFBS_OK : TFBS_ERR_CUDA;
+}
+int tfbs_host_unregister(void* ptr) {
+    if (!ptr) return TFBS_OK;
+    return cudaHostUnregister(ptr) == cudaSuccess ? TFBS_OK : TFBS_ERR_CUDA;
+}
+
 void* tfbs_stream(const tfbs_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 }  // extern "C"

@@ -230,6 +230,11 @@ int tfbs_run_resident(tfbs_ctx* ctx);
 
 int tfbs_get_stats(const tfbs_ctx* ctx, tfbs_stats* out);
 
+/* Page-lock / unlock caller buffers (cudaHostRegister) so that tfbs_submit_block copies them at full PCIe speed.
+ * Optional: pageable buffers work, only slower. */
+int tfbs_host_register(void* ptr, size_t bytes);
+int tfbs_host_unregister(void* ptr);
+
 /* The CUDA stream (cudaStream_t) all work of this context is enqueued on. */
 void* tfbs_stream(const tfbs_ctx* ctx);
 
