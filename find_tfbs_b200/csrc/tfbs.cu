@@ -74,6 +74,7 @@ struct tfbs_ctx {
     uint32_t table_budget = 96 * 1024;
     int scan_ctas_per_sm = 0;  // < 0: fixed grid size (debugging)
     int delta = 1;             // delta scoring of patched haplotypes
+    int64_t refhit_cap_opt = 0; // testing: capacity of the reference-hit buffer (0 = automatic)
 
     // patterns
     bool have_patterns = false;
@@ -453,7 +454,7 @@ int run_pipeline(tfbs_ctx* ctx) {
         CK(ctx->d_flag.reserve(std::max<uint64_t>(1, n_keys) * 4));
         CK(ctx->d_rowidx.reserve((n_keys + 1) * 8));
         const uint64_t items_cap = n_d + n_seq;
-        const uint32_t refhit_cap = (uint32_t)std::min<uint64_t>(256ull * nr + 4096, 1u << 26);
+        const uint32_t refhit_cap = ctx->refhit_cap_opt ? (uint32_t)ctx->refhit_cap_opt : (uint32_t)std::min<uint64_t>(256ull * nr + 4096, 1u << 26);
         CK(ctx->d_seq_nitems.reserve(n_seq * 4));
         CK(ctx->d_item_off.reserve((n_seq + 1) * 8));
         CK(ctx->d_items.reserve(std::max<uint64_t>(1, items_cap) * sizeof(ScanItem)));
@@ -822,6 +823,7 @@ int tfbs_set_option(tfbs_ctx* ctx, const char* key, int64_t value) {
     else if (k == "table_budget_kb") { ctx->table_budget = (uint32_t)std::max<int64_t>(8, value) * 1024; ctx->have_patterns = false; }
     else if (k == "scan_ctas_per_sm") ctx->scan_ctas_per_sm = (int)value;
     else if (k == "delta") ctx->delta = value != 0;
+    else if (k == "refhit_cap") ctx->refhit_cap_opt = std::max<int64_t>(0, value);
     else return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "unknown option " + k);
     return TFBS_OK;
 }

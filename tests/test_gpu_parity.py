@@ -319,3 +319,23 @@ def test_config3_like_many_samples_many_pwms():
     hp.assert_rows_equal(a, b)
     v = a["left"].astype(np.int64) + a["right"]
     assert np.array_equal(v.min(axis=1), a["vmin"]) and np.array_equal(v.max(axis=1), a["vmax"]) and np.all(a["vmin"] != a["vmax"])
+
+
+def test_delta_scoring_corner_cases():
+    """Delta scoring paths the other tests do not reach: several pattern chunks, several region batches, the fall-back to a full scan
+    when the reference-hit buffer overflows, long regions (several tiles / plane rounds per sequence) and 32-column patterns."""
+    pats = synth.make_pwms(30, seed=31, lmin=8, lmax=30)
+    lmax = max(p["weights"].shape[0] for p in pats)
+    blk = synth.make_cohort(10, 80, seed=31, lmax_pattern=lmax, region_len=(100, 400), two_beds=True)
+    ps = PatternSet(pats)
+    base = hp.run_oracle(ps, blk, binding.ROWS_ALL_KEYS, False)
+    for opts in ({"table_budget_kb": 16}, {"scratch_mb": 64}, {"refhit_cap": 3}, {"table_budget_kb": 24, "scratch_mb": 64, "refhit_cap": 50}):
+        g = hp.run_gpu(ps, blk, binding.ROWS_ALL_KEYS, False, opts)
+        hp.assert_rows_equal(g, base)
+        hp.check_stats(g["stats"], base)
+    # long regions and the longest supported patterns
+    pats = synth.make_pwms(3, seed=32, lmin=31, lmax=32) + synth.make_pwms(2, seed=33, lmin=1, lmax=3)
+    for i, p in enumerate(pats):
+        p["pattern_id"] = i // 2
+    blk = synth.make_cohort(6, 4, seed=32, lmax_pattern=32, region_len=(2500, 4200), variant_rate=1 / 40.0, frac_ins=0.1, frac_del=0.1)
+    hp.check_parity(PatternSet(pats), blk, rows_mode=binding.ROWS_ALL_KEYS)
