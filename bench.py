@@ -237,7 +237,7 @@ def main():
     for _ in range(args.steps):
         step_resident()
         st = ctx.stats()
-        scan_ms.append(st["ms_scan"])
+        scan_ms.append(st["ms_scan_kernel"])
         launches += st["total_launches"]
     e1.record(stream)
     barrier()
@@ -262,7 +262,7 @@ def main():
         fs_ms = []
         for _ in range(2):
             ctx.run_resident()
-            fs_ms.append(ctx.stats()["ms_scan"])
+            fs_ms.append(ctx.stats()["ms_scan_kernel"])
         fst = ctx.stats()
         full_scan = (fst["evaluated_cells"], sum(fs_ms) / len(fs_ms) * 1e-3)
         ctx.set_option("delta", 1)
@@ -289,7 +289,7 @@ def main():
 
     pk = peaks()
     scan_s = (sum(scan_ms) / len(scan_ms)) * 1e-3
-    achieved = st["evaluated_cells"] / scan_s  # this rank's scan stage: cells really scored / CUDA-event time of its launches
+    achieved = st["evaluated_cells"] / scan_s  # this rank's k_scan launches: cells really scored / CUDA-event time around them
     f_max = pk["sm_max_mhz"] * 1e6
     roof = SM_COUNT * LDS64_PER_CLK_PER_SM * CELLS_PER_LDS64 * f_max
     f_obs = (clocks["sm_mhz"] or pk["sm_max_mhz"]) * 1e6
@@ -310,7 +310,8 @@ def main():
            "evaluated_cells_per_step": evaluated, "scan_items_per_step": st["n_scan_items"],
            "cells": "nominal = every haplotype of every sample x every pattern; executed = distinct haplotypes only (what the reference scans); "
                     "evaluated = what k_scan scored (delta scoring inherits untouched windows from the reference haplotype)",
-           "stages_ms": {k: st[k] for k in ("ms_group", "ms_build", "ms_scan", "ms_count", "ms_total")},
+           "stages_ms": {k: st[k] for k in ("ms_group", "ms_build", "ms_scan", "ms_scan_kernel", "ms_count", "ms_total")},
+           "groups_dropped_per_step": st["n_dropped"], "haplotypes_truncated_per_step": st["n_truncated"],
            "groups_per_step": st["n_groups"], "hits_per_step": st["n_hits"], "rows_per_step": st["n_rows"],
            "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
     if not args.no_cpu_baseline:

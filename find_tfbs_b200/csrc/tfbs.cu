@@ -119,7 +119,7 @@ struct tfbs_ctx {
     bool ran = false;
 
     tfbs_stats stats{};
-    cudaEvent_t ev[8]{};
+    cudaEvent_t ev[10]{};
 };
 
 namespace {
@@ -424,6 +424,7 @@ int run_pipeline(tfbs_ctx* ctx) {
 
     float ms_build = 0, ms_scan = 0, ms_count = 0;
     uint64_t n_items_total = 0, n_hits_before = 0;
+    float ms_scan_kernel = 0;
     uint32_t r0 = 0;
     while (r0 < R) {
         uint64_t n_seq = 0, n_d = 0, n_units = 0, n_c = 0, n_keys = 0;
@@ -588,6 +589,7 @@ int run_pipeline(tfbs_ctx* ctx) {
                 launches += 2;
             }
             const u32 per_grab = delta ? 8u : 1u;
+            CK(cudaEventRecord(ctx->ev[8], st));
             for (uint32_t c = 0; c < ctx->cp.chunks.size() && n_list_host; ++c) {
                 CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
                 if (wide) k_scan<2><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, drh, ctx->d_list.as<u32>(), d_n_list, per_grab, dst, c, delta);
@@ -595,6 +597,7 @@ int run_pipeline(tfbs_ctx* ctx) {
                 ++launches;
                 ++ctx->stats.scan_launches;
             }
+            CK(cudaEventRecord(ctx->ev[9], st));
             if (delta) {
                 k_lost<<<(unsigned)std::min<uint64_t>(refhit_cap, (uint64_t)ctx->prop.multiProcessorCount * 16), 128, 0, st>>>(
                     db, sq, ctx->dpat, dc, drh, ctx->d_ngroups.as<u32>(), ctx->d_ref_used.as<u32>(), dst);
@@ -704,6 +707,8 @@ int run_pipeline(tfbs_ctx* ctx) {
         ms_scan += t;
         CK(cudaEventElapsedTime(&t, ctx->ev[4], ctx->ev[5]));
         ms_count += t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[8], ctx->ev[9]));
+        ms_scan_kernel += t;
         r0 = r1;
     }
     CK(cudaEventRecord(ctx->ev[6], st));
@@ -748,6 +753,9 @@ int run_pipeline(tfbs_ctx* ctx) {
     ctx->stats.n_rows = ctx->n_rows;
     ctx->stats.evaluated_cells = hs.evaluated_cells;
     ctx->stats.n_scan_items = n_items_total;
+    ctx->stats.ms_scan_kernel = ms_scan_kernel;
+    ctx->stats.n_dropped = hs.n_dropped;
+    ctx->stats.n_truncated = hs.n_truncated;
     ctx->ran = true;
     return TFBS_OK;
 }

@@ -185,6 +185,10 @@ typedef struct tfbs_stats {
     uint32_t scan_ctas;
     uint64_t evaluated_cells;   /* cells the scan kernel really scored: == executed_cells without delta scoring, less with it */
     uint64_t n_scan_items;      /* ranges of window starts handed to the scan kernel */
+    float ms_scan_kernel;       /* device time of the k_scan launches alone (CUDA events around them), summed over batches */
+    uint32_t n_dropped;         /* groups overwritten in the sequence-keyed map (haplotype.rs:84) */
+    uint32_t n_truncated;       /* haplotypes truncated by an overlapping variant (haplotype.rs:144-149) */
+    uint32_t reserved;
 } tfbs_stats;
 
 typedef struct tfbs_ctx tfbs_ctx;
