@@ -355,8 +355,10 @@ struct RefHit {
     u32 pid;      // pid_index of the pattern
 };
 struct DevRefHits {
-    RefHit* buf;
-    u32 cap;
+    RefHit* buf;   // slab of `capr` entries per region of the batch
+    u32* cnt;      // hits per region of the batch (may exceed capr: then the batch falls back to a full scan)
+    u32 capr;
+    u32 r0;        // first region of the batch
 };
 
 // Sequence table of a batch: q = gbase[r] - gbase[r0] + g.
@@ -717,7 +719,8 @@ struct ScanEnv {
 };
 
 // Rare path: a window scored above the threshold in at least one field.
-__device__ __noinline__ void scan_on_hit(u64 hit, u32 t, u32 i, u32 item_index, ChunkDesc cd, const ScanEnv* env) {
+__device__ __noinline__ u32 scan_on_hit(u64 hit, u32 t, u32 i, u32 item_index, ChunkDesc cd, const ScanEnv* env) {
+    u32 counted = 0;  // hits of a full scan: the caller adds them to the statistics once per work grab
     const DevSeqs& sq = *env->sq;
     const DevBlock& b = *env->b;
     const DevPatterns& pt = *env->pt;
@@ -756,11 +759,12 @@ __device__ __noinline__ void scan_on_hit(u64 hit, u32 t, u32 i, u32 item_index, 
         } else {
             crow = env->ct->C + (env->ct->cbase[r] - env->ct->cbase0) + (u64)g * pt.n_pid * nk;
             if (mode == 1) {
-                u32 slot = atomicAdd(&st->n_refhits, 1u);
-                if (slot < env->rh->cap) env->rh->buf[slot] = RefHit{r, (int)hs, L, pl};
+                const u32 rr = r - env->rh->r0;
+                u32 slot = atomicAdd(&env->rh->cnt[rr], 1u);
+                if (slot < env->rh->capr) env->rh->buf[(u64)rr * env->rh->capr + slot] = RefHit{r, (int)hs, L, pl};
                 else st->refhit_overflow = 1;
             } else {
-                atomicAdd(&st->n_hits, 1ULL);
+                ++counted;
             }
         }
         for (u32 k = 0; k < nk; ++k) {
@@ -778,6 +782,7 @@ __device__ __noinline__ void scan_on_hit(u64 hit, u32 t, u32 i, u32 item_index, 
             }
         }
     }
+    return counted;
 }
 
 // Sum of the G table words of one triple, as a balanced tree (short dependency chains).
@@ -794,21 +799,21 @@ __device__ __forceinline__ u64 pair_sum(const u8* tb, const u32 (&idx)[kMaxGroup
 // All triples of one run (same number of column pairs G): G LDS.64 + 64-bit adds per triple and lane.
 template <int G, int FIELDS>
 __device__ __forceinline__ void scan_run(const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i, u32 item_index,
-                                         const ChunkDesc& cd, const ScanEnv* env) {
+                                         const ChunkDesc& cd, const ScanEnv* env, u32& n_counted) {
 #pragma unroll SCAN_UNROLL
     for (u32 t = 0; t < n_trip; ++t) {
         u64 acc = pair_sum<0, G>(tb, idx);
         u64 hit = acc & HitMask<FIELDS>::value;
-        if (hit && i != 0xffffffffu) scan_on_hit(hit, t0 + t, i, item_index, cd, env);
+        if (hit && i != 0xffffffffu) n_counted += scan_on_hit(hit, t0 + t, i, item_index, cd, env);
         tb += G * (kPairEntries * 8);
     }
 }
 
 template <int FIELDS>
 __device__ __forceinline__ void scan_dispatch(u32 G, const u8* tb, u32 n_trip, u32 t0, const u32 (&idx)[kMaxGroups], u32 i, u32 item_index,
-                                              const ChunkDesc& cd, const ScanEnv* env) {
+                                              const ChunkDesc& cd, const ScanEnv* env, u32& n_counted) {
     switch (G) {
-#define TFBS_CASE(N) case N: scan_run<N, FIELDS>(tb, n_trip, t0, idx, i, item_index, cd, env); break;
+#define TFBS_CASE(N) case N: scan_run<N, FIELDS>(tb, n_trip, t0, idx, i, item_index, cd, env, n_counted); break;
         TFBS_CASE(1) TFBS_CASE(2) TFBS_CASE(3) TFBS_CASE(4) TFBS_CASE(5) TFBS_CASE(6) TFBS_CASE(7) TFBS_CASE(8)
         TFBS_CASE(9) TFBS_CASE(10) TFBS_CASE(11) TFBS_CASE(12) TFBS_CASE(13) TFBS_CASE(14) TFBS_CASE(15) TFBS_CASE(16)
 #undef TFBS_CASE
@@ -1031,6 +1036,7 @@ __global__ void __launch_bounds__(SCAN_CTA, 1)
         if (li >= n_list) break;
         const u64 lend = li + per_grab < n_list ? li + per_grab : n_list;
         u32 done_in_item = 0;  // starts of entry li already scored
+        u32 n_counted = 0;
         while (li < lend) {
             __syncwarp();
             // a round: pack entries (long items in tiles of TILE_POS starts) into the planes until they are full
@@ -1094,84 +1100,79 @@ __global__ void __launch_bounds__(SCAN_CTA, 1)
                 u32 t0 = 0;
                 for (u32 rn = 0; rn < n_runs; ++rn) {
                     const RunDesc rd = cs->runs[rn];
-                    scan_dispatch<FIELDS>(rd.groups, tb, rd.n_triples, t0, idx, i, item_index, cd, &env);
+                    scan_dispatch<FIELDS>(rd.groups, tb, rd.n_triples, t0, idx, i, item_index, cd, &env, n_counted);
                     tb += (size_t)rd.n_triples * rd.groups * (kPairEntries * 8);
                     t0 += rd.n_triples;
                 }
             }
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_counted += __shfl_xor_sync(0xffffffffu, n_counted, o);
+        if (lane == 0 && n_counted) atomicAdd(&st->n_hits, (u64)n_counted);
     }
 }
 
-// Delta scoring, second half: a hit of the reference haplotype is inherited by a patched haplotype iff the hit's window lies
-// inside one of its reference-copy segments; otherwise it is taken back from that haplotype's count row (the rows hold
-// differences to the reference row, in wrapping u32 arithmetic).  One CTA per reference hit, threads over the groups.
-__global__ void k_lost(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, DevRefHits rh, const u32* ngroups, const u32* ref_used,
-                       DevStatus* st) {
-    __shared__ u32 s_kept;
-    const u32 n = st->n_refhits < rh.cap ? st->n_refhits : rh.cap;
-    for (u32 j = blockIdx.x; j < n; j += gridDim.x) {
-        const RefHit h = rh.buf[j];
-        const u32 r = h.region;
-        const u32 ng = ngroups[r];
-        const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
-        const tfbs_inner_region* inner = b.inner + b.inner_off[r];
-        const i64 rs = b.region_start[r];
-        const u64 qb = sq.gbase[r] - sq.gbase0;
-        u32* Cr = ct.C + (ct.cbase[r] - ct.cbase0);
-        if (threadIdx.x == 0) s_kept = ref_used[r] ? 1u : 0u;
-        __syncthreads();
-        u32 kept = 0;
-        for (u32 g = 1 + threadIdx.x; g < ng; g += blockDim.x) {
-            const u64 q = qb + g;
-            if (sq.seq_flags[q] & 2) continue;
-            const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * q;
+// Delta scoring, second half, one warp per sequence:
+//  * a hit of the region's reference haplotype is inherited by a patched haplotype iff the hit's window lies inside ONE of its
+//    reference-copy segments; otherwise it is taken back from the haplotype's count row (the rows hold differences to the
+//    reference row, in wrapping u32 arithmetic);
+//  * the count vectors of the (shared) items the haplotype is made of are added to its row.
+__global__ void k_group_finish(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, DevRefHits rh, const u32* ref_used, DevStatus* st) {
+    __shared__ unsigned long long s_hits;  // one global atomic per CTA: a single address takes ~1 atomic per clock
+    if (threadIdx.x == 0) s_hits = 0;
+    __syncthreads();
+    // 8 lanes per sequence: the work per sequence is a handful of dependent loads, so more sequences in flight hide the latency
+    constexpr u32 GS = 8;
+    const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) / GS;
+    const u32 lane = threadIdx.x % GS;
+    u32 total = 0;
+    if (q < sq.n_seq) {
+        const u32 g = seq_group(sq, q);
+        const u32 r = sq.seq_region[q];
+        const u32 nh = min(rh.cnt[r - rh.r0], rh.capr);
+        if (g == 0) {  // the reference haplotype keeps all of its hits, if anybody has it (main.rs:129)
+            if (lane == 0 && ref_used[r]) total = nh;
+        } else if (!(sq.seq_flags[q] & 2)) {  // not overwritten in the sequence-keyed map
+            const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
+            const u32 nkeys = pt.n_pid * nk;
+            const tfbs_inner_region* inner = b.inner + b.inner_off[r];
+            const i64 rs = b.region_start[r];
+            u32* crow = ct.C + (ct.cbase[r] - ct.cbase0) + (u64)g * nkeys;
+            const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
             const u32 ns = sq.seq_nseg[q];
-            bool inside = false;
-            for (u32 s = 0; s < ns && !inside; ++s)
-                inside = sg[s].kind == 0 && sg[s].relpos <= h.relpos &&
-                         (i64)h.relpos + h.len <= (i64)sg[s].relpos + (i64)(sg[s + 1].out_start - sg[s].out_start);
-            if (inside) { ++kept; continue; }
-            const i64 hs = h.relpos, he = hs + h.len - 1;
-            for (u32 k = 0; k < nk; ++k) {
-                i64 is = inner[k].start - rs, ie = inner[k].end - rs;
-                if ((hs >= is && hs <= ie) || (he >= is && he <= ie))
-                    atomicSub(&Cr[(u64)g * pt.n_pid * nk + (u64)h.pid * nk + k], inner[k].multiplicity);
+            const RefHit* hits = rh.buf + (u64)(r - rh.r0) * rh.capr;
+            for (u32 j = lane; j < nh; j += GS) {
+                const RefHit h = hits[j];
+                bool inside = false;
+                for (u32 s = 0; s < ns && !inside; ++s)
+                    inside = sg[s].kind == 0 && sg[s].relpos <= h.relpos &&
+                             (i64)h.relpos + h.len <= (i64)sg[s].relpos + (i64)(sg[s + 1].out_start - sg[s].out_start);
+                if (inside) { ++total; continue; }
+                const i64 hs = h.relpos, he = hs + h.len - 1;
+                for (u32 k = 0; k < nk; ++k) {
+                    i64 is = inner[k].start - rs, ie = inner[k].end - rs;
+                    if ((hs >= is && hs <= ie) || (he >= is && he <= ie)) atomicSub(&crow[(u64)h.pid * nk + k], inner[k].multiplicity);
+                }
+            }
+            const u64 i0 = sq.item_off[q], i1 = sq.item_off[q + 1];
+            for (u64 w = i0; w < i1; ++w) {
+                const u32 owner = sq.items[w].owner;
+                const u32 n = sq.item_hits[owner];
+                if (!n) continue;
+                if (lane == 0) total += n;
+                const u32* src = sq.item_cnt + sq.item_coff[owner];
+                for (u32 k = lane; k < nkeys; k += GS) {
+                    u32 v = src[k];
+                    if (v) atomicAdd(&crow[k], v);
+                }
             }
         }
-        if (kept) atomicAdd(&s_kept, kept);
-        __syncthreads();
-        if (threadIdx.x == 0 && s_kept) atomicAdd(&st->n_hits, (u64)s_kept);
-        __syncthreads();
     }
-}
-
-// Delta scoring, third half: every patched haplotype adds the count vectors of the (shared) items it is made of to its row.
-// One warp per sequence; lanes over the keys of the region.
-__global__ void k_item_gather(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts ct, DevStatus* st) {
-    const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const u32 lane = threadIdx.x & 31;
-    if (q >= sq.n_seq) return;
-    const u32 g = seq_group(sq, q);
-    const u64 i0 = sq.item_off[q], i1 = sq.item_off[q + 1];
-    if (g == 0 || i0 == i1) return;
-    const u32 r = sq.seq_region[q];
-    const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
-    const u32 nkeys = pt.n_pid * nk;
-    u32* crow = ct.C + (ct.cbase[r] - ct.cbase0) + (u64)g * nkeys;
-    u32 hits = 0;
-    for (u64 w = i0; w < i1; ++w) {
-        const u32 owner = sq.items[w].owner;
-        const u32 nh = sq.item_hits[owner];
-        if (!nh) continue;
-        hits += nh;
-        const u32* src = sq.item_cnt + sq.item_coff[owner];
-        for (u32 k = lane; k < nkeys; k += 32) {
-            u32 v = src[k];
-            if (v) crow[k] += v;  // this warp owns the row here (k_lost ran before)
-        }
-    }
-    if (lane == 0 && hits) atomicAdd(&st->n_hits, (u64)hits);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if ((threadIdx.x & 31) == 0 && total) atomicAdd(&s_hits, (unsigned long long)total);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_hits) atomicAdd(&st->n_hits, s_hits);
 }
 
 // executed cells = sum over scanned sequences and patterns of max(0, len - L + 1) * L (pattern.rs:147-150)

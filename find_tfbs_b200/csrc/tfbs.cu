@@ -105,7 +105,7 @@ struct tfbs_ctx {
     // phase 2 scratch
     DevBuf d_seq_region, d_seq_leader, d_seq_nd, d_seq_doff, d_dlist, d_segs, d_seq_nseg, d_seq_len, d_ent_units, d_ent_uoff, d_pk,
         d_nm, d_seq_hash, d_seq_flags, d_tile_sums, d_C, d_vmin, d_vmax, d_flag, d_rowidx, d_seq_nitems, d_item_off, d_items, d_refhits,
-        d_item_key, d_item_hits, d_item_coff, d_item_cnt, d_score_flag, d_count_size, d_score_idx, d_list;
+        d_item_key, d_item_hits, d_item_coff, d_item_cnt, d_score_flag, d_count_size, d_score_idx, d_list, d_refcnt;
     DevBuf d_status;
     DevBuf d_rows_region, d_rows_inner, d_rows_pid, d_rows_vmin, d_rows_vmax, d_rows_left, d_rows_right;
     DevBuf d_m_region, d_m_pattern, d_m_group, d_m_start;
@@ -455,7 +455,11 @@ int run_pipeline(tfbs_ctx* ctx) {
         CK(ctx->d_flag.reserve(std::max<uint64_t>(1, n_keys) * 4));
         CK(ctx->d_rowidx.reserve((n_keys + 1) * 8));
         const uint64_t items_cap = n_d + n_seq;
-        const uint32_t refhit_cap = ctx->refhit_cap_opt ? (uint32_t)ctx->refhit_cap_opt : (uint32_t)std::min<uint64_t>(256ull * nr + 4096, 1u << 26);
+        // reference hits live in a slab of capr entries per region; a region with more hits sends the batch to the full scan
+        const uint32_t capr = ctx->refhit_cap_opt ? (uint32_t)std::max<int64_t>(1, ctx->refhit_cap_opt / std::max<uint32_t>(1, nr))
+                                                  : (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(256, (1ull << 28) / std::max<uint32_t>(1, nr) / sizeof(RefHit) / 16));
+        const uint64_t refhit_cap = (uint64_t)capr * nr;
+        CK(ctx->d_refcnt.reserve((size_t)nr * 4));
         CK(ctx->d_seq_nitems.reserve(n_seq * 4));
         CK(ctx->d_item_off.reserve((n_seq + 1) * 8));
         CK(ctx->d_items.reserve(std::max<uint64_t>(1, items_cap) * sizeof(ScanItem)));
@@ -497,7 +501,7 @@ int run_pipeline(tfbs_ctx* ctx) {
         sq.item_hits = ctx->d_item_hits.as<u32>();
         sq.item_coff = ctx->d_item_coff.as<u64>();
         sq.item_cnt = nullptr;  // sized once the owners are known
-        DevRefHits drh{ctx->d_refhits.as<RefHit>(), refhit_cap};
+        DevRefHits drh{ctx->d_refhits.as<RefHit>(), ctx->d_refcnt.as<u32>(), capr, r0};
 
         {   // hits so far, in case this batch has to be re-scored without delta scoring
             CK(cudaMemcpyAsync(ctx->h_status.p, dst, sizeof(DevStatus), cudaMemcpyDeviceToHost, st));
@@ -542,6 +546,7 @@ int run_pipeline(tfbs_ctx* ctx) {
         auto scan_pass = [&](int delta) -> int {
             int rc2;
             if (n_c) CK(cudaMemsetAsync(ctx->d_C.p, 0, n_c * 4, st));
+            CK(cudaMemsetAsync(ctx->d_refcnt.p, 0, (size_t)nr * 4, st));
             uint32_t tcap = 1024;
             if (delta) {
                 while (tcap < 2 * items_cap) tcap <<= 1;
@@ -599,10 +604,8 @@ int run_pipeline(tfbs_ctx* ctx) {
             }
             CK(cudaEventRecord(ctx->ev[9], st));
             if (delta) {
-                k_lost<<<(unsigned)std::min<uint64_t>(refhit_cap, (uint64_t)ctx->prop.multiProcessorCount * 16), 128, 0, st>>>(
-                    db, sq, ctx->dpat, dc, drh, ctx->d_ngroups.as<u32>(), ctx->d_ref_used.as<u32>(), dst);
-                k_item_gather<<<grid_for(n_seq * 32, 256), 256, 0, st>>>(db, sq, ctx->dpat, dc, dst);
-                launches += 2;
+                k_group_finish<<<grid_for(n_seq * 8, 256), 256, 0, st>>>(db, sq, ctx->dpat, dc, drh, ctx->d_ref_used.as<u32>(), dst);
+                ++launches;
             }
             CK(cudaGetLastError());
             return TFBS_OK;
