@@ -852,7 +852,7 @@ __device__ __forceinline__ u64 item_signature(const DevBlock& b, const DevSeqs& 
 }
 
 __device__ __forceinline__ bool items_equal(const DevBlock& b, const DevSeqs& sq, const ScanItem& x, const ScanItem& y, u32 max_len) {
-    if (x.p1 - x.p0 != y.p1 - y.p0) return false;
+    if (x.p1 - x.p0 != y.p1 - y.p0 || sq.seq_region[x.q] != sq.seq_region[y.q]) return false;
     const Seg* sa = sq.segs + 2 * sq.seq_doff[x.q] + 2 * (u64)x.q;
     const Seg* sb = sq.segs + 2 * sq.seq_doff[y.q] + 2 * (u64)y.q;
     const u32 la = sq.seq_len[x.q], lb = sq.seq_len[y.q];

@@ -412,7 +412,9 @@ int run_pipeline(tfbs_ctx* ctx) {
         *n_keys = (uint64_t)n_pid * nk;
     };
     auto bytes_of = [&](uint64_t n_seq, uint64_t n_d, uint64_t n_units, uint64_t n_c, uint64_t n_keys) {
-        return n_seq * (4 * 6 + 8 * 3 + 1 + 32) + n_d * (4 + 32) + n_units * 12 + n_c * 4 + n_keys * 24 + n_seq * 2 * 12 * 2;
+        // sequences, diff lists + segments, packed bases (all of them when delta scoring is off), counts, keys, the sequence-keyed map,
+        // and per possible item (<= n_d + n_seq): the item record, key, owner bookkeeping, list entry and its share of the item map
+        return n_seq * (4 * 6 + 8 * 3 + 1 + 32) + n_d * (4 + 32) + n_units * 12 + n_c * 4 + n_keys * 24 + n_seq * 2 * 12 * 2 + (n_d + n_seq) * 96;
     };
     const int smem_bytes = (int)(sizeof(CtaShared) + SCAN_WARPS * sizeof(WarpShared) + ((ctx->cp.max_chunk_bytes + 15) & ~15u));
     const bool wide = ctx->cp.fields == 2;
@@ -432,12 +434,15 @@ int run_pipeline(tfbs_ctx* ctx) {
         while (r1 < R) {
             uint64_t a, b2, c2, d2, e2;
             region_cost(r1, &a, &b2, &c2, &d2, &e2);
-            if (r1 > r0 && (bytes_of(n_seq + a, n_d + b2, n_units + c2, n_c + d2, n_keys + e2) > ctx->scratch_bytes || n_seq + a > 0x7fffffffull)) break;
+            if (r1 > r0 && (bytes_of(n_seq + a, n_d + b2, n_units + c2, n_c + d2, n_keys + e2) > ctx->scratch_bytes || n_seq + a > 0x7fffffffull ||
+                            n_seq + a + n_d + b2 > (1ull << 30)))
+                break;
             n_seq += a; n_d += b2; n_units += c2; n_c += d2; n_keys += e2;
             ++r1;
         }
         const uint32_t nr = r1 - r0;
-        if (n_seq > 0xfffffff0ull) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "a single region has more than 2^32 haplotype groups");
+        if (n_seq > 0x7fffffffull || n_seq + n_d > (1ull << 30))
+            return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "a single region has more haplotype groups / carried variants than one batch can hold");
 
         CK(ctx->d_seq_region.reserve(n_seq * 4));
         CK(ctx->d_seq_leader.reserve(n_seq * 4));
