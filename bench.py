@@ -288,6 +288,12 @@ def main():
         return
 
     pk = peaks()
+    # DRAM traffic of one k_scan launch of this workload, from the committed `ncu --set full` capture (profiles/): not a live number
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k_scan_traffic.json")
+    if os.path.exists(tpath) and args.scale == 1.0:
+        tj = json.load(open(tpath))
+        traffic = tj.get("dram_bytes_per_launch")
     scan_s = (sum(scan_ms) / len(scan_ms)) * 1e-3
     achieved = st["evaluated_cells"] / scan_s  # this rank's k_scan launches: cells really scored / CUDA-event time around them
     f_max = pk["sm_max_mhz"] * 1e6
@@ -299,7 +305,8 @@ def main():
                 "peak_basis": "148 SMs x 128 B/clk shared memory = 16 LDS.64/clk/SM x 6 cells per LDS.64 (3 packed patterns x 2 columns) at sm_max_mhz from %s" % pk["source"],
                 "frac_at_observed_clock": achieved / (roof * f_obs / f_max), "observed_sm_mhz": clocks["sm_mhz"],
                 "frac_of_one_lookup_per_cell_roof": achieved / (SM_COUNT * 32 * f_max), "frac_of_int32_issue_roof": achieved / (SM_COUNT * 128 * f_max),
-                "ms_per_launch": scan_s * 1e3, "cells_per_launch": st["evaluated_cells"], "traffic": None,
+                "ms_per_launch": scan_s * 1e3, "cells_per_launch": st["evaluated_cells"], "traffic": traffic,
+                "traffic_source": "profiles/k_scan_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one k_scan launch, ncu --set full)" if traffic else None,
                 "hbm": {"achieved_gbs": None, "peak_gbs": pk["hbm_gbs"]},
                 "full_scan": {"note": "same block, delta scoring off (every distinct haplotype scored in full, like the reference)",
                               "cells_per_launch": full_scan[0], "ms_per_launch": full_scan[1] * 1e3,
