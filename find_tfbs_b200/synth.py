@@ -97,7 +97,7 @@ def _concat_ranges(lo, hi):
 
 def make_cohort(n_samples, n_regions, seed, lmax_pattern, region_len=(200, 2000), gap=(100, 1500), variant_rate=1.0 / 35,
                 frac_ins=0.05, frac_del=0.05, indel_max=10, n_runs=0, lowercase_frac=0.0, two_beds=False, same_pos_frac=0.0,
-                ld_blocks=0):
+                ld_blocks=0, bed_b_frac=0.55):
     """Random genome + regions + variants with a 1/k allele-count spectrum and uniform carriers.
 
     lmax_pattern: largest pattern length (the halo of main.rs:404-407 is lmax_pattern - 1 on both sides).
@@ -131,7 +131,7 @@ def make_cohort(n_samples, n_regions, seed, lmax_pattern, region_len=(200, 2000)
     if two_beds:
         bed_b = []
         for s, e in bed_a:
-            u = rng.random()
+            u = rng.random() * 0.55 / bed_b_frac  # bed_b_frac = share of the first set's regions that get a partner in the second
             if u < 0.25:
                 bed_b.append((s + (e - s) // 3, e + int(rng.integers(0, 300))))      # overlaps the right edge
             elif u < 0.4:
@@ -259,4 +259,13 @@ def config2(scale=1.0, seed=2):
     pats = make_pwms(50, seed=1000 + seed)
     lmax = max(p["weights"].shape[0] for p in pats)
     blk = make_cohort(100, max(1, int(10000 * scale)), seed=seed, lmax_pattern=lmax)
+    return pats, blk
+
+
+def config3(scale=1.0, seed=3, n_pwms=401):
+    """BASELINE.json configs[2]: 2,504 samples (1000G-like) x 2 BED sets x 5,000 regions each (partly overlapping) x the HOCOMOCO
+    v11 core collection size (401 PWMs, both strands; SURVEY D7: the count is a parameter).  The genome only spans the regions."""
+    pats = make_pwms(n_pwms, seed=3000 + seed, lmin=7, lmax=25)
+    lmax = max(p["weights"].shape[0] for p in pats)
+    blk = make_cohort(2504, max(1, int(5000 * scale)), seed=seed, lmax_pattern=lmax, two_beds=True, n_runs=20, bed_b_frac=1.0)
     return pats, blk
