@@ -462,7 +462,7 @@ int run_pipeline(tfbs_ctx* ctx) {
         const uint64_t items_cap = n_d + n_seq;
         // reference hits live in a slab of capr entries per region; a region with more hits sends the batch to the full scan
         const uint32_t capr = ctx->refhit_cap_opt ? (uint32_t)std::max<int64_t>(1, ctx->refhit_cap_opt / std::max<uint32_t>(1, nr))
-                                                  : (uint32_t)std::min<uint64_t>(4096, std::max<uint64_t>(256, (1ull << 28) / std::max<uint32_t>(1, nr) / sizeof(RefHit) / 16));
+                                                  : (uint32_t)std::min<uint64_t>(32768, std::max<uint64_t>(512, (1ull << 30) / std::max<uint32_t>(1, nr) / sizeof(RefHit)));  // <= 1 GB of slabs
         const uint64_t refhit_cap = (uint64_t)capr * nr;
         CK(ctx->d_refcnt.reserve((size_t)nr * 4));
         CK(ctx->d_seq_nitems.reserve(n_seq * 4));
