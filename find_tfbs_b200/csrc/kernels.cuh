@@ -59,7 +59,7 @@ struct DevBlock {
 
 // Error / status word: the smallest key wins so that the reported failure is deterministic.
 // key = (sequence index << 32) | (relpos + 2^27) << 4 | code
-enum { DEV_OK = 0, DEV_REF_MISMATCH = 1, DEV_MISSING_CASE = 2, DEV_SIG_COLLISION = 3, DEV_SEQ_COLLISION = 4, DEV_MATCH_OVERFLOW = 5 };
+enum { DEV_OK = 0, DEV_REF_MISMATCH = 1, DEV_MISSING_CASE = 2 };
 
 struct DevStatus {
     u64 err_key;          // ~0 = none
@@ -75,7 +75,7 @@ struct DevStatus {
     u32 sig_collision;
     u32 seq_collision;
     u32 work_counter;     // dynamic scheduler of k_scan
-    u32 n_refhits;        // cursor of the reference-hit buffer (delta scoring)
+    u32 n_refhits;        // unused (reference hits are counted per region, DevRefHits::cnt)
     u64 evaluated_cells;  // cells the scan kernel really scored
     u32 refhit_overflow;
     u32 pad;
