@@ -178,7 +178,7 @@ typedef struct tfbs_stats {
     uint32_t total_launches;    /* all kernel launches of the run */
     float ms_group;             /* K0: signature hash + grouping */
     float ms_build;             /* K1: haplotype build */
-    float ms_scan;              /* K2: PWM scan (sum over launches) */
+    float ms_scan;              /* K2: work list, packing of the scored bases, PWM scan, finish (sum over batches) */
     float ms_count;             /* K3: fan-out, filter, row compaction */
     float ms_total;             /* first launch to last, device time */
     uint32_t sm_count;
