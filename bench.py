@@ -195,6 +195,10 @@ def main():
     for kv in args.option:
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
+    ctx.set_option("rows_width", 0)  # counts come back in the narrowest type that holds them (tfbs_rows.count_bytes)
+    for kv in args.option:
+        k, v = kv.split("=")
+        ctx.set_option(k, int(v))
     ctx.set_patterns(ps)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
 

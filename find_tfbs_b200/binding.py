@@ -50,7 +50,7 @@ class TfbsBlock(C.Structure):
 
 
 class TfbsRows(C.Structure):
-    _fields_ = [("n_rows", C.c_uint64), ("n_samples", C.c_uint32), ("reserved", C.c_uint32),
+    _fields_ = [("n_rows", C.c_uint64), ("n_samples", C.c_uint32), ("count_bytes", C.c_uint32),
                 ("region", C.POINTER(C.c_uint32)), ("inner", C.POINTER(C.c_uint32)), ("pattern_id", C.POINTER(C.c_uint16)),
                 ("vmin", C.POINTER(C.c_uint32)), ("vmax", C.POINTER(C.c_uint32)),
                 ("left", C.POINTER(C.c_uint32)), ("right", C.POINTER(C.c_uint32))]
@@ -277,10 +277,18 @@ class Context:
             a = np.ctypeslib.as_array(p, shape=(cnt,))
             return a.astype(dt, copy=True) if copy else a
 
+        ctype, dt = {1: (C.c_uint8, np.uint8), 2: (C.c_uint16, np.uint16), 4: (C.c_uint32, np.uint32)}[rows.count_bytes or 4]
+
+        def counts(p):  # left / right come back as u32 unless option rows_width = 0 chose a narrower type (tfbs_rows.count_bytes)
+            if n * S == 0:
+                return np.zeros((n, S), dtype=np.uint32)
+            a = np.ctypeslib.as_array(C.cast(p, C.POINTER(ctype)), shape=(n * S,)).reshape(n, S)
+            return a.astype(np.uint32) if copy else a
+
         return {"region": arr(rows.region, n, np.uint32), "inner": arr(rows.inner, n, np.uint32),
                 "pattern_id": arr(rows.pattern_id, n, np.uint16), "vmin": arr(rows.vmin, n, np.uint32),
-                "vmax": arr(rows.vmax, n, np.uint32), "left": arr(rows.left, n * S, np.uint32).reshape(n, S),
-                "right": arr(rows.right, n * S, np.uint32).reshape(n, S)}
+                "vmax": arr(rows.vmax, n, np.uint32), "left": counts(rows.left), "right": counts(rows.right),
+                "count_bytes": int(rows.count_bytes or 4)}
 
     def matches(self, n_regions):
         m = TfbsMatches()

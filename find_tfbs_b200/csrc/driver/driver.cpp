@@ -672,7 +672,8 @@ struct RowText {
     std::string info, genotypes;
 };
 
-RowText finalise_row(const uint32_t* l, const uint32_t* r, uint32_t S, uint32_t lowest, uint32_t highest, uint32_t min_maf) {
+template <class T>
+RowText finalise_row(const T* l, const T* r, uint32_t S, uint32_t lowest, uint32_t highest, uint32_t min_maf) {
     RowText t;
     if (lowest == highest) return t;  // main.rs:456-458 (the library already filtered these)
     const uint32_t i1 = (lowest * 1000u * 3u + highest * 1000u) / 4u;  // :461
@@ -683,7 +684,7 @@ RowText finalise_row(const uint32_t* l, const uint32_t* r, uint32_t S, uint32_t 
     t.genotypes.reserve((size_t)S * 12);
     char buf[48];
     for (uint32_t s = 0; s < S; ++s) {
-        uint32_t x = l[s] + r[s];
+        uint32_t x = (uint32_t)l[s] + (uint32_t)r[s];
         if (x == lowest) { t.genotypes += "\t0|0:0.0"; ++zero; }
         else if (x == highest) { t.genotypes += "\t1|1:2.0"; ++two; }
         else {
@@ -785,6 +786,7 @@ int main(int argc, char** argv) {
         tfbs_ctx* ctx = nullptr;
         if (tfbs_create(device, &ctx) != TFBS_OK) die(std::string(tfbs_last_error(nullptr)));
         TF(tfbs_set_patterns(ctx, cpat.data(), (uint32_t)cpat.size()));
+        TF(tfbs_set_option(ctx, "rows_width", 0));
         Fasta fa(o.reference, o.chromosome);  // private readers per worker, like main.rs:345-346
         for (;;) {
             size_t c = next.fetch_add(1);
@@ -813,7 +815,10 @@ int main(int argc, char** argv) {
                 return rows.pattern_id[a] < rows.pattern_id[b];
             });
             for (uint64_t i : order) {
-                RowText t = finalise_row(rows.left + i * S, rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf);
+                // counts arrive in the narrowest type that holds them (option rows_width = 0, tfbs_rows.count_bytes)
+                RowText t = rows.count_bytes == 1 ? finalise_row((const uint8_t*)rows.left + i * S, (const uint8_t*)rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf)
+                          : rows.count_bytes == 2 ? finalise_row((const uint16_t*)rows.left + i * S, (const uint16_t*)rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf)
+                                                  : finalise_row(rows.left + i * S, rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf);
                 if (!t.keep) continue;
                 const tfbs_inner_region& ir = bd.inner[rows.inner[i]];
                 // POS is filled in by the writer (a running counter, main.rs:329,424-425)

@@ -81,7 +81,7 @@ struct DevStatus {
     u32 n_refhits;        // unused (reference hits are counted per region, DevRefHits::cnt)
     u64 evaluated_cells;  // cells the scan kernel really scored
     u32 refhit_overflow;
-    u32 pad;
+    u32 max_count;        // largest per-sample count of an emitted row in this batch (decides the width of the returned counts)
 };
 
 __device__ __forceinline__ u64 mix64(u64 x) {
@@ -1232,8 +1232,9 @@ __global__ void k_item_stats(DevSeqs sq, DevPatterns pt, const u32* list, const 
 // One CTA per region, one thread per key (pid, inner): v[s] = C[group(left)] + C[group(right)]
 // (main.rs:441-448), min and max over samples (:450-451).  flag: 1 = row is emitted.
 __global__ void k_rows_minmax(DevBlock b, u32 r0, const u32* hap_group, DevCounts ct, const u64* gbase, u32 n_pid, const u64* kbase,
-                              u64 kbase0, int rows_mode, int delta, u32* vmin, u32* vmax, u32* flag) {
+                              u64 kbase0, int rows_mode, int delta, u32* vmin, u32* vmax, u32* flag, u32* max_count) {
     u32 r = r0 + blockIdx.x;
+    u32 row_max = 0;
     u32 nk = b.inner_off[r + 1] - b.inner_off[r];
     u32 nkeys = n_pid * nk;
     const u32* C = ct.C + (ct.cbase[r] - ct.cbase0);
@@ -1254,8 +1255,13 @@ __global__ void k_rows_minmax(DevBlock b, u32 r0, const u32* hap_group, DevCount
         vmax[ko + key] = hi;
         // keys exist once a hit of any scanned haplotype touched the inner region (main.rs:517-528);
         // every scanned group has at least one member, so that is hi > 0
-        flag[ko + key] = (rows_mode == TFBS_ROWS_VARYING) ? (lo != hi ? 1u : 0u) : (hi > 0 ? 1u : 0u);
+        const u32 f = (rows_mode == TFBS_ROWS_VARYING) ? (lo != hi ? 1u : 0u) : (hi > 0 ? 1u : 0u);
+        flag[ko + key] = f;
+        if (f) row_max = max(row_max, hi);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) row_max = max(row_max, __shfl_xor_sync(0xffffffffu, row_max, o));
+    if ((threadIdx.x & 31) == 0 && row_max) atomicMax(max_count, row_max);
 }
 
 struct DevRows {
@@ -1264,11 +1270,12 @@ struct DevRows {
     u16* pattern_id;
     u32* vmin;
     u32* vmax;
-    u32* left;
-    u32* right;
+    void* left;    // [rows][S] of T
+    void* right;
 };
 
-// One warp per emitted row.
+// One warp per emitted row; T = u8 / u16 / u32, the narrowest type that holds every count of the batch (or u32 on request).
+template <class T>
 __global__ void k_rows_write(DevBlock b, u32 r0, u32 nr, const u32* hap_group, DevCounts ct, u32 n_pid, const u16* pid_list,
                              const u64* kbase, u64 kbase0, u64 n_keys, const u32* vmin, const u32* vmax, const u32* flag,
                              const u64* rowidx, DevRows rows, u64 row_base, int delta) {
@@ -1297,10 +1304,12 @@ __global__ void k_rows_write(DevBlock b, u32 r0, u32 nr, const u32* hap_group, D
     const u32* C = ct.C + (ct.cbase[r] - ct.cbase0);
     const u32* hg = hap_group + (size_t)r * b.H;
     const u32 base = delta ? C[kk] : 0u;
+    T* left = reinterpret_cast<T*>(rows.left) + row * b.S;
+    T* right = reinterpret_cast<T*>(rows.right) + row * b.S;
     for (u32 s = lane; s < b.S; s += 32) {
         u32 g0 = hg[2 * s], g1 = hg[2 * s + 1];
-        rows.left[row * b.S + s] = C[(size_t)g0 * nkeys + kk] + (g0 ? base : 0u);
-        rows.right[row * b.S + s] = C[(size_t)g1 * nkeys + kk] + (g1 ? base : 0u);
+        left[s] = (T)(C[(size_t)g0 * nkeys + kk] + (g0 ? base : 0u));
+        right[s] = (T)(C[(size_t)g1 * nkeys + kk] + (g1 ? base : 0u));
     }
 }
 

@@ -75,6 +75,8 @@ struct tfbs_ctx {
     int scan_ctas_per_sm = 0;  // < 0: fixed grid size (debugging)
     int delta = 1;             // delta scoring of patched haplotypes
     int64_t refhit_cap_opt = 0; // testing: capacity of the reference-hit buffer (0 = automatic)
+    int rows_width = 32;        // 32: counts are returned as u32; 0: narrowest of u8 / u16 / u32 that holds every count of the block
+    uint32_t row_bytes = 4;     // element size of the rows held for tfbs_collect
 
     // patterns
     bool have_patterns = false;
@@ -627,7 +629,8 @@ int run_pipeline(tfbs_ctx* ctx) {
             if (!n_keys) return TFBS_OK;
             int rc2;
             k_rows_minmax<<<nr, 128, 0, st>>>(db, r0, ctx->d_hap_group.as<u32>(), dc, ctx->d_gbase.as<u64>(), n_pid, ctx->d_kbase.as<u64>(),
-                                              ctx->h_kbase[r0], ctx->rows_mode, delta, ctx->d_vmin.as<u32>(), ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>());
+                                              ctx->h_kbase[r0], ctx->rows_mode, delta, ctx->d_vmin.as<u32>(), ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(),
+                                              &dst->max_count);
             ++launches;
             if ((rc2 = device_scan(ctx, ctx->d_flag.as<u32>(), n_keys, ctx->d_rowidx.as<u64>()))) return rc2;
             CK(cudaMemcpyAsync(ctx->h_totals.p, ctx->d_rowidx.as<u64>() + n_keys, 8, cudaMemcpyDeviceToHost, st));
@@ -675,25 +678,47 @@ int run_pipeline(tfbs_ctx* ctx) {
 
         if (batch_rows) {
             uint64_t tot = ctx->n_rows + batch_rows;
+            // element width of left / right: u32 like the reference's Vec<u32>, or (option rows_width = 0) the narrowest type that
+            // holds every count of the block: the rows are the dominant PCIe traffic of large cohorts
+            uint32_t eb = 4;
+            if (ctx->rows_width == 0) eb = hs.max_count < 256 ? 1 : (hs.max_count < 65536 ? 2 : 4);
+            if (ctx->n_rows == 0) ctx->row_bytes = eb;
+            if (eb > ctx->row_bytes) {  // an earlier batch of this block was stored narrower: widen it in place (rare)
+                const uint64_t n = ctx->n_rows * S;
+                CK(ctx->h_rows_left.reserve(tot * S * eb, true));
+                CK(ctx->h_rows_right.reserve(tot * S * eb, true));
+                for (HostBuf* hb : {&ctx->h_rows_left, &ctx->h_rows_right})
+                    for (uint64_t i = n; i-- > 0;) {
+                        uint32_t v = ctx->row_bytes == 1 ? hb->as<uint8_t>()[i] : hb->as<uint16_t>()[i];
+                        if (eb == 2) hb->as<uint16_t>()[i] = (uint16_t)v; else hb->as<uint32_t>()[i] = v;
+                    }
+                ctx->row_bytes = eb;
+            }
+            eb = ctx->row_bytes;
             CK(ctx->d_rows_region.reserve(batch_rows * 4));
             CK(ctx->d_rows_inner.reserve(batch_rows * 4));
             CK(ctx->d_rows_pid.reserve(batch_rows * 2));
             CK(ctx->d_rows_vmin.reserve(batch_rows * 4));
             CK(ctx->d_rows_vmax.reserve(batch_rows * 4));
-            CK(ctx->d_rows_left.reserve(batch_rows * S * 4));
-            CK(ctx->d_rows_right.reserve(batch_rows * S * 4));
+            CK(ctx->d_rows_left.reserve(batch_rows * S * eb));
+            CK(ctx->d_rows_right.reserve(batch_rows * S * eb));
             CK(ctx->h_rows_region.reserve(tot * 4, true));
             CK(ctx->h_rows_inner.reserve(tot * 4, true));
             CK(ctx->h_rows_pid.reserve(tot * 2, true));
             CK(ctx->h_rows_vmin.reserve(tot * 4, true));
             CK(ctx->h_rows_vmax.reserve(tot * 4, true));
-            CK(ctx->h_rows_left.reserve(tot * S * 4, true));
-            CK(ctx->h_rows_right.reserve(tot * S * 4, true));
+            CK(ctx->h_rows_left.reserve(tot * S * eb, true));
+            CK(ctx->h_rows_right.reserve(tot * S * eb, true));
             DevRows dr{ctx->d_rows_region.as<u32>(), ctx->d_rows_inner.as<u32>(), ctx->d_rows_pid.as<u16>(), ctx->d_rows_vmin.as<u32>(),
-                       ctx->d_rows_vmax.as<u32>(), ctx->d_rows_left.as<u32>(), ctx->d_rows_right.as<u32>()};
-            k_rows_write<<<grid_for(n_keys * 32, 256), 256, 0, st>>>(db, r0, nr, ctx->d_hap_group.as<u32>(), dc, n_pid, ctx->d_pid_list.as<u16>(),
-                                                                     ctx->d_kbase.as<u64>(), ctx->h_kbase[r0], n_keys, ctx->d_vmin.as<u32>(),
-                                                                     ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(), ctx->d_rowidx.as<u64>(), dr, 0, use_delta);
+                       ctx->d_rows_vmax.as<u32>(), ctx->d_rows_left.p, ctx->d_rows_right.p};
+#define TFBS_ROWS_WRITE(T)                                                                                                              \
+    k_rows_write<T><<<grid_for(n_keys * 32, 256), 256, 0, st>>>(db, r0, nr, ctx->d_hap_group.as<u32>(), dc, n_pid, ctx->d_pid_list.as<u16>(), \
+                                                                ctx->d_kbase.as<u64>(), ctx->h_kbase[r0], n_keys, ctx->d_vmin.as<u32>(),   \
+                                                                ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(), ctx->d_rowidx.as<u64>(), dr, 0, use_delta)
+            if (eb == 1) TFBS_ROWS_WRITE(u8);
+            else if (eb == 2) TFBS_ROWS_WRITE(u16);
+            else TFBS_ROWS_WRITE(u32);
+#undef TFBS_ROWS_WRITE
             ++launches;
             uint64_t o = ctx->n_rows;
             CK(cudaMemcpyAsync(ctx->h_rows_region.as<u32>() + o, dr.region, batch_rows * 4, cudaMemcpyDeviceToHost, st));
@@ -701,9 +726,9 @@ int run_pipeline(tfbs_ctx* ctx) {
             CK(cudaMemcpyAsync(ctx->h_rows_pid.as<u16>() + o, dr.pattern_id, batch_rows * 2, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(ctx->h_rows_vmin.as<u32>() + o, dr.vmin, batch_rows * 4, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(ctx->h_rows_vmax.as<u32>() + o, dr.vmax, batch_rows * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ctx->h_rows_left.as<u32>() + o * S, dr.left, batch_rows * S * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ctx->h_rows_right.as<u32>() + o * S, dr.right, batch_rows * S * 4, cudaMemcpyDeviceToHost, st));
-            ctx->stats.d2h_bytes += batch_rows * (4 * 4 + 2 + 8ull * S);
+            CK(cudaMemcpyAsync(ctx->h_rows_left.as<uint8_t>() + o * S * eb, dr.left, batch_rows * S * eb, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_rows_right.as<uint8_t>() + o * S * eb, dr.right, batch_rows * S * eb, cudaMemcpyDeviceToHost, st));
+            ctx->stats.d2h_bytes += batch_rows * (4 * 4 + 2 + 2ull * eb * S);
             ctx->n_rows = tot;
         }
         CK(cudaEventRecord(ctx->ev[5], st));
@@ -840,6 +865,10 @@ int tfbs_set_option(tfbs_ctx* ctx, const char* key, int64_t value) {
     else if (k == "scan_ctas_per_sm") ctx->scan_ctas_per_sm = (int)value;
     else if (k == "delta") ctx->delta = value != 0;
     else if (k == "refhit_cap") ctx->refhit_cap_opt = std::max<int64_t>(0, value);
+    else if (k == "rows_width") {
+        if (value != 0 && value != 32) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "rows_width must be 32 or 0 (automatic)");
+        ctx->rows_width = (int)value;
+    }
     else return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "unknown option " + k);
     return TFBS_OK;
 }
@@ -920,7 +949,7 @@ int tfbs_collect(tfbs_ctx* ctx, tfbs_rows* out) {
     CK(cudaStreamSynchronize(ctx->stream));
     out->n_rows = ctx->n_rows;
     out->n_samples = ctx->S;
-    out->reserved = 0;
+    out->count_bytes = ctx->n_rows ? ctx->row_bytes : 4;
     out->region = ctx->h_rows_region.as<uint32_t>();
     out->inner = ctx->h_rows_inner.as<uint32_t>();
     out->pattern_id = ctx->h_rows_pid.as<uint16_t>();

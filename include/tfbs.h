@@ -134,13 +134,14 @@ typedef struct tfbs_block {
 typedef struct tfbs_rows {
     uint64_t n_rows;
     uint32_t n_samples;
-    uint32_t reserved;
+    uint32_t count_bytes;          /* size of one element of left / right: 4 (uint32_t) unless option "rows_width" = 0 let the
+                                      library return the narrowest type that holds every count of the block (1, 2 or 4) */
     const uint32_t* region;        /* [n_rows] index of the merged region inside the block */
     const uint32_t* inner;         /* [n_rows] index into tfbs_block.inner */
     const uint16_t* pattern_id;    /* [n_rows] */
     const uint32_t* vmin;          /* [n_rows] min over samples of left + right (main.rs:450) */
     const uint32_t* vmax;          /* [n_rows] max over samples of left + right (main.rs:451) */
-    const uint32_t* left;          /* [n_rows * n_samples] */
+    const uint32_t* left;          /* [n_rows * n_samples] elements of count_bytes bytes (uint32_t by default) */
     const uint32_t* right;         /* [n_rows * n_samples] */
 } tfbs_rows;
 
@@ -210,7 +211,8 @@ const char* tfbs_last_error(const tfbs_ctx* ctx);
  * "scan_format" (0 auto, 1 force 32-bit tables), "delta" (default 1: score a patched haplotype only where its windows
  * touch a variant and inherit every other hit from the region's reference haplotype -- exact, scores are integers; 0: score
  * every distinct haplotype in full like the reference does; forced to 0 while "record_matches" is on), "scratch_mb",
- * "table_budget_kb". */
+ * "table_budget_kb", "rows_width" (32 = counts come back as uint32_t, the reference's Vec<u32>; 0 = the narrowest of 8/16/32 bits
+ * that holds every count of the block, see tfbs_rows.count_bytes -- result rows are the dominant PCIe traffic of large cohorts). */
 int tfbs_set_option(tfbs_ctx* ctx, const char* key, int64_t value);
 
 /* Replace the pattern list (the reference's pwm_list, src/main.rs:237). */

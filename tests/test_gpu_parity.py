@@ -339,3 +339,22 @@ def test_delta_scoring_corner_cases():
         p["pattern_id"] = i // 2
     blk = synth.make_cohort(6, 4, seed=32, lmax_pattern=32, region_len=(2500, 4200), variant_rate=1 / 40.0, frac_ins=0.1, frac_del=0.1)
     hp.check_parity(PatternSet(pats), blk, rows_mode=binding.ROWS_ALL_KEYS)
+
+
+def test_narrow_row_counts():
+    """Option rows_width = 0: counts come back as u8 / u16 / u32, whichever holds the largest count of the block; values are unchanged.
+    Large counts are forced with duplicate BED lines (the multiplicity of an inner region)."""
+    pats = synth.make_pwms(6, seed=91, lmin=6, lmax=16, pvalue=1e-2)
+    ps = PatternSet(pats)
+    for mult, width in ((1, 1), (300, 2), (70000, 4)):
+        blk = synth.make_cohort(9, 25, seed=91, lmax_pattern=16, region_len=(150, 500))
+        blk.inner["multiplicity"] = mult
+        o = hp.run_oracle(ps, blk) if mult == 1 else None
+        base = hp.run_gpu(ps, blk)
+        assert base["count_bytes"] == 4
+        if o is not None:
+            hp.assert_rows_equal(base, o)
+        for opts in ({"rows_width": 0}, {"rows_width": 0, "scratch_mb": 64}):
+            g = hp.run_gpu(ps, blk, options=opts)
+            assert g["count_bytes"] == width, (g["count_bytes"], int(base["vmax"].max()))
+            hp.assert_rows_equal(g, base)
