@@ -967,10 +967,11 @@ __global__ void k_item_lists(DevSeqs sq, const u64* n_items_ptr, const u32* scor
 }
 
 // K1, second half: pack the bases the scored entries need (2 bits per base + N mask), gathered through the segment lists.
-// One warp per list entry, one lane per unit of 32 bases.
+// EMIT_LANES lanes per list entry (a short item has 4-5 units), one lane per unit of 32 bases.
+constexpr u32 EMIT_LANES = 8;
 __global__ void k_emit_list(DevBlock b, DevSeqs sq, const u32* list, const u64* n_list_ptr) {
-    const u64 e = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const u32 lane = threadIdx.x & 31;
+    const u64 e = ((u64)blockIdx.x * blockDim.x + threadIdx.x) / EMIT_LANES;
+    const u32 lane = threadIdx.x % EMIT_LANES;
     if (e >= *n_list_ptr) return;
     const ScanItem it = sq.items[list[e]];
     const u32 q = it.q;
@@ -980,7 +981,7 @@ __global__ void k_emit_list(DevBlock b, DevSeqs sq, const u32* list, const u64* 
     const u8* refc = b.ref_codes + b.ref_off[sq.seq_region[q]];
     const u32 ubase = it.p0 >> 5, nu = sq.ent_units[e];
     const u64 uoff = sq.ent_uoff[e];
-    for (u32 u = lane; u < nu; u += 32) {
+    for (u32 u = lane; u < nu; u += EMIT_LANES) {
         const u32 i0 = (ubase + u) * 32;
         u64 pk = 0;
         u32 nm = 0;

@@ -596,7 +596,7 @@ int run_pipeline(tfbs_ctx* ctx) {
             sq.pk = ctx->d_pk.as<u64>();
             sq.nm = ctx->d_nm.as<u32>();
             if (n_list_host) {
-                k_emit_list<<<grid_for(n_list_host * 32, 256), 256, 0, st>>>(db, sq, ctx->d_list.as<u32>(), d_n_list);
+                k_emit_list<<<grid_for(n_list_host * EMIT_LANES, 256), 256, 0, st>>>(db, sq, ctx->d_list.as<u32>(), d_n_list);
                 k_item_stats<<<grid_for(n_list_host, 256), 256, 0, st>>>(sq, ctx->dpat, ctx->d_list.as<u32>(), d_n_list, dst);
                 launches += 2;
             }
