@@ -684,7 +684,10 @@ constexpr int PLANE_BYTES = TILE_POS / 2 + 32;       // pair codes of even / odd
 constexpr int RAW_UNITS = TILE_POS / 32 + 3;
 constexpr int MAX_RUNS = 16;
 constexpr int MAX_PIECES = 16;                       // items (or tiles of a long item) scanned together by one warp
-constexpr int MERGE_GAP = 24;                        // dirty ranges closer than this are scored as one item
+#ifndef TFBS_MERGE_GAP
+#define TFBS_MERGE_GAP 0   /* measured on B200 (configs[1]): 0 -> 8.02 ms/step, 8 -> 8.26, 24 -> 9.05, 64 -> 12.5: short items are shared more */
+#endif
+constexpr int MERGE_GAP = TFBS_MERGE_GAP;            // touched ranges closer than this are scored as one item (overlapping ones always are)
 
 // Private to one warp: a warp owns the pieces of a round, so the scan needs no CTA-wide barrier.
 struct __align__(16) WarpShared {

@@ -600,7 +600,10 @@ int run_pipeline(tfbs_ctx* ctx) {
                 k_item_stats<<<grid_for(n_list_host, 256), 256, 0, st>>>(sq, ctx->dpat, ctx->d_list.as<u32>(), d_n_list, dst);
                 launches += 2;
             }
-            const u32 per_grab = delta ? 8u : 1u;
+#ifndef TFBS_PER_GRAB
+#define TFBS_PER_GRAB 8
+#endif
+            const u32 per_grab = delta ? (u32)TFBS_PER_GRAB : 1u;
             CK(cudaEventRecord(ctx->ev[8], st));
             for (uint32_t c = 0; c < ctx->cp.chunks.size() && n_list_host; ++c) {
                 CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
