@@ -1,0 +1,157 @@
+"""CPU tests of the C++ driver's host logic (find_tfbs_b200/csrc/driver/driver.cpp compiled with a test shim, no GPU, no main):
+weight / threshold / PWM parsing, range merging, BCF and FASTA decoding and the row finaliser, each against the oracle or the
+reference's fixtures."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from find_tfbs_b200 import synth
+from oracle import pyoracle as ora
+import file_writers as fw
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def drv(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("drv") / "libdrvhost.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-DTFBS_DRIVER_NO_MAIN", "-DTFBS_DRIVER_TEST_SHIM",
+                           "-static-libstdc++", "-static-libgcc", "-Wl,-Bsymbolic", "-Wl,--exclude-libs,ALL", "-o", so,
+                           os.path.join(ROOT, "find_tfbs_b200", "csrc", "driver", "driver.cpp"), "-lz"])
+    lib = C.CDLL(so)
+    lib.drv_last_error.restype = C.c_char_p
+    return lib
+
+
+def test_parse_weight_matches_oracle(drv):
+    rng = np.random.default_rng(0)
+    cases = ["1.0", "3.999", "-4.4", "0.0625", "-0.0625", "0.0005", "2.5e-3", "-28.912716067144597", "0", "1e-9", "7.7515"]
+    cases += ["%.*f" % (int(rng.integers(1, 9)), x) for x in rng.normal(0, 3, size=300)]
+    for s in cases:
+        out = C.c_int32()
+        assert drv.drv_parse_weight(s.encode(), C.byref(out)) == 0
+        assert out.value == ora.parse_weight(s), s
+    assert drv.drv_parse_weight(b"abc", C.byref(C.c_int32())) == -1
+
+
+def test_threshold_and_pwm_parsing(drv, golden_dir, tmp_path):
+    for thr in (1e-4, 1e-3, 0.5, 1e-6, 2.0):
+        out = C.c_int32()
+        found = drv.drv_parse_threshold_file(os.path.join(golden_dir, "ACGT.thr").encode(), C.c_float(thr), C.byref(out))
+        exp = ora.parse_threshold_file(os.path.join(golden_dir, "ACGT.thr"), thr)
+        assert (out.value if found else None) == exp
+    pats = synth.make_pwms(7, seed=4, lmin=5, lmax=20)
+    pwm = str(tmp_path / "pwms.txt")
+    fw.write_pwms(pwm, str(tmp_path / "thr"), pats)
+    names = [p["name"] for p in pats if p["direction"] == 0]
+    wanted = [names[3], names[0], "MISSING", names[5]]  # pattern_id follows the FILE order of the wanted PWMs (pattern.rs:61,69,81)
+    for fwd_only in (0, 1):
+        cap = 64
+        lens = (C.c_uint32 * cap)()
+        ms = (C.c_int32 * cap)()
+        pid = (C.c_uint16 * cap)()
+        dr = (C.c_uint8 * cap)()
+        w = (C.c_int32 * 8192)()
+        # the threshold file of MISSING does not exist: the reference panics in read_lines (pattern.rs:115)
+        assert drv.drv_parse_pwms(pwm.encode(), str(tmp_path / "thr").encode(), C.c_float(1e-4), ",".join(wanted).encode(), fwd_only,
+                                  cap, lens, ms, pid, dr, w, 8192) == -1
+        assert b"Could not open file" in drv.drv_last_error()
+        ok = [x for x in wanted if x != "MISSING"]
+        n = drv.drv_parse_pwms(pwm.encode(), str(tmp_path / "thr").encode(), C.c_float(1e-4), ",".join(ok).encode(), fwd_only, cap, lens, ms, pid,
+                               dr, w, 8192)
+        exp = ora.parse_pwm_files(pwm, str(tmp_path / "thr"), 1e-4, ok, not fwd_only)
+        assert n == len(exp)
+        off = 0
+        for i, p in enumerate(exp):
+            L = p["weights"].shape[0]
+            assert (lens[i], ms[i], pid[i], dr[i]) == (L, p["min_score"], p["pattern_id"], p["direction"])
+            assert [w[off + k] for k in range(4 * L)] == p["weights"].reshape(-1).tolist()
+            off += 4 * L
+
+
+def test_merge_ranges_matches_oracle(drv, tmp_path):
+    rng = np.random.default_rng(1)
+    for _ in range(40):
+        n = int(rng.integers(1, 40))
+        s = rng.integers(0, 500, size=n).astype(np.uint64)
+        e = (s + rng.integers(0, 60, size=n).astype(np.uint64)).astype(np.uint64)
+        os_ = (C.c_uint64 * n)()
+        oe = (C.c_uint64 * n)()
+        m = drv.drv_merge_ranges(s.ctypes.data_as(C.POINTER(C.c_uint64)), e.ctypes.data_as(C.POINTER(C.c_uint64)), n, os_, oe)
+        bed = str(tmp_path / "r.bed")
+        with open(bed, "w") as f:
+            for a, b in zip(s, e):
+                f.write("chrT\t%d\t%d\n" % (a, b))
+        merged, _ = ora.load_peak_files([bed], "chrT", 0)
+        assert [(os_[i], oe[i]) for i in range(m)] == merged
+
+
+def test_finalise_row_matches_oracle(drv):
+    rng = np.random.default_rng(2)
+    for trial in range(300):
+        S = int(rng.integers(1, 40))
+        hi = int(rng.choice([1, 2, 3, 8, 40, 1000]))
+        l = rng.integers(0, hi + 1, size=S).astype(np.uint32)
+        r = rng.integers(0, hi + 1, size=S).astype(np.uint32)
+        if trial % 7 == 0:
+            r = (hi - l).astype(np.uint32)  # constant sum: the row is dropped (main.rs:456-458)
+        min_maf = int(rng.integers(0, 4))
+        info = C.create_string_buffer(4096)
+        gt = C.create_string_buffer(64 * S + 64)
+        keep = drv.drv_finalise_row(l.ctypes.data_as(C.POINTER(C.c_uint32)), r.ctypes.data_as(C.POINTER(C.c_uint32)), S, min_maf, info, 4096, gt, len(gt))
+        exp = ora.counts_as_genotypes(l, r)
+        if exp is None or exp["maf"] < min_maf:
+            assert keep == 0
+            continue
+        assert keep == 1
+        assert info.value.decode() == "COUNTS=%s;freqs=%d/%d/%d" % (",".join(str(c) for c in exp["counts"]), *exp["freqs"])
+        assert gt.value.decode() == exp["genotypes"]
+
+
+def test_bcf_and_fasta_decoding(drv, golden_dir, tmp_path):
+    def load(bcf, samples, chrom, cap=100000, ccap=4000000):
+        pos = (C.c_int64 * cap)()
+        na = (C.c_uint32 * cap)()
+        row = (C.c_uint32 * cap)()
+        car = (C.c_uint32 * ccap)()
+        n = C.c_uint32()
+        ns = C.c_uint32()
+        pitch = C.c_uint32()
+        rc = drv.drv_load_bcf(bcf.encode(), (samples or "").encode(), chrom.encode(), cap, pos, na, row, car, ccap, C.byref(n), C.byref(ns), C.byref(pitch))
+        assert rc == 0, drv.drv_last_error()
+        return [pos[i] for i in range(n.value)], [na[i] for i in range(n.value)], [row[i] for i in range(n.value)], car, ns.value, pitch.value
+
+    # the reference's fixture: one record at 100, INDIVIDUAL1 = 1|0
+    pos, na, row, car, ns, pitch = load(os.path.join(golden_dir, "genotypes2.bcf"), os.path.join(golden_dir, "samples"), "chr1")
+    assert (pos, na, row, ns, pitch) == ([100], [2], [0], 4, 1) and car[0] == 1
+    # a synthetic cohort written by the test writers: carrier bits equal the generator's, multi-allelic records get no row
+    pats = synth.make_pwms(2, seed=5, lmin=6, lmax=10)
+    blk = synth.make_cohort(21, 12, seed=5, lmax_pattern=10, region_len=(50, 150), variant_rate=0.05)
+    a = fw.cohort_to_files(blk, pats, str(tmp_path / "c"), multiallelic_every=5)
+    pos, na, row, car, ns, pitch = load(a["bcf"], None, a["chromosome"])
+    o = ora.read_bcf(a["bcf"])
+    assert pos == o["pos"] and na == [len(x) for x in o["alleles"]] and ns == 21 and pitch == blk.carriers.shape[1]
+    rows = [r for r in row if r != 0xFFFFFFFF]
+    assert rows == list(range(len(blk.meta["var_pos"])))
+    got = np.array([car[i] for i in range(len(rows) * pitch)], dtype=np.uint32).reshape(len(rows), pitch)
+    assert np.array_equal(got, blk.carriers[:len(rows)])
+    # sample subset: columns follow the BCF order whatever the file order is (main.rs:293-313)
+    sub = str(tmp_path / "subset")
+    open(sub, "w").write("\n".join([a["samples"][9], a["samples"][2], "x", a["samples"][17]]) + "\n")
+    pos2, _, row2, car2, ns2, pitch2 = load(a["bcf"], sub, a["chromosome"])
+    assert ns2 == 3 and pitch2 == 1
+    bits = np.unpackbits(blk.carriers.view(np.uint8), axis=1, bitorder="little")
+    want = bits[:len(rows), [4, 5, 18, 19, 34, 35]]
+    got2 = np.array([[(car2[i] >> k) & 1 for k in range(6)] for i in range(len(rows))], dtype=np.uint8)
+    assert np.array_equal(got2, want)
+    # FASTA slices through the .fai, clipped at the contig end
+    g = blk.meta["genome"].tobytes()
+    for start, stop in ((0, 10), (57, 63), (59, 61), (60, 200), (len(g) - 5, len(g) + 50), (123, 123)):
+        buf = (C.c_uint8 * 4096)()
+        n = C.c_uint64()
+        assert drv.drv_fasta_fetch(a["reference"].encode(), a["chromosome"].encode(), start, stop, buf, 4096, C.byref(n)) == 0
+        assert bytes(buf[:n.value]) == g[start:min(stop, len(g))]
+    assert drv.drv_fasta_fetch(a["reference"].encode(), b"chrNope", 0, 5, (C.c_uint8 * 16)(), 16, C.byref(C.c_uint64())) == -1
