@@ -22,9 +22,13 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <fstream>
 #include <map>
+#include <memory>
+#include <mutex>
 #include <set>
 #include <sstream>
 #include <stdexcept>
@@ -888,13 +892,41 @@ int main(int argc, char** argv) {
         if (tfbs_create(device, &ctx) != TFBS_OK) die(std::string(tfbs_last_error(nullptr)));
         TF(tfbs_set_patterns(ctx, cpat.data(), (uint32_t)cpat.size()));
         TF(tfbs_set_option(ctx, "rows_width", 0));
-        Fasta fa(o.reference, o.chromosome);  // private readers per worker, like main.rs:345-346
+        // a builder thread prepares the next blocks (FASTA windows, inner regions, records) while the GPU works on the current one;
+        // private readers per worker, like main.rs:345-346
+        struct Ready { size_t c; std::unique_ptr<BlockData> bd; };
+        std::mutex mu;
+        std::condition_variable cv;
+        std::deque<Ready> ready;
+        bool finished = false;
+        std::thread builder([&] {
+            Fasta fa(o.reference, o.chromosome);
+            for (;;) {
+                size_t c = next.fetch_add(1);
+                if (c >= n_chunks) break;
+                std::unique_ptr<BlockData> bd(new BlockData());
+                build_block(merged, c * o.chunk, std::min(merged.size(), (c + 1) * (size_t)o.chunk), peak_map, co, fa, largest, bd.get());
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return ready.size() < 2; });
+                ready.push_back(Ready{c, std::move(bd)});
+                cv.notify_all();
+            }
+            std::lock_guard<std::mutex> lk(mu);
+            finished = true;
+            cv.notify_all();
+        });
         for (;;) {
-            size_t c = next.fetch_add(1);
-            if (c >= n_chunks) break;
-            size_t m0 = c * o.chunk, m1 = std::min(merged.size(), m0 + o.chunk);
-            BlockData bd;
-            build_block(merged, m0, m1, peak_map, co, fa, largest, &bd);
+            Ready item;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return !ready.empty() || finished; });
+                if (ready.empty()) break;
+                item = std::move(ready.front());
+                ready.pop_front();
+                cv.notify_all();
+            }
+            const size_t c = item.c, m0 = c * o.chunk, m1 = std::min(merged.size(), m0 + o.chunk);
+            BlockData& bd = *item.bd;
             tfbs_block blk = bd.view(co);
             TF(tfbs_submit_block(ctx, &blk));
             tfbs_rows rows;
@@ -915,21 +947,36 @@ int main(int argc, char** argv) {
                 if (ia.end != ib.end) return ia.end < ib.end;
                 return rows.pattern_id[a] < rows.pattern_id[b];
             });
-            for (uint64_t i : order) {
-                // counts arrive in the narrowest type that holds them (option rows_width = 0, tfbs_rows.count_bytes)
-                RowText t = rows.count_bytes == 1 ? finalise_row((const uint8_t*)rows.left + i * S, (const uint8_t*)rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf)
-                          : rows.count_bytes == 2 ? finalise_row((const uint16_t*)rows.left + i * S, (const uint16_t*)rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf)
-                                                  : finalise_row(rows.left + i * S, rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf);
-                if (!t.keep) continue;
-                const tfbs_inner_region& ir = bd.inner[rows.inner[i]];
-                // POS is filled in by the writer (a running counter, main.rs:329,424-425)
-                outs[c].rows.push_back("\t" + bed_names[ir.bed_index] + "," + pwm_name[rows.pattern_id[i]] + "," + std::to_string(ir.start) + "-" +
-                                       std::to_string(ir.end) + "\t.\t.\t.\tPASS\t" + t.info + "\tGT:DS" + t.genotypes + "\n");
+            // row text on --threads host threads (the reference formats inside its worker threads, main.rs:415-425)
+            std::vector<std::string> text(order.size());
+            auto format_range = [&](size_t a, size_t b) {
+                for (size_t k = a; k < b; ++k) {
+                    const uint64_t i = order[k];
+                    // counts arrive in the narrowest type that holds them (option rows_width = 0, tfbs_rows.count_bytes)
+                    RowText t = rows.count_bytes == 1 ? finalise_row((const uint8_t*)rows.left + i * S, (const uint8_t*)rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf)
+                              : rows.count_bytes == 2 ? finalise_row((const uint16_t*)rows.left + i * S, (const uint16_t*)rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf)
+                                                      : finalise_row(rows.left + i * S, rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf);
+                    if (!t.keep) continue;
+                    const tfbs_inner_region& ir = bd.inner[rows.inner[i]];
+                    // POS is filled in by the writer (a running counter, main.rs:329,424-425)
+                    text[k] = "\t" + bed_names[ir.bed_index] + "," + pwm_name.at(rows.pattern_id[i]) + "," + std::to_string(ir.start) + "-" +
+                              std::to_string(ir.end) + "\t.\t.\t.\tPASS\t" + t.info + "\tGT:DS" + t.genotypes + "\n";
+                }
+            };
+            const size_t nt = std::max<size_t>(1, std::min<size_t>(o.threads, order.size() / 64 + 1));
+            if (nt == 1) format_range(0, order.size());
+            else {
+                std::vector<std::thread> ft;
+                for (size_t t = 0; t < nt; ++t) ft.emplace_back(format_range, order.size() * t / nt, order.size() * (t + 1) / nt);
+                for (auto& t : ft) t.join();
             }
+            for (std::string& row : text)
+                if (!row.empty()) outs[c].rows.push_back(std::move(row));
             if (o.verbose)
                 printf("\nChunk %zu/%zu\tregions %zu-%zu\t%llu haplotypes\t%llu hits\n", c + 1, n_chunks, m0, m1, (unsigned long long)st.n_groups,
                        (unsigned long long)st.n_hits);
         }
+        builder.join();
         tfbs_destroy(ctx);
     };
     if (o.devices.size() <= 1) worker(o.devices.empty() ? 0 : o.devices[0]);
