@@ -52,7 +52,17 @@ def _typed_str(s):
     return bytes([0xF7, 0x12]) + struct.pack("<h", len(b)) + b
 
 
-def write_bcf(path, chrom, contig_len, samples, records, member_bytes=40000):
+def bgzf_block(data):
+    """One BGZF member: gzip header with the BC extra subfield (BSIZE), raw deflate, CRC32, ISIZE."""
+    import zlib
+    co = zlib.compressobj(6, zlib.DEFLATED, -15)
+    comp = co.compress(data) + co.flush()
+    bsize = len(comp) + 25
+    return (b"\x1f\x8b\x08\x04\0\0\0\0\0\xff\x06\0BC\x02\0" + struct.pack("<H", bsize) + comp +
+            struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
+
+
+def write_bcf(path, chrom, contig_len, samples, records, member_bytes=40000, bgzf=False):
     """records: list of (pos, [alleles...], gt) with gt an (n_samples, 2) int array of raw BCF codes, sorted by pos."""
     text = ("##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed\">\n##contig=<ID=chrOther,length=1000>\n"
             "##contig=<ID=%s,length=%d>\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
@@ -70,10 +80,13 @@ def write_bcf(path, chrom, contig_len, samples, records, member_bytes=40000):
         out += struct.pack("<II", len(shared), len(indiv)) + shared + indiv
     with open(path, "wb") as f:
         for i in range(0, len(out), member_bytes):  # several gzip members, like BGZF blocks
-            f.write(gzip.compress(bytes(out[i:i + member_bytes]), 6))
+            chunk = bytes(out[i:i + member_bytes])
+            f.write(bgzf_block(chunk) if bgzf else gzip.compress(chunk, 6))
+        if bgzf:
+            f.write(bgzf_block(b""))  # the EOF marker block
 
 
-def cohort_to_files(blk, pats, dirname, chrom="chrS", multiallelic_every=0):
+def cohort_to_files(blk, pats, dirname, chrom="chrS", multiallelic_every=0, bgzf=False, member_bytes=40000):
     """Writes the file set of a synth.make_cohort block; returns the arguments of the reference's CLI."""
     m = blk.meta
     os.makedirs(dirname, exist_ok=True)
@@ -101,7 +114,7 @@ def cohort_to_files(blk, pats, dirname, chrom="chrS", multiallelic_every=0):
         if multiallelic_every and v % multiallelic_every == 0:  # skipped by the reference (haplotype.rs:27,53-55)
             g2 = np.tile(np.array([[2, 7]], dtype=np.int8), (S, 1))
             recs.append((int(m["var_pos"][v]), [ref, "A", "C"], g2))
-    write_bcf(os.path.join(dirname, "cohort.bcf"), chrom, m["genome_len"], samples, recs)
+    write_bcf(os.path.join(dirname, "cohort.bcf"), chrom, m["genome_len"], samples, recs, member_bytes=member_bytes, bgzf=bgzf)
     names = [p["name"] for p in pats if p["direction"] == 0]
     return {"chromosome": chrom, "bcf": os.path.join(dirname, "cohort.bcf"), "beds": beds, "reference": fa, "pwm_file": pwm,
             "threshold_dir": os.path.join(dirname, "thr"), "names": names, "samples": samples}

@@ -131,6 +131,9 @@ def test_bcf_and_fasta_decoding(drv, golden_dir, tmp_path):
     pats = synth.make_pwms(2, seed=5, lmin=6, lmax=10)
     blk = synth.make_cohort(21, 12, seed=5, lmax_pattern=10, region_len=(50, 150), variant_rate=0.05)
     a = fw.cohort_to_files(blk, pats, str(tmp_path / "c"), multiallelic_every=5)
+    b = fw.cohort_to_files(blk, pats, str(tmp_path / "b"), multiallelic_every=5, bgzf=True, member_bytes=1500)  # dozens of real BGZF members: parallel inflate
+    assert ora.read_bcf(b["bcf"])["pos"] == ora.read_bcf(a["bcf"])["pos"]
+    assert load(b["bcf"], None, b["chromosome"])[:3] == load(a["bcf"], None, a["chromosome"])[:3]
     pos, na, row, car, ns, pitch = load(a["bcf"], None, a["chromosome"])
     o = ora.read_bcf(a["bcf"])
     assert pos == o["pos"] and na == [len(x) for x in o["alleles"]] and ns == 21 and pitch == blk.carriers.shape[1]
