@@ -549,10 +549,14 @@ Cohort load_bcf(const Options& o) {
     if (rid < 0) die("called `Result::unwrap()` on an `Err` value: UnknownSequence (" + o.chromosome + ")");  // haplotype.rs:78
     const uint32_t S = (uint32_t)co.samples.size();
     co.pitch = std::max<uint32_t>(1, (2 * S + 31) / 32);
+    // pass 1 (serial, a few bytes per record): positions, alleles, carrier rows; the genotype blocks are only located
+    struct Pending { uint32_t row; const uint8_t* indiv; uint32_t l_indiv, n_fmt, n_sample; };
+    std::vector<Pending> pending;
     while (c.p < c.e) {
         uint32_t l_shared = c.u32(), l_indiv = c.u32();
         c.need((size_t)l_shared + l_indiv);
-        Cursor s{c.p, c.p + l_shared}, d{c.p + l_shared, c.p + l_shared + l_indiv};
+        Cursor s{c.p, c.p + l_shared};
+        const uint8_t* indiv = c.p + l_shared;
         c.p += (size_t)l_shared + l_indiv;
         int32_t chrom = s.i32();
         Record r;
@@ -571,36 +575,66 @@ Cohort load_bcf(const Options& o) {
         check_letters(r.alt);
         r.carrier_row = UINT32_MAX;
         if (r.n_allele == 2) {
-            r.carrier_row = (uint32_t)(co.carriers.size() / co.pitch);
-            co.carriers.resize(co.carriers.size() + co.pitch, 0);
-            uint32_t* row = co.carriers.data() + (size_t)r.carrier_row * co.pitch;
-            bool have_gt = false;
-            for (uint32_t f = 0; f < n_fmt; ++f) {
-                int kt, vt; uint32_t kl, vl;
-                d.desc(&kt, &kl);
-                int32_t key = d.tint(kt);
-                d.desc(&vt, &vl);
-                size_t bytes = Cursor::tsize(vt) * vl * (size_t)n_sample;
-                d.need(bytes);
-                if (key == gt_key && vt >= 1 && vt <= 3) {
-                    have_gt = true;
-                    if (vl != 2 && S) die("Inconsistent number of alleles");  // haplotype.rs:32
-                    const size_t es = Cursor::tsize(vt);
-                    for (uint32_t k = 0; k < S; ++k) {
-                        Cursor g{d.p + co.sample_positions[k] * 2 * es, d.p + bytes};
-                        int32_t g0 = g.tint(vt), g1 = g.tint(vt);
-                        if (g0 == 4) row[(2 * k) >> 5] |= 1u << ((2 * k) & 31);          // Unphased(1), haplotype.rs:34-37
-                        if (g1 == 5) row[(2 * k + 1) >> 5] |= 1u << ((2 * k + 1) & 31);  // Phased(1),   haplotype.rs:38-41
-                    }
-                }
-                d.p += bytes;
-            }
-            if (!have_gt && S) die("called `Result::unwrap()` on an `Err` value: missing GT");  // haplotype.rs:24
+            r.carrier_row = (uint32_t)pending.size();
+            pending.push_back(Pending{r.carrier_row, indiv, l_indiv, n_fmt, n_sample});
         } else {
             printf("Unusual number of alleles: %u\n", r.n_allele);  // haplotype.rs:53-55
         }
         co.max_rlen = std::max(co.max_rlen, std::max(1, r.rlen));
         co.records.push_back(std::move(r));
+    }
+    // pass 2 (--threads host threads): GT of the selected samples -> carrier bits (haplotype.rs:30-51), the O(records x samples) part
+    co.carriers.assign(pending.size() * (size_t)co.pitch, 0);
+    std::atomic<size_t> next_rec{0};
+    std::mutex err_mu;
+    std::string err;
+    auto decode = [&] {
+        try {
+            for (;;) {
+                const size_t base = next_rec.fetch_add(256);
+                if (base >= pending.size()) return;
+                for (size_t k2 = base; k2 < std::min(pending.size(), base + 256); ++k2) {
+                    const Pending& pd = pending[k2];
+                    Cursor d{pd.indiv, pd.indiv + pd.l_indiv};
+                    uint32_t* row = co.carriers.data() + (size_t)pd.row * co.pitch;
+                    bool have_gt = false;
+                    for (uint32_t f = 0; f < pd.n_fmt; ++f) {
+                        int kt, vt; uint32_t kl, vl;
+                        d.desc(&kt, &kl);
+                        int32_t key = d.tint(kt);
+                        d.desc(&vt, &vl);
+                        size_t bytes = Cursor::tsize(vt) * vl * (size_t)pd.n_sample;
+                        d.need(bytes);
+                        if (key == gt_key && vt >= 1 && vt <= 3) {
+                            have_gt = true;
+                            if (vl != 2 && S) die("Inconsistent number of alleles");  // haplotype.rs:32
+                            const size_t es = Cursor::tsize(vt);
+                            for (uint32_t k = 0; k < S; ++k) {
+                                Cursor g{d.p + co.sample_positions[k] * 2 * es, d.p + bytes};
+                                int32_t g0 = g.tint(vt), g1 = g.tint(vt);
+                                if (g0 == 4) row[(2 * k) >> 5] |= 1u << ((2 * k) & 31);          // Unphased(1), haplotype.rs:34-37
+                                if (g1 == 5) row[(2 * k + 1) >> 5] |= 1u << ((2 * k + 1) & 31);  // Phased(1),   haplotype.rs:38-41
+                            }
+                        }
+                        d.p += bytes;
+                    }
+                    if (!have_gt && S) die("called `Result::unwrap()` on an `Err` value: missing GT");  // haplotype.rs:24
+                }
+            }
+        } catch (const std::exception& e) {  // only under the test shim, where die() throws
+            std::lock_guard<std::mutex> lk(err_mu);
+            if (err.empty()) err = e.what();
+        }
+    };
+    {
+        const unsigned nt = std::max(1u, std::min<unsigned>(std::max(1u, o.threads), (unsigned)(pending.size() / 256 + 1)));
+        if (nt == 1) decode();
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back(decode);
+            for (auto& t : th) t.join();
+        }
+        if (!err.empty()) die(err);
     }
     if (!std::is_sorted(co.records.begin(), co.records.end(), [](const Record& a, const Record& b) { return a.pos < b.pos; }))
         die("the BCF is not sorted by position (an indexed BCF always is)");
