@@ -69,7 +69,7 @@ def test_driver_matches_oracle_on_synthetic_files(tmp_path):
     a = fw.cohort_to_files(blk, pats, str(tmp_path), multiallelic_every=11)
     expected = ora.run(a["chromosome"], a["bcf"], a["beds"], a["reference"], None, a["pwm_file"], a["threshold_dir"], 1e-4, a["names"])
     assert len(expected.splitlines()) > 5
-    for extra in ([], ["--chunk", "7"], ["--plain"], ["--chunk", "5", "--threads", "3"]):
+    for extra in ([], ["--chunk", "7"], ["--plain"], ["--chunk", "5", "--threads", "3"], ["--chunk", "4", "--devices", "0,0"]):  # last: two contexts, one per worker thread
         out = str(tmp_path / "out.vcf.gz")
         a["extra"] = extra
         p = run_driver(a, out)
