@@ -295,6 +295,42 @@ def main():
     e2e = {"value": nominal / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(total(st2["h2d_bytes"])),
            "d2h_bytes_per_step": int(total(st2["d2h_bytes"])), "ms_per_step": ms_e2e}
 
+    # ---- the same end-to-end step driven the way the reference runs (one context per worker thread, main.rs:333-373): two host
+    # threads with one context each on this GPU, so that the PCIe copies and host work of one block overlap the kernels of the other.
+    # Auxiliary number (wall clock between device synchronisations); `e2e` above stays the single-context figure.
+    e2e2 = None
+    try:
+        if world > 1:
+            raise RuntimeError("measured at N=1 only")
+        ctx2 = binding.Context(local_rank)
+        ctx2.set_option("rows_width", 0)
+        for kv in args.option:
+            k, v = kv.split("=")
+            ctx2.set_option(k, int(v))
+        ctx2.set_patterns(ps)
+
+        def pump(c, n):
+            for _ in range(n):
+                c.submit_block(blk)
+                c.collect(copy=False)
+
+        pump(ctx2, 1)
+        n_each = max(1, args.steps // 2)
+        barrier()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=pump, args=(c, n_each)) for c in (ctx, ctx2)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        torch.cuda.synchronize()
+        ms2 = (time.perf_counter() - t0) * 1e3 / (2 * n_each)
+        e2e2 = {"value": nominal / (ms2 * 1e-3), "unit": UNIT, "ms_per_step": ms2, "steps": 2 * n_each,
+                "note": "two contexts on two host threads per GPU (the reference's worker-thread pattern); wall clock"}
+        ctx2.close()
+    except Exception as exc:  # never let the auxiliary measurement break the contract line
+        e2e2 = {"skipped": str(exc)[:200]}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -334,7 +370,7 @@ def main():
            "stages_ms": {k: st[k] for k in ("ms_group", "ms_build", "ms_scan", "ms_scan_kernel", "ms_count", "ms_total")},
            "groups_dropped_per_step": st["n_dropped"], "haplotypes_truncated_per_step": st["n_truncated"],
            "groups_per_step": st["n_groups"], "hits_per_step": st["n_hits"], "rows_per_step": st["n_rows"],
-           "roofline": roofline, "e2e": e2e, "gpu_launches": launches, "clocks": clocks}
+           "roofline": roofline, "e2e": e2e, "e2e_two_contexts": e2e2, "gpu_launches": launches, "clocks": clocks}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_reference_rate(ps, blk, args.cpu_seconds, os.cpu_count() or 1)
     emit(out)
