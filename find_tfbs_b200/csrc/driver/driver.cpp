@@ -376,47 +376,73 @@ std::vector<uint8_t> gunzip_bgzf(const std::vector<uint8_t>& in, const std::stri
 // BGZF writer: independent gzip members of <= 64 KiB with the BC extra field, terminated by the empty EOF block.
 class BgzfWriter {
 public:
-    explicit BgzfWriter(const std::string& path) : f_(path, std::ios::binary) {
+    BgzfWriter(const std::string& path, unsigned threads) : f_(path, std::ios::binary), threads_(std::max(1u, threads)) {
         if (!f_) die("Could not create output file");
     }
     void write(const std::string& s) {
         buf_ += s;
-        while (buf_.size() >= kBlock) { block(buf_.data(), kBlock); buf_.erase(0, kBlock); }
+        if (buf_.size() >= kBlock * 8 * threads_) flush(false);
     }
     void finish() {
-        if (!buf_.empty()) block(buf_.data(), buf_.size());
-        buf_.clear();
-        block(nullptr, 0);  // EOF marker
+        flush(true);
+        const std::string eof = compress(nullptr, 0);  // EOF marker
+        f_.write(eof.data(), (std::streamsize)eof.size());
         f_.close();
     }
 
 private:
     static constexpr size_t kBlock = 0xff00;
-    void block(const char* data, size_t n) {
-        uint8_t out[0x10000 + 64];
+    // the blocks are independent gzip members: compressed on several threads, written in order
+    void flush(bool all) {
+        const size_t n_full = buf_.size() / kBlock, n = n_full + ((all && buf_.size() % kBlock) ? 1 : 0);
+        if (n == 0) return;
+        std::vector<std::string> out(n);
+        std::atomic<size_t> next{0};
+        auto work = [&] {
+            for (;;) {
+                size_t k = next.fetch_add(1);
+                if (k >= n) return;
+                out[k] = compress(buf_.data() + k * kBlock, std::min(kBlock, buf_.size() - k * kBlock));
+            }
+        };
+        const unsigned nt = (unsigned)std::min<size_t>(threads_, n);
+        if (nt <= 1) work();
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back(work);
+            for (auto& t : th) t.join();
+        }
+        for (const std::string& blk : out) f_.write(blk.data(), (std::streamsize)blk.size());
+        buf_.erase(0, std::min(buf_.size(), n * kBlock));
+    }
+    static std::string compress(const char* data, size_t n) {
+        std::string out(0x10000 + 64, '\0');
+        uint8_t* o = (uint8_t*)&out[0];
         z_stream zs;
         memset(&zs, 0, sizeof zs);
         deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
         zs.next_in = (Bytef*)data;
         zs.avail_in = (uInt)n;
-        zs.next_out = out + 18;
-        zs.avail_out = sizeof(out) - 18 - 8;
+        zs.next_out = o + 18;
+        zs.avail_out = (uInt)(out.size() - 18 - 8);
         if (deflate(&zs, Z_FINISH) != Z_STREAM_END) die("deflate failed");
         size_t clen = zs.total_out;
         deflateEnd(&zs);
         const uint8_t hdr[12] = {0x1f, 0x8b, 8, 4, 0, 0, 0, 0, 0, 0xff, 6, 0};
-        memcpy(out, hdr, 12);
-        out[12] = 'B'; out[13] = 'C'; out[14] = 2; out[15] = 0;
+        memcpy(o, hdr, 12);
+        o[12] = 'B'; o[13] = 'C'; o[14] = 2; o[15] = 0;
         size_t bsize = clen + 25;  // total block size - 1
-        out[16] = bsize & 0xff; out[17] = (bsize >> 8) & 0xff;
+        o[16] = bsize & 0xff; o[17] = (bsize >> 8) & 0xff;
         uint32_t crc = (uint32_t)crc32(crc32(0L, Z_NULL, 0), (const Bytef*)data, (uInt)n);
         uint32_t isize = (uint32_t)n;
-        memcpy(out + 18 + clen, &crc, 4);
-        memcpy(out + 22 + clen, &isize, 4);
-        f_.write((const char*)out, (std::streamsize)(clen + 26));
+        memcpy(o + 18 + clen, &crc, 4);
+        memcpy(o + 22 + clen, &isize, 4);
+        out.resize(clen + 26);
+        return out;
     }
     std::ofstream f_;
     std::string buf_;
+    unsigned threads_;
 };
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -876,6 +902,15 @@ int drv_load_bcf(const char* bcf, const char* samples_file, const char* chrom, u
     } catch (const std::exception& e) { g_shim_err = e.what(); return -1; }
 }
 
+int drv_write_bgzf(const char* path, const char* data, uint64_t n, uint32_t threads, uint32_t piece) {
+    try {
+        BgzfWriter w(path, threads);
+        for (uint64_t p = 0; p < n; p += piece) w.write(std::string(data + p, (size_t)std::min<uint64_t>(piece, n - p)));
+        w.finish();
+        return 0;
+    } catch (const std::exception& e) { g_shim_err = e.what(); return -1; }
+}
+
 int drv_fasta_fetch(const char* path, const char* chrom, uint64_t start, uint64_t stop, uint8_t* out, uint64_t cap, uint64_t* n) {
     try {
         Fasta fa(path, chrom);
@@ -954,7 +989,7 @@ int main(int argc, char** argv) {
     for (size_t p; (p = chr.find("chr")) != std::string::npos;) chr.erase(p, 3);
 
     const std::string part = o.output + ".part";
-    BgzfWriter* gz = o.plain_text ? nullptr : new BgzfWriter(part);
+    BgzfWriter* gz = o.plain_text ? nullptr : new BgzfWriter(part, o.threads);
     std::ofstream plain;
     if (o.plain_text) { plain.open(part, std::ios::binary); if (!plain) die("Could not create output file"); }
     auto emit = [&](const std::string& s) { if (gz) gz->write(s); else plain << s; };

@@ -158,3 +158,30 @@ def test_bcf_and_fasta_decoding(drv, golden_dir, tmp_path):
         assert drv.drv_fasta_fetch(a["reference"].encode(), a["chromosome"].encode(), start, stop, buf, 4096, C.byref(n)) == 0
         assert bytes(buf[:n.value]) == g[start:min(stop, len(g))]
     assert drv.drv_fasta_fetch(a["reference"].encode(), b"chrNope", 0, 5, (C.c_uint8 * 16)(), 16, C.byref(C.c_uint64())) == -1
+
+
+def test_bgzf_writer(drv, tmp_path):
+    """The VCF writer (main.rs:264-290 uses bgzip::BGzWriter): valid BGZF members (BC subfield, BSIZE, CRC, ISIZE, EOF block) whatever
+    the write granularity and thread count; the concatenation inflates to the input; the driver's own parallel reader reads it back."""
+    import struct
+    import zlib
+    rng = np.random.default_rng(3)
+    text = "\n".join("1\t%d\tregions.bed,PWM%d,%d-%d\t.\t.\t.\tPASS\tCOUNTS=0,1;freqs=5/0/1\tGT:DS" % (i, i % 7, i * 10, i * 10 + 300) +
+                     "".join(rng.choice(["\t0|0:0.0", "\t1|1:2.0", "\t0|1:0.6667"], size=40)) for i in range(4000)).encode()
+    for threads, piece in ((1, 1 << 20), (4, 777), (3, 200000)):
+        path = str(tmp_path / ("t%d.vcf.gz" % threads))
+        assert drv.drv_write_bgzf(path.encode(), text, len(text), threads, piece) == 0
+        raw = open(path, "rb").read()
+        off, out, n_members = 0, b"", 0
+        while off < len(raw):
+            assert raw[off:off + 4] == b"\x1f\x8b\x08\x04" and raw[off + 12:off + 16] == b"BC\x02\x00"
+            bsize = struct.unpack("<H", raw[off + 16:off + 18])[0] + 1
+            crc, isize = struct.unpack("<II", raw[off + bsize - 8:off + bsize])
+            data = zlib.decompress(raw[off + 18:off + bsize - 8], -15)
+            assert len(data) == isize <= 0xff00 and zlib.crc32(data) & 0xFFFFFFFF == crc
+            out += data
+            off += bsize
+            n_members += 1
+        assert out == text and n_members > 5
+        assert raw.endswith(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))  # the BGZF EOF block
+        assert ora.gunzip_file(path).encode() == text
