@@ -953,6 +953,7 @@ int main(int argc, char** argv) {
     Options o = parse_args(argc, argv);
     if (o.tabix && system("command -v tabix > /dev/null 2>&1") != 0) die("tabix cannot in found in PATH");  // main.rs:220-223
     auto t_start = std::chrono::steady_clock::now();
+    auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
 
     std::vector<Pwm> pwms = parse_pwm_files(o);
     if (pwms.empty()) die("assertion failed: pwm_list.len() > 0");  // main.rs:238
@@ -982,7 +983,9 @@ int main(int argc, char** argv) {
     std::vector<Range> merged = merge_ranges(all);
     printf("Merged all region files: %zu merged regions\n", merged.size());
 
+    const double t_before_bcf = since();
     Cohort co = load_bcf(o);
+    const double t_after_bcf = since();
     const uint32_t S = (uint32_t)co.samples.size();
 
     std::string chr = o.chromosome;  // main.rs:402
@@ -1014,11 +1017,15 @@ int main(int argc, char** argv) {
     std::vector<ChunkOut> outs(n_chunks);
     std::atomic<size_t> next{0};
     std::atomic<uint64_t> total_cells{0}, total_hits{0};
+    std::atomic<uint64_t> us_create{0}, us_wait{0}, us_gpu{0}, us_sort{0}, us_format{0};
+    auto now_us = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
     auto worker = [&](int device) {
         tfbs_ctx* ctx = nullptr;
+        uint64_t tc = now_us();
         if (tfbs_create(device, &ctx) != TFBS_OK) die(std::string(tfbs_last_error(nullptr)));
         TF(tfbs_set_patterns(ctx, cpat.data(), (uint32_t)cpat.size()));
         TF(tfbs_set_option(ctx, "rows_width", 0));
+        us_create += now_us() - tc;
         // a builder thread prepares the next blocks (FASTA windows, inner regions, records) while the GPU works on the current one;
         // private readers per worker, like main.rs:345-346
         struct Ready { size_t c; std::unique_ptr<BlockData> bd; };
@@ -1044,6 +1051,7 @@ int main(int argc, char** argv) {
         });
         for (;;) {
             Ready item;
+            uint64_t tw = now_us();
             {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return !ready.empty() || finished; });
@@ -1054,10 +1062,14 @@ int main(int argc, char** argv) {
             }
             const size_t c = item.c, m0 = c * o.chunk, m1 = std::min(merged.size(), m0 + o.chunk);
             BlockData& bd = *item.bd;
+            us_wait += now_us() - tw;
+            uint64_t tg = now_us();
             tfbs_block blk = bd.view(co);
             TF(tfbs_submit_block(ctx, &blk));
             tfbs_rows rows;
             TF(tfbs_collect(ctx, &rows));
+            us_gpu += now_us() - tg;
+            uint64_t ts = now_us();
             tfbs_stats st;
             tfbs_get_stats(ctx, &st);
             total_cells += st.nominal_cells;
@@ -1074,6 +1086,8 @@ int main(int argc, char** argv) {
                 if (ia.end != ib.end) return ia.end < ib.end;
                 return rows.pattern_id[a] < rows.pattern_id[b];
             });
+            us_sort += now_us() - ts;
+            uint64_t tf = now_us();
             // row text on --threads host threads (the reference formats inside its worker threads, main.rs:415-425)
             std::vector<std::string> text(order.size());
             auto format_range = [&](size_t a, size_t b) {
@@ -1099,6 +1113,7 @@ int main(int argc, char** argv) {
             }
             for (std::string& row : text)
                 if (!row.empty()) outs[c].rows.push_back(std::move(row));
+            us_format += now_us() - tf;
             if (o.verbose)
                 printf("\nChunk %zu/%zu\tregions %zu-%zu\t%llu haplotypes\t%llu hits\n", c + 1, n_chunks, m0, m1, (unsigned long long)st.n_groups,
                        (unsigned long long)st.n_hits);
@@ -1112,6 +1127,7 @@ int main(int argc, char** argv) {
         for (int d : o.devices) th.emplace_back(worker, d);
         for (auto& t : th) t.join();
     }
+    const double t_after_gpu = since();
     uint64_t fake_position = 1;
     for (const ChunkOut& co2 : outs)
         for (const std::string& row : co2.rows) emit(chr + "\t" + std::to_string(fake_position++) + row);
@@ -1122,7 +1138,10 @@ int main(int argc, char** argv) {
         if (system(cmd.c_str()) == 0) printf("Tabixed file %s\n", o.output.c_str());
         else printf("Failed to tabix file %s\n", o.output.c_str());
     }
-    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    double secs = since();
+    printf("phases: PWM+BED %.2f s, BCF %.2f s, blocks+GPU+rows %.2f s (context %.2f, waiting for blocks %.2f, submit+collect %.2f, sort %.2f, "
+           "row text %.2f; summed over devices), VCF write %.2f s\n", t_before_bcf, t_after_bcf - t_before_bcf, t_after_gpu - t_after_bcf,
+           us_create / 1e6, us_wait / 1e6, us_gpu / 1e6, us_sort / 1e6, us_format / 1e6, secs - t_after_gpu);
     printf("%zu merged regions, %llu rows, %llu hits, %.3e nominal cells in %.2f s\nEnd of program.\n", merged.size(),
            (unsigned long long)(fake_position - 1), (unsigned long long)total_hits.load(), (double)total_cells.load(), secs);
     return 0;
