@@ -983,9 +983,36 @@ int main(int argc, char** argv) {
     std::vector<Range> merged = merge_ranges(all);
     printf("Merged all region files: %zu merged regions\n", merged.size());
 
+    // one context per device; chunks of merged regions are dealt round-robin (regions are independent, main.rs:395-429)
+    std::vector<tfbs_pattern> cpat(pwms.size());
+    for (size_t i = 0; i < pwms.size(); ++i) {
+        cpat[i].weights = pwms[i].w.data();
+        cpat[i].len = (uint32_t)(pwms[i].w.size() / 4);
+        cpat[i].min_score = pwms[i].min_score;
+        cpat[i].pattern_id = pwms[i].pattern_id;
+        cpat[i].direction = pwms[i].direction;
+        cpat[i].kind = TFBS_PATTERN_PWM;
+    }
+    // the CUDA contexts are created (and the pattern tables compiled and uploaded) while the BCF is read
+    std::atomic<uint64_t> us_create{0};
+    auto now_us = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    if (o.devices.empty()) o.devices.push_back(0);
+    std::vector<tfbs_ctx*> ctxs(o.devices.size(), nullptr);
+    std::vector<std::thread> pre;
+    for (size_t k = 0; k < o.devices.size(); ++k)
+        pre.emplace_back([&, k] {
+            const uint64_t tc = now_us();
+            tfbs_ctx* ctx = nullptr;
+            if (tfbs_create(o.devices[k], &ctx) != TFBS_OK) die(std::string(tfbs_last_error(nullptr)));
+            TF(tfbs_set_patterns(ctx, cpat.data(), (uint32_t)cpat.size()));
+            TF(tfbs_set_option(ctx, "rows_width", 0));
+            ctxs[k] = ctx;
+            us_create += now_us() - tc;
+        });
     const double t_before_bcf = since();
     Cohort co = load_bcf(o);
     const double t_after_bcf = since();
+    for (auto& t : pre) t.join();
     const uint32_t S = (uint32_t)co.samples.size();
 
     std::string chr = o.chromosome;  // main.rs:402
@@ -1002,30 +1029,14 @@ int main(int argc, char** argv) {
         emit(hdr + "\n");
     }
 
-    // one context per device; chunks of merged regions are dealt round-robin (regions are independent, main.rs:395-429)
-    std::vector<tfbs_pattern> cpat(pwms.size());
-    for (size_t i = 0; i < pwms.size(); ++i) {
-        cpat[i].weights = pwms[i].w.data();
-        cpat[i].len = (uint32_t)(pwms[i].w.size() / 4);
-        cpat[i].min_score = pwms[i].min_score;
-        cpat[i].pattern_id = pwms[i].pattern_id;
-        cpat[i].direction = pwms[i].direction;
-        cpat[i].kind = TFBS_PATTERN_PWM;
-    }
     const size_t n_chunks = (merged.size() + o.chunk - 1) / o.chunk;
     struct ChunkOut { std::vector<std::string> rows; };
     std::vector<ChunkOut> outs(n_chunks);
     std::atomic<size_t> next{0};
     std::atomic<uint64_t> total_cells{0}, total_hits{0};
-    std::atomic<uint64_t> us_create{0}, us_wait{0}, us_gpu{0}, us_sort{0}, us_format{0};
-    auto now_us = [] { return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    auto worker = [&](int device) {
-        tfbs_ctx* ctx = nullptr;
-        uint64_t tc = now_us();
-        if (tfbs_create(device, &ctx) != TFBS_OK) die(std::string(tfbs_last_error(nullptr)));
-        TF(tfbs_set_patterns(ctx, cpat.data(), (uint32_t)cpat.size()));
-        TF(tfbs_set_option(ctx, "rows_width", 0));
-        us_create += now_us() - tc;
+    std::atomic<uint64_t> us_wait{0}, us_gpu{0}, us_sort{0}, us_format{0};
+    auto worker = [&](size_t slot) {
+        tfbs_ctx* ctx = ctxs[slot];
         // a builder thread prepares the next blocks (FASTA windows, inner regions, records) while the GPU works on the current one;
         // private readers per worker, like main.rs:345-346
         struct Ready { size_t c; std::unique_ptr<BlockData> bd; };
@@ -1121,10 +1132,10 @@ int main(int argc, char** argv) {
         builder.join();
         tfbs_destroy(ctx);
     };
-    if (o.devices.size() <= 1) worker(o.devices.empty() ? 0 : o.devices[0]);
+    if (o.devices.size() <= 1) worker(0);
     else {
         std::vector<std::thread> th;
-        for (int d : o.devices) th.emplace_back(worker, d);
+        for (size_t k = 0; k < o.devices.size(); ++k) th.emplace_back(worker, k);
         for (auto& t : th) t.join();
     }
     const double t_after_gpu = since();
