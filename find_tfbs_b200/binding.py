@@ -22,7 +22,7 @@ DIR_P, DIR_N = 0, 1
 
 EXPORTS = ["tfbs_abi_version", "tfbs_create", "tfbs_destroy", "tfbs_last_error", "tfbs_set_option", "tfbs_set_patterns",
            "tfbs_submit_block", "tfbs_collect", "tfbs_get_matches", "tfbs_upload_block", "tfbs_run_resident", "tfbs_get_stats",
-           "tfbs_stream", "tfbs_host_register", "tfbs_host_unregister"]
+           "tfbs_stream", "tfbs_host_register", "tfbs_host_unregister", "tfbs_audit_block"]
 
 
 class TfbsPattern(C.Structure):
@@ -60,6 +60,16 @@ class TfbsMatches(C.Structure):
     _fields_ = [("n_matches", C.c_uint64), ("region", C.POINTER(C.c_uint32)), ("pattern_index", C.POINTER(C.c_uint32)),
                 ("group", C.POINTER(C.c_uint32)), ("start", C.POINTER(C.c_int64)), ("hap_group", C.POINTER(C.c_uint32)),
                 ("n_samples", C.c_uint32), ("truncated", C.c_uint32)]
+
+
+class TfbsAudit(C.Structure):
+    _fields_ = [("n_ties", C.c_uint64), ("tie_region", C.POINTER(C.c_uint32)), ("tie_pattern_index", C.POINTER(C.c_uint32)),
+                ("tie_group", C.POINTER(C.c_uint32)), ("tie_start", C.POINTER(C.c_int64)), ("hap_group", C.POINTER(C.c_uint32)),
+                ("hap_flags", C.POINTER(C.c_uint8)), ("n_regions", C.c_uint32), ("n_samples", C.c_uint32),
+                ("truncated", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+HAP_TRUNCATED, HAP_OVERWRITTEN = 1, 2
 
 
 class TfbsStats(C.Structure):
@@ -111,6 +121,7 @@ def lib():
         L.tfbs_collect.argtypes = [C.c_void_p, C.POINTER(TfbsRows)]
         L.tfbs_get_matches.argtypes = [C.c_void_p, C.POINTER(TfbsMatches)]
         L.tfbs_get_stats.argtypes = [C.c_void_p, C.POINTER(TfbsStats)]
+        L.tfbs_audit_block.argtypes = [C.c_void_p, C.POINTER(TfbsAudit)]
         L.tfbs_stream.argtypes = [C.c_void_p]
         L.tfbs_stream.restype = C.c_void_p
         L.tfbs_host_register.argtypes = [C.c_void_p, C.c_size_t]
@@ -303,6 +314,22 @@ class Context:
         return {"region": arr(m.region, n, np.uint32), "pattern_index": arr(m.pattern_index, n, np.uint32),
                 "group": arr(m.group, n, np.uint32), "start": arr(m.start, n, np.int64),
                 "hap_group": arr(m.hap_group, n_regions * 2 * m.n_samples, np.uint32), "truncated": bool(m.truncated)}
+
+    def audit(self):
+        """tfbs_audit_block on the resident block: windows scoring exactly min_score and the per-haplotype flags."""
+        a = TfbsAudit()
+        self._check(self._lib.tfbs_audit_block(self._h, C.byref(a)))
+        n, nh = a.n_ties, a.n_regions * 2 * a.n_samples
+
+        def arr(p, cnt, dt):
+            if cnt == 0:
+                return np.zeros(0, dtype=dt)
+            return np.ctypeslib.as_array(p, shape=(cnt,)).astype(dt, copy=True)
+
+        return {"region": arr(a.tie_region, n, np.uint32), "pattern_index": arr(a.tie_pattern_index, n, np.uint32),
+                "group": arr(a.tie_group, n, np.uint32), "start": arr(a.tie_start, n, np.int64),
+                "hap_group": arr(a.hap_group, nh, np.uint32), "hap_flags": arr(a.hap_flags, nh, np.uint8),
+                "truncated": bool(a.truncated)}
 
     def stats(self):
         s = TfbsStats()

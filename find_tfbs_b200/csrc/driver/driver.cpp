@@ -60,6 +60,7 @@ struct Range {
 // ---------------------------------------------------------------------------------------------------------------
 struct Options {
     std::string chromosome, bcf, output, reference, pwm_file, threshold_dir, samples_file;
+    std::string audit_file;  // --audit: threshold ties, truncated and overwritten haplotypes (tfbs_audit_block), tab-separated
     std::vector<std::string> beds, pwm_names;
     float pwm_threshold = 0;
     bool forward_only = false, tabix = false, verbose = false, has_samples = false, plain_text = false;
@@ -85,7 +86,7 @@ void usage() {
          "USAGE: find-tfbs-b200 --chromosome CHROM --input IN.bcf --output OUT.vcf.gz --reference REF.fa --bed A.bed[,B.bed]\n"
          "         --pwm_names NAME[,NAME] --pwm_file PWM.txt --pwm_threshold_directory DIR --pwm_threshold P\n"
          "         [--forward_only] [--threads N] [--min_maf N] [--after_position POS] [--samples FILE] [--tabix] [--verbose]\n"
-         "         [--devices 0,1,...] [--chunk REGIONS_PER_BLOCK] [--plain]");
+         "         [--devices 0,1,...] [--chunk REGIONS_PER_BLOCK] [--plain] [--audit AUDIT.tsv]");
 }
 
 Options parse_args(int argc, char** argv) {
@@ -147,6 +148,7 @@ Options parse_args(int argc, char** argv) {
     o.after_position = num("after_position", 0, "Cannot parse after_position");
     o.chunk = (uint32_t)std::max<uint64_t>(1, num("chunk", 2000, "Cannot parse chunk"));
     if (kv.count("samples")) { o.has_samples = true; o.samples_file = kv["samples"]; }
+    if (kv.count("audit")) o.audit_file = kv["audit"];
     if (kv.count("devices")) {
         o.devices.clear();
         for (auto& d : split(kv["devices"], ',')) o.devices.push_back(atoi(d.c_str()));
@@ -1030,7 +1032,7 @@ int main(int argc, char** argv) {
     }
 
     const size_t n_chunks = (merged.size() + o.chunk - 1) / o.chunk;
-    struct ChunkOut { std::vector<std::string> rows; };
+    struct ChunkOut { std::vector<std::string> rows; std::string audit; };
     std::vector<ChunkOut> outs(n_chunks);
     std::atomic<size_t> next{0};
     std::atomic<uint64_t> total_cells{0}, total_hits{0};
@@ -1076,7 +1078,36 @@ int main(int argc, char** argv) {
             us_wait += now_us() - tw;
             uint64_t tg = now_us();
             tfbs_block blk = bd.view(co);
-            TF(tfbs_submit_block(ctx, &blk));
+            if (o.audit_file.empty()) {
+                TF(tfbs_submit_block(ctx, &blk));
+            } else {
+                // the audit scores the block twice (thresholds lowered by one, then as given) and leaves the rows of the normal run
+                TF(tfbs_upload_block(ctx, &blk));
+                tfbs_audit au;
+                TF(tfbs_audit_block(ctx, &au));
+                if (au.truncated) die("--audit: the match buffer overflowed; use a smaller --chunk");
+                std::string& out = outs[c].audit;
+                const uint32_t H = 2 * au.n_samples;
+                auto region_name = [&](uint32_t r) { return std::to_string(merged[m0 + r].start) + "-" + std::to_string(merged[m0 + r].end); };
+                for (uint64_t i = 0; i < au.n_ties; ++i) {
+                    const uint32_t r = au.tie_region[i], g = au.tie_group[i];
+                    uint32_t first = UINT32_MAX, members = 0;  // the group's first haplotype names it
+                    for (uint32_t h = 0; h < H; ++h)
+                        if (au.hap_group[(size_t)r * H + h] == g) { if (first == UINT32_MAX) first = h; ++members; }
+                    const Pwm& pw = pwms[au.tie_pattern_index[i]];
+                    out += "tie\t" + chr + "\t" + region_name(r) + "\t" + pw.name + "\t" + (pw.direction == TFBS_DIR_P ? "P" : "N") + "\t" +
+                           std::to_string(au.tie_start[i]) + "\t" + std::to_string(pw.min_score) + "\t" +
+                           (g == 0 ? std::string("reference") : co.samples[first / 2] + (first % 2 ? ":R" : ":L")) + "\t" + std::to_string(members) + "\n";
+                }
+                for (uint32_t r = 0; r < au.n_regions; ++r)
+                    for (uint32_t h = 0; h < H; ++h) {
+                        const uint8_t fl = au.hap_flags[(size_t)r * H + h];
+                        if (fl & TFBS_HAP_TRUNCATED)
+                            out += "truncated\t" + chr + "\t" + region_name(r) + "\t" + co.samples[h / 2] + (h % 2 ? ":R" : ":L") + "\n";
+                        if (fl & TFBS_HAP_OVERWRITTEN)
+                            out += "overwritten\t" + chr + "\t" + region_name(r) + "\t" + co.samples[h / 2] + (h % 2 ? ":R" : ":L") + "\n";
+                    }
+            }
             tfbs_rows rows;
             TF(tfbs_collect(ctx, &rows));
             us_gpu += now_us() - tg;
@@ -1143,6 +1174,15 @@ int main(int argc, char** argv) {
     for (const ChunkOut& co2 : outs)
         for (const std::string& row : co2.rows) emit(chr + "\t" + std::to_string(fake_position++) + row);
     if (gz) { gz->finish(); delete gz; } else plain.close();
+    if (!o.audit_file.empty()) {
+        // tie: a window scoring exactly min_score (not a hit, pattern.rs:151); truncated: haplotype.rs:144-149; overwritten: the
+        // haplotype's entry of the sequence-keyed map was replaced (haplotype.rs:84), it is counted with the reference haplotype and
+        // the reference program's choice between the colliding entries depends on HashMap order
+        std::ofstream af(o.audit_file, std::ios::binary);
+        if (!af) die("Could not create audit file");
+        af << "#tie\tCHROM\tREGION\tPWM\tSTRAND\tSTART\tMIN_SCORE\tGROUP\tHAPLOTYPES\n#truncated|overwritten\tCHROM\tREGION\tHAPLOTYPE\n";
+        for (const ChunkOut& co2 : outs) af << co2.audit;
+    }
     if (rename(part.c_str(), o.output.c_str()) != 0) die("Could not rename " + part + " into " + o.output);
     if (o.tabix) {
         std::string cmd = "tabix -f -p vcf '" + o.output + "'";

@@ -627,12 +627,15 @@ __global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32
     }
 }
 
-__global__ void k_redirect(u32 H, u32 r0, u32 nr, DevSeqs sq, u32* hap_group, u32* ref_used) {
+// hap_flags (audit only, else NULL): the flags of the haplotype's own diff list, taken before the redirect (TFBS_HAP_* bits).
+__global__ void k_redirect(u32 H, u32 r0, u32 nr, DevSeqs sq, u32* hap_group, u32* ref_used, u8* hap_flags) {
     u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (u64)nr * H) return;
     u32 r = r0 + (u32)(idx / H), h = (u32)(idx % H);
     u32 g = hap_group[(size_t)r * H + h];
-    if (g && (sq.seq_flags[sq.gbase[r] - sq.gbase0 + g] & 2)) { g = 0; hap_group[(size_t)r * H + h] = 0; }
+    const u8 fl = g ? sq.seq_flags[sq.gbase[r] - sq.gbase0 + g] : (u8)0;
+    if (hap_flags) hap_flags[(size_t)r * H + h] = fl;
+    if (fl & 2) { g = 0; hap_group[(size_t)r * H + h] = 0; }
     if (g == 0) ref_used[r] = 1;
 }
 

@@ -7,6 +7,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -77,9 +78,12 @@ struct tfbs_ctx {
     int64_t refhit_cap_opt = 0; // testing: capacity of the reference-hit buffer (0 = automatic)
     int rows_width = 32;        // 32: counts are returned as u32; 0: narrowest of u8 / u16 / u32 that holds every count of the block
     uint32_t row_bytes = 4;     // element size of the rows held for tfbs_collect
+    int audit = 0;              // set by tfbs_audit_block: per-haplotype flags are kept
 
     // patterns
     bool have_patterns = false;
+    std::vector<tfbs_pattern> orig_patterns;          // the caller's list (tfbs_audit_block re-compiles it with lowered thresholds)
+    std::vector<std::vector<int32_t>> orig_weights;
     CompiledPatterns cp;
     DevBuf d_table, d_chunks, d_runs, d_trip_pat, d_pat_len, d_pat_pid, d_pid_list;
     DevPatterns dpat{};
@@ -111,11 +115,15 @@ struct tfbs_ctx {
     DevBuf d_status;
     DevBuf d_rows_region, d_rows_inner, d_rows_pid, d_rows_vmin, d_rows_vmax, d_rows_left, d_rows_right;
     DevBuf d_m_region, d_m_pattern, d_m_group, d_m_start;
+    DevBuf d_hap_flags;
 
     // results (host, pinned)
     HostBuf h_rows_region, h_rows_inner, h_rows_pid, h_rows_vmin, h_rows_vmax, h_rows_left, h_rows_right;
     HostBuf h_m_region, h_m_pattern, h_m_group, h_m_start, h_hap_group;
     HostBuf h_status, h_totals;
+    HostBuf h_hap_flags;
+    std::vector<uint32_t> tie_region, tie_pattern, tie_group;  // tfbs_audit_block
+    std::vector<int64_t> tie_start;
     uint64_t n_rows = 0, n_matches = 0;
     bool matches_truncated = false;
     bool ran = false;
@@ -327,6 +335,7 @@ int run_pipeline(tfbs_ctx* ctx) {
     CK(ctx->d_ngroups.reserve((size_t)R * 4));
     CK(ctx->d_sum_nd.reserve((size_t)R * 4));
     CK(ctx->d_ref_used.reserve((size_t)R * 4));
+    if (ctx->audit) CK(ctx->d_hap_flags.reserve(RH));
     const uint64_t max_pairs = 1ull << 25;
     uint32_t regions_per_super = (uint32_t)std::max<uint64_t>(1, max_pairs / std::max<uint32_t>(1, H));
     uint64_t seed = 0x243f6a8885a308d3ull;
@@ -536,7 +545,8 @@ int run_pipeline(tfbs_ctx* ctx) {
             CK(cudaMemsetAsync(ctx->d_ref_used.as<u32>() + r0, 0, (size_t)nr * 4, st));
             k_seq_insert<<<grid_for(n_seq, 256), 256, 0, st>>>(sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1);
             k_seq_resolve<<<grid_for(n_seq, 128), 128, 0, st>>>(db, sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1, dst);
-            k_redirect<<<grid_for((uint64_t)nr * H, 256), 256, 0, st>>>(H, r0, nr, sq, ctx->d_hap_group.as<u32>(), ctx->d_ref_used.as<u32>());
+            k_redirect<<<grid_for((uint64_t)nr * H, 256), 256, 0, st>>>(H, r0, nr, sq, ctx->d_hap_group.as<u32>(), ctx->d_ref_used.as<u32>(),
+                                                                        ctx->audit ? ctx->d_hap_flags.as<u8>() : nullptr);
             launches += 3;
         }
         CK(cudaEventRecord(ctx->ev[3], st));
@@ -753,6 +763,10 @@ int run_pipeline(tfbs_ctx* ctx) {
         CK(ctx->h_hap_group.reserve(RH * 4, false));
         CK(cudaMemcpyAsync(ctx->h_hap_group.p, ctx->d_hap_group.p, RH * 4, cudaMemcpyDeviceToHost, st));
     }
+    if (ctx->audit) {
+        CK(ctx->h_hap_flags.reserve(RH, false));
+        CK(cudaMemcpyAsync(ctx->h_hap_flags.p, ctx->d_hap_flags.p, RH, cudaMemcpyDeviceToHost, st));
+    }
     CK(cudaStreamSynchronize(st));
     DevStatus hs;
     memcpy(&hs, ctx->h_status.p, sizeof hs);
@@ -876,8 +890,8 @@ int tfbs_set_option(tfbs_ctx* ctx, const char* key, int64_t value) {
     return TFBS_OK;
 }
 
-int tfbs_set_patterns(tfbs_ctx* ctx, const tfbs_pattern* patterns, uint32_t n_patterns) {
-    if (!ctx || (!patterns && n_patterns)) return TFBS_ERR_INVALID_ARGUMENT;
+// Compile the pattern list into scan tables and upload them.
+static int install_patterns(tfbs_ctx* ctx, const tfbs_pattern* patterns, uint32_t n_patterns) {
     CK(cudaSetDevice(ctx->device));
     ctx->have_patterns = false;
     if (n_patterns == 0) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "assertion failed: pwm_list.len() > 0");  // main.rs:238
@@ -916,6 +930,23 @@ int tfbs_set_patterns(tfbs_ctx* ctx, const tfbs_pattern* patterns, uint32_t n_pa
     d.sum_len = c.sum_len;
     d.sum_len_sq = c.sum_len_sq;
     ctx->have_patterns = true;
+    return TFBS_OK;
+}
+
+int tfbs_set_patterns(tfbs_ctx* ctx, const tfbs_pattern* patterns, uint32_t n_patterns) {
+    if (!ctx || (!patterns && n_patterns)) return TFBS_ERR_INVALID_ARGUMENT;
+    int rc = install_patterns(ctx, patterns, n_patterns);
+    if (rc != TFBS_OK) return rc;
+    // keep the caller's list: tfbs_audit_block compiles it a second time with every threshold lowered by one
+    ctx->orig_patterns.assign(patterns, patterns + n_patterns);
+    ctx->orig_weights.assign(n_patterns, std::vector<int32_t>());
+    for (uint32_t i = 0; i < n_patterns; ++i)
+        if (patterns[i].kind == TFBS_PATTERN_PWM && patterns[i].weights && patterns[i].len) {
+            ctx->orig_weights[i].assign(patterns[i].weights, patterns[i].weights + 4 * (size_t)patterns[i].len);
+            ctx->orig_patterns[i].weights = ctx->orig_weights[i].data();
+        } else {
+            ctx->orig_patterns[i].weights = nullptr;
+        }
     return TFBS_OK;
 }
 
@@ -974,6 +1005,80 @@ int tfbs_get_matches(tfbs_ctx* ctx, tfbs_matches* out) {
     out->hap_group = ctx->h_hap_group.as<uint32_t>();
     out->n_samples = ctx->S;
     out->truncated = ctx->matches_truncated ? 1 : 0;
+    return TFBS_OK;
+}
+
+// Ties = windows reported with min_score - 1 but not with min_score, i.e. score == min_score (pattern.rs:151 is strict).
+int tfbs_audit_block(tfbs_ctx* ctx, tfbs_audit* out) {
+    if (!ctx || !out) return TFBS_ERR_INVALID_ARGUMENT;
+    memset(out, 0, sizeof *out);
+    if (!ctx->have_block) return fail(ctx, TFBS_ERR_STATE, "tfbs_audit_block needs a block (tfbs_submit_block / tfbs_upload_block first)");
+    if (ctx->orig_patterns.empty()) return fail(ctx, TFBS_ERR_STATE, "tfbs_set_patterns has not been called");
+    CK(cudaSetDevice(ctx->device));
+    struct Hit {
+        uint32_t region, pattern, group;
+        int64_t start;
+        bool operator<(const Hit& o) const {
+            if (region != o.region) return region < o.region;
+            if (pattern != o.pattern) return pattern < o.pattern;
+            if (group != o.group) return group < o.group;
+            return start < o.start;
+        }
+        bool operator==(const Hit& o) const { return region == o.region && pattern == o.pattern && group == o.group && start == o.start; }
+    };
+    auto take_hits = [&](std::vector<Hit>* v) {
+        v->resize(ctx->n_matches);
+        for (uint64_t i = 0; i < ctx->n_matches; ++i)
+            (*v)[i] = Hit{ctx->h_m_region.as<uint32_t>()[i], ctx->h_m_pattern.as<uint32_t>()[i], ctx->h_m_group.as<uint32_t>()[i],
+                          ctx->h_m_start.as<int64_t>()[i]};
+        std::sort(v->begin(), v->end());
+    };
+    const int keep_record = ctx->record_matches;
+    ctx->record_matches = 1;  // forces the full scan of every distinct haplotype
+    ctx->audit = 1;
+    std::vector<tfbs_pattern> lowered = ctx->orig_patterns;
+    for (tfbs_pattern& p : lowered)
+        if (p.min_score > INT32_MIN) p.min_score -= 1;  // score > INT32_MIN - 1 cannot be expressed; such a pattern has no tie list
+    std::vector<Hit> with_ties, hits;
+    bool overflow = false;
+    int rc = install_patterns(ctx, lowered.data(), (uint32_t)lowered.size());
+    if (rc == TFBS_OK) rc = run_pipeline(ctx);
+    if (rc == TFBS_OK) {
+        take_hits(&with_ties);
+        overflow = ctx->matches_truncated;
+    }
+    // always put the caller's thresholds back, and leave the context with a normal run of the block
+    int rc2 = install_patterns(ctx, ctx->orig_patterns.data(), (uint32_t)ctx->orig_patterns.size());
+    if (rc2 == TFBS_OK && rc == TFBS_OK) rc2 = run_pipeline(ctx);
+    ctx->record_matches = keep_record;
+    ctx->audit = 0;
+    if (rc != TFBS_OK) return rc;
+    if (rc2 != TFBS_OK) return rc2;
+    take_hits(&hits);
+    overflow = overflow || ctx->matches_truncated;
+    ctx->tie_region.clear();
+    ctx->tie_pattern.clear();
+    ctx->tie_group.clear();
+    ctx->tie_start.clear();
+    size_t j = 0;
+    for (const Hit& h : with_ties) {  // sorted set difference
+        while (j < hits.size() && hits[j] < h) ++j;
+        if (j < hits.size() && hits[j] == h) continue;
+        ctx->tie_region.push_back(h.region);
+        ctx->tie_pattern.push_back(h.pattern);
+        ctx->tie_group.push_back(h.group);
+        ctx->tie_start.push_back(h.start);
+    }
+    out->n_ties = ctx->tie_region.size();
+    out->tie_region = ctx->tie_region.data();
+    out->tie_pattern_index = ctx->tie_pattern.data();
+    out->tie_group = ctx->tie_group.data();
+    out->tie_start = ctx->tie_start.data();
+    out->hap_group = ctx->h_hap_group.as<uint32_t>();
+    out->hap_flags = ctx->h_hap_flags.as<uint8_t>();
+    out->n_regions = ctx->R;
+    out->n_samples = ctx->S;
+    out->truncated = overflow ? 1 : 0;
     return TFBS_OK;
 }
 

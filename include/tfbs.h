@@ -158,6 +158,32 @@ typedef struct tfbs_matches {
     uint32_t truncated;            /* 1 if the match buffer overflowed (n_matches is then a lower bound) */
 } tfbs_matches;
 
+/*
+ * Audit of one block (tfbs_audit_block): everything about it that the reference leaves undefined or that sits exactly on a
+ * threshold, so that a bit-exact comparison can enumerate those places instead of tripping over them.
+ *   ties       windows whose score EQUALS min_score.  They are not hits (pattern.rs:151 is a strict >), but they are the windows
+ *              a +-1 difference in a weight or threshold (f32 parsing, pattern.rs:13-16) would flip.  Same tuple as a match.
+ *   hap_flags  per (region, haplotype): TFBS_HAP_TRUNCATED = its diff list ran into the truncation exit of patch_haplotype
+ *              (overlapping variants, haplotype.rs:144-149); TFBS_HAP_OVERWRITTEN = its diff list patched to the same
+ *              (nuc, pos) vector as another one's, its entry of the sequence-keyed map was overwritten (haplotype.rs:84) and it is
+ *              counted with the reference haplotype (main.rs:103-105,129-131).  Which of the colliding lists survives depends on
+ *              HashMap order in the reference ("reference undefined"); here the one with the smallest first haplotype does.
+ */
+enum { TFBS_HAP_TRUNCATED = 1, TFBS_HAP_OVERWRITTEN = 2 };
+typedef struct tfbs_audit {
+    uint64_t n_ties;
+    const uint32_t* tie_region;        /* [n_ties] */
+    const uint32_t* tie_pattern_index; /* [n_ties] index into the array given to tfbs_set_patterns */
+    const uint32_t* tie_group;         /* [n_ties] group inside the region (hap_group numbering), 0 = reference */
+    const int64_t* tie_start;          /* [n_ties] pos of the window's first base */
+    const uint32_t* hap_group;         /* [n_regions * 2 * n_samples] */
+    const uint8_t* hap_flags;          /* [n_regions * 2 * n_samples] TFBS_HAP_* bits */
+    uint32_t n_regions;
+    uint32_t n_samples;
+    uint32_t truncated;                /* 1 if a match buffer overflowed (raise "max_matches"): the tie list is then incomplete */
+    uint32_t reserved;
+} tfbs_audit;
+
 /* Row filter: which keys tfbs_collect returns. */
 enum {
     TFBS_ROWS_VARYING = 0, /* only keys with min != max, i.e. those counts_as_genotypes keeps (main.rs:456-458) */
@@ -227,6 +253,12 @@ int tfbs_collect(tfbs_ctx* ctx, tfbs_rows* out);
 
 /* Matches of the last run when "record_matches" was on (call after tfbs_collect). */
 int tfbs_get_matches(tfbs_ctx* ctx, tfbs_matches* out);
+
+/* Audit of the block most recently given to tfbs_submit_block / tfbs_upload_block (it is still resident): scores it twice with
+ * every distinct haplotype scanned in full, once with the thresholds lowered by one, and returns the windows that only the lowered
+ * run reports (score == min_score) together with the per-haplotype flags.  Afterwards the context holds the results of a normal
+ * run of the block (tfbs_collect works); options are left as they were.  Pointers stay valid until the next run. */
+int tfbs_audit_block(tfbs_ctx* ctx, tfbs_audit* out);
 
 /* Device-resident path for benchmarking: upload once, run the device pipeline on the
  * resident block any number of times.  tfbs_run_resident returns after the device work of

@@ -157,6 +157,7 @@ LoadedHaplotypes load_haplotypes(const Range& peak, const std::vector<std::vecto
     for (const Raw& r : raw) {
         HaplotypeGroup g;
         g.sequence = patch_haplotype(peak, *r.diffs, ref_haplotype, &g.truncated);
+        if (g.truncated) res.truncated_ids.insert(res.truncated_ids.end(), r.ids->begin(), r.ids->end());
         auto it = by_sequence.find(g.sequence);
         if (it != by_sequence.end()) {
             // a later insert would overwrite the earlier one in the reference; here the group with
@@ -328,6 +329,8 @@ RegionMatches find_all_matches(const Range& peak, const std::vector<std::vector<
     LoadedHaplotypes xs = load_haplotypes(peak, diffs_by_haplotype, variant_count, ref_haplotype);  // :99
     rm.number_of_variants = xs.variant_count;
     rm.sequence_collision = xs.sequence_collision;
+    rm.overwritten_ids = xs.overwritten_ids;
+    rm.truncated_ids = xs.truncated_ids;
     std::vector<uint8_t> has_reference(2 * (size_t)sample_count, 1);  // all_haplotype_ids :74-81
     rm.group_ids.emplace_back();                                      // group 0 = reference haplotype
     rm.group_len.push_back((uint32_t)ref_haplotype.size());
@@ -603,6 +606,9 @@ void process_block_range(const std::vector<Pattern>& pwm_list, const tfbs_block&
             out->hap_group.resize(base + H, 0);
             for (uint32_t g = 0; g < rm.group_ids.size(); ++g)
                 for (uint32_t h : rm.group_ids[g]) out->hap_group[base + h] = g;
+            out->hap_flags.resize(base + H, 0);
+            for (uint32_t h : rm.truncated_ids) out->hap_flags[base + h] |= 1;
+            for (uint32_t h : rm.overwritten_ids) out->hap_flags[base + h] |= 2;
         }
         // nominal = every haplotype of every sample scanned on its own sequence
         for (uint32_t g = 0; g < rm.group_ids.size(); ++g)
@@ -645,6 +651,7 @@ void process_block(const std::vector<Pattern>& pwm_list, const tfbs_block& blk, 
         for (BlockRow& r : p.rows) out->rows.push_back(std::move(r));
         out->matches.insert(out->matches.end(), p.matches.begin(), p.matches.end());
         out->hap_group.insert(out->hap_group.end(), p.hap_group.begin(), p.hap_group.end());
+        out->hap_flags.insert(out->hap_flags.end(), p.hap_flags.begin(), p.hap_flags.end());
         out->executed_cells += p.executed_cells;
         out->nominal_cells += p.nominal_cells;
         out->n_groups += p.n_groups;

@@ -125,6 +125,7 @@ struct LoadedHaplotypes {
     uint32_t variant_count = 0;
     std::vector<HaplotypeGroup> groups;      // survivors of the sequence-keyed map, by ascending first id
     std::vector<uint32_t> overwritten_ids;   // haplotypes that fell back to the reference (App. A.6 Q4)
+    std::vector<uint32_t> truncated_ids;     // haplotypes whose diff list ran into the truncation exit (haplotype.rs:144-149)
     bool sequence_collision = false;         // two diff lists patched to the same non-reference sequence
 };
 
@@ -155,6 +156,7 @@ struct RegionMatches {
     uint64_t executed_cells = 0;
     bool sequence_collision = false;
     bool truncated = false;
+    std::vector<uint32_t> overwritten_ids, truncated_ids;  // audit lists, see LoadedHaplotypes
 };
 RegionMatches find_all_matches(const Range& peak, const std::vector<std::vector<Diff>>& diffs_by_haplotype,
                                uint32_t variant_count, const std::vector<NucleotidePos>& ref_haplotype,
@@ -232,6 +234,7 @@ struct BlockResult {
     std::vector<BlockRow> rows;
     std::vector<BlockMatch> matches;           // if requested
     std::vector<uint32_t> hap_group;           // [n_regions * 2S], if requested
+    std::vector<uint8_t> hap_flags;            // [n_regions * 2S], if requested: bit0 truncated, bit1 overwritten (-> reference)
     uint64_t executed_cells = 0, nominal_cells = 0, n_groups = 0, n_hits = 0;
     uint32_t collision_regions = 0, truncated_regions = 0;
 };

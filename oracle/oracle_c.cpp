@@ -63,6 +63,8 @@ typedef struct ora_block_result {
     uint32_t* hap_group;
     uint64_t executed_cells, nominal_cells, n_groups, n_hits;
     uint32_t collision_regions, truncated_regions;
+    uint64_t n_hap_flags;
+    uint8_t* hap_flags;
 } ora_block_result;
 
 int ora_process_block(const tfbs_pattern* patterns, uint32_t n_patterns, const tfbs_block* blk, int rows_mode, int want_matches,
@@ -114,6 +116,8 @@ int ora_process_block(const tfbs_pattern* patterns, uint32_t n_patterns, const t
         out->n_hits = r.n_hits;
         out->collision_regions = r.collision_regions;
         out->truncated_regions = r.truncated_regions;
+        out->n_hap_flags = r.hap_flags.size();
+        out->hap_flags = dup(r.hap_flags);
         return 0;
     } catch (const OracleError& e) {
         return fail(e);
@@ -122,7 +126,7 @@ int ora_process_block(const tfbs_pattern* patterns, uint32_t n_patterns, const t
 
 void ora_free_block_result(ora_block_result* r) {
     free(r->region); free(r->inner); free(r->pattern_id); free(r->vmin); free(r->vmax); free(r->left); free(r->right);
-    free(r->m_region); free(r->m_pattern_index); free(r->m_group); free(r->m_start); free(r->hap_group);
+    free(r->m_region); free(r->m_pattern_index); free(r->m_group); free(r->m_start); free(r->hap_group); free(r->hap_flags);
     memset(r, 0, sizeof *r);
 }
 

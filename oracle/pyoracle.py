@@ -77,7 +77,8 @@ class _BlockResult(C.Structure):
                 ("m_group", C.POINTER(C.c_uint32)), ("m_start", C.POINTER(C.c_int64)),
                 ("n_hap_group", C.c_uint64), ("hap_group", C.POINTER(C.c_uint32)),
                 ("executed_cells", C.c_uint64), ("nominal_cells", C.c_uint64), ("n_groups", C.c_uint64), ("n_hits", C.c_uint64),
-                ("collision_regions", C.c_uint32), ("truncated_regions", C.c_uint32)]
+                ("collision_regions", C.c_uint32), ("truncated_regions", C.c_uint32),
+                ("n_hap_flags", C.c_uint64), ("hap_flags", C.POINTER(C.c_uint8))]
 
 
 def _arr(ptr, n, dtype):
@@ -105,6 +106,7 @@ def process_block(c_patterns, n_patterns, c_block, n_samples, rows_mode=0, want_
         "m_group": _arr(res.m_group, res.n_matches, np.uint32),
         "m_start": _arr(res.m_start, res.n_matches, np.int64),
         "hap_group": _arr(res.hap_group, res.n_hap_group, np.uint32),
+        "hap_flags": _arr(res.hap_flags, res.n_hap_flags, np.uint8),
         "executed_cells": int(res.executed_cells), "nominal_cells": int(res.nominal_cells),
         "n_groups": int(res.n_groups), "n_hits": int(res.n_hits),
         "collision_regions": int(res.collision_regions), "truncated_regions": int(res.truncated_regions),

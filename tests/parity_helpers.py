@@ -148,3 +148,39 @@ def hand_block(n_samples, regions, variants, carriers_by_variant, inner=None):
         inner_off[r + 1] = k
     return Block(n_samples, rs, re, ref_off, np.frombuffer(ref, dtype=np.uint8) if ref else np.zeros(0, np.uint8), inner_off, inn, var_off, var,
                  np.frombuffer(bytes(allele), dtype=np.uint8) if allele else np.zeros(0, np.uint8), car)
+
+
+def lowered(pattern_set):
+    """The same patterns with every threshold lowered by one: hits of that list = hits + windows scoring exactly min_score."""
+    return binding.PatternSet([dict(p, min_score=int(p.get("min_score", 0)) - 1) for p in pattern_set.items])
+
+
+def oracle_audit(pattern_set, block):
+    """Ties (score == min_score) as the difference of two oracle hit lists, keyed by (region, pattern, group leader, start);
+    per-haplotype flags from the oracle's load_haplotypes."""
+    a = run_oracle(lowered(pattern_set), block, 1, True)
+    b = run_oracle(pattern_set, block, 1, True)
+    assert np.array_equal(a["hap_group"], b["hap_group"])
+    H = 2 * block.n_samples
+    _, table = group_leaders(b["hap_group"], block.n_regions) if H else (None, {})
+
+    def keyed(o):
+        return set((int(r), int(p), table.get((int(r), int(g)), -1), int(s)) for r, p, g, s in zip(o["m_region"], o["m_pattern_index"], o["m_group"], o["m_start"]))
+
+    return {"ties": keyed(a) - keyed(b), "hap_flags": b["hap_flags"], "n_hits": b["n_hits"]}
+
+
+def gpu_audit(pattern_set, block):
+    ctx = binding.Context(0)
+    try:
+        ctx.set_patterns(pattern_set)
+        ctx.upload_block(block)
+        au = ctx.audit()
+        rows = ctx.collect()  # the audit leaves a normal run of the block behind
+        st = ctx.stats()
+    finally:
+        ctx.close()
+    H = 2 * block.n_samples
+    _, table = group_leaders(au["hap_group"], block.n_regions) if H else (None, {})
+    au["ties"] = set((int(r), int(p), table.get((int(r), int(g)), -1), int(s)) for r, p, g, s in zip(au["region"], au["pattern_index"], au["group"], au["start"]))
+    return au, rows, st

@@ -92,6 +92,30 @@ def test_driver_matches_oracle_on_synthetic_files(tmp_path):
 
 
 @pytest.mark.gpu
+def test_driver_audit_file(golden_dir, tmp_path):
+    """--audit: the VCF is unchanged, the fixture (ACGT scores 4000 > 3999, next best 3000) has no tie, no truncated haplotype;
+    a synthetic file set with overlapping records lists its truncated haplotypes."""
+    out, aud = str(tmp_path / "o.vcf.gz"), str(tmp_path / "audit.tsv")
+    a = golden_args(golden_dir, "genotypes2.bcf")
+    a["extra"] += ["--audit", aud]
+    p = run_driver(a, out)
+    assert p.returncode == 0, p.stderr
+    assert ora.gunzip_file(out) == ora.gunzip_file(os.path.join(golden_dir, "expected_output_2.vcf.gz"))
+    assert [ln for ln in open(aud).read().splitlines() if not ln.startswith("#")] == []
+    pats = synth.make_pwms(3, seed=19, lmin=6, lmax=12)
+    blk = synth.make_cohort(8, 20, seed=19, lmax_pattern=12, region_len=(80, 300), variant_rate=1 / 8.0, frac_del=0.3, same_pos_frac=0.1)
+    f = fw.cohort_to_files(blk, pats, str(tmp_path))
+    expected = ora.run(f["chromosome"], f["bcf"], f["beds"], f["reference"], None, f["pwm_file"], f["threshold_dir"], 1e-4, f["names"])
+    f["extra"] = ["--audit", aud, "--chunk", "6"]
+    p = run_driver(f, out)
+    assert p.returncode == 0, p.stderr
+    assert ora.gunzip_file(out) == expected
+    lines = [ln.split("\t") for ln in open(aud).read().splitlines() if not ln.startswith("#")]
+    assert any(ln[0] == "truncated" for ln in lines)
+    assert all(ln[0] in ("tie", "truncated", "overwritten") for ln in lines)
+
+
+@pytest.mark.gpu
 def test_driver_reports_reference_panics(golden_dir, tmp_path):
     bad = golden_args(golden_dir, "genotypes2.bcf")
     bad["names"] = ["NOPE"]

@@ -190,6 +190,37 @@ def test_threshold_boundary_ties():
     assert counts[0] >= counts[1] >= counts[2] >= counts[3] and counts[0] > counts[3]
 
 
+def test_audit_enumerates_ties_and_flags():
+    """tfbs_audit_block: the windows scoring exactly min_score (strict >, pattern.rs:151) and the truncated / overwritten haplotypes
+    (haplotype.rs:144-149, :84) are the same sets the oracle finds; the context is left with a normal run of the block."""
+    rng = np.random.default_rng(3)
+    w = rng.integers(-3, 4, size=(8, 4)).astype(np.int32) * 100   # coarse weights: many attainable ties
+    best = int(w.max(axis=1).sum())
+    pats = [{"weights": w, "min_score": best - 400, "pattern_id": 1, "direction": 0},
+            {"weights": w[::-1, ::-1].copy(), "min_score": best - 400, "pattern_id": 1, "direction": 1}]
+    pats += synth.make_pwms(2, seed=77, lmin=6, lmax=14)
+    for p in pats[2:]:
+        p["pattern_id"] += 2
+    ps = PatternSet(pats)
+    blk = synth.make_cohort(12, 24, seed=13, lmax_pattern=14, region_len=(100, 500), variant_rate=1 / 10.0, frac_ins=0.15, frac_del=0.2,
+                            same_pos_frac=0.1, n_runs=3, two_beds=True)
+    oa = hp.oracle_audit(ps, blk)
+    au, rows, st = hp.gpu_audit(ps, blk)
+    assert not au["truncated"]
+    assert len(oa["ties"]) > 0 and au["ties"] == oa["ties"]
+    assert np.array_equal(au["hap_flags"], oa["hap_flags"])
+    assert (au["hap_flags"] & binding.HAP_TRUNCATED).any()
+    hp.assert_rows_equal(rows, hp.run_oracle(ps, blk))
+    assert st["n_hits"] == oa["n_hits"]
+    # a fixture without any tie: ACGT scores 4000 against min_score 3999, the next best window scores 3000
+    au2, _, _ = hp.gpu_audit(acgt_patterns(), fixture_block([0]))
+    assert len(au2["ties"]) == 0 and not au2["hap_flags"].any()
+    # min_score 4000 makes the perfect ACGT windows ties instead of hits: 7 reference-carrying haplotypes share group 0, one window per strand
+    tie_ps = PatternSet([dict(ACGT, min_score=4000, direction=0), dict(ACGT, min_score=4000, direction=1)])
+    au3, rows3, _ = hp.gpu_audit(tie_ps, fixture_block([0]))
+    assert au3["ties"] == {(0, 0, -1, 100), (0, 1, -1, 100)} and len(rows3["region"]) == 0
+
+
 def test_wide_fields_and_forced_format():
     """Weights too large for the 21-bit packed fields use the two-32-bit-field tables; results must not change."""
     pats = synth.make_pwms(4, seed=21, lmin=10, lmax=20)
