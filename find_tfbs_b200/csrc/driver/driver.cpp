@@ -14,6 +14,10 @@
 //
 // Third-party formats the reference reads through crates (rust-htslib 0.26.1, bio 0.28.2, bgzip 0.0.3) are decoded here
 // directly: BGZF (gzip members), BCF2.2, .fai-indexed FASTA, BED.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
@@ -67,6 +71,7 @@ struct Options {
     uint32_t min_maf = 0, threads = 1, chunk = 2000;
     uint64_t after_position = 0;
     std::vector<int> devices{0};
+    bool use_index = true;   // --no_index: ignore <bcf>.csi and scan the whole BCF
 };
 
 std::vector<std::string> split(const std::string& s, char sep) {
@@ -86,13 +91,13 @@ void usage() {
          "USAGE: find-tfbs-b200 --chromosome CHROM --input IN.bcf --output OUT.vcf.gz --reference REF.fa --bed A.bed[,B.bed]\n"
          "         --pwm_names NAME[,NAME] --pwm_file PWM.txt --pwm_threshold_directory DIR --pwm_threshold P\n"
          "         [--forward_only] [--threads N] [--min_maf N] [--after_position POS] [--samples FILE] [--tabix] [--verbose]\n"
-         "         [--devices 0,1,...] [--chunk REGIONS_PER_BLOCK] [--plain] [--audit AUDIT.tsv]");
+         "         [--devices 0,1,...] [--chunk REGIONS_PER_BLOCK] [--plain] [--audit AUDIT.tsv] [--no_index]");
 }
 
 Options parse_args(int argc, char** argv) {
     Options o;
     std::map<std::string, std::string> kv;
-    std::set<std::string> flags{"forward_only", "tabix", "verbose", "plain", "help"};
+    std::set<std::string> flags{"forward_only", "tabix", "verbose", "plain", "help", "no_index"};
     std::map<std::string, std::string> shorts{{"-c", "chromosome"}, {"-i", "input"}, {"-o", "output"}, {"-r", "reference"}, {"-b", "bed"},
                                               {"-p", "pwm_file"}, {"-f", "forward_only"}, {"-m", "min_maf"}, {"-s", "samples"},
                                               {"-z", "tabix"}, {"-v", "verbose"}};
@@ -135,6 +140,7 @@ Options parse_args(int argc, char** argv) {
     o.tabix = kv.count("tabix");
     o.verbose = kv.count("verbose");
     o.plain_text = kv.count("plain");
+    o.use_index = !kv.count("no_index");
     auto num = [&](const char* k, uint64_t dflt, const char* what) -> uint64_t {
         if (!kv.count(k)) return dflt;
         char* e = nullptr;
@@ -287,21 +293,46 @@ std::string basename_of(const std::string& s) {
 // ---------------------------------------------------------------------------------------------------------------
 // gzip / BGZF
 // ---------------------------------------------------------------------------------------------------------------
-std::vector<uint8_t> read_file(const std::string& path, const char* what) {
-    std::ifstream f(path, std::ios::binary);
-    if (!f) die(std::string(what) + " " + path);
-    return std::vector<uint8_t>((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
-}
+// A file mapped read-only: pages are read when they are touched, so a reader that follows the index only pays for the blocks it uses.
+class MappedFile {
+public:
+    MappedFile(const std::string& path, const char* what) {
+        fd_ = open(path.c_str(), O_RDONLY);
+        if (fd_ < 0) die(std::string(what) + " " + path);
+        struct stat st;
+        if (fstat(fd_, &st) != 0) die(std::string(what) + " " + path);
+        size_ = (size_t)st.st_size;
+        if (size_) {
+            void* m = mmap(nullptr, size_, PROT_READ, MAP_PRIVATE, fd_, 0);
+            if (m == MAP_FAILED) die(std::string(what) + " " + path + " (mmap failed)");
+            data_ = (const uint8_t*)m;
+        }
+    }
+    ~MappedFile() {
+        if (data_) munmap((void*)data_, size_);
+        if (fd_ >= 0) close(fd_);
+    }
+    MappedFile(const MappedFile&) = delete;
+    MappedFile& operator=(const MappedFile&) = delete;
+    const uint8_t* data() const { return data_; }
+    size_t size() const { return size_; }
 
-std::vector<uint8_t> gunzip_members(const std::vector<uint8_t>& in, const std::string& what) {
+private:
+    int fd_ = -1;
+    const uint8_t* data_ = nullptr;
+    size_t size_ = 0;
+};
+
+// Inflates gzip members one after the other; stops early once `limit` bytes are there (the BCF header is read this way).
+std::vector<uint8_t> gunzip_members(const uint8_t* in, size_t n_in, const std::string& what, size_t limit = SIZE_MAX) {
     std::vector<uint8_t> out;
     size_t off = 0;
-    while (off < in.size()) {
+    while (off < n_in && out.size() < limit) {
         z_stream zs;
         memset(&zs, 0, sizeof zs);
         if (inflateInit2(&zs, 15 + 16) != Z_OK) die("zlib initialisation failed");
-        zs.next_in = const_cast<Bytef*>(in.data() + off);
-        zs.avail_in = (uInt)std::min<size_t>(in.size() - off, 1u << 30);
+        zs.next_in = const_cast<Bytef*>(in + off);
+        zs.avail_in = (uInt)std::min<size_t>(n_in - off, 1u << 30);
         int rc;
         do {
             size_t old = out.size();
@@ -321,24 +352,31 @@ std::vector<uint8_t> gunzip_members(const std::vector<uint8_t>& in, const std::s
 // BGZF: every gzip member carries its own size (BSIZE in the 'BC' extra subfield) and its uncompressed size (ISIZE), so the
 // members can be located without inflating and inflated independently on several threads.  Falls back to the serial reader for a
 // plain gzip stream.
-std::vector<uint8_t> gunzip_bgzf(const std::vector<uint8_t>& in, const std::string& what, unsigned threads) {
+// Size of the BGZF member at in[off..): 0 if it is not one (plain gzip, truncated).
+size_t bgzf_member_size(const uint8_t* in, size_t n_in, size_t off) {
+    if (n_in - off < 28 || in[off] != 0x1f || in[off + 1] != 0x8b || !(in[off + 3] & 4)) return 0;
+    const size_t xlen = in[off + 10] | (in[off + 11] << 8);
+    size_t p = off + 12, bsize = 0;
+    const size_t xend = p + xlen;
+    if (xend > n_in) return 0;
+    while (p + 4 <= xend) {
+        const size_t slen = in[p + 2] | (in[p + 3] << 8);
+        if (in[p] == 'B' && in[p + 1] == 'C' && slen == 2 && p + 6 <= xend) bsize = (size_t)(in[p + 4] | (in[p + 5] << 8)) + 1;
+        p += 4 + slen;
+    }
+    if (bsize < 26 || off + bsize > n_in) return 0;
+    return bsize;
+}
+
+std::vector<uint8_t> gunzip_bgzf(const uint8_t* in, size_t n_in, const std::string& what, unsigned threads) {
     struct Member { size_t off, csize, uoff; uint32_t isize; };
     std::vector<Member> ms;
     size_t off = 0, total = 0;
-    while (off < in.size()) {
-        if (in.size() - off < 28 || in[off] != 0x1f || in[off + 1] != 0x8b || !(in[off + 3] & 4)) return gunzip_members(in, what);
-        const size_t xlen = in[off + 10] | (in[off + 11] << 8);
-        size_t p = off + 12, bsize = 0;
-        const size_t xend = p + xlen;
-        if (xend > in.size()) return gunzip_members(in, what);
-        while (p + 4 <= xend) {
-            const size_t slen = in[p + 2] | (in[p + 3] << 8);
-            if (in[p] == 'B' && in[p + 1] == 'C' && slen == 2 && p + 6 <= xend) bsize = (size_t)(in[p + 4] | (in[p + 5] << 8)) + 1;
-            p += 4 + slen;
-        }
-        if (bsize < 26 || off + bsize > in.size()) return gunzip_members(in, what);
+    while (off < n_in) {
+        const size_t bsize = bgzf_member_size(in, n_in, off);
+        if (!bsize) return gunzip_members(in, n_in, what);
         uint32_t isize;
-        memcpy(&isize, in.data() + off + bsize - 4, 4);
+        memcpy(&isize, in + off + bsize - 4, 4);
         ms.push_back(Member{off, bsize, total, isize});
         total += isize;
         off += bsize;
@@ -355,7 +393,7 @@ std::vector<uint8_t> gunzip_bgzf(const std::vector<uint8_t>& in, const std::stri
             z_stream zs;
             memset(&zs, 0, sizeof zs);
             if (inflateInit2(&zs, 15 + 16) != Z_OK) { bad = true; return; }
-            zs.next_in = const_cast<Bytef*>(in.data() + m.off);
+            zs.next_in = const_cast<Bytef*>(in + m.off);
             zs.avail_in = (uInt)m.csize;
             zs.next_out = out.data() + m.uoff;
             zs.avail_out = m.isize;
@@ -547,13 +585,70 @@ void check_letters(const std::string& s) {  // util.rs:4-16
             die("Unknown nucleotide " + std::to_string((int)l));
 }
 
+// Where the records of contig `rid` live in the BGZF file, from the CSI index next to the BCF (<bcf>.csi).  The reference reads
+// through htslib's IndexedReader, which seeks with the same index (haplotype.rs:78-79); here the whole contig is taken at once.
+// Virtual offsets are (compressed offset of the member << 16) | offset inside the inflated member.
+struct CsiSpan {
+    bool found = false;   // an index was read and holds this contig
+    bool empty = false;   // ... and the contig has no record
+    uint64_t vbeg = 0, vend = 0;
+};
+CsiSpan csi_contig_span(const std::string& bcf_path, int rid) {
+    CsiSpan sp;
+    std::ifstream probe(bcf_path + ".csi", std::ios::binary);
+    if (!probe) return sp;
+    probe.close();
+    MappedFile f(bcf_path + ".csi", "Error while opening the index");
+    std::vector<uint8_t> d = gunzip_bgzf(f.data(), f.size(), bcf_path + ".csi", 1);
+    Cursor c{d.data(), d.data() + d.size()};
+    auto u64 = [&] { c.need(8); uint64_t v; memcpy(&v, c.p, 8); c.p += 8; return v; };
+    if (d.size() < 16 || memcmp(c.p, "CSI\1", 4) != 0) return sp;
+    c.p += 4;
+    c.i32();  // min_shift
+    const int32_t depth = c.i32();
+    const int32_t l_aux = c.i32();
+    if (l_aux < 0 || depth < 0 || depth > 10) return sp;
+    c.need((size_t)l_aux);
+    c.p += l_aux;
+    const int32_t n_ref = c.i32();
+    if (rid < 0 || rid >= n_ref) return sp;
+    const uint32_t pseudo_bin = (uint32_t)((((uint64_t)1 << (3 * depth + 3)) - 1) / 7 + 1);  // holds statistics, not records
+    for (int32_t r = 0; r <= rid; ++r) {
+        const int32_t n_bin = c.i32();
+        for (int32_t b = 0; b < n_bin; ++b) {
+            const uint32_t bin = c.u32();
+            u64();  // loffset
+            const int32_t n_chunk = c.i32();
+            for (int32_t k = 0; k < n_chunk; ++k) {
+                const uint64_t beg = u64(), end = u64();
+                if (r != rid || bin == pseudo_bin) continue;
+                if (!sp.found || beg < sp.vbeg) sp.vbeg = beg;
+                if (!sp.found || end > sp.vend) sp.vend = end;
+                sp.found = true;
+            }
+        }
+    }
+    if (!sp.found) { sp.found = true; sp.empty = true; }
+    return sp;
+}
+
 Cohort load_bcf(const Options& o) {
-    std::vector<uint8_t> raw = gunzip_bgzf(read_file(o.bcf, "Error while opening the bcf file"), o.bcf, std::max(1u, o.threads));
-    Cursor c{raw.data(), raw.data() + raw.size()};
+    MappedFile file(o.bcf, "Error while opening the bcf file");
     Cohort co;
     std::vector<std::string> contigs;
     int gt_key;
-    parse_bcf_header(c, &contigs, &co.bcf_samples, &gt_key);
+    size_t header_bytes = 0;
+    {   // the header sits in the first members: inflate only as many as it needs
+        std::vector<uint8_t> head = gunzip_members(file.data(), file.size(), o.bcf, 9);
+        if (head.size() >= 9 && memcmp(head.data(), "BCF\2", 4) == 0) {
+            uint32_t l_text;
+            memcpy(&l_text, head.data() + 5, 4);
+            header_bytes = 9 + (size_t)l_text;
+            if (head.size() < header_bytes) head = gunzip_members(file.data(), file.size(), o.bcf, header_bytes);
+        }
+        Cursor hc{head.data(), head.data() + head.size()};
+        parse_bcf_header(hc, &contigs, &co.bcf_samples, &gt_key);
+    }
     // main.rs:293-313: the selection is always in BCF column order
     if (!o.has_samples) {
         co.samples = co.bcf_samples;
@@ -577,6 +672,23 @@ Cohort load_bcf(const Options& o) {
     if (rid < 0) die("called `Result::unwrap()` on an `Err` value: UnknownSequence (" + o.chromosome + ")");  // haplotype.rs:78
     const uint32_t S = (uint32_t)co.samples.size();
     co.pitch = std::max<uint32_t>(1, (2 * S + 31) / 32);
+    // With a CSI index only the BGZF members that hold the wanted contig are read and inflated; without one the whole file is.
+    std::vector<uint8_t> raw;
+    size_t first_record = header_bytes;
+    const CsiSpan span = o.use_index ? csi_contig_span(o.bcf, rid) : CsiSpan();
+    const bool indexed = span.found && (span.empty || ((span.vbeg >> 16) < file.size() && bgzf_member_size(file.data(), file.size(), span.vbeg >> 16)));
+    if (indexed && !span.empty) {
+        const size_t cbeg = (size_t)(span.vbeg >> 16);
+        size_t cend = std::min<size_t>(file.size(), (size_t)(span.vend >> 16));
+        if ((span.vend & 0xffff) && cend < file.size()) cend += bgzf_member_size(file.data(), file.size(), cend);  // the last member is used in part
+        if (cend <= cbeg) cend = file.size();
+        raw = gunzip_bgzf(file.data() + cbeg, cend - cbeg, o.bcf, std::max(1u, o.threads));
+        first_record = (size_t)(span.vbeg & 0xffff);
+    } else if (!indexed) {
+        raw = gunzip_bgzf(file.data(), file.size(), o.bcf, std::max(1u, o.threads));
+    }
+    if (first_record > raw.size()) die("truncated BCF");
+    Cursor c{raw.data() + first_record, raw.data() + raw.size()};
     // pass 1 (serial, a few bytes per record): positions, alleles, carrier rows; the genotype blocks are only located
     struct Pending { uint32_t row; const uint8_t* indiv; uint32_t l_indiv, n_fmt, n_sample; };
     std::vector<Pending> pending;
@@ -594,7 +706,10 @@ Cohort load_bcf(const Options& o) {
         uint32_t nai = s.u32(), nfs = s.u32();
         r.n_allele = nai >> 16;
         uint32_t n_fmt = nfs >> 24, n_sample = nfs & 0xffffff;
-        if (chrom != rid) continue;
+        if (chrom != rid) {
+            if (indexed) break;  // the index pointed at the contig's first record: its records end here (the file is sorted)
+            continue;
+        }
         s.tstr();
         if (r.n_allele < 2) die("index out of bounds: the len is " + std::to_string(r.n_allele) + " but the index is 1");  // haplotype.rs:22
         r.ref = s.tstr();
@@ -883,9 +998,10 @@ int drv_finalise_row(const uint32_t* l, const uint32_t* r, uint32_t S, uint32_t 
 
 // load_bcf: positions, allele counts and the carrier bit rows of the biallelic records of one chromosome
 int drv_load_bcf(const char* bcf, const char* samples_file, const char* chrom, uint32_t cap, int64_t* pos, uint32_t* n_allele, uint32_t* carrier_row,
-                 uint32_t* carriers, uint32_t carriers_cap, uint32_t* n_records, uint32_t* n_samples, uint32_t* pitch) {
+                 uint32_t* carriers, uint32_t carriers_cap, uint32_t* n_records, uint32_t* n_samples, uint32_t* pitch, int use_index) {
     try {
         Options o;
+        o.use_index = use_index != 0;
         o.bcf = bcf;
         o.chromosome = chrom;
         if (samples_file && *samples_file) { o.has_samples = true; o.samples_file = samples_file; }

@@ -62,31 +62,63 @@ def bgzf_block(data):
             struct.pack("<II", zlib.crc32(data) & 0xFFFFFFFF, len(data)))
 
 
-def write_bcf(path, chrom, contig_len, samples, records, member_bytes=40000, bgzf=False):
-    """records: list of (pos, [alleles...], gt) with gt an (n_samples, 2) int array of raw BCF codes, sorted by pos."""
+def write_bcf(path, chrom, contig_len, samples, records, member_bytes=40000, bgzf=False, flank_records=0, write_csi=False):
+    """records: list of (pos, [alleles...], gt) with gt an (n_samples, 2) int array of raw BCF codes, sorted by pos.
+    flank_records: that many records of contig chrOther before and of contig chrZ after the wanted contig (a multi-contig file);
+    write_csi: also write <path>.csi (one bin per contig holding one chunk = the contig's records), needs bgzf."""
     text = ("##fileformat=VCFv4.2\n##FILTER=<ID=PASS,Description=\"All filters passed\">\n##contig=<ID=chrOther,length=1000>\n"
-            "##contig=<ID=%s,length=%d>\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
+            "##contig=<ID=%s,length=%d>\n##contig=<ID=chrZ,length=1000>\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"Genotype\">\n"
             "#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t%s\n" % (chrom, contig_len, "\t".join(samples))).encode() + b"\0"
     out = bytearray(b"BCF\2\2" + struct.pack("<I", len(text)) + text)
     n = len(samples)
-    for pos, alleles, gt in records:
-        rlen = len(alleles[0])
-        shared = struct.pack("<iiiIII", 1, pos, rlen, 0x7F800001, (len(alleles) << 16), (1 << 24) | n)
-        shared += bytes([0x07])
-        for a in alleles:
-            shared += _typed_str(a)
-        shared += bytes([0x00])
-        indiv = bytes([0x11, 1, 0x21]) + np.asarray(gt, dtype=np.int8).tobytes()
-        out += struct.pack("<II", len(shared), len(indiv)) + shared + indiv
+    flank_gt = np.tile(np.array([[4, 5]], dtype=np.int8), (n, 1))  # everybody 1|1: would change every count if it leaked in
+    flank = [(10 + 7 * k, ["A", "C"], flank_gt) for k in range(flank_records)]
+    spans = {}  # rid -> (first byte, end byte) of its records in the uncompressed stream
+    for rid, recs in ((0, flank), (1, records), (2, flank)):
+        begin = len(out)
+        for pos, alleles, gt in recs:
+            rlen = len(alleles[0])
+            shared = struct.pack("<iiiIII", rid, pos, rlen, 0x7F800001, (len(alleles) << 16), (1 << 24) | n)
+            shared += bytes([0x07])
+            for a in alleles:
+                shared += _typed_str(a)
+            shared += bytes([0x00])
+            indiv = bytes([0x11, 1, 0x21]) + np.asarray(gt, dtype=np.int8).tobytes()
+            out += struct.pack("<II", len(shared), len(indiv)) + shared + indiv
+        if recs:
+            spans[rid] = (begin, len(out))
+    member_off = []  # compressed offset of every member
     with open(path, "wb") as f:
         for i in range(0, len(out), member_bytes):  # several gzip members, like BGZF blocks
             chunk = bytes(out[i:i + member_bytes])
+            member_off.append(f.tell())
             f.write(bgzf_block(chunk) if bgzf else gzip.compress(chunk, 6))
+        member_off.append(f.tell())
         if bgzf:
             f.write(bgzf_block(b""))  # the EOF marker block
+    if write_csi:
+        assert bgzf
+
+        def voff(byte):  # virtual offset of an uncompressed byte position
+            k = byte // member_bytes
+            return (member_off[k] << 16) | (byte - k * member_bytes)
+
+        idx = bytearray(b"CSI\1" + struct.pack("<iii", 14, 5, 0) + struct.pack("<i", 3))
+        pseudo = ((1 << 18) - 1) // 7 + 1
+        for rid in range(3):
+            if rid not in spans:
+                idx += struct.pack("<i", 0)
+                continue
+            b, e = voff(spans[rid][0]), voff(spans[rid][1])
+            idx += struct.pack("<i", 2)
+            idx += struct.pack("<IQi", 0, b, 1) + struct.pack("<QQ", b, e)
+            idx += struct.pack("<IQi", pseudo, 0, 2) + struct.pack("<QQ", b, e) + struct.pack("<QQ", len(records), 0)  # statistics, not a chunk
+        idx += struct.pack("<Q", 0)
+        with open(path + ".csi", "wb") as f:
+            f.write(bgzf_block(bytes(idx)) + bgzf_block(b""))
 
 
-def cohort_to_files(blk, pats, dirname, chrom="chrS", multiallelic_every=0, bgzf=False, member_bytes=40000):
+def cohort_to_files(blk, pats, dirname, chrom="chrS", multiallelic_every=0, bgzf=False, member_bytes=40000, flank_records=0, write_csi=False):
     """Writes the file set of a synth.make_cohort block; returns the arguments of the reference's CLI."""
     m = blk.meta
     os.makedirs(dirname, exist_ok=True)
@@ -114,7 +146,8 @@ def cohort_to_files(blk, pats, dirname, chrom="chrS", multiallelic_every=0, bgzf
         if multiallelic_every and v % multiallelic_every == 0:  # skipped by the reference (haplotype.rs:27,53-55)
             g2 = np.tile(np.array([[2, 7]], dtype=np.int8), (S, 1))
             recs.append((int(m["var_pos"][v]), [ref, "A", "C"], g2))
-    write_bcf(os.path.join(dirname, "cohort.bcf"), chrom, m["genome_len"], samples, recs, member_bytes=member_bytes, bgzf=bgzf)
+    write_bcf(os.path.join(dirname, "cohort.bcf"), chrom, m["genome_len"], samples, recs, member_bytes=member_bytes, bgzf=bgzf,
+              flank_records=flank_records, write_csi=write_csi)
     names = [p["name"] for p in pats if p["direction"] == 0]
     return {"chromosome": chrom, "bcf": os.path.join(dirname, "cohort.bcf"), "beds": beds, "reference": fa, "pwm_file": pwm,
             "threshold_dir": os.path.join(dirname, "thr"), "names": names, "samples": samples}

@@ -34,7 +34,7 @@ def test_file_writers_roundtrip_through_oracle_reader(tmp_path):
     blk = synth.make_cohort(5, 8, seed=3, lmax_pattern=10, region_len=(50, 120), variant_rate=0.05, two_beds=True)
     a = fw.cohort_to_files(blk, pats, str(tmp_path), multiallelic_every=7)
     b = ora.read_bcf(a["bcf"])
-    assert b["samples"] == a["samples"] and b["contigs"] == ["chrOther", "chrS"]
+    assert b["samples"] == a["samples"] and b["contigs"] == ["chrOther", "chrS", "chrZ"]
     biallelic = [i for i, al in enumerate(b["alleles"]) if len(al) == 2]
     assert [b["pos"][i] for i in biallelic] == blk.meta["var_pos"].tolist()
     bits = np.unpackbits(blk.carriers.view(np.uint8), axis=1, bitorder="little")[:, :10]
@@ -76,6 +76,15 @@ def test_driver_matches_oracle_on_synthetic_files(tmp_path):
         assert p.returncode == 0, p.stderr
         got = open(out).read() if "--plain" in extra else ora.gunzip_file(out)
         assert got == expected
+    # the same cohort inside a multi-contig BGZF file with a CSI index (read through the index) and with --no_index (whole-file scan)
+    ix = fw.cohort_to_files(blk, pats, str(tmp_path / "indexed"), multiallelic_every=11, bgzf=True, member_bytes=3000, flank_records=25, write_csi=True)
+    assert ora.run(ix["chromosome"], ix["bcf"], ix["beds"], ix["reference"], None, ix["pwm_file"], ix["threshold_dir"], 1e-4, ix["names"]) == expected
+    for extra in ([], ["--no_index"]):
+        out = str(tmp_path / "out_ix.vcf.gz")
+        ix["extra"] = extra
+        p = run_driver(ix, out)
+        assert p.returncode == 0, p.stderr
+        assert ora.gunzip_file(out) == expected
     # options: --min_maf, --forward_only, --after_position, --samples subset
     sub = str(tmp_path / "subset.txt")
     open(sub, "w").write("\n".join(a["samples"][1::2]) + "\n")

@@ -112,7 +112,7 @@ def test_finalise_row_matches_oracle(drv):
 
 
 def test_bcf_and_fasta_decoding(drv, golden_dir, tmp_path):
-    def load(bcf, samples, chrom, cap=100000, ccap=4000000):
+    def load(bcf, samples, chrom, cap=100000, ccap=4000000, use_index=1):
         pos = (C.c_int64 * cap)()
         na = (C.c_uint32 * cap)()
         row = (C.c_uint32 * cap)()
@@ -120,7 +120,7 @@ def test_bcf_and_fasta_decoding(drv, golden_dir, tmp_path):
         n = C.c_uint32()
         ns = C.c_uint32()
         pitch = C.c_uint32()
-        rc = drv.drv_load_bcf(bcf.encode(), (samples or "").encode(), chrom.encode(), cap, pos, na, row, car, ccap, C.byref(n), C.byref(ns), C.byref(pitch))
+        rc = drv.drv_load_bcf(bcf.encode(), (samples or "").encode(), chrom.encode(), cap, pos, na, row, car, ccap, C.byref(n), C.byref(ns), C.byref(pitch), use_index)
         assert rc == 0, drv.drv_last_error()
         return [pos[i] for i in range(n.value)], [na[i] for i in range(n.value)], [row[i] for i in range(n.value)], car, ns.value, pitch.value
 
@@ -141,6 +141,18 @@ def test_bcf_and_fasta_decoding(drv, golden_dir, tmp_path):
     assert rows == list(range(len(blk.meta["var_pos"])))
     got = np.array([car[i] for i in range(len(rows) * pitch)], dtype=np.uint32).reshape(len(rows), pitch)
     assert np.array_equal(got, blk.carriers[:len(rows)])
+    # a multi-contig BGZF file with a CSI index: only the members of the wanted contig are read, the records are the same as
+    # without the index (whole-file scan) and as in the single-contig file; the other contigs' records never show up
+    for mb in (1500, 700, 100000):
+        c = fw.cohort_to_files(blk, pats, str(tmp_path / ("i%d" % mb)), multiallelic_every=5, bgzf=True, member_bytes=mb, flank_records=40, write_csi=True)
+        assert os.path.exists(c["bcf"] + ".csi")
+        with_index = load(c["bcf"], None, c["chromosome"])
+        assert with_index[:3] == load(c["bcf"], None, c["chromosome"], use_index=0)[:3] == load(a["bcf"], None, a["chromosome"])[:3]
+        assert [with_index[3][i] for i in range(len(rows) * pitch)] == [car[i] for i in range(len(rows) * pitch)]
+        assert len(load(c["bcf"], None, "chrOther")[0]) == 40 and len(load(c["bcf"], None, "chrZ")[0]) == 40
+        assert load(c["bcf"], None, "chrZ")[0] == load(c["bcf"], None, "chrZ", use_index=0)[0]
+    # the reference's own index (written by bcftools): same single record with and without it
+    assert load(os.path.join(golden_dir, "genotypes2.bcf"), None, "chr1")[:3] == load(os.path.join(golden_dir, "genotypes2.bcf"), None, "chr1", use_index=0)[:3] == ([100], [2], [0])
     # sample subset: columns follow the BCF order whatever the file order is (main.rs:293-313)
     sub = str(tmp_path / "subset")
     open(sub, "w").write("\n".join([a["samples"][9], a["samples"][2], "x", a["samples"][17]]) + "\n")
