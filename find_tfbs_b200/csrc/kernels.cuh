@@ -19,6 +19,15 @@
 #include "../../include/tfbs.h"
 #include "tables.hpp"
 
+// Launch syntax and the dynamic shared-memory declaration are spelled as macros: tests/cuda_emu redefines them to run these very
+// kernels, thread by thread, on the host of the GPU-less build container (a test of the kernel logic; not a product path).
+#ifndef TFBS_LAUNCH
+#define TFBS_LAUNCH(kernel, grid, block, smem, stream) kernel<<<(grid), (block), (smem), (stream)>>>
+#endif
+#ifndef TFBS_DYNAMIC_SHARED
+#define TFBS_DYNAMIC_SHARED(name) extern __shared__ __align__(16) unsigned char name[]
+#endif
+
 namespace tfbs {
 
 typedef unsigned long long u64;
@@ -1019,7 +1028,7 @@ __global__ void __launch_bounds__(SCAN_CTA, 1)
     k_scan(const __grid_constant__ DevBlock b, const __grid_constant__ DevSeqs sq, const __grid_constant__ DevPatterns pt,
            const __grid_constant__ DevCounts ct, const __grid_constant__ DevMatches mt, const __grid_constant__ DevRefHits rh,
            const u32* list, const u64* n_list_ptr, u32 per_grab, DevStatus* st, u32 chunk, int delta) {
-    extern __shared__ __align__(16) u8 smem_raw[];
+    TFBS_DYNAMIC_SHARED(smem_raw);
     CtaShared* cs = reinterpret_cast<CtaShared*>(smem_raw);
     WarpShared* ws = reinterpret_cast<WarpShared*>(smem_raw + sizeof(CtaShared)) + (threadIdx.x >> 5);
     u8* tbl = smem_raw + sizeof(CtaShared) + SCAN_WARPS * sizeof(WarpShared);

@@ -166,9 +166,9 @@ int device_scan(tfbs_ctx* ctx, const uint32_t* d_in, uint64_t n, u64* d_out) {
         return TFBS_OK;
     }
     CK(ctx->d_tile_sums.reserve((size_t)tiles * 8));
-    k_prefix_tiles<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(d_in, n, d_out, ctx->d_tile_sums.as<u64>());
-    k_prefix_sums<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->d_tile_sums.as<u64>(), tiles, d_out + n);
-    k_prefix_add<<<tiles, SCAN_THREADS, 0, ctx->stream>>>(d_out, n, ctx->d_tile_sums.as<u64>());
+    TFBS_LAUNCH(k_prefix_tiles, tiles, SCAN_THREADS, 0, ctx->stream)(d_in, n, d_out, ctx->d_tile_sums.as<u64>());
+    TFBS_LAUNCH(k_prefix_sums, 1, SCAN_THREADS, 0, ctx->stream)(ctx->d_tile_sums.as<u64>(), tiles, d_out + n);
+    TFBS_LAUNCH(k_prefix_add, tiles, SCAN_THREADS, 0, ctx->stream)(d_out, n, ctx->d_tile_sums.as<u64>());
     ctx->stats.total_launches += 3;
     CK(cudaGetLastError());
     return TFBS_OK;
@@ -312,18 +312,18 @@ int run_pipeline(tfbs_ctx* ctx) {
 
     // ---- input encoding -----------------------------------------------------------------------
     if (ctx->n_ref_bytes) {
-        k_encode<<<std::min<unsigned>(grid_for(ctx->n_ref_bytes, 256), 148 * 16), 256, 0, st>>>(ctx->d_ref_ascii.as<u8>(), ctx->d_ref_codes.as<u8>(),
+        TFBS_LAUNCH(k_encode, std::min<unsigned>(grid_for(ctx->n_ref_bytes, 256), 148 * 16), 256, 0, st)(ctx->d_ref_ascii.as<u8>(), ctx->d_ref_codes.as<u8>(),
                                                                                                  ctx->n_ref_bytes, &dst->bad_ref_base);
         ++launches;
     }
     if (ctx->n_allele_bytes) {
-        k_encode<<<std::min<unsigned>(grid_for(ctx->n_allele_bytes, 256), 148 * 16), 256, 0, st>>>(
+        TFBS_LAUNCH(k_encode, std::min<unsigned>(grid_for(ctx->n_allele_bytes, 256), 148 * 16), 256, 0, st)(
             ctx->d_allele_ascii.as<u8>(), ctx->d_allele_codes.as<u8>(), ctx->n_allele_bytes, &dst->bad_allele_base);
         ++launches;
     }
     DevBlock db = dev_block(ctx);
-    k_variant_prep<<<R, 128, 0, st>>>(db, 0, ctx->d_var_class.as<u32>(), ctx->d_var_inwin.as<u8>());
-    k_ref_prefix<<<R, SCAN_THREADS, 0, st>>>(db, 0, ctx->d_ref_prefix.as<u64>());
+    TFBS_LAUNCH(k_variant_prep, R, 128, 0, st)(db, 0, ctx->d_var_class.as<u32>(), ctx->d_var_inwin.as<u8>());
+    TFBS_LAUNCH(k_ref_prefix, R, SCAN_THREADS, 0, st)(db, 0, ctx->d_ref_prefix.as<u64>());
     launches += 2;
 
     // ---- phase 1: grouping (K0), over super-batches bounded by the hash table ---------------------
@@ -349,11 +349,11 @@ int run_pipeline(tfbs_ctx* ctx) {
             CK(ctx->d_vals.reserve((size_t)cap * 4));
             CK(cudaMemsetAsync(ctx->d_keys.p, 0, (size_t)cap * 8, st));
             CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, (size_t)cap * 4, st));
-            k_signatures<<<grid_for(pairs, 256), 256, 0, st>>>(db, r0, nr, seed, ctx->d_sig.as<u64>(), ctx->d_nd_in.as<u32>());
-            k_group_insert<<<grid_for(pairs, 256), 256, 0, st>>>(H, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1);
-            k_group_lookup<<<grid_for(pairs, 256), 256, 0, st>>>(db, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1,
+            TFBS_LAUNCH(k_signatures, grid_for(pairs, 256), 256, 0, st)(db, r0, nr, seed, ctx->d_sig.as<u64>(), ctx->d_nd_in.as<u32>());
+            TFBS_LAUNCH(k_group_insert, grid_for(pairs, 256), 256, 0, st)(H, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1);
+            TFBS_LAUNCH(k_group_lookup, grid_for(pairs, 256), 256, 0, st)(db, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1,
                                                                  ctx->d_leader.as<u32>(), dst);
-            k_group_rank<<<nr, 256, 0, st>>>(H, r0, ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), ctx->d_hap_group.as<u32>(),
+            TFBS_LAUNCH(k_group_rank, nr, 256, 0, st)(H, r0, ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), ctx->d_hap_group.as<u32>(),
                                              ctx->d_ngroups.as<u32>(), ctx->d_sum_nd.as<u32>());
             launches += 4;
         }
@@ -529,10 +529,10 @@ int run_pipeline(tfbs_ctx* ctx) {
         }
         CK(cudaEventRecord(ctx->ev[2], st));
         // K1 build
-        k_seq_init<<<nr, 128, 0, st>>>(H, r0, ctx->d_hap_group.as<u32>(), ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), sq);
+        TFBS_LAUNCH(k_seq_init, nr, 128, 0, st)(H, r0, ctx->d_hap_group.as<u32>(), ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), sq);
         ++launches;
         if ((rc = device_scan(ctx, sq.seq_nd, n_seq, sq.seq_doff))) return rc;
-        k_walk<<<grid_for(n_seq, 128), 128, 0, st>>>(db, sq, dst);
+        TFBS_LAUNCH(k_walk, grid_for(n_seq, 128), 128, 0, st)(db, sq, dst);
         ++launches;
         // the sequence-keyed map of load_haplotypes
         {
@@ -543,9 +543,9 @@ int run_pipeline(tfbs_ctx* ctx) {
             CK(cudaMemsetAsync(ctx->d_keys.p, 0, (size_t)cap * 8, st));
             CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, (size_t)cap * 4, st));
             CK(cudaMemsetAsync(ctx->d_ref_used.as<u32>() + r0, 0, (size_t)nr * 4, st));
-            k_seq_insert<<<grid_for(n_seq, 256), 256, 0, st>>>(sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1);
-            k_seq_resolve<<<grid_for(n_seq, 128), 128, 0, st>>>(db, sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1, dst);
-            k_redirect<<<grid_for((uint64_t)nr * H, 256), 256, 0, st>>>(H, r0, nr, sq, ctx->d_hap_group.as<u32>(), ctx->d_ref_used.as<u32>(),
+            TFBS_LAUNCH(k_seq_insert, grid_for(n_seq, 256), 256, 0, st)(sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1);
+            TFBS_LAUNCH(k_seq_resolve, grid_for(n_seq, 128), 128, 0, st)(db, sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1, dst);
+            TFBS_LAUNCH(k_redirect, grid_for((uint64_t)nr * H, 256), 256, 0, st)(H, r0, nr, sq, ctx->d_hap_group.as<u32>(), ctx->d_ref_used.as<u32>(),
                                                                         ctx->audit ? ctx->d_hap_flags.as<u8>() : nullptr);
             launches += 3;
         }
@@ -575,19 +575,19 @@ int run_pipeline(tfbs_ctx* ctx) {
             CK(cudaMemsetAsync(ctx->d_score_flag.p, 0, ic * 4, st));
             CK(cudaMemsetAsync(ctx->d_count_size.p, 0, ic * 4, st));
             CK(cudaMemsetAsync(ctx->d_ent_units.p, 0, ic * 4, st));
-            k_items<false><<<grid_for(n_seq, 128), 128, 0, st>>>(db, sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta, ctx->d_keys.as<u64>(),
+            TFBS_LAUNCH(k_items<false>, grid_for(n_seq, 128), 128, 0, st)(db, sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta, ctx->d_keys.as<u64>(),
                                                                 ctx->d_vals.as<u32>(), tcap - 1);
             ++launches;
             if ((rc2 = device_scan(ctx, sq.seq_nitems, n_seq, sq.item_off))) return rc2;
-            k_items<true><<<grid_for(n_seq, 128), 128, 0, st>>>(db, sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta, ctx->d_keys.as<u64>(),
+            TFBS_LAUNCH(k_items<true>, grid_for(n_seq, 128), 128, 0, st)(db, sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta, ctx->d_keys.as<u64>(),
                                                                ctx->d_vals.as<u32>(), tcap - 1);
-            k_item_resolve<<<grid_for(items_cap, 128), 128, 0, st>>>(db, sq, ctx->dpat, d_n_items, delta, ctx->cp.max_len, ctx->d_keys.as<u64>(),
+            TFBS_LAUNCH(k_item_resolve, grid_for(items_cap, 128), 128, 0, st)(db, sq, ctx->dpat, d_n_items, delta, ctx->cp.max_len, ctx->d_keys.as<u64>(),
                                                                     ctx->d_vals.as<u32>(), tcap - 1, ctx->d_score_flag.as<u32>(),
                                                                     ctx->d_count_size.as<u32>());
             launches += 2;
             if ((rc2 = device_scan(ctx, ctx->d_score_flag.as<u32>(), items_cap, ctx->d_score_idx.as<u64>()))) return rc2;
             if ((rc2 = device_scan(ctx, ctx->d_count_size.as<u32>(), items_cap, sq.item_coff))) return rc2;
-            k_item_lists<<<grid_for(items_cap, 256), 256, 0, st>>>(sq, d_n_items, ctx->d_score_flag.as<u32>(), ctx->d_score_idx.as<u64>(),
+            TFBS_LAUNCH(k_item_lists, grid_for(items_cap, 256), 256, 0, st)(sq, d_n_items, ctx->d_score_flag.as<u32>(), ctx->d_score_idx.as<u64>(),
                                                                   ctx->d_list.as<u32>());
             ++launches;
             if ((rc2 = device_scan(ctx, sq.ent_units, items_cap, sq.ent_uoff))) return rc2;
@@ -606,8 +606,8 @@ int run_pipeline(tfbs_ctx* ctx) {
             sq.pk = ctx->d_pk.as<u64>();
             sq.nm = ctx->d_nm.as<u32>();
             if (n_list_host) {
-                k_emit_list<<<grid_for(n_list_host * EMIT_LANES, 256), 256, 0, st>>>(db, sq, ctx->d_list.as<u32>(), d_n_list);
-                k_item_stats<<<grid_for(n_list_host, 256), 256, 0, st>>>(sq, ctx->dpat, ctx->d_list.as<u32>(), d_n_list, dst);
+                TFBS_LAUNCH(k_emit_list, grid_for(n_list_host * EMIT_LANES, 256), 256, 0, st)(db, sq, ctx->d_list.as<u32>(), d_n_list);
+                TFBS_LAUNCH(k_item_stats, grid_for(n_list_host, 256), 256, 0, st)(sq, ctx->dpat, ctx->d_list.as<u32>(), d_n_list, dst);
                 launches += 2;
             }
 #ifndef TFBS_PER_GRAB
@@ -617,14 +617,14 @@ int run_pipeline(tfbs_ctx* ctx) {
             CK(cudaEventRecord(ctx->ev[8], st));
             for (uint32_t c = 0; c < ctx->cp.chunks.size() && n_list_host; ++c) {
                 CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
-                if (wide) k_scan<2><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, drh, ctx->d_list.as<u32>(), d_n_list, per_grab, dst, c, delta);
-                else k_scan<3><<<scan_grid, SCAN_CTA, smem_bytes, st>>>(db, sq, ctx->dpat, dc, dm, drh, ctx->d_list.as<u32>(), d_n_list, per_grab, dst, c, delta);
+                if (wide) TFBS_LAUNCH(k_scan<2>, scan_grid, SCAN_CTA, smem_bytes, st)(db, sq, ctx->dpat, dc, dm, drh, ctx->d_list.as<u32>(), d_n_list, per_grab, dst, c, delta);
+                else TFBS_LAUNCH(k_scan<3>, scan_grid, SCAN_CTA, smem_bytes, st)(db, sq, ctx->dpat, dc, dm, drh, ctx->d_list.as<u32>(), d_n_list, per_grab, dst, c, delta);
                 ++launches;
                 ++ctx->stats.scan_launches;
             }
             CK(cudaEventRecord(ctx->ev[9], st));
             if (delta) {
-                k_group_finish<<<grid_for(n_seq * 8, 256), 256, 0, st>>>(db, sq, ctx->dpat, dc, drh, ctx->d_ref_used.as<u32>(), dst);
+                TFBS_LAUNCH(k_group_finish, grid_for(n_seq * 8, 256), 256, 0, st)(db, sq, ctx->dpat, dc, drh, ctx->d_ref_used.as<u32>(), dst);
                 ++launches;
             }
             CK(cudaGetLastError());
@@ -635,13 +635,13 @@ int run_pipeline(tfbs_ctx* ctx) {
         CK(cudaEventRecord(ctx->ev[4], st));
 
         // K3 rows
-        k_nominal<<<grid_for((uint64_t)nr * H, 256), 256, 0, st>>>(db, r0, nr, ctx->d_hap_group.as<u32>(), sq, ctx->dpat, dst);
-        k_seq_stats<<<grid_for(n_seq, 256), 256, 0, st>>>(sq, ctx->dpat, ctx->d_ref_used.as<u32>(), dst);
+        TFBS_LAUNCH(k_nominal, grid_for((uint64_t)nr * H, 256), 256, 0, st)(db, r0, nr, ctx->d_hap_group.as<u32>(), sq, ctx->dpat, dst);
+        TFBS_LAUNCH(k_seq_stats, grid_for(n_seq, 256), 256, 0, st)(sq, ctx->dpat, ctx->d_ref_used.as<u32>(), dst);
         launches += 2;
         auto rows_pass = [&](int delta) -> int {
             if (!n_keys) return TFBS_OK;
             int rc2;
-            k_rows_minmax<<<nr, 128, 0, st>>>(db, r0, ctx->d_hap_group.as<u32>(), dc, ctx->d_gbase.as<u64>(), n_pid, ctx->d_kbase.as<u64>(),
+            TFBS_LAUNCH(k_rows_minmax, nr, 128, 0, st)(db, r0, ctx->d_hap_group.as<u32>(), dc, ctx->d_gbase.as<u64>(), n_pid, ctx->d_kbase.as<u64>(),
                                               ctx->h_kbase[r0], ctx->rows_mode, delta, ctx->d_vmin.as<u32>(), ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(),
                                               &dst->max_count);
             ++launches;
@@ -725,7 +725,7 @@ int run_pipeline(tfbs_ctx* ctx) {
             DevRows dr{ctx->d_rows_region.as<u32>(), ctx->d_rows_inner.as<u32>(), ctx->d_rows_pid.as<u16>(), ctx->d_rows_vmin.as<u32>(),
                        ctx->d_rows_vmax.as<u32>(), ctx->d_rows_left.p, ctx->d_rows_right.p};
 #define TFBS_ROWS_WRITE(T)                                                                                                              \
-    k_rows_write<T><<<grid_for(n_keys * 32, 256), 256, 0, st>>>(db, r0, nr, ctx->d_hap_group.as<u32>(), dc, n_pid, ctx->d_pid_list.as<u16>(), \
+    TFBS_LAUNCH(k_rows_write<T>, grid_for(n_keys * 32, 256), 256, 0, st)(db, r0, nr, ctx->d_hap_group.as<u32>(), dc, n_pid, ctx->d_pid_list.as<u16>(), \
                                                                 ctx->d_kbase.as<u64>(), ctx->h_kbase[r0], n_keys, ctx->d_vmin.as<u32>(),   \
                                                                 ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(), ctx->d_rowidx.as<u64>(), dr, 0, use_delta)
             if (eb == 1) TFBS_ROWS_WRITE(u8);

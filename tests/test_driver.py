@@ -10,7 +10,7 @@ from oracle import pyoracle as ora
 import file_writers as fw
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-DRIVER = os.path.join(ROOT, "find_tfbs_b200", "find-tfbs-b200")
+DRIVER = os.environ.get("TFBS_B200_DRIVER") or os.path.join(ROOT, "find_tfbs_b200", "find-tfbs-b200")  # the override is tests/cuda_emu
 
 
 def run_driver(args, out):
