@@ -79,7 +79,8 @@ class TfbsStats(C.Structure):
                 ("ms_group", C.c_float), ("ms_build", C.c_float), ("ms_scan", C.c_float), ("ms_count", C.c_float),
                 ("ms_total", C.c_float), ("sm_count", C.c_uint32), ("scan_ctas", C.c_uint32),
                 ("evaluated_cells", C.c_uint64), ("n_scan_items", C.c_uint64), ("ms_scan_kernel", C.c_float),
-                ("n_dropped", C.c_uint32), ("n_truncated", C.c_uint32), ("reserved", C.c_uint32)]
+                ("n_dropped", C.c_uint32), ("n_truncated", C.c_uint32), ("reserved", C.c_uint32),
+                ("scan_input_bytes", C.c_uint64)]
 
 
 INNER_DTYPE = np.dtype([("start", "<i8"), ("end", "<i8"), ("bed_index", "<u4"), ("multiplicity", "<u4")])

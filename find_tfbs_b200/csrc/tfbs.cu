@@ -621,6 +621,7 @@ int run_pipeline(tfbs_ctx* ctx) {
                 else TFBS_LAUNCH(k_scan<3>, scan_grid, SCAN_CTA, smem_bytes, st)(db, sq, ctx->dpat, dc, dm, drh, ctx->d_list.as<u32>(), d_n_list, per_grab, dst, c, delta);
                 ++launches;
                 ++ctx->stats.scan_launches;
+                ctx->stats.scan_input_bytes += ent_units_total * 12 + (uint64_t)ctx->cp.chunks[c].tbl_words * 8 * scan_grid;
             }
             CK(cudaEventRecord(ctx->ev[9], st));
             if (delta) {

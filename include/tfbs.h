@@ -216,6 +216,8 @@ typedef struct tfbs_stats {
     uint32_t n_dropped;         /* groups overwritten in the sequence-keyed map (haplotype.rs:84) */
     uint32_t n_truncated;       /* haplotypes truncated by an overlapping variant (haplotype.rs:144-149) */
     uint32_t reserved;
+    uint64_t scan_input_bytes;  /* algorithmic HBM bytes the scan launches read: 12 B per 32 packed bases (2 bit + N mask) of every
+                                   scored entry, once per pattern chunk, plus the chunk's tables once per CTA */
 } tfbs_stats;
 
 typedef struct tfbs_ctx tfbs_ctx;

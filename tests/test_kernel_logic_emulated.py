@@ -60,3 +60,41 @@ def test_parity_suite_on_emulated_kernels(emu_env):
 def test_driver_on_emulated_kernels(emu_env):
     """The C++ driver end to end on the CPU: the reference's two integration outputs (main.rs:548-568) and the synthetic file sets."""
     run_marked_gpu_tests(emu_env, "tests/test_driver.py", "", workers=2)
+
+
+CONTRACT_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
+                 "config", "roofline", "e2e", "gpu_launches", "clocks", "cpu_baseline")
+
+
+def test_bench_control_flow_dry_run(emu_env):
+    """bench.py end to end with torch.cuda stubbed and the emulated library (tests/cuda_emu/run_bench_emulated.py): the one JSON
+    line carries every contract key and internally consistent counters.  The numbers themselves mean nothing here."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(EMU, "run_bench_emulated.py"), "--scale", "0.001", "--steps", "2", "--warmup", "1",
+                        "--cpu-seconds", "0.5", "--no-full-scan"], cwd=ROOT, env=emu_env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in CONTRACT_KEYS:
+        assert k in d, k
+    assert d["metric"] == "pwm_cells_per_s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["higher_is_better"] is True
+    rf = d["roofline"]
+    for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "hbm"):
+        assert k in rf, k
+    assert rf["hbm"]["algorithmic_bytes_per_launch"] > 0 and rf["cells_per_launch"] == d["evaluated_cells_per_step"]
+    assert d["nominal_cells_per_step"] >= d["executed_cells_per_step"] >= d["evaluated_cells_per_step"] > 0
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+
+
+def test_bench_reference_arm():
+    """`bench.py --impl reference` needs no GPU: the CPU restatement on the host cores, same metric / config keys, impl = reference."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scale", "0.004", "--steps", "2", "--warmup", "1",
+                        "--ref-seconds-per-step", "0.3"], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][-1])
+    assert d["impl"] == "reference" and d["metric"] == "pwm_cells_per_s" and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
