@@ -21,6 +21,12 @@ namespace {
 
 thread_local std::string g_create_error;
 
+// Buffers grow with some slack so that a slightly larger next block does not reallocate; the sanitizer build of tests/cuda_emu sets
+// the slack to zero so that every out-of-bounds access is caught.
+#ifndef TFBS_ALLOC_SLACK
+#define TFBS_ALLOC_SLACK(bytes) ((bytes) / 8 + 256)
+#endif
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -30,7 +36,7 @@ struct DevBuf {
         if (p) cudaFree(p);
         p = nullptr;
         cap = 0;
-        size_t want = bytes + bytes / 8 + 256;
+        size_t want = bytes + TFBS_ALLOC_SLACK(bytes);
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) cap = want;
         return e;

@@ -272,11 +272,20 @@ inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp* p, int) {
     p->totalGlobalMem = (size_t)8 << 30;
     return cudaSuccess;
 }
-inline cudaError_t cudaMalloc(void** p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+// device memory comes back filled with garbage, like the real thing: a kernel that relies on zeroed memory fails here
+inline cudaError_t cudaMalloc(void** p, size_t n) {
+    *p = malloc(n ? n : 1);
+    if (*p) memset(*p, 0xCD, n ? n : 1);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 template <class T>
 inline cudaError_t cudaMalloc(T** p, size_t n) { return cudaMalloc((void**)p, n); }
 inline cudaError_t cudaFree(void* p) { free(p); return cudaSuccess; }
-inline cudaError_t cudaMallocHost(void** p, size_t n) { *p = calloc(1, n ? n : 1); return *p ? cudaSuccess : cudaErrorMemoryAllocation; }
+inline cudaError_t cudaMallocHost(void** p, size_t n) {
+    *p = malloc(n ? n : 1);
+    if (*p) memset(*p, 0xCD, n ? n : 1);
+    return *p ? cudaSuccess : cudaErrorMemoryAllocation;
+}
 inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { if (n) memmove(d, s, n); return cudaSuccess; }
 inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { if (n) memset(d, v, n); return cudaSuccess; }
