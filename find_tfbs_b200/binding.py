@@ -91,7 +91,7 @@ VARIANT_DTYPE = np.dtype([("pos", "<i8"), ("ref_off", "<u4"), ("ref_len", "<u4")
 def build(force=False):
     """Compile libtfbs_b200.so for sm_100a with nvcc (in-tree, so that the .so travels with the repo)."""
     csrc = os.path.join(_HERE, "csrc")
-    srcs = [os.path.join(csrc, f) for f in ("tfbs.cu", "kernels.cuh", "tables.cpp", "tables.hpp", "Makefile")]
+    srcs = [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith((".cu", ".cuh", ".cpp", ".hpp")) or f == "Makefile"]
     srcs.append(os.path.join(_HERE, "..", "include", "tfbs.h"))
     if force or not os.path.exists(LIB_PATH) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs):
         subprocess.check_call(["make", "-C", csrc], stdout=subprocess.DEVNULL)
