@@ -164,22 +164,6 @@ int upload(tfbs_ctx* ctx, DevBuf& buf, const T* src, size_t n) {
 
 inline unsigned grid_for(uint64_t n, unsigned block) { return (unsigned)std::max<uint64_t>(1, (n + block - 1) / block); }
 
-// exclusive scan of d_in[0..n) into d_out[0..n], total into d_out[n]
-int device_scan(tfbs_ctx* ctx, const uint32_t* d_in, uint64_t n, u64* d_out) {
-    uint32_t tiles = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
-    if (tiles == 0) {
-        CK(cudaMemsetAsync(d_out, 0, sizeof(u64), ctx->stream));
-        return TFBS_OK;
-    }
-    CK(ctx->d_tile_sums.reserve((size_t)tiles * 8));
-    TFBS_LAUNCH(k_prefix_tiles, tiles, SCAN_THREADS, 0, ctx->stream)(d_in, n, d_out, ctx->d_tile_sums.as<u64>());
-    TFBS_LAUNCH(k_prefix_sums, 1, SCAN_THREADS, 0, ctx->stream)(ctx->d_tile_sums.as<u64>(), tiles, d_out + n);
-    TFBS_LAUNCH(k_prefix_add, tiles, SCAN_THREADS, 0, ctx->stream)(d_out, n, ctx->d_tile_sums.as<u64>());
-    ctx->stats.total_launches += 3;
-    CK(cudaGetLastError());
-    return TFBS_OK;
-}
-
 DevBlock dev_block(const tfbs_ctx* ctx) {
     DevBlock b{};
     b.R = ctx->R;
@@ -281,144 +265,246 @@ int do_upload(tfbs_ctx* ctx, const tfbs_block* b) {
     return TFBS_OK;
 }
 
-std::string nuc_letter(unsigned c) { return std::string(1, "ACGTN"[c < 5 ? c : 4]); }
-
 // ---- the device pipeline on the resident block ---------------------------------------------------
-int run_pipeline(tfbs_ctx* ctx) {
-    if (!ctx->have_patterns) return fail(ctx, TFBS_ERR_STATE, "tfbs_set_patterns has not been called");
-    if (!ctx->have_block) return fail(ctx, TFBS_ERR_STATE, "no block has been uploaded");
-    cudaStream_t st = ctx->stream;
-    const uint32_t R = ctx->R, S = ctx->S, H = ctx->H;
-    uint64_t h2d_keep = ctx->stats.h2d_bytes;
-    memset(&ctx->stats, 0, sizeof ctx->stats);
-    ctx->stats.h2d_bytes = h2d_keep;
-    ctx->stats.sm_count = (uint32_t)ctx->prop.multiProcessorCount;
-    ctx->n_rows = 0;
-    ctx->n_matches = 0;
-    ctx->matches_truncated = false;
-    ctx->ran = false;
-    auto& launches = ctx->stats.total_launches;
+//
+// One run = phase 1 over the whole block (input encoding, K0 grouping, per-region prefix arrays), then phase 2 in batches of
+// regions sized to the scratch budget: K1 build, K2 work list + scan (+ the finish pass of delta scoring), K3 rows.
+struct Pipeline {
+    tfbs_ctx* ctx;
+    cudaStream_t st;
+    const uint32_t R, S, H;
+    const uint64_t RH;
+    DevStatus* dst = nullptr;
+    DevBlock db{};
+    DevMatches dm{};
+    uint32_t n_pid = 0;
+    int smem_bytes = 0;
+    bool wide = false;
+    uint32_t scan_grid = 0;
+    // accumulated over the batches
+    float ms_build = 0, ms_scan = 0, ms_count = 0, ms_scan_kernel = 0;
+    uint64_t n_items_total = 0;
+    uint64_t hits_done = 0;  // hits of the finished batches: what n_hits falls back to when a batch is re-scored in full
 
-    CK(ctx->d_status.reserve(sizeof(DevStatus)));
-    CK(ctx->h_status.reserve(sizeof(DevStatus), false));
-    CK(ctx->h_totals.reserve(64, false));
-    DevStatus* dst = ctx->d_status.as<DevStatus>();
-    DevStatus init{};
-    init.err_key = ~0ull;
-    init.bad_ref_base = ~0ull;
-    init.bad_allele_base = ~0ull;
-    memcpy(ctx->h_status.p, &init, sizeof init);
-    CK(cudaMemcpyAsync(dst, ctx->h_status.p, sizeof init, cudaMemcpyHostToDevice, st));
-    CK(cudaEventRecord(ctx->ev[0], st));
-    if (R == 0 || S == 0) {
-        CK(cudaStreamSynchronize(st));
-        ctx->ran = true;
+    // a batch of regions [r0, r1) and the sizes its scratch arrays are planned for
+    struct Batch {
+        uint32_t r0 = 0, r1 = 0, nr = 0;
+        uint64_t n_seq = 0, n_d = 0, n_units = 0, n_c = 0, n_keys = 0;
+        uint64_t items_cap = 0, ic = 1;
+        uint32_t capr = 0;  // reference hits kept per region
+        DevSeqs sq{};
+        DevRefHits drh{};
+        DevCounts dc{};
+        const u64* d_n_items = nullptr;
+        const u64* d_n_list = nullptr;
+        uint64_t n_list_host = 0;
+        int use_delta = 0;
+        DevStatus hs{};  // status word after the batch's rows pass
+    };
+
+    explicit Pipeline(tfbs_ctx* c) : ctx(c), st(c->stream), R(c->R), S(c->S), H(c->H), RH((uint64_t)c->R * c->H) {}
+
+    int run() {
+        int rc;
+        if ((rc = begin())) return rc;
+        if (R == 0 || S == 0) {
+            CK(cudaStreamSynchronize(st));
+            ctx->ran = true;
+            return TFBS_OK;
+        }
+        if ((rc = encode_inputs())) return rc;
+        if ((rc = group_haplotypes())) return rc;
+        if ((rc = region_prefixes())) return rc;
+        if ((rc = setup_scan())) return rc;
+        for (uint32_t r0 = 0; r0 < R;) {
+            Batch b;
+            if ((rc = plan_batch(r0, &b))) return rc;
+            if ((rc = reserve_batch(&b))) return rc;
+            CK(cudaEventRecord(ctx->ev[2], st));
+            if ((rc = build_sequences(b))) return rc;
+            CK(cudaEventRecord(ctx->ev[3], st));
+            b.use_delta = (ctx->delta && !ctx->record_matches) ? 1 : 0;
+            if ((rc = scan_pass(&b, b.use_delta))) return rc;
+            CK(cudaEventRecord(ctx->ev[4], st));
+            if ((rc = count_and_filter(&b))) return rc;
+            if ((rc = fetch_rows(b))) return rc;
+            if ((rc = batch_timers())) return rc;
+            r0 = b.r1;
+        }
+        return finish();
+    }
+
+private:
+    uint32_t& launches() { return ctx->stats.total_launches; }
+
+    // exclusive scan of d_in[0..n) into d_out[0..n], total into d_out[n]
+    int device_scan(const uint32_t* d_in, uint64_t n, u64* d_out) {
+        uint32_t tiles = (uint32_t)((n + SCAN_TILE - 1) / SCAN_TILE);
+        if (tiles == 0) {
+            CK(cudaMemsetAsync(d_out, 0, sizeof(u64), st));
+            return TFBS_OK;
+        }
+        CK(ctx->d_tile_sums.reserve((size_t)tiles * 8));
+        TFBS_LAUNCH(k_prefix_tiles, tiles, SCAN_THREADS, 0, st)(d_in, n, d_out, ctx->d_tile_sums.as<u64>());
+        TFBS_LAUNCH(k_prefix_sums, 1, SCAN_THREADS, 0, st)(ctx->d_tile_sums.as<u64>(), tiles, d_out + n);
+        TFBS_LAUNCH(k_prefix_add, tiles, SCAN_THREADS, 0, st)(d_out, n, ctx->d_tile_sums.as<u64>());
+        launches() += 3;
+        CK(cudaGetLastError());
         return TFBS_OK;
     }
 
-    // ---- input encoding -----------------------------------------------------------------------
-    if (ctx->n_ref_bytes) {
-        TFBS_LAUNCH(k_encode, std::min<unsigned>(grid_for(ctx->n_ref_bytes, 256), 148 * 16), 256, 0, st)(ctx->d_ref_ascii.as<u8>(), ctx->d_ref_codes.as<u8>(),
-                                                                                                 ctx->n_ref_bytes, &dst->bad_ref_base);
-        ++launches;
-    }
-    if (ctx->n_allele_bytes) {
-        TFBS_LAUNCH(k_encode, std::min<unsigned>(grid_for(ctx->n_allele_bytes, 256), 148 * 16), 256, 0, st)(
-            ctx->d_allele_ascii.as<u8>(), ctx->d_allele_codes.as<u8>(), ctx->n_allele_bytes, &dst->bad_allele_base);
-        ++launches;
-    }
-    DevBlock db = dev_block(ctx);
-    TFBS_LAUNCH(k_variant_prep, R, 128, 0, st)(db, 0, ctx->d_var_class.as<u32>(), ctx->d_var_inwin.as<u8>());
-    TFBS_LAUNCH(k_ref_prefix, R, SCAN_THREADS, 0, st)(db, 0, ctx->d_ref_prefix.as<u64>());
-    launches += 2;
-
-    // ---- phase 1: grouping (K0), over super-batches bounded by the hash table ---------------------
-    const uint64_t RH = (uint64_t)R * H;
-    CK(ctx->d_sig.reserve(RH * 8));
-    CK(ctx->d_nd_in.reserve(RH * 4));
-    CK(ctx->d_leader.reserve(RH * 4));
-    CK(ctx->d_hap_group.reserve(RH * 4));
-    CK(ctx->d_ngroups.reserve((size_t)R * 4));
-    CK(ctx->d_sum_nd.reserve((size_t)R * 4));
-    CK(ctx->d_ref_used.reserve((size_t)R * 4));
-    if (ctx->audit) CK(ctx->d_hap_flags.reserve(RH));
-    const uint64_t max_pairs = 1ull << 25;
-    uint32_t regions_per_super = (uint32_t)std::max<uint64_t>(1, max_pairs / std::max<uint32_t>(1, H));
-    uint64_t seed = 0x243f6a8885a308d3ull;
-    for (int attempt = 0;; ++attempt) {
-        for (uint32_t r0 = 0; r0 < R; r0 += regions_per_super) {
-            uint32_t nr = std::min(regions_per_super, R - r0);
-            uint64_t pairs = (uint64_t)nr * H;
-            uint32_t cap = 1024;
-            while (cap < 2 * pairs) cap <<= 1;
-            CK(ctx->d_keys.reserve((size_t)cap * 8));
-            CK(ctx->d_vals.reserve((size_t)cap * 4));
-            CK(cudaMemsetAsync(ctx->d_keys.p, 0, (size_t)cap * 8, st));
-            CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, (size_t)cap * 4, st));
-            TFBS_LAUNCH(k_signatures, grid_for(pairs, 256), 256, 0, st)(db, r0, nr, seed, ctx->d_sig.as<u64>(), ctx->d_nd_in.as<u32>());
-            TFBS_LAUNCH(k_group_insert, grid_for(pairs, 256), 256, 0, st)(H, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1);
-            TFBS_LAUNCH(k_group_lookup, grid_for(pairs, 256), 256, 0, st)(db, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1,
-                                                                 ctx->d_leader.as<u32>(), dst);
-            TFBS_LAUNCH(k_group_rank, nr, 256, 0, st)(H, r0, ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), ctx->d_hap_group.as<u32>(),
-                                             ctx->d_ngroups.as<u32>(), ctx->d_sum_nd.as<u32>());
-            launches += 4;
-        }
-        CK(cudaGetLastError());
-        ctx->h_ngroups.resize(R);
-        ctx->h_sum_nd.resize(R);
-        CK(cudaMemcpyAsync(ctx->h_ngroups.data(), ctx->d_ngroups.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ctx->h_sum_nd.data(), ctx->d_sum_nd.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+    int read_status(DevStatus* hs) {
         CK(cudaMemcpyAsync(ctx->h_status.p, dst, sizeof(DevStatus), cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
-        DevStatus hs;
-        memcpy(&hs, ctx->h_status.p, sizeof hs);
-        if (hs.bad_ref_base != ~0ull || hs.bad_allele_base != ~0ull) {
-            // util.rs:15 panic!("Unknown nucleotide {}", l)
-            return fail(ctx, TFBS_ERR_UNKNOWN_NUCLEOTIDE,
-                        std::string("Unknown nucleotide at byte ") +
-                            std::to_string(hs.bad_ref_base != ~0ull ? hs.bad_ref_base : hs.bad_allele_base) +
-                            (hs.bad_ref_base != ~0ull ? " of ref_bases" : " of allele_bases"));
+        memcpy(hs, ctx->h_status.p, sizeof *hs);
+        return TFBS_OK;
+    }
+
+    int begin() {
+        if (!ctx->have_patterns) return fail(ctx, TFBS_ERR_STATE, "tfbs_set_patterns has not been called");
+        if (!ctx->have_block) return fail(ctx, TFBS_ERR_STATE, "no block has been uploaded");
+        uint64_t h2d_keep = ctx->stats.h2d_bytes;
+        memset(&ctx->stats, 0, sizeof ctx->stats);
+        ctx->stats.h2d_bytes = h2d_keep;
+        ctx->stats.sm_count = (uint32_t)ctx->prop.multiProcessorCount;
+        ctx->n_rows = 0;
+        ctx->n_matches = 0;
+        ctx->matches_truncated = false;
+        ctx->ran = false;
+        CK(ctx->d_status.reserve(sizeof(DevStatus)));
+        CK(ctx->h_status.reserve(sizeof(DevStatus), false));
+        CK(ctx->h_totals.reserve(64, false));
+        dst = ctx->d_status.as<DevStatus>();
+        DevStatus init{};
+        init.err_key = ~0ull;
+        init.bad_ref_base = ~0ull;
+        init.bad_allele_base = ~0ull;
+        memcpy(ctx->h_status.p, &init, sizeof init);
+        CK(cudaMemcpyAsync(dst, ctx->h_status.p, sizeof init, cudaMemcpyHostToDevice, st));
+        CK(cudaEventRecord(ctx->ev[0], st));
+        return TFBS_OK;
+    }
+
+    // ASCII -> nucleotide codes, Diff classes, prefix hashes of the reference windows
+    int encode_inputs() {
+        if (ctx->n_ref_bytes) {
+            TFBS_LAUNCH(k_encode, std::min<unsigned>(grid_for(ctx->n_ref_bytes, 256), 148 * 16), 256, 0, st)(ctx->d_ref_ascii.as<u8>(), ctx->d_ref_codes.as<u8>(),
+                                                                                                     ctx->n_ref_bytes, &dst->bad_ref_base);
+            ++launches();
         }
-        if (hs.sig_collision == 0 || !ctx->verify_groups) break;
-        if (attempt >= 3) return fail(ctx, TFBS_ERR_INTERNAL, "haplotype signature hash collision persisted over 4 seeds");
-        seed = seed * 0x9e3779b97f4a7c15ull + 0x7f4a7c15ull;
-        CK(cudaMemsetAsync(&dst->sig_collision, 0, 4, st));
+        if (ctx->n_allele_bytes) {
+            TFBS_LAUNCH(k_encode, std::min<unsigned>(grid_for(ctx->n_allele_bytes, 256), 148 * 16), 256, 0, st)(
+                ctx->d_allele_ascii.as<u8>(), ctx->d_allele_codes.as<u8>(), ctx->n_allele_bytes, &dst->bad_allele_base);
+            ++launches();
+        }
+        db = dev_block(ctx);
+        TFBS_LAUNCH(k_variant_prep, R, 128, 0, st)(db, 0, ctx->d_var_class.as<u32>(), ctx->d_var_inwin.as<u8>());
+        TFBS_LAUNCH(k_ref_prefix, R, SCAN_THREADS, 0, st)(db, 0, ctx->d_ref_prefix.as<u64>());
+        launches() += 2;
+        return TFBS_OK;
     }
-    CK(cudaEventRecord(ctx->ev[1], st));
 
-    // per region prefix arrays
-    const uint32_t n_pid = (uint32_t)ctx->cp.pid_list.size();
-    ctx->h_gbase.assign(R + 1, 0);
-    ctx->h_cbase.assign(R + 1, 0);
-    ctx->h_kbase.assign(R + 1, 0);
-    for (uint32_t r = 0; r < R; ++r) {
-        uint64_t nk = ctx->h_inner_off[r + 1] - ctx->h_inner_off[r];
-        ctx->h_gbase[r + 1] = ctx->h_gbase[r] + ctx->h_ngroups[r];
-        ctx->h_cbase[r + 1] = ctx->h_cbase[r] + (uint64_t)ctx->h_ngroups[r] * n_pid * nk;
-        ctx->h_kbase[r + 1] = ctx->h_kbase[r] + (uint64_t)n_pid * nk;
+    // ---- phase 1: grouping (K0), over super-batches bounded by the hash table; a signature collision retries with another seed ----
+    int group_haplotypes() {
+        CK(ctx->d_sig.reserve(RH * 8));
+        CK(ctx->d_nd_in.reserve(RH * 4));
+        CK(ctx->d_leader.reserve(RH * 4));
+        CK(ctx->d_hap_group.reserve(RH * 4));
+        CK(ctx->d_ngroups.reserve((size_t)R * 4));
+        CK(ctx->d_sum_nd.reserve((size_t)R * 4));
+        CK(ctx->d_ref_used.reserve((size_t)R * 4));
+        if (ctx->audit) CK(ctx->d_hap_flags.reserve(RH));
+        const uint64_t max_pairs = 1ull << 25;
+        uint32_t regions_per_super = (uint32_t)std::max<uint64_t>(1, max_pairs / std::max<uint32_t>(1, H));
+        uint64_t seed = 0x243f6a8885a308d3ull;
+        for (int attempt = 0;; ++attempt) {
+            for (uint32_t r0 = 0; r0 < R; r0 += regions_per_super) {
+                uint32_t nr = std::min(regions_per_super, R - r0);
+                uint64_t pairs = (uint64_t)nr * H;
+                uint32_t cap = 1024;
+                while (cap < 2 * pairs) cap <<= 1;
+                CK(ctx->d_keys.reserve((size_t)cap * 8));
+                CK(ctx->d_vals.reserve((size_t)cap * 4));
+                CK(cudaMemsetAsync(ctx->d_keys.p, 0, (size_t)cap * 8, st));
+                CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, (size_t)cap * 4, st));
+                TFBS_LAUNCH(k_signatures, grid_for(pairs, 256), 256, 0, st)(db, r0, nr, seed, ctx->d_sig.as<u64>(), ctx->d_nd_in.as<u32>());
+                TFBS_LAUNCH(k_group_insert, grid_for(pairs, 256), 256, 0, st)(H, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1);
+                TFBS_LAUNCH(k_group_lookup, grid_for(pairs, 256), 256, 0, st)(db, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1,
+                                                                     ctx->d_leader.as<u32>(), dst);
+                TFBS_LAUNCH(k_group_rank, nr, 256, 0, st)(H, r0, ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), ctx->d_hap_group.as<u32>(),
+                                                 ctx->d_ngroups.as<u32>(), ctx->d_sum_nd.as<u32>());
+                launches() += 4;
+            }
+            CK(cudaGetLastError());
+            ctx->h_ngroups.resize(R);
+            ctx->h_sum_nd.resize(R);
+            CK(cudaMemcpyAsync(ctx->h_ngroups.data(), ctx->d_ngroups.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(ctx->h_sum_nd.data(), ctx->d_sum_nd.p, (size_t)R * 4, cudaMemcpyDeviceToHost, st));
+            DevStatus hs;
+            int rc = read_status(&hs);
+            if (rc) return rc;
+            if (hs.bad_ref_base != ~0ull || hs.bad_allele_base != ~0ull) {
+                // util.rs:15 panic!("Unknown nucleotide {}", l)
+                return fail(ctx, TFBS_ERR_UNKNOWN_NUCLEOTIDE,
+                            std::string("Unknown nucleotide at byte ") +
+                                std::to_string(hs.bad_ref_base != ~0ull ? hs.bad_ref_base : hs.bad_allele_base) +
+                                (hs.bad_ref_base != ~0ull ? " of ref_bases" : " of allele_bases"));
+            }
+            if (hs.sig_collision == 0 || !ctx->verify_groups) break;
+            if (attempt >= 3) return fail(ctx, TFBS_ERR_INTERNAL, "haplotype signature hash collision persisted over 4 seeds");
+            seed = seed * 0x9e3779b97f4a7c15ull + 0x7f4a7c15ull;
+            CK(cudaMemsetAsync(&dst->sig_collision, 0, 4, st));
+        }
+        CK(cudaEventRecord(ctx->ev[1], st));
+        return TFBS_OK;
     }
-    int rc;
-    if ((rc = upload(ctx, ctx->d_gbase, ctx->h_gbase.data(), R + 1))) return rc;
-    if ((rc = upload(ctx, ctx->d_cbase, ctx->h_cbase.data(), R + 1))) return rc;
-    if ((rc = upload(ctx, ctx->d_kbase, ctx->h_kbase.data(), R + 1))) return rc;
-    ctx->stats.h2d_bytes -= 3ull * (R + 1) * 8;  // internal traffic, not the caller's inputs
 
-    if (ctx->record_matches) {
-        CK(ctx->d_m_region.reserve(ctx->max_matches * 4));
-        CK(ctx->d_m_pattern.reserve(ctx->max_matches * 4));
-        CK(ctx->d_m_group.reserve(ctx->max_matches * 4));
-        CK(ctx->d_m_start.reserve(ctx->max_matches * 8));
+    // per region: first sequence (gbase), first count word (cbase) and first key (kbase), block-wide
+    int region_prefixes() {
+        n_pid = (uint32_t)ctx->cp.pid_list.size();
+        ctx->h_gbase.assign(R + 1, 0);
+        ctx->h_cbase.assign(R + 1, 0);
+        ctx->h_kbase.assign(R + 1, 0);
+        for (uint32_t r = 0; r < R; ++r) {
+            uint64_t nk = ctx->h_inner_off[r + 1] - ctx->h_inner_off[r];
+            ctx->h_gbase[r + 1] = ctx->h_gbase[r] + ctx->h_ngroups[r];
+            ctx->h_cbase[r + 1] = ctx->h_cbase[r] + (uint64_t)ctx->h_ngroups[r] * n_pid * nk;
+            ctx->h_kbase[r + 1] = ctx->h_kbase[r] + (uint64_t)n_pid * nk;
+        }
+        int rc;
+        if ((rc = upload(ctx, ctx->d_gbase, ctx->h_gbase.data(), R + 1))) return rc;
+        if ((rc = upload(ctx, ctx->d_cbase, ctx->h_cbase.data(), R + 1))) return rc;
+        if ((rc = upload(ctx, ctx->d_kbase, ctx->h_kbase.data(), R + 1))) return rc;
+        ctx->stats.h2d_bytes -= 3ull * (R + 1) * 8;  // internal traffic, not the caller's inputs
+        return TFBS_OK;
     }
-    DevMatches dm{};
-    dm.enabled = ctx->record_matches ? 1u : 0u;
-    dm.cap = (u32)std::min<uint64_t>(ctx->max_matches, 0xffffffffu);
-    dm.region = ctx->d_m_region.as<u32>();
-    dm.pattern_index = ctx->d_m_pattern.as<u32>();
-    dm.group = ctx->d_m_group.as<u32>();
-    dm.start = ctx->d_m_start.as<i64>();
+
+    // match buffer, shared-memory size and grid of the scan kernel
+    int setup_scan() {
+        if (ctx->record_matches) {
+            CK(ctx->d_m_region.reserve(ctx->max_matches * 4));
+            CK(ctx->d_m_pattern.reserve(ctx->max_matches * 4));
+            CK(ctx->d_m_group.reserve(ctx->max_matches * 4));
+            CK(ctx->d_m_start.reserve(ctx->max_matches * 8));
+        }
+        dm.enabled = ctx->record_matches ? 1u : 0u;
+        dm.cap = (u32)std::min<uint64_t>(ctx->max_matches, 0xffffffffu);
+        dm.region = ctx->d_m_region.as<u32>();
+        dm.pattern_index = ctx->d_m_pattern.as<u32>();
+        dm.group = ctx->d_m_group.as<u32>();
+        dm.start = ctx->d_m_start.as<i64>();
+        smem_bytes = (int)(sizeof(CtaShared) + SCAN_WARPS * sizeof(WarpShared) + ((ctx->cp.max_chunk_bytes + 15) & ~15u));
+        wide = ctx->cp.fields == 2;
+        if (wide) CK(cudaFuncSetAttribute(k_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        else CK(cudaFuncSetAttribute(k_scan<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        scan_grid = (uint32_t)ctx->prop.multiProcessorCount;  // persistent: one CTA per SM shares one copy of the tables
+        if (ctx->scan_ctas_per_sm < 0) scan_grid = (uint32_t)std::max(1, -ctx->scan_ctas_per_sm);  // debugging: fixed grid size
+        ctx->stats.scan_ctas = scan_grid;
+        return TFBS_OK;
+    }
 
     // ---- phase 2: batches under the scratch budget ---------------------------------------------------
-    auto region_cost = [&](uint32_t r, uint64_t* n_seq, uint64_t* n_d, uint64_t* n_units, uint64_t* n_c, uint64_t* n_keys) {
+    void region_cost(uint32_t r, uint64_t* n_seq, uint64_t* n_d, uint64_t* n_units, uint64_t* n_c, uint64_t* n_keys) const {
         uint64_t g = ctx->h_ngroups[r];
         uint64_t W = (uint64_t)(ctx->h_region_end[r] - ctx->h_region_start[r] + 1) + ctx->h_ins_extra[r];
         uint64_t nk = ctx->h_inner_off[r + 1] - ctx->h_inner_off[r];
@@ -427,40 +513,40 @@ int run_pipeline(tfbs_ctx* ctx) {
         *n_units = g * ((W + 31) / 32 + 1);
         *n_c = g * n_pid * nk;
         *n_keys = (uint64_t)n_pid * nk;
-    };
-    auto bytes_of = [&](uint64_t n_seq, uint64_t n_d, uint64_t n_units, uint64_t n_c, uint64_t n_keys) {
+    }
+    static uint64_t bytes_of(uint64_t n_seq, uint64_t n_d, uint64_t n_units, uint64_t n_c, uint64_t n_keys) {
         // sequences, diff lists + segments, packed bases (all of them when delta scoring is off), counts, keys, the sequence-keyed map,
         // and per possible item (<= n_d + n_seq): the item record, key, owner bookkeeping, list entry and its share of the item map
         return n_seq * (4 * 6 + 8 * 3 + 1 + 32) + n_d * (4 + 32) + n_units * 12 + n_c * 4 + n_keys * 24 + n_seq * 2 * 12 * 2 + (n_d + n_seq) * 96;
-    };
-    const int smem_bytes = (int)(sizeof(CtaShared) + SCAN_WARPS * sizeof(WarpShared) + ((ctx->cp.max_chunk_bytes + 15) & ~15u));
-    const bool wide = ctx->cp.fields == 2;
-    if (wide) CK(cudaFuncSetAttribute(k_scan<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    else CK(cudaFuncSetAttribute(k_scan<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    uint32_t scan_grid = (uint32_t)ctx->prop.multiProcessorCount;  // persistent: one CTA per SM shares one copy of the tables
-    if (ctx->scan_ctas_per_sm < 0) scan_grid = (uint32_t)std::max(1, -ctx->scan_ctas_per_sm);  // debugging: fixed grid size
-    ctx->stats.scan_ctas = scan_grid;
+    }
 
-    float ms_build = 0, ms_scan = 0, ms_count = 0;
-    uint64_t n_items_total = 0, n_hits_before = 0;
-    float ms_scan_kernel = 0;
-    uint32_t r0 = 0;
-    while (r0 < R) {
-        uint64_t n_seq = 0, n_d = 0, n_units = 0, n_c = 0, n_keys = 0;
+    int plan_batch(uint32_t r0, Batch* b) {
+        b->r0 = r0;
         uint32_t r1 = r0;
         while (r1 < R) {
             uint64_t a, b2, c2, d2, e2;
             region_cost(r1, &a, &b2, &c2, &d2, &e2);
-            if (r1 > r0 && (bytes_of(n_seq + a, n_d + b2, n_units + c2, n_c + d2, n_keys + e2) > ctx->scratch_bytes || n_seq + a > 0x7fffffffull ||
-                            n_seq + a + n_d + b2 > (1ull << 30)))
+            if (r1 > r0 && (bytes_of(b->n_seq + a, b->n_d + b2, b->n_units + c2, b->n_c + d2, b->n_keys + e2) > ctx->scratch_bytes ||
+                            b->n_seq + a > 0x7fffffffull || b->n_seq + a + b->n_d + b2 > (1ull << 30)))
                 break;
-            n_seq += a; n_d += b2; n_units += c2; n_c += d2; n_keys += e2;
+            b->n_seq += a; b->n_d += b2; b->n_units += c2; b->n_c += d2; b->n_keys += e2;
             ++r1;
         }
-        const uint32_t nr = r1 - r0;
-        if (n_seq > 0x7fffffffull || n_seq + n_d > (1ull << 30))
+        b->r1 = r1;
+        b->nr = r1 - r0;
+        if (b->n_seq > 0x7fffffffull || b->n_seq + b->n_d > (1ull << 30))
             return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "a single region has more haplotype groups / carried variants than one batch can hold");
+        b->items_cap = b->n_d + b->n_seq;
+        if (b->items_cap > 0xfffffff0ull) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "batch too large for the scan scheduler");
+        b->ic = std::max<uint64_t>(1, b->items_cap);
+        // reference hits live in a slab of capr entries per region; a region with more hits sends the batch to the full scan
+        b->capr = ctx->refhit_cap_opt ? (uint32_t)std::max<int64_t>(1, ctx->refhit_cap_opt / std::max<uint32_t>(1, b->nr))
+                                      : (uint32_t)std::min<uint64_t>(32768, std::max<uint64_t>(512, (1ull << 30) / std::max<uint32_t>(1, b->nr) / sizeof(RefHit)));  // <= 1 GB of slabs
+        return TFBS_OK;
+    }
 
+    int reserve_batch(Batch* b) {
+        const uint64_t n_seq = b->n_seq, n_d = b->n_d, n_c = b->n_c, n_keys = b->n_keys, ic = b->ic;
         CK(ctx->d_seq_region.reserve(n_seq * 4));
         CK(ctx->d_seq_leader.reserve(n_seq * 4));
         CK(ctx->d_seq_nd.reserve(n_seq * 4));
@@ -476,17 +562,11 @@ int run_pipeline(tfbs_ctx* ctx) {
         CK(ctx->d_vmax.reserve(std::max<uint64_t>(1, n_keys) * 4));
         CK(ctx->d_flag.reserve(std::max<uint64_t>(1, n_keys) * 4));
         CK(ctx->d_rowidx.reserve((n_keys + 1) * 8));
-        const uint64_t items_cap = n_d + n_seq;
-        // reference hits live in a slab of capr entries per region; a region with more hits sends the batch to the full scan
-        const uint32_t capr = ctx->refhit_cap_opt ? (uint32_t)std::max<int64_t>(1, ctx->refhit_cap_opt / std::max<uint32_t>(1, nr))
-                                                  : (uint32_t)std::min<uint64_t>(32768, std::max<uint64_t>(512, (1ull << 30) / std::max<uint32_t>(1, nr) / sizeof(RefHit)));  // <= 1 GB of slabs
-        const uint64_t refhit_cap = (uint64_t)capr * nr;
-        CK(ctx->d_refcnt.reserve((size_t)nr * 4));
+        CK(ctx->d_refcnt.reserve((size_t)b->nr * 4));
         CK(ctx->d_seq_nitems.reserve(n_seq * 4));
         CK(ctx->d_item_off.reserve((n_seq + 1) * 8));
-        CK(ctx->d_items.reserve(std::max<uint64_t>(1, items_cap) * sizeof(ScanItem)));
-        CK(ctx->d_refhits.reserve((size_t)refhit_cap * sizeof(RefHit)));
-        const uint64_t ic = std::max<uint64_t>(1, items_cap);
+        CK(ctx->d_items.reserve(ic * sizeof(ScanItem)));
+        CK(ctx->d_refhits.reserve((size_t)b->capr * b->nr * sizeof(RefHit)));
         CK(ctx->d_item_key.reserve(ic * 8));
         CK(ctx->d_item_hits.reserve(ic * 4));
         CK(ctx->d_item_coff.reserve((ic + 1) * 8));
@@ -497,10 +577,10 @@ int run_pipeline(tfbs_ctx* ctx) {
         CK(ctx->d_ent_units.reserve(ic * 4));
         CK(ctx->d_ent_uoff.reserve((ic + 1) * 8));
 
-        DevSeqs sq{};
+        DevSeqs& sq = b->sq;
         sq.n_seq = (u32)n_seq;
         sq.gbase = ctx->d_gbase.as<u64>();
-        sq.gbase0 = ctx->h_gbase[r0];
+        sq.gbase0 = ctx->h_gbase[b->r0];
         sq.seq_region = ctx->d_seq_region.as<u32>();
         sq.seq_leader = ctx->d_seq_leader.as<u32>();
         sq.seq_nd = ctx->d_seq_nd.as<u32>();
@@ -518,158 +598,151 @@ int run_pipeline(tfbs_ctx* ctx) {
         sq.seq_nitems = ctx->d_seq_nitems.as<u32>();
         sq.item_off = ctx->d_item_off.as<u64>();
         sq.items = ctx->d_items.as<ScanItem>();
-        sq.n_items_cap = (u32)std::min<uint64_t>(items_cap, 0xffffffffu);
+        sq.n_items_cap = (u32)std::min<uint64_t>(b->items_cap, 0xffffffffu);
         sq.item_key = ctx->d_item_key.as<u64>();
         sq.item_hits = ctx->d_item_hits.as<u32>();
         sq.item_coff = ctx->d_item_coff.as<u64>();
         sq.item_cnt = nullptr;  // sized once the owners are known
-        DevRefHits drh{ctx->d_refhits.as<RefHit>(), ctx->d_refcnt.as<u32>(), capr, r0};
+        b->drh = DevRefHits{ctx->d_refhits.as<RefHit>(), ctx->d_refcnt.as<u32>(), b->capr, b->r0};
+        b->dc.C = ctx->d_C.as<u32>();
+        b->dc.cbase = ctx->d_cbase.as<u64>();
+        b->dc.cbase0 = ctx->h_cbase[b->r0];
+        b->d_n_items = sq.item_off + n_seq;
+        b->d_n_list = ctx->d_score_idx.as<u64>() + b->items_cap;
+        return TFBS_OK;
+    }
 
-        {   // hits so far, in case this batch has to be re-scored without delta scoring
-            CK(cudaMemcpyAsync(ctx->h_status.p, dst, sizeof(DevStatus), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            DevStatus cur;
-            memcpy(&cur, ctx->h_status.p, sizeof cur);
-            n_hits_before = cur.n_hits;
-            CK(cudaMemsetAsync(&dst->n_refhits, 0, 4, st));
-        }
-        CK(cudaEventRecord(ctx->ev[2], st));
-        // K1 build
-        TFBS_LAUNCH(k_seq_init, nr, 128, 0, st)(H, r0, ctx->d_hap_group.as<u32>(), ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), sq);
-        ++launches;
-        if ((rc = device_scan(ctx, sq.seq_nd, n_seq, sq.seq_doff))) return rc;
-        TFBS_LAUNCH(k_walk, grid_for(n_seq, 128), 128, 0, st)(db, sq, dst);
-        ++launches;
-        // the sequence-keyed map of load_haplotypes
-        {
-            uint32_t cap = 1024;
-            while (cap < 2 * n_seq) cap <<= 1;
-            CK(ctx->d_keys.reserve((size_t)cap * 8));
-            CK(ctx->d_vals.reserve((size_t)cap * 4));
-            CK(cudaMemsetAsync(ctx->d_keys.p, 0, (size_t)cap * 8, st));
-            CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, (size_t)cap * 4, st));
-            CK(cudaMemsetAsync(ctx->d_ref_used.as<u32>() + r0, 0, (size_t)nr * 4, st));
-            TFBS_LAUNCH(k_seq_insert, grid_for(n_seq, 256), 256, 0, st)(sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1);
-            TFBS_LAUNCH(k_seq_resolve, grid_for(n_seq, 128), 128, 0, st)(db, sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1, dst);
-            TFBS_LAUNCH(k_redirect, grid_for((uint64_t)nr * H, 256), 256, 0, st)(H, r0, nr, sq, ctx->d_hap_group.as<u32>(), ctx->d_ref_used.as<u32>(),
+    // K1: segments + hash of every distinct haplotype, then the sequence-keyed map of load_haplotypes
+    int build_sequences(Batch& b) {
+        int rc;
+        const uint64_t n_seq = b.n_seq;
+        TFBS_LAUNCH(k_seq_init, b.nr, 128, 0, st)(H, b.r0, ctx->d_hap_group.as<u32>(), ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), b.sq);
+        ++launches();
+        if ((rc = device_scan(b.sq.seq_nd, n_seq, b.sq.seq_doff))) return rc;
+        TFBS_LAUNCH(k_walk, grid_for(n_seq, 128), 128, 0, st)(db, b.sq, dst);
+        ++launches();
+        uint32_t cap = 1024;
+        while (cap < 2 * n_seq) cap <<= 1;
+        CK(ctx->d_keys.reserve((size_t)cap * 8));
+        CK(ctx->d_vals.reserve((size_t)cap * 4));
+        CK(cudaMemsetAsync(ctx->d_keys.p, 0, (size_t)cap * 8, st));
+        CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, (size_t)cap * 4, st));
+        CK(cudaMemsetAsync(ctx->d_ref_used.as<u32>() + b.r0, 0, (size_t)b.nr * 4, st));
+        TFBS_LAUNCH(k_seq_insert, grid_for(n_seq, 256), 256, 0, st)(b.sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1);
+        TFBS_LAUNCH(k_seq_resolve, grid_for(n_seq, 128), 128, 0, st)(db, b.sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), cap - 1, dst);
+        TFBS_LAUNCH(k_redirect, grid_for((uint64_t)b.nr * H, 256), 256, 0, st)(H, b.r0, b.nr, b.sq, ctx->d_hap_group.as<u32>(), ctx->d_ref_used.as<u32>(),
                                                                         ctx->audit ? ctx->d_hap_flags.as<u8>() : nullptr);
-            launches += 3;
-        }
-        CK(cudaEventRecord(ctx->ev[3], st));
+        launches() += 3;
+        return TFBS_OK;
+    }
 
-        // K2 scan (+ the inherit / lose pass of delta scoring)
-        DevCounts dc{};
-        dc.C = ctx->d_C.as<u32>();
-        dc.cbase = ctx->d_cbase.as<u64>();
-        dc.cbase0 = ctx->h_cbase[r0];
-        if (items_cap > 0xfffffff0ull) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "batch too large for the scan scheduler");
-        const u64* d_n_items = sq.item_off + n_seq;
-        const u64* d_n_list = ctx->d_score_idx.as<u64>() + items_cap;
-        uint64_t n_list_host = 0;
-        auto scan_pass = [&](int delta) -> int {
-            int rc2;
-            if (n_c) CK(cudaMemsetAsync(ctx->d_C.p, 0, n_c * 4, st));
-            CK(cudaMemsetAsync(ctx->d_refcnt.p, 0, (size_t)nr * 4, st));
-            uint32_t tcap = 1024;
-            if (delta) {
-                while (tcap < 2 * items_cap) tcap <<= 1;
-                CK(ctx->d_keys.reserve((size_t)tcap * 8));
-                CK(ctx->d_vals.reserve((size_t)tcap * 4));
-                CK(cudaMemsetAsync(ctx->d_keys.p, 0, (size_t)tcap * 8, st));
-                CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, (size_t)tcap * 4, st));
-            }
-            CK(cudaMemsetAsync(ctx->d_score_flag.p, 0, ic * 4, st));
-            CK(cudaMemsetAsync(ctx->d_count_size.p, 0, ic * 4, st));
-            CK(cudaMemsetAsync(ctx->d_ent_units.p, 0, ic * 4, st));
-            TFBS_LAUNCH(k_items<false>, grid_for(n_seq, 128), 128, 0, st)(db, sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta, ctx->d_keys.as<u64>(),
-                                                                ctx->d_vals.as<u32>(), tcap - 1);
-            ++launches;
-            if ((rc2 = device_scan(ctx, sq.seq_nitems, n_seq, sq.item_off))) return rc2;
-            TFBS_LAUNCH(k_items<true>, grid_for(n_seq, 128), 128, 0, st)(db, sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta, ctx->d_keys.as<u64>(),
-                                                               ctx->d_vals.as<u32>(), tcap - 1);
-            TFBS_LAUNCH(k_item_resolve, grid_for(items_cap, 128), 128, 0, st)(db, sq, ctx->dpat, d_n_items, delta, ctx->cp.max_len, ctx->d_keys.as<u64>(),
-                                                                    ctx->d_vals.as<u32>(), tcap - 1, ctx->d_score_flag.as<u32>(),
-                                                                    ctx->d_count_size.as<u32>());
-            launches += 2;
-            if ((rc2 = device_scan(ctx, ctx->d_score_flag.as<u32>(), items_cap, ctx->d_score_idx.as<u64>()))) return rc2;
-            if ((rc2 = device_scan(ctx, ctx->d_count_size.as<u32>(), items_cap, sq.item_coff))) return rc2;
-            TFBS_LAUNCH(k_item_lists, grid_for(items_cap, 256), 256, 0, st)(sq, d_n_items, ctx->d_score_flag.as<u32>(), ctx->d_score_idx.as<u64>(),
-                                                                  ctx->d_list.as<u32>());
-            ++launches;
-            if ((rc2 = device_scan(ctx, sq.ent_units, items_cap, sq.ent_uoff))) return rc2;
-            CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 16, sq.item_coff + items_cap, 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 24, d_n_list, 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 32, sq.ent_uoff + items_cap, 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            const uint64_t cnt_words = ctx->h_totals.as<uint64_t>()[2];
-            n_list_host = ctx->h_totals.as<uint64_t>()[3];
-            const uint64_t ent_units_total = ctx->h_totals.as<uint64_t>()[4];
-            CK(ctx->d_item_cnt.reserve(std::max<uint64_t>(1, cnt_words) * 4));
-            if (cnt_words) CK(cudaMemsetAsync(ctx->d_item_cnt.p, 0, cnt_words * 4, st));
-            sq.item_cnt = ctx->d_item_cnt.as<u32>();
-            CK(ctx->d_pk.reserve(std::max<uint64_t>(1, ent_units_total) * 8));
-            CK(ctx->d_nm.reserve(std::max<uint64_t>(1, ent_units_total) * 4));
-            sq.pk = ctx->d_pk.as<u64>();
-            sq.nm = ctx->d_nm.as<u32>();
-            if (n_list_host) {
-                TFBS_LAUNCH(k_emit_list, grid_for(n_list_host * EMIT_LANES, 256), 256, 0, st)(db, sq, ctx->d_list.as<u32>(), d_n_list);
-                TFBS_LAUNCH(k_item_stats, grid_for(n_list_host, 256), 256, 0, st)(sq, ctx->dpat, ctx->d_list.as<u32>(), d_n_list, dst);
-                launches += 2;
-            }
+    // K2: work list, packing of the scored bases, the scan (one launch per pattern chunk), the finish pass of delta scoring
+    int scan_pass(Batch* bp, int delta) {
+        Batch& b = *bp;
+        DevSeqs& sq = b.sq;
+        int rc;
+        const uint64_t n_seq = b.n_seq, items_cap = b.items_cap, ic = b.ic;
+        if (b.n_c) CK(cudaMemsetAsync(ctx->d_C.p, 0, b.n_c * 4, st));
+        CK(cudaMemsetAsync(ctx->d_refcnt.p, 0, (size_t)b.nr * 4, st));
+        uint32_t tcap = 1024;
+        if (delta) {
+            while (tcap < 2 * items_cap) tcap <<= 1;
+            CK(ctx->d_keys.reserve((size_t)tcap * 8));
+            CK(ctx->d_vals.reserve((size_t)tcap * 4));
+            CK(cudaMemsetAsync(ctx->d_keys.p, 0, (size_t)tcap * 8, st));
+            CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, (size_t)tcap * 4, st));
+        }
+        CK(cudaMemsetAsync(ctx->d_score_flag.p, 0, ic * 4, st));
+        CK(cudaMemsetAsync(ctx->d_count_size.p, 0, ic * 4, st));
+        CK(cudaMemsetAsync(ctx->d_ent_units.p, 0, ic * 4, st));
+        TFBS_LAUNCH(k_items<false>, grid_for(n_seq, 128), 128, 0, st)(db, sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta, ctx->d_keys.as<u64>(),
+                                                            ctx->d_vals.as<u32>(), tcap - 1);
+        ++launches();
+        if ((rc = device_scan(sq.seq_nitems, n_seq, sq.item_off))) return rc;
+        TFBS_LAUNCH(k_items<true>, grid_for(n_seq, 128), 128, 0, st)(db, sq, ctx->d_ref_used.as<u32>(), ctx->cp.max_len, delta, ctx->d_keys.as<u64>(),
+                                                           ctx->d_vals.as<u32>(), tcap - 1);
+        TFBS_LAUNCH(k_item_resolve, grid_for(items_cap, 128), 128, 0, st)(db, sq, ctx->dpat, b.d_n_items, delta, ctx->cp.max_len, ctx->d_keys.as<u64>(),
+                                                                ctx->d_vals.as<u32>(), tcap - 1, ctx->d_score_flag.as<u32>(),
+                                                                ctx->d_count_size.as<u32>());
+        launches() += 2;
+        if ((rc = device_scan(ctx->d_score_flag.as<u32>(), items_cap, ctx->d_score_idx.as<u64>()))) return rc;
+        if ((rc = device_scan(ctx->d_count_size.as<u32>(), items_cap, sq.item_coff))) return rc;
+        TFBS_LAUNCH(k_item_lists, grid_for(items_cap, 256), 256, 0, st)(sq, b.d_n_items, ctx->d_score_flag.as<u32>(), ctx->d_score_idx.as<u64>(),
+                                                              ctx->d_list.as<u32>());
+        ++launches();
+        if ((rc = device_scan(sq.ent_units, items_cap, sq.ent_uoff))) return rc;
+        // the sizes of the owners' count vectors and of the packed bases decide two allocations: one round trip to the host
+        CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 16, sq.item_coff + items_cap, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 24, b.d_n_list, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 32, sq.ent_uoff + items_cap, 8, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        const uint64_t cnt_words = ctx->h_totals.as<uint64_t>()[2];
+        b.n_list_host = ctx->h_totals.as<uint64_t>()[3];
+        const uint64_t ent_units_total = ctx->h_totals.as<uint64_t>()[4];
+        CK(ctx->d_item_cnt.reserve(std::max<uint64_t>(1, cnt_words) * 4));
+        if (cnt_words) CK(cudaMemsetAsync(ctx->d_item_cnt.p, 0, cnt_words * 4, st));
+        sq.item_cnt = ctx->d_item_cnt.as<u32>();
+        CK(ctx->d_pk.reserve(std::max<uint64_t>(1, ent_units_total) * 8));
+        CK(ctx->d_nm.reserve(std::max<uint64_t>(1, ent_units_total) * 4));
+        sq.pk = ctx->d_pk.as<u64>();
+        sq.nm = ctx->d_nm.as<u32>();
+        if (b.n_list_host) {
+            TFBS_LAUNCH(k_emit_list, grid_for(b.n_list_host * EMIT_LANES, 256), 256, 0, st)(db, sq, ctx->d_list.as<u32>(), b.d_n_list);
+            TFBS_LAUNCH(k_item_stats, grid_for(b.n_list_host, 256), 256, 0, st)(sq, ctx->dpat, ctx->d_list.as<u32>(), b.d_n_list, dst);
+            launches() += 2;
+        }
 #ifndef TFBS_PER_GRAB
 #define TFBS_PER_GRAB 8
 #endif
-            const u32 per_grab = delta ? (u32)TFBS_PER_GRAB : 1u;
-            CK(cudaEventRecord(ctx->ev[8], st));
-            for (uint32_t c = 0; c < ctx->cp.chunks.size() && n_list_host; ++c) {
-                CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
-                if (wide) TFBS_LAUNCH(k_scan<2>, scan_grid, SCAN_CTA, smem_bytes, st)(db, sq, ctx->dpat, dc, dm, drh, ctx->d_list.as<u32>(), d_n_list, per_grab, dst, c, delta);
-                else TFBS_LAUNCH(k_scan<3>, scan_grid, SCAN_CTA, smem_bytes, st)(db, sq, ctx->dpat, dc, dm, drh, ctx->d_list.as<u32>(), d_n_list, per_grab, dst, c, delta);
-                ++launches;
-                ++ctx->stats.scan_launches;
-                ctx->stats.scan_input_bytes += ent_units_total * 12 + (uint64_t)ctx->cp.chunks[c].tbl_words * 8 * scan_grid;
-            }
-            CK(cudaEventRecord(ctx->ev[9], st));
-            if (delta) {
-                TFBS_LAUNCH(k_group_finish, grid_for(n_seq * 8, 256), 256, 0, st)(db, sq, ctx->dpat, dc, drh, ctx->d_ref_used.as<u32>(), dst);
-                ++launches;
-            }
-            CK(cudaGetLastError());
-            return TFBS_OK;
-        };
-        int use_delta = (ctx->delta && !ctx->record_matches) ? 1 : 0;
-        if ((rc = scan_pass(use_delta))) return rc;
-        CK(cudaEventRecord(ctx->ev[4], st));
-
-        // K3 rows
-        TFBS_LAUNCH(k_nominal, grid_for((uint64_t)nr * H, 256), 256, 0, st)(db, r0, nr, ctx->d_hap_group.as<u32>(), sq, ctx->dpat, dst);
-        TFBS_LAUNCH(k_seq_stats, grid_for(n_seq, 256), 256, 0, st)(sq, ctx->dpat, ctx->d_ref_used.as<u32>(), dst);
-        launches += 2;
-        auto rows_pass = [&](int delta) -> int {
-            if (!n_keys) return TFBS_OK;
-            int rc2;
-            TFBS_LAUNCH(k_rows_minmax, nr, 128, 0, st)(db, r0, ctx->d_hap_group.as<u32>(), dc, ctx->d_gbase.as<u64>(), n_pid, ctx->d_kbase.as<u64>(),
-                                              ctx->h_kbase[r0], ctx->rows_mode, delta, ctx->d_vmin.as<u32>(), ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(),
-                                              &dst->max_count);
-            ++launches;
-            if ((rc2 = device_scan(ctx, ctx->d_flag.as<u32>(), n_keys, ctx->d_rowidx.as<u64>()))) return rc2;
-            CK(cudaMemcpyAsync(ctx->h_totals.p, ctx->d_rowidx.as<u64>() + n_keys, 8, cudaMemcpyDeviceToHost, st));
-            return TFBS_OK;
-        };
-        uint64_t batch_rows = 0;
-        if ((rc = rows_pass(use_delta))) return rc;
-        CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 8, d_n_items, 8, cudaMemcpyDeviceToHost, st));
-        CK(cudaMemcpyAsync(ctx->h_status.p, dst, sizeof(DevStatus), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
+        const u32 per_grab = delta ? (u32)TFBS_PER_GRAB : 1u;
+        CK(cudaEventRecord(ctx->ev[8], st));
+        for (uint32_t c = 0; c < ctx->cp.chunks.size() && b.n_list_host; ++c) {
+            CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
+            if (wide) TFBS_LAUNCH(k_scan<2>, scan_grid, SCAN_CTA, smem_bytes, st)(db, sq, ctx->dpat, b.dc, dm, b.drh, ctx->d_list.as<u32>(), b.d_n_list, per_grab, dst, c, delta);
+            else TFBS_LAUNCH(k_scan<3>, scan_grid, SCAN_CTA, smem_bytes, st)(db, sq, ctx->dpat, b.dc, dm, b.drh, ctx->d_list.as<u32>(), b.d_n_list, per_grab, dst, c, delta);
+            ++launches();
+            ++ctx->stats.scan_launches;
+            ctx->stats.scan_input_bytes += ent_units_total * 12 + (uint64_t)ctx->cp.chunks[c].tbl_words * 8 * scan_grid;
+        }
+        CK(cudaEventRecord(ctx->ev[9], st));
+        if (delta) {
+            TFBS_LAUNCH(k_group_finish, grid_for(n_seq * 8, 256), 256, 0, st)(db, sq, ctx->dpat, b.dc, b.drh, ctx->d_ref_used.as<u32>(), dst);
+            ++launches();
+        }
         CK(cudaGetLastError());
-        DevStatus hs;
-        memcpy(&hs, ctx->h_status.p, sizeof hs);
+        return TFBS_OK;
+    }
+
+    // min / max per key and the row index of every emitted key; the row count lands in h_totals[0]
+    int rows_pass(Batch& b, int delta) {
+        if (!b.n_keys) return TFBS_OK;
+        int rc;
+        TFBS_LAUNCH(k_rows_minmax, b.nr, 128, 0, st)(db, b.r0, ctx->d_hap_group.as<u32>(), b.dc, ctx->d_gbase.as<u64>(), n_pid, ctx->d_kbase.as<u64>(),
+                                          ctx->h_kbase[b.r0], ctx->rows_mode, delta, ctx->d_vmin.as<u32>(), ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(),
+                                          &dst->max_count);
+        ++launches();
+        if ((rc = device_scan(ctx->d_flag.as<u32>(), b.n_keys, ctx->d_rowidx.as<u64>()))) return rc;
+        CK(cudaMemcpyAsync(ctx->h_totals.p, ctx->d_rowidx.as<u64>() + b.n_keys, 8, cudaMemcpyDeviceToHost, st));
+        return TFBS_OK;
+    }
+
+    // K3 up to the row count; reports the reference's panics; re-scores the batch in full when the reference-hit slabs overflowed
+    int count_and_filter(Batch* bp) {
+        Batch& b = *bp;
+        int rc;
+        TFBS_LAUNCH(k_nominal, grid_for((uint64_t)b.nr * H, 256), 256, 0, st)(db, b.r0, b.nr, ctx->d_hap_group.as<u32>(), b.sq, ctx->dpat, dst);
+        TFBS_LAUNCH(k_seq_stats, grid_for(b.n_seq, 256), 256, 0, st)(b.sq, ctx->dpat, ctx->d_ref_used.as<u32>(), dst);
+        launches() += 2;
+        if ((rc = rows_pass(b, b.use_delta))) return rc;
+        if ((rc = read_status(&b.hs))) return rc;
+        CK(cudaGetLastError());
+        const DevStatus& hs = b.hs;
         if (hs.err_key != ~0ull) {
             uint32_t q = (uint32_t)(hs.err_key >> 32);
             int64_t rel = (int64_t)((hs.err_key >> 4) & 0xfffffff) - (1 << 27);
             uint32_t code = (uint32_t)(hs.err_key & 15);
             // region of sequence q: last r with gbase[r] - gbase[r0] <= q
-            uint32_t r = (uint32_t)(std::upper_bound(ctx->h_gbase.begin() + r0, ctx->h_gbase.begin() + r1, ctx->h_gbase[r0] + q) - ctx->h_gbase.begin() - 1);
+            uint32_t r = (uint32_t)(std::upper_bound(ctx->h_gbase.begin() + b.r0, ctx->h_gbase.begin() + b.r1, ctx->h_gbase[b.r0] + q) - ctx->h_gbase.begin() - 1);
             int64_t pos = ctx->h_region_start[r] + rel;
             if (code == DEV_REF_MISMATCH)
                 return fail(ctx, TFBS_ERR_REF_MISMATCH,
@@ -678,30 +751,35 @@ int run_pipeline(tfbs_ctx* ctx) {
             return fail(ctx, TFBS_ERR_MISSING_CASE, "Missing case in haplotype patcher (ref_position=" + std::to_string(pos) + " region=" + std::to_string(r) + ")");
         }
         if (hs.seq_collision) return fail(ctx, TFBS_ERR_INTERNAL, "sequence hash collision between distinct haplotypes");
-        if (use_delta && hs.refhit_overflow) {
-            // more reference hits than the buffer holds (very permissive thresholds): score this batch in full instead
+        if (b.use_delta && hs.refhit_overflow) {
+            // more reference hits than the slabs hold (very permissive thresholds): score this batch in full instead
             DevStatus fix = hs;
             fix.refhit_overflow = 0;
             fix.n_refhits = 0;
-            fix.n_hits = n_hits_before;
+            fix.n_hits = hits_done;
             memcpy(ctx->h_status.p, &fix, sizeof fix);
             CK(cudaMemcpyAsync(dst, ctx->h_status.p, sizeof fix, cudaMemcpyHostToDevice, st));
-            use_delta = 0;
-            if ((rc = scan_pass(0))) return rc;
-            if ((rc = rows_pass(0))) return rc;
-            CK(cudaMemcpyAsync((char*)ctx->h_totals.p + 8, d_n_items, 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+            b.use_delta = 0;
+            if ((rc = scan_pass(bp, 0))) return rc;
+            if ((rc = rows_pass(b, 0))) return rc;
+            if ((rc = read_status(&b.hs))) return rc;
             CK(cudaGetLastError());
         }
-        n_items_total += n_list_host;
-        if (n_keys) batch_rows = *ctx->h_totals.as<uint64_t>();
+        hits_done = b.hs.n_hits;
+        n_items_total += b.n_list_host;
+        return TFBS_OK;
+    }
 
+    // compaction of the emitted rows and their copy into the pinned result buffers (appended to the rows of earlier batches)
+    int fetch_rows(Batch& b) {
+        const uint64_t batch_rows = b.n_keys ? *ctx->h_totals.as<uint64_t>() : 0;
         if (batch_rows) {
+            const uint64_t n_keys = b.n_keys;
             uint64_t tot = ctx->n_rows + batch_rows;
             // element width of left / right: u32 like the reference's Vec<u32>, or (option rows_width = 0) the narrowest type that
             // holds every count of the block: the rows are the dominant PCIe traffic of large cohorts
             uint32_t eb = 4;
-            if (ctx->rows_width == 0) eb = hs.max_count < 256 ? 1 : (hs.max_count < 65536 ? 2 : 4);
+            if (ctx->rows_width == 0) eb = b.hs.max_count < 256 ? 1 : (b.hs.max_count < 65536 ? 2 : 4);
             if (ctx->n_rows == 0) ctx->row_bytes = eb;
             if (eb > ctx->row_bytes) {  // an earlier batch of this block was stored narrower: widen it in place (rare)
                 const uint64_t n = ctx->n_rows * S;
@@ -732,14 +810,14 @@ int run_pipeline(tfbs_ctx* ctx) {
             DevRows dr{ctx->d_rows_region.as<u32>(), ctx->d_rows_inner.as<u32>(), ctx->d_rows_pid.as<u16>(), ctx->d_rows_vmin.as<u32>(),
                        ctx->d_rows_vmax.as<u32>(), ctx->d_rows_left.p, ctx->d_rows_right.p};
 #define TFBS_ROWS_WRITE(T)                                                                                                              \
-    TFBS_LAUNCH(k_rows_write<T>, grid_for(n_keys * 32, 256), 256, 0, st)(db, r0, nr, ctx->d_hap_group.as<u32>(), dc, n_pid, ctx->d_pid_list.as<u16>(), \
-                                                                ctx->d_kbase.as<u64>(), ctx->h_kbase[r0], n_keys, ctx->d_vmin.as<u32>(),   \
-                                                                ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(), ctx->d_rowidx.as<u64>(), dr, 0, use_delta)
+    TFBS_LAUNCH(k_rows_write<T>, grid_for(n_keys * 32, 256), 256, 0, st)(db, b.r0, b.nr, ctx->d_hap_group.as<u32>(), b.dc, n_pid, ctx->d_pid_list.as<u16>(), \
+                                                                ctx->d_kbase.as<u64>(), ctx->h_kbase[b.r0], n_keys, ctx->d_vmin.as<u32>(),   \
+                                                                ctx->d_vmax.as<u32>(), ctx->d_flag.as<u32>(), ctx->d_rowidx.as<u64>(), dr, 0, b.use_delta)
             if (eb == 1) TFBS_ROWS_WRITE(u8);
             else if (eb == 2) TFBS_ROWS_WRITE(u16);
             else TFBS_ROWS_WRITE(u32);
 #undef TFBS_ROWS_WRITE
-            ++launches;
+            ++launches();
             uint64_t o = ctx->n_rows;
             CK(cudaMemcpyAsync(ctx->h_rows_region.as<u32>() + o, dr.region, batch_rows * 4, cudaMemcpyDeviceToHost, st));
             CK(cudaMemcpyAsync(ctx->h_rows_inner.as<u32>() + o, dr.inner, batch_rows * 4, cudaMemcpyDeviceToHost, st));
@@ -753,6 +831,10 @@ int run_pipeline(tfbs_ctx* ctx) {
         }
         CK(cudaEventRecord(ctx->ev[5], st));
         CK(cudaStreamSynchronize(st));
+        return TFBS_OK;
+    }
+
+    int batch_timers() {
         float t;
         CK(cudaEventElapsedTime(&t, ctx->ev[2], ctx->ev[3]));
         ms_build += t;
@@ -762,60 +844,66 @@ int run_pipeline(tfbs_ctx* ctx) {
         ms_count += t;
         CK(cudaEventElapsedTime(&t, ctx->ev[8], ctx->ev[9]));
         ms_scan_kernel += t;
-        r0 = r1;
+        return TFBS_OK;
     }
-    CK(cudaEventRecord(ctx->ev[6], st));
-    CK(cudaMemcpyAsync(ctx->h_status.p, dst, sizeof(DevStatus), cudaMemcpyDeviceToHost, st));
-    if (ctx->record_matches) {
-        CK(ctx->h_hap_group.reserve(RH * 4, false));
-        CK(cudaMemcpyAsync(ctx->h_hap_group.p, ctx->d_hap_group.p, RH * 4, cudaMemcpyDeviceToHost, st));
-    }
-    if (ctx->audit) {
-        CK(ctx->h_hap_flags.reserve(RH, false));
-        CK(cudaMemcpyAsync(ctx->h_hap_flags.p, ctx->d_hap_flags.p, RH, cudaMemcpyDeviceToHost, st));
-    }
-    CK(cudaStreamSynchronize(st));
-    DevStatus hs;
-    memcpy(&hs, ctx->h_status.p, sizeof hs);
-    if (ctx->record_matches) {
-        uint64_t n = std::min<uint64_t>(hs.n_matches, dm.cap);
-        ctx->matches_truncated = hs.n_matches > dm.cap;
-        CK(ctx->h_m_region.reserve(std::max<uint64_t>(1, n) * 4, false));
-        CK(ctx->h_m_pattern.reserve(std::max<uint64_t>(1, n) * 4, false));
-        CK(ctx->h_m_group.reserve(std::max<uint64_t>(1, n) * 4, false));
-        CK(ctx->h_m_start.reserve(std::max<uint64_t>(1, n) * 8, false));
-        if (n) {
-            CK(cudaMemcpyAsync(ctx->h_m_region.p, dm.region, n * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ctx->h_m_pattern.p, dm.pattern_index, n * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ctx->h_m_group.p, dm.group, n * 4, cudaMemcpyDeviceToHost, st));
-            CK(cudaMemcpyAsync(ctx->h_m_start.p, dm.start, n * 8, cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
+
+    // final status word, the match list and the audit flags, timings and counters of the run
+    int finish() {
+        CK(cudaEventRecord(ctx->ev[6], st));
+        if (ctx->record_matches) {
+            CK(ctx->h_hap_group.reserve(RH * 4, false));
+            CK(cudaMemcpyAsync(ctx->h_hap_group.p, ctx->d_hap_group.p, RH * 4, cudaMemcpyDeviceToHost, st));
         }
-        ctx->n_matches = n;
+        if (ctx->audit) {
+            CK(ctx->h_hap_flags.reserve(RH, false));
+            CK(cudaMemcpyAsync(ctx->h_hap_flags.p, ctx->d_hap_flags.p, RH, cudaMemcpyDeviceToHost, st));
+        }
+        DevStatus hs;
+        int rc = read_status(&hs);
+        if (rc) return rc;
+        if (ctx->record_matches) {
+            uint64_t n = std::min<uint64_t>(hs.n_matches, dm.cap);
+            ctx->matches_truncated = hs.n_matches > dm.cap;
+            CK(ctx->h_m_region.reserve(std::max<uint64_t>(1, n) * 4, false));
+            CK(ctx->h_m_pattern.reserve(std::max<uint64_t>(1, n) * 4, false));
+            CK(ctx->h_m_group.reserve(std::max<uint64_t>(1, n) * 4, false));
+            CK(ctx->h_m_start.reserve(std::max<uint64_t>(1, n) * 8, false));
+            if (n) {
+                CK(cudaMemcpyAsync(ctx->h_m_region.p, dm.region, n * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(ctx->h_m_pattern.p, dm.pattern_index, n * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(ctx->h_m_group.p, dm.group, n * 4, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(ctx->h_m_start.p, dm.start, n * 8, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+            }
+            ctx->n_matches = n;
+        }
+        float t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
+        ctx->stats.ms_group = t;
+        CK(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[6]));
+        ctx->stats.ms_total = t;
+        ctx->stats.ms_build = ms_build;
+        ctx->stats.ms_scan = ms_scan;
+        ctx->stats.ms_count = ms_count;
+        ctx->stats.n_regions = R;
+        ctx->stats.n_groups = hs.n_scanned;
+        ctx->stats.executed_cells = hs.executed_cells;
+        ctx->stats.nominal_cells = hs.nominal_cells;
+        ctx->stats.n_hits = hs.n_hits;
+        ctx->stats.n_keys = ctx->h_kbase[R];
+        ctx->stats.n_rows = ctx->n_rows;
+        ctx->stats.evaluated_cells = hs.evaluated_cells;
+        ctx->stats.n_scan_items = n_items_total;
+        ctx->stats.ms_scan_kernel = ms_scan_kernel;
+        ctx->stats.n_dropped = hs.n_dropped;
+        ctx->stats.n_truncated = hs.n_truncated;
+        ctx->ran = true;
+        return TFBS_OK;
     }
-    float t;
-    CK(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[1]));
-    ctx->stats.ms_group = t;
-    CK(cudaEventElapsedTime(&t, ctx->ev[0], ctx->ev[6]));
-    ctx->stats.ms_total = t;
-    ctx->stats.ms_build = ms_build;
-    ctx->stats.ms_scan = ms_scan;
-    ctx->stats.ms_count = ms_count;
-    ctx->stats.n_regions = R;
-    ctx->stats.n_groups = hs.n_scanned;
-    ctx->stats.executed_cells = hs.executed_cells;
-    ctx->stats.nominal_cells = hs.nominal_cells;
-    ctx->stats.n_hits = hs.n_hits;
-    ctx->stats.n_keys = ctx->h_kbase[R];
-    ctx->stats.n_rows = ctx->n_rows;
-    ctx->stats.evaluated_cells = hs.evaluated_cells;
-    ctx->stats.n_scan_items = n_items_total;
-    ctx->stats.ms_scan_kernel = ms_scan_kernel;
-    ctx->stats.n_dropped = hs.n_dropped;
-    ctx->stats.n_truncated = hs.n_truncated;
-    ctx->ran = true;
-    return TFBS_OK;
-}
+};
+
+int run_pipeline(tfbs_ctx* ctx) { return Pipeline(ctx).run(); }
+
 
 }  // namespace
 
