@@ -1,0 +1,308 @@
+// bcf.hpp -- BCF2 decoding: records, GT -> carrier bits (haplotype.rs:13-62), CSI index
+// Host side of find-tfbs-b200 (see driver.cpp for the map); header-only, one translation unit.
+#pragma once
+#include "options.hpp"
+#include "bgzf.hpp"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------------
+// BCF2 (what rust-htslib's IndexedReader gives load_diffs: pos, alleles, GT of the selected samples)
+// ---------------------------------------------------------------------------------------------------------------
+struct Cursor {
+    const uint8_t* p;
+    const uint8_t* e;
+    void need(size_t n) const { if ((size_t)(e - p) < n) die("truncated BCF"); }
+    uint8_t u8() { need(1); return *p++; }
+    int32_t i32() { need(4); int32_t v; memcpy(&v, p, 4); p += 4; return v; }
+    uint32_t u32() { need(4); uint32_t v; memcpy(&v, p, 4); p += 4; return v; }
+    int32_t tint(int t) {
+        if (t == 1) { need(1); return (int8_t)*p++; }
+        if (t == 2) { need(2); int16_t v; memcpy(&v, p, 2); p += 2; return v; }
+        if (t == 3) return i32();
+        die("BCF: integer expected");
+    }
+    void desc(int* t, uint32_t* n) {
+        uint8_t b = u8();
+        *t = b & 15;
+        *n = b >> 4;
+        if (*n == 15) { int t2; uint32_t n2; desc(&t2, &n2); *n = (uint32_t)tint(t2); }
+    }
+    static size_t tsize(int t) {
+        switch (t) { case 0: return 0; case 1: case 7: return 1; case 2: return 2; case 3: case 5: return 4; }
+        die("BCF: unknown value type");
+    }
+    std::string tstr() {
+        int t; uint32_t n;
+        desc(&t, &n);
+        if (t != 7 && !(t == 0 && n == 0)) die("BCF: string expected");
+        need(n);
+        std::string s((const char*)p, n);
+        p += n;
+        return s;
+    }
+};
+
+struct Record {
+    int64_t pos;
+    int32_t rlen;
+    uint32_t n_allele;
+    std::string ref, alt;   // alleles[0], alleles[1]
+    uint32_t carrier_row;   // row in Cohort::carriers (biallelic records only), else UINT32_MAX
+};
+
+struct Cohort {
+    std::vector<std::string> bcf_samples, samples;  // all columns / selected, in BCF order
+    std::vector<size_t> sample_positions;
+    std::vector<Record> records;                    // of the wanted chromosome, file order (sorted by pos)
+    std::vector<uint32_t> carriers;                 // [rows][pitch]
+    uint32_t pitch = 1;
+    int32_t max_rlen = 1;
+};
+
+void parse_bcf_header(Cursor& c, std::vector<std::string>* contigs, std::vector<std::string>* samples, int* gt_key) {
+    c.need(9);
+    if (memcmp(c.p, "BCF\2", 4) != 0) die("Error while opening the bcf file: not a BCF2 file");
+    c.p += 5;
+    uint32_t l_text = c.u32();
+    c.need(l_text);
+    std::string text((const char*)c.p, l_text);
+    c.p += l_text;
+    std::vector<std::string> dict{"PASS"};
+    auto dict_set = [&](const std::string& id, int idx) {
+        if (idx < 0) { if (std::find(dict.begin(), dict.end(), id) == dict.end()) dict.push_back(id); }
+        else { if ((size_t)idx >= dict.size()) dict.resize(idx + 1); dict[idx] = id; }
+    };
+    for (std::string line : split(text, '\n')) {
+        while (!line.empty() && (line.back() == '\0' || line.back() == '\r')) line.pop_back();
+        auto field = [&](const std::string& key) -> std::string {
+            size_t p = line.find(key + "=");
+            while (p != std::string::npos && p > 0 && line[p - 1] != '<' && line[p - 1] != ',') p = line.find(key + "=", p + 1);
+            if (p == std::string::npos) return "";
+            p += key.size() + 1;
+            size_t q = line.find_first_of(",>", p);
+            return line.substr(p, q == std::string::npos ? std::string::npos : q - p);
+        };
+        if (line.rfind("##contig=", 0) == 0) {
+            std::string id = field("ID"), idx = field("IDX");
+            if (!idx.empty()) { size_t k = (size_t)atoi(idx.c_str()); if (k >= contigs->size()) contigs->resize(k + 1); (*contigs)[k] = id; }
+            else contigs->push_back(id);
+        } else if (line.rfind("##FILTER=", 0) == 0 || line.rfind("##INFO=", 0) == 0 || line.rfind("##FORMAT=", 0) == 0) {
+            std::string id = field("ID"), idx = field("IDX");
+            dict_set(id, idx.empty() ? -1 : atoi(idx.c_str()));
+        } else if (line.rfind("#CHROM", 0) == 0) {
+            auto f = split(line, '\t');
+            for (size_t i = 9; i < f.size(); ++i) samples->push_back(f[i]);
+        }
+    }
+    *gt_key = -1;
+    for (size_t i = 0; i < dict.size(); ++i)
+        if (dict[i] == "GT") *gt_key = (int)i;
+}
+
+void check_letters(const std::string& s) {  // util.rs:4-16
+    for (unsigned char l : s)
+        if (!(l == 65 || l == 97 || l == 67 || l == 99 || l == 71 || l == 103 || l == 84 || l == 116 || l == 78 || l == 110))
+            die("Unknown nucleotide " + std::to_string((int)l));
+}
+
+// Where the records of contig `rid` live in the BGZF file, from the CSI index next to the BCF (<bcf>.csi).  The reference reads
+// through htslib's IndexedReader, which seeks with the same index (haplotype.rs:78-79); here the whole contig is taken at once.
+// Virtual offsets are (compressed offset of the member << 16) | offset inside the inflated member.
+struct CsiSpan {
+    bool found = false;   // an index was read and holds this contig
+    bool empty = false;   // ... and the contig has no record
+    uint64_t vbeg = 0, vend = 0;
+};
+CsiSpan csi_contig_span(const std::string& bcf_path, int rid) {
+    CsiSpan sp;
+    std::ifstream probe(bcf_path + ".csi", std::ios::binary);
+    if (!probe) return sp;
+    probe.close();
+    MappedFile f(bcf_path + ".csi", "Error while opening the index");
+    std::vector<uint8_t> d = gunzip_bgzf(f.data(), f.size(), bcf_path + ".csi", 1);
+    Cursor c{d.data(), d.data() + d.size()};
+    auto u64 = [&] { c.need(8); uint64_t v; memcpy(&v, c.p, 8); c.p += 8; return v; };
+    if (d.size() < 16 || memcmp(c.p, "CSI\1", 4) != 0) return sp;
+    c.p += 4;
+    c.i32();  // min_shift
+    const int32_t depth = c.i32();
+    const int32_t l_aux = c.i32();
+    if (l_aux < 0 || depth < 0 || depth > 10) return sp;
+    c.need((size_t)l_aux);
+    c.p += l_aux;
+    const int32_t n_ref = c.i32();
+    if (rid < 0 || rid >= n_ref) return sp;
+    const uint32_t pseudo_bin = (uint32_t)((((uint64_t)1 << (3 * depth + 3)) - 1) / 7 + 1);  // holds statistics, not records
+    for (int32_t r = 0; r <= rid; ++r) {
+        const int32_t n_bin = c.i32();
+        for (int32_t b = 0; b < n_bin; ++b) {
+            const uint32_t bin = c.u32();
+            u64();  // loffset
+            const int32_t n_chunk = c.i32();
+            for (int32_t k = 0; k < n_chunk; ++k) {
+                const uint64_t beg = u64(), end = u64();
+                if (r != rid || bin == pseudo_bin) continue;
+                if (!sp.found || beg < sp.vbeg) sp.vbeg = beg;
+                if (!sp.found || end > sp.vend) sp.vend = end;
+                sp.found = true;
+            }
+        }
+    }
+    if (!sp.found) { sp.found = true; sp.empty = true; }
+    return sp;
+}
+
+Cohort load_bcf(const Options& o) {
+    MappedFile file(o.bcf, "Error while opening the bcf file");
+    Cohort co;
+    std::vector<std::string> contigs;
+    int gt_key;
+    size_t header_bytes = 0;
+    {   // the header sits in the first members: inflate only as many as it needs
+        std::vector<uint8_t> head = gunzip_members(file.data(), file.size(), o.bcf, 9);
+        if (head.size() >= 9 && memcmp(head.data(), "BCF\2", 4) == 0) {
+            uint32_t l_text;
+            memcpy(&l_text, head.data() + 5, 4);
+            header_bytes = 9 + (size_t)l_text;
+            if (head.size() < header_bytes) head = gunzip_members(file.data(), file.size(), o.bcf, header_bytes);
+        }
+        Cursor hc{head.data(), head.data() + head.size()};
+        parse_bcf_header(hc, &contigs, &co.bcf_samples, &gt_key);
+    }
+    // main.rs:293-313: the selection is always in BCF column order
+    if (!o.has_samples) {
+        co.samples = co.bcf_samples;
+        for (size_t i = 0; i < co.bcf_samples.size(); ++i) co.sample_positions.push_back(i);
+    } else {
+        std::ifstream sf(o.samples_file);
+        if (!sf) die("Could not open sample file " + o.samples_file);
+        std::set<std::string> wanted;
+        std::string l;
+        while (std::getline(sf, l)) {
+            if (!l.empty() && l.back() == '\r') l.pop_back();
+            if (l.size() > 1) wanted.insert(l);
+        }
+        for (size_t i = 0; i < co.bcf_samples.size(); ++i)
+            if (wanted.count(co.bcf_samples[i])) { co.sample_positions.push_back(i); co.samples.push_back(co.bcf_samples[i]); }
+    }
+    printf("Reading %zu samples out of %zu\n", co.samples.size(), co.bcf_samples.size());
+    int rid = -1;
+    for (size_t i = 0; i < contigs.size(); ++i)
+        if (contigs[i] == o.chromosome) rid = (int)i;
+    if (rid < 0) die("called `Result::unwrap()` on an `Err` value: UnknownSequence (" + o.chromosome + ")");  // haplotype.rs:78
+    const uint32_t S = (uint32_t)co.samples.size();
+    co.pitch = std::max<uint32_t>(1, (2 * S + 31) / 32);
+    // With a CSI index only the BGZF members that hold the wanted contig are read and inflated; without one the whole file is.
+    std::vector<uint8_t> raw;
+    size_t first_record = header_bytes;
+    const CsiSpan span = o.use_index ? csi_contig_span(o.bcf, rid) : CsiSpan();
+    const bool indexed = span.found && (span.empty || ((span.vbeg >> 16) < file.size() && bgzf_member_size(file.data(), file.size(), span.vbeg >> 16)));
+    if (indexed && !span.empty) {
+        const size_t cbeg = (size_t)(span.vbeg >> 16);
+        size_t cend = std::min<size_t>(file.size(), (size_t)(span.vend >> 16));
+        if ((span.vend & 0xffff) && cend < file.size()) cend += bgzf_member_size(file.data(), file.size(), cend);  // the last member is used in part
+        if (cend <= cbeg) cend = file.size();
+        raw = gunzip_bgzf(file.data() + cbeg, cend - cbeg, o.bcf, std::max(1u, o.threads));
+        first_record = (size_t)(span.vbeg & 0xffff);
+    } else if (!indexed) {
+        raw = gunzip_bgzf(file.data(), file.size(), o.bcf, std::max(1u, o.threads));
+    }
+    if (first_record > raw.size()) die("truncated BCF");
+    Cursor c{raw.data() + first_record, raw.data() + raw.size()};
+    // pass 1 (serial, a few bytes per record): positions, alleles, carrier rows; the genotype blocks are only located
+    struct Pending { uint32_t row; const uint8_t* indiv; uint32_t l_indiv, n_fmt, n_sample; };
+    std::vector<Pending> pending;
+    while (c.p < c.e) {
+        uint32_t l_shared = c.u32(), l_indiv = c.u32();
+        c.need((size_t)l_shared + l_indiv);
+        Cursor s{c.p, c.p + l_shared};
+        const uint8_t* indiv = c.p + l_shared;
+        c.p += (size_t)l_shared + l_indiv;
+        int32_t chrom = s.i32();
+        Record r;
+        r.pos = s.i32();
+        r.rlen = s.i32();
+        s.u32();
+        uint32_t nai = s.u32(), nfs = s.u32();
+        r.n_allele = nai >> 16;
+        uint32_t n_fmt = nfs >> 24, n_sample = nfs & 0xffffff;
+        if (chrom != rid) {
+            if (indexed) break;  // the index pointed at the contig's first record: its records end here (the file is sorted)
+            continue;
+        }
+        s.tstr();
+        if (r.n_allele < 2) die("index out of bounds: the len is " + std::to_string(r.n_allele) + " but the index is 1");  // haplotype.rs:22
+        r.ref = s.tstr();
+        r.alt = s.tstr();
+        check_letters(r.ref);  // haplotype.rs:21-22 convert alleles[0] and [1] of every record
+        check_letters(r.alt);
+        r.carrier_row = UINT32_MAX;
+        if (r.n_allele == 2) {
+            r.carrier_row = (uint32_t)pending.size();
+            pending.push_back(Pending{r.carrier_row, indiv, l_indiv, n_fmt, n_sample});
+        } else {
+            printf("Unusual number of alleles: %u\n", r.n_allele);  // haplotype.rs:53-55
+        }
+        co.max_rlen = std::max(co.max_rlen, std::max(1, r.rlen));
+        co.records.push_back(std::move(r));
+    }
+    // pass 2 (--threads host threads): GT of the selected samples -> carrier bits (haplotype.rs:30-51), the O(records x samples) part
+    co.carriers.assign(pending.size() * (size_t)co.pitch, 0);
+    std::atomic<size_t> next_rec{0};
+    std::mutex err_mu;
+    std::string err;
+    auto decode = [&] {
+        try {
+            for (;;) {
+                const size_t base = next_rec.fetch_add(256);
+                if (base >= pending.size()) return;
+                for (size_t k2 = base; k2 < std::min(pending.size(), base + 256); ++k2) {
+                    const Pending& pd = pending[k2];
+                    Cursor d{pd.indiv, pd.indiv + pd.l_indiv};
+                    uint32_t* row = co.carriers.data() + (size_t)pd.row * co.pitch;
+                    bool have_gt = false;
+                    for (uint32_t f = 0; f < pd.n_fmt; ++f) {
+                        int kt, vt; uint32_t kl, vl;
+                        d.desc(&kt, &kl);
+                        int32_t key = d.tint(kt);
+                        d.desc(&vt, &vl);
+                        size_t bytes = Cursor::tsize(vt) * vl * (size_t)pd.n_sample;
+                        d.need(bytes);
+                        if (key == gt_key && vt >= 1 && vt <= 3) {
+                            have_gt = true;
+                            if (vl != 2 && S) die("Inconsistent number of alleles");  // haplotype.rs:32
+                            const size_t es = Cursor::tsize(vt);
+                            for (uint32_t k = 0; k < S; ++k) {
+                                Cursor g{d.p + co.sample_positions[k] * 2 * es, d.p + bytes};
+                                int32_t g0 = g.tint(vt), g1 = g.tint(vt);
+                                if (g0 == 4) row[(2 * k) >> 5] |= 1u << ((2 * k) & 31);          // Unphased(1), haplotype.rs:34-37
+                                if (g1 == 5) row[(2 * k + 1) >> 5] |= 1u << ((2 * k + 1) & 31);  // Phased(1),   haplotype.rs:38-41
+                            }
+                        }
+                        d.p += bytes;
+                    }
+                    if (!have_gt && S) die("called `Result::unwrap()` on an `Err` value: missing GT");  // haplotype.rs:24
+                }
+            }
+        } catch (const std::exception& e) {  // only under the test shim, where die() throws
+            std::lock_guard<std::mutex> lk(err_mu);
+            if (err.empty()) err = e.what();
+        }
+    };
+    {
+        const unsigned nt = std::max(1u, std::min<unsigned>(std::max(1u, o.threads), (unsigned)(pending.size() / 256 + 1)));
+        if (nt == 1) decode();
+        else {
+            std::vector<std::thread> th;
+            for (unsigned t = 0; t < nt; ++t) th.emplace_back(decode);
+            for (auto& t : th) t.join();
+        }
+        if (!err.empty()) die(err);
+    }
+    if (!std::is_sorted(co.records.begin(), co.records.end(), [](const Record& a, const Record& b) { return a.pos < b.pos; }))
+        die("the BCF is not sorted by position (an indexed BCF always is)");
+    return co;
+}
+
+}  // namespace
