@@ -186,7 +186,8 @@ DevBlock dev_block(const tfbs_ctx* ctx) {
     return b;
 }
 
-int validate_block(tfbs_ctx* ctx, const tfbs_block* b) {
+// Shape of the block: everything that is read on the host to size the copies.
+int validate_regions(tfbs_ctx* ctx, const tfbs_block* b) {
     if (!b) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "block is NULL");
     if (b->n_regions && (!b->region_start || !b->region_end || !b->ref_off || !b->inner_off || !b->var_off))
         return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "block has NULL region arrays");
@@ -205,21 +206,29 @@ int validate_block(tfbs_ctx* ctx, const tfbs_block* b) {
         if (b->inner_off[r + 1] < b->inner_off[r] || b->var_off[r + 1] < b->var_off[r])
             return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "offset arrays must be non-decreasing");
     }
-    uint32_t nv = b->n_regions ? b->var_off[b->n_regions] : 0;
-    for (uint32_t v = 0; v < nv; ++v) {
-        const tfbs_variant& x = b->variants[v];
-        if (x.ref_len == 0 || x.alt_len == 0) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "variant " + std::to_string(v) + " has an empty allele");
-        if ((uint64_t)x.ref_off + x.ref_len > b->allele_bytes || (uint64_t)x.alt_off + x.alt_len > b->allele_bytes)
-            return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "variant " + std::to_string(v) + " points outside allele_bases");
-        if (x.carrier_row >= b->n_carrier_rows) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "variant " + std::to_string(v) + " has no carrier row");
-    }
+    return TFBS_OK;
+}
+
+// The records: allele ranges and carrier rows (what the kernels index with), and per region the bases insertions can add.
+// Runs while the copies of the block are in flight.
+int validate_variants(tfbs_ctx* ctx, const tfbs_block* b) {
+    ctx->h_ins_extra.assign(b->n_regions, 0);
+    for (uint32_t r = 0; r < b->n_regions; ++r)
+        for (uint32_t v = b->var_off[r]; v < b->var_off[r + 1]; ++v) {
+            const tfbs_variant& x = b->variants[v];
+            if (x.ref_len == 0 || x.alt_len == 0) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "variant " + std::to_string(v) + " has an empty allele");
+            if ((uint64_t)x.ref_off + x.ref_len > b->allele_bytes || (uint64_t)x.alt_off + x.alt_len > b->allele_bytes)
+                return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "variant " + std::to_string(v) + " points outside allele_bases");
+            if (x.carrier_row >= b->n_carrier_rows) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "variant " + std::to_string(v) + " has no carrier row");
+            if (x.alt_len > 1) ctx->h_ins_extra[r] += x.alt_len - 1;
+        }
     return TFBS_OK;
 }
 
 int do_upload(tfbs_ctx* ctx, const tfbs_block* b) {
-    int rc = validate_block(ctx, b);
-    if (rc) return rc;
     ctx->have_block = false;
+    int rc = validate_regions(ctx, b);
+    if (rc) return rc;
     ctx->R = b->n_regions;
     ctx->S = b->n_samples;
     ctx->H = 2 * b->n_samples;
@@ -241,10 +250,7 @@ int do_upload(tfbs_ctx* ctx, const tfbs_block* b) {
         ctx->h_inner_off.assign(1, 0);
         ctx->h_var_off.assign(1, 0);
     }
-    ctx->h_ins_extra.assign(R, 0);
-    for (uint32_t r = 0; r < R; ++r)
-        for (uint32_t v = b->var_off[r]; v < b->var_off[r + 1]; ++v)
-            if (b->variants[v].alt_len > 1) ctx->h_ins_extra[r] += b->variants[v].alt_len - 1;
+    if (R && ctx->n_var && !b->variants) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "block has records but variants is NULL");
 
     if ((rc = upload(ctx, ctx->d_region_start, b->region_start, R))) return rc;
     if ((rc = upload(ctx, ctx->d_region_end, b->region_end, R))) return rc;
@@ -261,6 +267,11 @@ int do_upload(tfbs_ctx* ctx, const tfbs_block* b) {
     CK(ctx->d_var_class.reserve(std::max<uint64_t>(1, ctx->n_var) * 4));
     CK(ctx->d_var_inwin.reserve(std::max<uint64_t>(1, ctx->n_var)));
     CK(ctx->d_ref_prefix.reserve((ctx->n_ref_bytes + R + 1) * 8));
+    // the per-record checks overlap the copies (asynchronous when the caller's buffers are page-locked); no kernel has been enqueued yet
+    if ((rc = validate_variants(ctx, b))) {
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
     ctx->have_block = true;
     return TFBS_OK;
 }

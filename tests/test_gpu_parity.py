@@ -149,6 +149,50 @@ def test_empty_and_degenerate_blocks():
     hp.check_parity(ps2, fixture_block([0]), rows_mode=binding.ROWS_ALL_KEYS)
 
 
+def test_malformed_blocks_are_refused():
+    """Argument checks of tfbs_submit_block: a malformed block is an error (never an out-of-bounds access on the device), the
+    context stays usable and a failed submit leaves no block behind."""
+    ps = acgt_patterns()
+    good = fixture_block([0])
+    ctx = binding.Context(0)
+    ctx.set_patterns(ps)
+
+    def refused(mutate, text):
+        blk = fixture_block([0])
+        mutate(blk)
+        with pytest.raises(binding.TfbsError) as e:
+            ctx.submit_block(blk)
+        assert e.value.code == binding.ERR_INVALID_ARGUMENT and text in e.value.message, e.value.message
+        with pytest.raises(binding.TfbsError) as e2:  # nothing to collect, nothing resident
+            ctx.run_resident()
+        assert e2.value.code == binding.ERR_STATE
+
+    def set_variant(field, value):
+        def f(blk):
+            blk.variants[0][field] = value
+        return f
+
+    refused(set_variant("alt_len", 0), "empty allele")
+    refused(set_variant("ref_off", 10 ** 6), "outside allele_bases")
+    refused(set_variant("carrier_row", 77), "no carrier row")
+
+    def bad_window(blk):
+        blk.region_end[1] = blk.region_start[1] - 1
+    refused(bad_window, "invalid extended window")
+
+    def bad_offsets(blk):
+        blk.var_off[2] = 5
+        blk.var_off[3] = 1
+    refused(bad_offsets, "non-decreasing")
+
+    def long_ref(blk):
+        blk.ref_off[1:] += 100
+    refused(long_ref, "longer than the region")
+    ctx.submit_block(good)
+    hp.assert_rows_equal(ctx.collect(), hp.run_oracle(ps, good))
+    ctx.close()
+
+
 @pytest.mark.parametrize("seed", [1, 2, 3])
 def test_synthetic_small(seed):
     pats = synth.make_pwms(6, seed=seed, lmin=4, lmax=30)
