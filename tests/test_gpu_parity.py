@@ -322,6 +322,21 @@ def test_many_samples_few_groups():
     assert o["n_groups"] < 12 * 14
 
 
+def test_config4_biobank_shape():
+    """BASELINE.json configs[3] in shape: tens of thousands of haplotypes per region (here 40,000), few regions, founder classes so
+    that the oracle stays fast; exercises the per-region loops over H and the wide carrier rows.  Sample-block sharding of the same
+    block must concatenate to the same rows."""
+    from find_tfbs_b200 import sharding
+    pats = synth.make_pwms(3, seed=51, lmin=8, lmax=16, pvalue=3e-3)
+    ps = PatternSet(pats)
+    blk = synth.make_cohort(20000, 4, seed=52, lmax_pattern=16, region_len=(200, 400), ld_blocks=40)
+    g, o = hp.check_parity(ps, blk, rows_mode=binding.ROWS_ALL_KEYS, matches=False)
+    assert g["left"].shape[1] == 20000 and len(g["region"]) > 0
+    parts = [hp.run_gpu(ps, sharding.sample_block(blk, s0, s1), rows_mode=binding.ROWS_ALL_KEYS) for s0, s1 in ((0, 7000), (7000, 20000))]
+    merged = sharding.merge_sample_shards(parts)  # applies the min != max filter after the gather
+    hp.assert_rows_equal(merged, hp.run_oracle(ps, blk, binding.ROWS_VARYING))
+
+
 def test_config2_slice_properties():
     """configs[1] at 3% size against the oracle, plus size-independent properties of the rows."""
     pats, blk = synth.config2(scale=0.03)
