@@ -53,7 +53,13 @@ def one_case(seed):
         opts["rows_width"] = 0
     if rng.random() < 0.2:
         opts["scan_format"] = 1
-    hp.check_parity(binding.PatternSet(pats), blk, rows_mode=int(rng.integers(0, 2)), options=opts, resident=bool(rng.integers(0, 2)))
+    ps = binding.PatternSet(pats)
+    hp.check_parity(ps, blk, rows_mode=int(rng.integers(0, 2)), options=opts, resident=bool(rng.integers(0, 2)))
+    if rng.random() < 0.3 and all(p.get("weights") is not None for p in pats):  # the audit: ties and per-haplotype flags
+        oa = hp.oracle_audit(ps, blk)
+        au, rows, _ = hp.gpu_audit(ps, blk)
+        assert au["ties"] == oa["ties"] and np.array_equal(au["hap_flags"], oa["hap_flags"]) and not au["truncated"]
+        hp.assert_rows_equal(rows, hp.run_oracle(ps, blk))
 
 
 def main():
