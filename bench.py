@@ -348,14 +348,15 @@ def main():
     scan_s = (sum(scan_ms) / len(scan_ms)) * 1e-3
     achieved = st["evaluated_cells"] / scan_s  # this rank's k_scan launches: cells really scored / CUDA-event time around them
     f_max = pk["sm_max_mhz"] * 1e6
-    roof = SM_COUNT * LDS64_PER_CLK_PER_SM * CELLS_PER_LDS64 * f_max
+    sm_count = st["sm_count"] or SM_COUNT
+    roof = sm_count * LDS64_PER_CLK_PER_SM * CELLS_PER_LDS64 * f_max
     f_obs = (clocks["sm_mhz"] or pk["sm_max_mhz"]) * 1e6
     # algorithmic HBM bytes of the scan: 3 bits per base read once per pattern chunk + count rows written
     roofline = {"bound": "lookup-add (shared-memory table bandwidth; not hbm, not tensor: see DESIGN.md)", "kernel": "k_scan",
                 "achieved": achieved / 1e12, "peak": roof / 1e12, "unit": "Tcell/s", "frac": achieved / roof,
-                "peak_basis": "148 SMs x 128 B/clk shared memory = 16 LDS.64/clk/SM x 6 cells per LDS.64 (3 packed patterns x 2 columns) at sm_max_mhz from %s" % pk["source"],
+                "peak_basis": "%d SMs x 128 B/clk shared memory = 16 LDS.64/clk/SM x 6 cells per LDS.64 (3 packed patterns x 2 columns) at sm_max_mhz from %s" % (sm_count, pk["source"]),
                 "frac_at_observed_clock": achieved / (roof * f_obs / f_max), "observed_sm_mhz": clocks["sm_mhz"],
-                "frac_of_one_lookup_per_cell_roof": achieved / (SM_COUNT * 32 * f_max), "frac_of_int32_issue_roof": achieved / (SM_COUNT * 128 * f_max),
+                "frac_of_one_lookup_per_cell_roof": achieved / (sm_count * 32 * f_max), "frac_of_int32_issue_roof": achieved / (sm_count * 128 * f_max),
                 "ms_per_launch": scan_s * 1e3, "cells_per_launch": st["evaluated_cells"], "traffic": traffic,
                 "traffic_source": "profiles/k_scan_traffic.json (dram__bytes_read.sum + dram__bytes_write.sum of one k_scan launch, ncu --set full)" if traffic else None,
                 # the same launches seen from HBM: algorithmic bytes (12 B per 32 packed bases of every scored entry + the tables once per

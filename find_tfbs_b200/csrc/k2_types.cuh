@@ -56,6 +56,10 @@ constexpr int MAX_PIECES = 16;                       // items (or tiles of a lon
 #ifndef TFBS_MERGE_GAP
 #define TFBS_MERGE_GAP 0   /* measured on B200 (configs[1]): 0 -> 8.02 ms/step, 8 -> 8.26, 24 -> 9.05, 64 -> 12.5: short items are shared more */
 #endif
+#ifndef TFBS_PER_GRAB
+#define TFBS_PER_GRAB 8
+#endif
+constexpr int SCAN_PER_GRAB = TFBS_PER_GRAB;         // list entries a warp takes per trip to the work counter under delta scoring
 constexpr int MERGE_GAP = TFBS_MERGE_GAP;            // touched ranges closer than this are scored as one item (overlapping ones always are)
 
 // Private to one warp: a warp owns the pieces of a round, so the scan needs no CTA-wide barrier.

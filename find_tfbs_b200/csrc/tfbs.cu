@@ -399,12 +399,12 @@ private:
     // ASCII -> nucleotide codes, Diff classes, prefix hashes of the reference windows
     int encode_inputs() {
         if (ctx->n_ref_bytes) {
-            TFBS_LAUNCH(k_encode, std::min<unsigned>(grid_for(ctx->n_ref_bytes, 256), 148 * 16), 256, 0, st)(ctx->d_ref_ascii.as<u8>(), ctx->d_ref_codes.as<u8>(),
+            TFBS_LAUNCH(k_encode, std::min<unsigned>(grid_for(ctx->n_ref_bytes, 256), ctx->stats.sm_count * 16), 256, 0, st)(ctx->d_ref_ascii.as<u8>(), ctx->d_ref_codes.as<u8>(),
                                                                                                      ctx->n_ref_bytes, &dst->bad_ref_base);
             ++launches();
         }
         if (ctx->n_allele_bytes) {
-            TFBS_LAUNCH(k_encode, std::min<unsigned>(grid_for(ctx->n_allele_bytes, 256), 148 * 16), 256, 0, st)(
+            TFBS_LAUNCH(k_encode, std::min<unsigned>(grid_for(ctx->n_allele_bytes, 256), ctx->stats.sm_count * 16), 256, 0, st)(
                 ctx->d_allele_ascii.as<u8>(), ctx->d_allele_codes.as<u8>(), ctx->n_allele_bytes, &dst->bad_allele_base);
             ++launches();
         }
@@ -702,10 +702,7 @@ private:
             TFBS_LAUNCH(k_item_stats, grid_for(b.n_list_host, 256), 256, 0, st)(sq, ctx->dpat, ctx->d_list.as<u32>(), b.d_n_list, dst);
             launches() += 2;
         }
-#ifndef TFBS_PER_GRAB
-#define TFBS_PER_GRAB 8
-#endif
-        const u32 per_grab = delta ? (u32)TFBS_PER_GRAB : 1u;
+        const u32 per_grab = delta ? (u32)SCAN_PER_GRAB : 1u;  // short items: several list entries per trip to the work counter
         CK(cudaEventRecord(ctx->ev[8], st));
         for (uint32_t c = 0; c < ctx->cp.chunks.size() && b.n_list_host; ++c) {
             CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
