@@ -131,6 +131,7 @@ struct tfbs_ctx {
     std::vector<uint32_t> tie_region, tie_pattern, tie_group;  // tfbs_audit_block
     std::vector<int64_t> tie_start;
     uint64_t n_rows = 0, n_matches = 0;
+    uint64_t n_matches_found = 0;  // hits the last run produced, also those that did not fit into the match buffer
     bool matches_truncated = false;
     bool ran = false;
 
@@ -872,6 +873,7 @@ private:
         if (ctx->record_matches) {
             uint64_t n = std::min<uint64_t>(hs.n_matches, dm.cap);
             ctx->matches_truncated = hs.n_matches > dm.cap;
+            ctx->n_matches_found = hs.n_matches;
             CK(ctx->h_m_region.reserve(std::max<uint64_t>(1, n) * 4, false));
             CK(ctx->h_m_pattern.reserve(std::max<uint64_t>(1, n) * 4, false));
             CK(ctx->h_m_group.reserve(std::max<uint64_t>(1, n) * 4, false));
@@ -1144,16 +1146,27 @@ int tfbs_audit_block(tfbs_ctx* ctx, tfbs_audit* out) {
         if (p.min_score > INT32_MIN) p.min_score -= 1;  // score > INT32_MIN - 1 cannot be expressed; such a pattern has no tie list
     std::vector<Hit> with_ties, hits;
     bool overflow = false;
+    const uint64_t keep_max = ctx->max_matches;
+    // a run that overflows the match buffer says how many hits there were: run it once more with a buffer of that size
+    auto run_recorded = [&]() -> int {
+        int r = run_pipeline(ctx);
+        if (r == TFBS_OK && ctx->matches_truncated && ctx->n_matches_found < (1ull << 31)) {
+            ctx->max_matches = ctx->n_matches_found + ctx->n_matches_found / 8 + 1024;
+            r = run_pipeline(ctx);
+        }
+        return r;
+    };
     int rc = install_patterns(ctx, lowered.data(), (uint32_t)lowered.size());
-    if (rc == TFBS_OK) rc = run_pipeline(ctx);
+    if (rc == TFBS_OK) rc = run_recorded();
     if (rc == TFBS_OK) {
         take_hits(&with_ties);
         overflow = ctx->matches_truncated;
     }
     // always put the caller's thresholds back, and leave the context with a normal run of the block
     int rc2 = install_patterns(ctx, ctx->orig_patterns.data(), (uint32_t)ctx->orig_patterns.size());
-    if (rc2 == TFBS_OK && rc == TFBS_OK) rc2 = run_pipeline(ctx);
+    if (rc2 == TFBS_OK && rc == TFBS_OK) rc2 = run_recorded();
     ctx->record_matches = keep_record;
+    ctx->max_matches = keep_max;
     ctx->audit = 0;
     if (rc != TFBS_OK) return rc;
     if (rc2 != TFBS_OK) return rc2;

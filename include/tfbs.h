@@ -180,7 +180,7 @@ typedef struct tfbs_audit {
     const uint8_t* hap_flags;          /* [n_regions * 2 * n_samples] TFBS_HAP_* bits */
     uint32_t n_regions;
     uint32_t n_samples;
-    uint32_t truncated;                /* 1 if a match buffer overflowed (raise "max_matches"): the tie list is then incomplete */
+    uint32_t truncated;                /* 1 if the hits did not fit even into the enlarged match buffer (> 2^31): the tie list is incomplete */
     uint32_t reserved;
 } tfbs_audit;
 

@@ -170,9 +170,11 @@ def oracle_audit(pattern_set, block):
     return {"ties": keyed(a) - keyed(b), "hap_flags": b["hap_flags"], "n_hits": b["n_hits"]}
 
 
-def gpu_audit(pattern_set, block):
+def gpu_audit(pattern_set, block, options=None):
     ctx = binding.Context(0)
     try:
+        for k, v in (options or {}).items():
+            ctx.set_option(k, v)
         ctx.set_patterns(pattern_set)
         ctx.upload_block(block)
         au = ctx.audit()

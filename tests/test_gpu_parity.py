@@ -256,6 +256,9 @@ def test_audit_enumerates_ties_and_flags():
     assert (au["hap_flags"] & binding.HAP_TRUNCATED).any()
     hp.assert_rows_equal(rows, hp.run_oracle(ps, blk))
     assert st["n_hits"] == oa["n_hits"]
+    # a match buffer that is too small is enlarged by the audit itself
+    au_small, _, _ = hp.gpu_audit(ps, blk, {"max_matches": 50})
+    assert not au_small["truncated"] and au_small["ties"] == oa["ties"]
     # a fixture without any tie: ACGT scores 4000 against min_score 3999, the next best window scores 3000
     au2, _, _ = hp.gpu_audit(acgt_patterns(), fixture_block([0]))
     assert len(au2["ties"]) == 0 and not au2["hap_flags"].any()
