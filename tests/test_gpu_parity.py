@@ -360,6 +360,37 @@ def test_config2_slice_properties():
     assert np.array_equal(np.concatenate([a["region"], b["region"] + h]), g["region"])
 
 
+def test_config2_full_size_properties():
+    """BASELINE.json configs[1] at FULL size (the bench workload: 100 samples x 10,000 regions x 50 PWMs, both strands): the oracle
+    would need minutes for all of it, so the check is through properties that do not depend on size -- the two scan modes (every
+    distinct haplotype scored in full / delta scoring with shared items) must agree row for row and counter for counter, row
+    min / max and ordering must be consistent, and random slices of regions must equal the oracle's rows for those regions."""
+    import os
+    scale = float(os.environ.get("TFBS_TEST_SCALE", "1.0"))  # the emulated run of this file uses a small fraction
+    pats, blk = synth.config2(scale=scale)
+    ps = PatternSet(pats)
+    d = hp.run_gpu(ps, blk, options={"rows_width": 0})
+    f = hp.run_gpu(ps, blk, options={"delta": 0})
+    hp.assert_rows_equal(d, f)
+    for k in ("executed_cells", "nominal_cells", "n_hits", "n_groups", "n_rows", "n_dropped", "n_truncated"):
+        assert d["stats"][k] == f["stats"][k], k
+    assert f["stats"]["evaluated_cells"] == f["stats"]["executed_cells"] > d["stats"]["evaluated_cells"] > 0
+    assert d["count_bytes"] == 1 and f["count_bytes"] == 4
+    v = d["left"].astype(np.int64) + d["right"]
+    assert np.array_equal(v.min(axis=1), d["vmin"]) and np.array_equal(v.max(axis=1), d["vmax"]) and np.all(d["vmin"] != d["vmax"])
+    key = d["region"].astype(np.int64) * (1 << 32) + d["pattern_id"].astype(np.int64) * (1 << 16)
+    assert np.all(np.diff(key) >= 0)
+    rng = np.random.default_rng(5)
+    for r0 in rng.integers(0, max(1, blk.n_regions - 8), size=4):
+        r0 = int(r0)
+        r1 = min(blk.n_regions, r0 + 8)
+        o = hp.run_oracle(ps, blk.slice(r0, r1))
+        m = (d["region"] >= r0) & (d["region"] < r1)
+        assert int(m.sum()) == len(o["region"])
+        assert np.array_equal(d["region"][m] - r0, o["region"]) and np.array_equal(d["pattern_id"][m], o["pattern_id"])
+        assert np.array_equal(d["left"][m], o["left"]) and np.array_equal(d["right"][m], o["right"])
+
+
 def test_region_sharding_on_device():
     """The multi-GPU partition (find_tfbs_b200/sharding.py) run shard by shard on one device equals the unsharded rows."""
     from find_tfbs_b200 import sharding

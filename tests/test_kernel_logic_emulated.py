@@ -22,6 +22,7 @@ def emu_env():
     env = dict(os.environ)
     env["TFBS_B200_LIB"] = os.path.join(EMU, "libtfbs_emu.so")
     env["TFBS_B200_DRIVER"] = os.path.join(EMU, "find-tfbs-emu")
+    env["TFBS_TEST_SCALE"] = "0.004"  # the full-size property test shrinks to 40 regions under emulation
     return env
 
 
