@@ -214,6 +214,16 @@ Cohort load_bcf(const Options& o) {
     struct Pending { uint32_t row; const uint8_t* indiv; uint32_t l_indiv, n_fmt, n_sample; };
     std::vector<Pending> pending;
     while (c.p < c.e) {
+        if (indexed) {
+            // the last member of the contig's span may end inside the first record of the next contig: an incomplete record there
+            // is the end of the contig, not a truncated file
+            uint32_t ls = 0, li = 0;
+            if (c.e - c.p >= 8) { memcpy(&ls, c.p, 4); memcpy(&li, c.p + 4, 4); }
+            if (c.e - c.p < 8 || (size_t)(c.e - c.p) - 8 < (size_t)ls + li) {
+                if (c.e - c.p >= 12) { int32_t chrom_peek; memcpy(&chrom_peek, c.p + 8, 4); if (chrom_peek == rid) die("truncated BCF"); }
+                break;
+            }
+        }
         uint32_t l_shared = c.u32(), l_indiv = c.u32();
         c.need((size_t)l_shared + l_indiv);
         Cursor s{c.p, c.p + l_shared};

@@ -143,7 +143,7 @@ def test_bcf_and_fasta_decoding(drv, golden_dir, tmp_path):
     assert np.array_equal(got, blk.carriers[:len(rows)])
     # a multi-contig BGZF file with a CSI index: only the members of the wanted contig are read, the records are the same as
     # without the index (whole-file scan) and as in the single-contig file; the other contigs' records never show up
-    for mb in (1500, 700, 100000):
+    for mb in (1500, 700, 613, 631, 653, 777, 100000):  # the contig's last member usually ends inside a record of the next contig
         c = fw.cohort_to_files(blk, pats, str(tmp_path / ("i%d" % mb)), multiallelic_every=5, bgzf=True, member_bytes=mb, flank_records=40, write_csi=True)
         assert os.path.exists(c["bcf"] + ".csi")
         with_index = load(c["bcf"], None, c["chromosome"])
