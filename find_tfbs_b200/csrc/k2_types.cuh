@@ -48,11 +48,17 @@ struct DevMatches {
 constexpr int SCAN_UNROLL = TFBS_SCAN_UNROLL;
 constexpr int SCAN_WARPS = TFBS_SCAN_WARPS;          // warps per CTA; one CTA per SM shares one copy of the tables
 constexpr int SCAN_CTA = SCAN_WARPS * 32;
-constexpr int TILE_POS = 1024;                       // window starts staged per pass (per warp)
+#ifndef TFBS_TILE_POS
+#define TFBS_TILE_POS 1024   /* multiple of 64; 2048 still fits next to 96 KB of tables (24 warps x 4.8 KB) */
+#endif
+#ifndef TFBS_MAX_PIECES
+#define TFBS_MAX_PIECES 16
+#endif
+constexpr int TILE_POS = TFBS_TILE_POS;              // window starts staged per pass (per warp)
 constexpr int PLANE_BYTES = TILE_POS / 2 + 32;       // pair codes of even / odd starts (+ halo)
 constexpr int RAW_UNITS = TILE_POS / 32 + 3;
 constexpr int MAX_RUNS = 16;
-constexpr int MAX_PIECES = 16;                       // items (or tiles of a long item) scanned together by one warp
+constexpr int MAX_PIECES = TFBS_MAX_PIECES;          // items (or tiles of a long item) scanned together by one warp
 #ifndef TFBS_MERGE_GAP
 #define TFBS_MERGE_GAP 0   /* measured on B200 (configs[1]): 0 -> 8.02 ms/step, 8 -> 8.26, 24 -> 9.05, 64 -> 12.5: short items are shared more */
 #endif
