@@ -56,12 +56,20 @@ struct Barrier {
     unsigned alive = 0, arrived = 0, generation = 0;
 };
 
+// Barrier of the lanes named by a *_sync mask.  Disjoint masks (e.g. four groups of 8 lanes) synchronise independently, like on
+// the hardware; the slot of a mask is its lowest lane.  Lanes of the mask that have left the kernel count as arrived.
+struct MaskBarrier {
+    unsigned mask = 0, arrived = 0, generation = 0;
+};
+
 struct State {
     ucontext_t sched;
     Fiber fibers[kMaxThreads];
     char* stacks = nullptr;
     Barrier block_bar;
-    Barrier warp_bar[kMaxThreads / 32];
+    Barrier warp_bar[kMaxThreads / 32];            // alive lanes per warp (bookkeeping for the mask barriers)
+    MaskBarrier mask_bar[kMaxThreads / 32][32];
+    unsigned alive_mask[kMaxThreads / 32];
     unsigned long long warp_slot[kMaxThreads / 32][32];
     unsigned n_threads = 0;
     int cur = -1;
@@ -105,6 +113,32 @@ inline void barrier_leave(Barrier& b) {
     }
 }
 
+inline void mask_barrier_wait(unsigned mask) {
+    State& s = S();
+    const unsigned w = (unsigned)s.cur >> 5, lane = (unsigned)s.cur & 31u;
+    if (!((mask >> lane) & 1u)) { fprintf(stderr, "cuda_emu: lane %u calls a *_sync primitive with mask %08x that does not name it\n", lane, mask); abort(); }
+    MaskBarrier& b = s.mask_bar[w][__builtin_ctz(mask)];
+    if (b.arrived == 0) b.mask = mask;
+    else if (b.mask != mask) { fprintf(stderr, "cuda_emu: overlapping *_sync masks %08x / %08x in one warp\n", b.mask, mask); abort(); }
+    const unsigned gen = b.generation;
+    if (++b.arrived >= (unsigned)__builtin_popcount(mask & s.alive_mask[w])) {
+        b.arrived = 0;
+        ++b.generation;
+        return;
+    }
+    while (b.generation == gen) yield();
+}
+
+inline void mask_barrier_leave(unsigned w, unsigned lane) {
+    State& s = S();
+    s.alive_mask[w] &= ~(1u << lane);
+    for (MaskBarrier& b : s.mask_bar[w])
+        if (b.arrived && b.arrived >= (unsigned)__builtin_popcount(b.mask & s.alive_mask[w])) {
+            b.arrived = 0;
+            ++b.generation;
+        }
+}
+
 inline void trampoline() {
     State& s = S();
     s.entry(s.entry_arg);
@@ -112,6 +146,7 @@ inline void trampoline() {
     f.done = true;
     barrier_leave(s.block_bar);
     barrier_leave(s.warp_bar[s.cur / 32]);
+    mask_barrier_leave((unsigned)s.cur / 32, (unsigned)s.cur & 31u);
     swapcontext(&f.ctx, &s.sched);
 }
 
@@ -130,7 +165,12 @@ inline void run_grid(dim3 grid, dim3 block, void (*entry)(void*), void* arg) {
             for (unsigned bx = 0; bx < grid.x; ++bx) {
                 s.bid = uint3{bx, by, bz};
                 s.block_bar = Barrier{n, 0, 0};
-                for (unsigned w = 0; w < (n + 31) / 32; ++w) s.warp_bar[w] = Barrier{std::min(32u, n - 32 * w), 0, 0};
+                for (unsigned w = 0; w < (n + 31) / 32; ++w) {
+                    const unsigned lanes = std::min(32u, n - 32 * w);
+                    s.warp_bar[w] = Barrier{lanes, 0, 0};
+                    s.alive_mask[w] = lanes == 32 ? 0xffffffffu : ((1u << lanes) - 1);
+                    for (MaskBarrier& mb : s.mask_bar[w]) mb = MaskBarrier{};
+                }
                 for (unsigned t = 0; t < n; ++t) {
                     Fiber& f = s.fibers[t];
                     f.tid = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
@@ -172,16 +212,16 @@ inline unsigned lane_id() { return (unsigned)S().cur & 31u; }
 inline unsigned warp_id() { return (unsigned)S().cur >> 5; }
 
 template <class T>
-inline T shuffle(T v, unsigned src_lane) {
+inline T shuffle(unsigned mask, T v, unsigned src_lane) {
     static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
     State& s = S();
     const unsigned w = warp_id();
     unsigned long long raw = 0;
     memcpy(&raw, &v, sizeof(T));
     s.warp_slot[w][lane_id()] = raw;
-    barrier_wait(s.warp_bar[w]);
+    mask_barrier_wait(mask);
     raw = s.warp_slot[w][src_lane & 31u];
-    barrier_wait(s.warp_bar[w]);
+    mask_barrier_wait(mask);
     T out;
     memcpy(&out, &raw, sizeof(T));
     return out;
@@ -199,29 +239,36 @@ inline T shuffle(T v, unsigned src_lane) {
 
 // ---- device intrinsics ---------------------------------------------------------------------------------------------
 inline void __syncthreads() { emu::barrier_wait(emu::S().block_bar); }
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::barrier_wait(emu::S().warp_bar[emu::warp_id()]); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::mask_barrier_wait(mask); }
 template <class T>
-inline T __shfl_sync(unsigned, T v, int src) { return emu::shuffle(v, (unsigned)src); }
+inline T __shfl_sync(unsigned m, T v, int src) { return emu::shuffle(m, v, (unsigned)src); }
 template <class T>
-inline T __shfl_xor_sync(unsigned, T v, int mask) { return emu::shuffle(v, emu::lane_id() ^ (unsigned)mask); }
+inline T __shfl_xor_sync(unsigned m, T v, int lane_mask) { return emu::shuffle(m, v, emu::lane_id() ^ (unsigned)lane_mask); }
 template <class T>
-inline T __shfl_up_sync(unsigned, T v, unsigned delta) {
+inline T __shfl_up_sync(unsigned m, T v, unsigned delta) {
     const unsigned lane = emu::lane_id();
-    T got = emu::shuffle(v, lane >= delta ? lane - delta : lane);
+    T got = emu::shuffle(m, v, lane >= delta ? lane - delta : lane);
     return lane >= delta ? got : v;
 }
-inline unsigned __ballot_sync(unsigned, int pred) {
+template <class T>
+inline T __shfl_down_sync(unsigned m, T v, unsigned delta) {
+    const unsigned lane = emu::lane_id();
+    T got = emu::shuffle(m, v, lane + delta < 32 ? lane + delta : lane);
+    return lane + delta < 32 ? got : v;
+}
+inline unsigned __ballot_sync(unsigned m, int pred) {
     emu::State& s = emu::S();
     const unsigned w = emu::warp_id();
     s.warp_slot[w][emu::lane_id()] = pred ? 1ull : 0ull;
-    emu::barrier_wait(s.warp_bar[w]);
+    emu::mask_barrier_wait(m);
     unsigned out = 0;
-    const unsigned lanes = std::min(32u, s.n_threads - 32 * w);
-    for (unsigned l = 0; l < lanes; ++l)
-        if (!s.fibers[32 * w + l].done && s.warp_slot[w][l]) out |= 1u << l;
-    emu::barrier_wait(s.warp_bar[w]);
+    for (unsigned l = 0; l < 32; ++l)
+        if (((m & s.alive_mask[w]) >> l) & 1u)
+            if (s.warp_slot[w][l]) out |= 1u << l;
+    emu::mask_barrier_wait(m);
     return out;
 }
+inline unsigned __activemask() { return emu::S().alive_mask[emu::warp_id()]; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 
