@@ -3,6 +3,10 @@
 #pragma once
 #include "k2_worklist.cuh"
 
+#ifndef TFBS_FINISH_LANES
+#define TFBS_FINISH_LANES 0
+#endif
+
 namespace tfbs {
 
 // Delta scoring, second half, one warp per sequence:
@@ -48,6 +52,33 @@ __global__ void k_group_finish(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts
                 }
             }
             const u64 i0 = sq.item_off[q], i1 = sq.item_off[q + 1];
+#if TFBS_FINISH_LANES
+            // variant (not timed yet): the GS lanes of the sequence look up GS items at once (owner and its hit count: two dependent
+            // loads per item that the loop below does one item after the other), then walk together through the items that have hits
+            const u32 gshift = (threadIdx.x & 31u) & ~(GS - 1);
+            const u32 gmask = ((1u << GS) - 1) << gshift;
+            for (u64 w0 = i0; w0 < i1; w0 += GS) {
+                const u64 w = w0 + lane;
+                u32 owner = 0, n = 0;
+                if (w < i1) {
+                    owner = sq.items[w].owner;
+                    n = sq.item_hits[owner];
+                }
+                u32 have = (__ballot_sync(gmask, n != 0) >> gshift) & ((1u << GS) - 1);
+                while (have) {
+                    const u32 l = (u32)__ffs((int)have) - 1;
+                    have &= have - 1;
+                    const u32 ol = __shfl_sync(gmask, owner, (int)(gshift + l));
+                    const u32 nl = __shfl_sync(gmask, n, (int)(gshift + l));
+                    if (lane == 0) total += nl;
+                    const u32* src = sq.item_cnt + sq.item_coff[ol];
+                    for (u32 k = lane; k < nkeys; k += GS) {
+                        u32 v = src[k];
+                        if (v) atomicAdd(&crow[k], v);
+                    }
+                }
+            }
+#else
             for (u64 w = i0; w < i1; ++w) {
                 const u32 owner = sq.items[w].owner;
                 const u32 n = sq.item_hits[owner];
@@ -59,6 +90,7 @@ __global__ void k_group_finish(DevBlock b, DevSeqs sq, DevPatterns pt, DevCounts
                     if (v) atomicAdd(&crow[k], v);
                 }
             }
+#endif
         }
     }
 #pragma unroll

@@ -57,7 +57,8 @@ struct Barrier {
 };
 
 // Barrier of the lanes named by a *_sync mask.  Disjoint masks (e.g. four groups of 8 lanes) synchronise independently, like on
-// the hardware; the slot of a mask is its lowest lane.  Lanes of the mask that have left the kernel count as arrived.
+// the hardware, and so do different masks that share lanes (a group barrier and a later full-warp one).  Lanes of the mask that
+// have left the kernel count as arrived.
 struct MaskBarrier {
     unsigned mask = 0, arrived = 0, generation = 0;
 };
@@ -117,16 +118,21 @@ inline void mask_barrier_wait(unsigned mask) {
     State& s = S();
     const unsigned w = (unsigned)s.cur >> 5, lane = (unsigned)s.cur & 31u;
     if (!((mask >> lane) & 1u)) { fprintf(stderr, "cuda_emu: lane %u calls a *_sync primitive with mask %08x that does not name it\n", lane, mask); abort(); }
-    MaskBarrier& b = s.mask_bar[w][__builtin_ctz(mask)];
-    if (b.arrived == 0) b.mask = mask;
-    else if (b.mask != mask) { fprintf(stderr, "cuda_emu: overlapping *_sync masks %08x / %08x in one warp\n", b.mask, mask); abort(); }
-    const unsigned gen = b.generation;
-    if (++b.arrived >= (unsigned)__builtin_popcount(mask & s.alive_mask[w])) {
-        b.arrived = 0;
-        ++b.generation;
+    // the barrier in use for this mask, else a free one (different masks of one warp are different barriers, as on the hardware)
+    MaskBarrier* b = nullptr;
+    for (MaskBarrier& x : s.mask_bar[w])
+        if (x.arrived && x.mask == mask) { b = &x; break; }
+    if (!b)
+        for (MaskBarrier& x : s.mask_bar[w])
+            if (!x.arrived) { b = &x; b->mask = mask; break; }
+    if (!b) { fprintf(stderr, "cuda_emu: too many *_sync masks in flight in one warp\n"); abort(); }
+    const unsigned gen = b->generation;
+    if (++b->arrived >= (unsigned)__builtin_popcount(mask & s.alive_mask[w])) {
+        b->arrived = 0;
+        ++b->generation;
         return;
     }
-    while (b.generation == gen) yield();
+    while (b->generation == gen) yield();
 }
 
 inline void mask_barrier_leave(unsigned w, unsigned lane) {
@@ -270,6 +276,7 @@ inline unsigned __ballot_sync(unsigned m, int pred) {
 }
 inline unsigned __activemask() { return emu::S().alive_mask[emu::warp_id()]; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
+inline int __ffs(int x) { return __builtin_ffs(x); }
 inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 
 // one host thread runs all fibers, so plain read-modify-write is atomic
