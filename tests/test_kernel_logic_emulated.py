@@ -53,9 +53,9 @@ def test_product_binding_never_loads_the_emulator():
 
 def test_emulator_selftest(tmp_path):
     """The shim itself: block barriers, full-warp and 8-lane-group shuffles with divergent trip counts, ballot with exited lanes,
-    atomics, dynamic shared memory (tests/cuda_emu/selftest.cu)."""
+    atomics, dynamic shared memory (tests/cuda_emu/selftest.cpp)."""
     exe = str(tmp_path / "emu_selftest")
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-I", os.path.join(EMU, "include"), "-x", "c++", os.path.join(EMU, "selftest.cu"), "-o", exe])
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++17", "-I", os.path.join(EMU, "include"), "-x", "c++", os.path.join(EMU, "selftest.cpp"), "-o", exe])
     r = subprocess.run([exe], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=120)
     assert r.returncode == 0 and "selftest ok" in r.stdout, r.stdout
 
