@@ -22,7 +22,7 @@ DIR_P, DIR_N = 0, 1
 
 EXPORTS = ["tfbs_abi_version", "tfbs_create", "tfbs_destroy", "tfbs_last_error", "tfbs_set_option", "tfbs_set_patterns",
            "tfbs_submit_block", "tfbs_collect", "tfbs_get_matches", "tfbs_upload_block", "tfbs_run_resident", "tfbs_get_stats",
-           "tfbs_stream", "tfbs_host_register", "tfbs_host_unregister", "tfbs_audit_block"]
+           "tfbs_stream", "tfbs_host_register", "tfbs_host_unregister", "tfbs_audit_block", "tfbs_collect_grouped", "tfbs_expand_rows"]
 
 
 class TfbsPattern(C.Structure):
@@ -54,6 +54,15 @@ class TfbsRows(C.Structure):
                 ("region", C.POINTER(C.c_uint32)), ("inner", C.POINTER(C.c_uint32)), ("pattern_id", C.POINTER(C.c_uint16)),
                 ("vmin", C.POINTER(C.c_uint32)), ("vmax", C.POINTER(C.c_uint32)),
                 ("left", C.POINTER(C.c_uint32)), ("right", C.POINTER(C.c_uint32))]
+
+
+class TfbsGroupedRows(C.Structure):
+    _fields_ = [("n_rows", C.c_uint64), ("n_samples", C.c_uint32), ("n_regions", C.c_uint32),
+                ("region", C.POINTER(C.c_uint32)), ("inner", C.POINTER(C.c_uint32)), ("pattern_id", C.POINTER(C.c_uint16)),
+                ("vmin", C.POINTER(C.c_uint32)), ("vmax", C.POINTER(C.c_uint32)), ("base", C.POINTER(C.c_uint32)),
+                ("bits", C.POINTER(C.c_uint8)), ("offset", C.POINTER(C.c_uint64)), ("packed", C.POINTER(C.c_uint32)),
+                ("packed_words", C.c_uint64), ("n_groups", C.POINTER(C.c_uint32)), ("hap_group", C.c_void_p),
+                ("hap_group_bytes", C.c_uint32), ("reserved", C.c_uint32)]
 
 
 class TfbsMatches(C.Structure):
@@ -120,6 +129,8 @@ def lib():
         L.tfbs_upload_block.argtypes = [C.c_void_p, C.POINTER(TfbsBlock)]
         L.tfbs_run_resident.argtypes = [C.c_void_p]
         L.tfbs_collect.argtypes = [C.c_void_p, C.POINTER(TfbsRows)]
+        L.tfbs_collect_grouped.argtypes = [C.c_void_p, C.POINTER(TfbsGroupedRows)]
+        L.tfbs_expand_rows.argtypes = [C.POINTER(TfbsGroupedRows), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.tfbs_get_matches.argtypes = [C.c_void_p, C.POINTER(TfbsMatches)]
         L.tfbs_get_stats.argtypes = [C.c_void_p, C.POINTER(TfbsStats)]
         L.tfbs_audit_block.argtypes = [C.c_void_p, C.POINTER(TfbsAudit)]
@@ -301,6 +312,35 @@ class Context:
                 "pattern_id": arr(rows.pattern_id, n, np.uint16), "vmin": arr(rows.vmin, n, np.uint32),
                 "vmax": arr(rows.vmax, n, np.uint32), "left": counts(rows.left), "right": counts(rows.right),
                 "count_bytes": int(rows.count_bytes or 4)}
+
+    def collect_grouped(self, expand=False):
+        """tfbs_collect_grouped: the rows with one count per distinct haplotype (group) of the region.  Arrays are views of the
+        library's pinned buffers (valid until the next collect); expand=True adds `left` / `right` through tfbs_expand_rows."""
+        g = TfbsGroupedRows()
+        self._check(self._lib.tfbs_collect_grouped(self._h, C.byref(g)))
+        n, S, R = g.n_rows, g.n_samples, g.n_regions
+
+        def arr(p, cnt, ct):
+            if cnt == 0:
+                return np.zeros(0, dtype=np.dtype(ct))
+            return np.ctypeslib.as_array(C.cast(p, C.POINTER(ct)), shape=(cnt,))
+
+        hg_t = C.c_uint16 if g.hap_group_bytes == 2 else C.c_uint32
+        out = {"n_rows": n, "n_samples": S, "n_regions": R, "region": arr(g.region, n, C.c_uint32), "inner": arr(g.inner, n, C.c_uint32),
+               "pattern_id": arr(g.pattern_id, n, C.c_uint16), "vmin": arr(g.vmin, n, C.c_uint32), "vmax": arr(g.vmax, n, C.c_uint32),
+               "base": arr(g.base, n, C.c_uint32), "bits": arr(g.bits, n, C.c_uint8), "offset": arr(g.offset, n, C.c_uint64),
+               "packed": arr(g.packed, g.packed_words, C.c_uint32), "n_groups": arr(g.n_groups, R, C.c_uint32),
+               "hap_group": arr(g.hap_group, R * 2 * S, hg_t).reshape(R, 2 * S) if R * S else np.zeros((R, 2 * S), np.uint32),
+               "bytes": int(n * 31 + g.packed_words * 4 + R * 4 + R * 2 * S * g.hap_group_bytes), "_c": g}
+        if expand:
+            left = np.zeros((n, S), dtype=np.uint32)
+            right = np.zeros((n, S), dtype=np.uint32)
+            if n:
+                rc = self._lib.tfbs_expand_rows(C.byref(g), 0, n, _ptr(left, C.c_uint32), _ptr(right, C.c_uint32))
+                if rc != TFBS_OK:
+                    raise TfbsError(rc, "tfbs_expand_rows failed")
+            out["left"], out["right"] = left, right
+        return out
 
     def matches(self, n_regions):
         m = TfbsMatches()

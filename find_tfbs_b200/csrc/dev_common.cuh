@@ -62,6 +62,7 @@ struct DevStatus {
     u32 max_count;        // largest per-sample count of an emitted row in this batch (decides the width of the returned counts)
 };
 
+
 __device__ __forceinline__ u64 mix64(u64 x) {
     x ^= x >> 30;
     x *= 0xbf58476d1ce4e5b9ULL;

@@ -15,7 +15,7 @@ namespace tfbs {
 // haplotype; every other window is identical (bases and positions) to a window of the reference haplotype.
 struct ScanItem {
     u32 q, p0, p1;
-    u32 owner;   // index of the item whose count vector this one shares (itself if it is scored)
+    u32 index;   // its own index in the work list
 };
 
 // A hit of the reference haplotype, kept so that patched haplotypes can inherit or lose it.
@@ -34,7 +34,11 @@ struct DevRefHits {
 
 // Sequence table of a batch: q = gbase[r] - gbase[r0] + g.
 struct DevSeqs {
-    u32 n_seq;
+    u32 n_seq;               // sequences (an upper bound when n_seq_ptr is set: the count then lives on the device)
+    const u64* n_seq_ptr;    // NULL, or the device word that holds the real number of sequences
+    const u32* abort;        // NULL, or DevPlan::abort: an earlier stage ran out of scratch, the sequence arrays are not to be trusted
+    u32 n_ref;               // > 0: "virtual" sequences of the configuration path: q < n_ref is the reference haplotype of region q,
+                             // q >= n_ref a (cluster, carried records) configuration; 0: the distinct haplotypes of the regions
     const u64* gbase;        // per region (block-wide index), first sequence of the region (batch-relative after -gbase0)
     u64 gbase0;
     u32* seq_region;         // [n_seq]
@@ -51,22 +55,27 @@ struct DevSeqs {
     u32* nm;                 // N mask, bit b = base 32u+b is N
     u64* seq_hash;           // [n_seq]
     u8* seq_flags;           // bit0 truncated, bit1 dropped (overwritten in the sequence-keyed map)
+    u32* seq_ntake;          // [n_seq] diffs of dlist the walk consumed: nd, or k + 1 when it was truncated at dlist[k]
     // scan work list: ranges of window starts that have to be scored
     u32* seq_nitems;         // [n_seq]
     u64* item_off;           // [n_seq+1]
     ScanItem* items;         // flat, in sequence order
     u32 n_items_cap;
-    u64* item_key;           // [items] signature of the item (delta scoring, patched haplotypes)
-    u32* item_hits;          // [items] hits found in the item (owners only)
-    u64* item_coff;          // [items+1] offset of the owner's count vector in item_cnt
-    u32* item_cnt;           // count vectors [pid][inner] of the owners
+    u64 units_cap;           // capacity of pk / nm in units (0 = sized exactly, not checked)
 };
 
+
+__device__ __forceinline__ u32 seq_count(const DevSeqs& sq) {  // 0 once the run has been given up
+    if (sq.abort && *sq.abort) return 0;
+    if (!sq.n_seq_ptr) return sq.n_seq;
+    const u64 n = *sq.n_seq_ptr;
+    return n < sq.n_seq ? (u32)n : sq.n_seq;
+}
 
 __global__ void k_seq_init(u32 H, u32 r0, const u32* hap_group, const u32* leader, const u32* nd_in, DevSeqs sq) {
     u32 r = r0 + blockIdx.x;
     u64 qb = sq.gbase[r] - sq.gbase0;
-    if (threadIdx.x == 0) {
+    if (threadIdx.x == 0 && qb < sq.n_seq) {
         sq.seq_region[qb] = r;
         sq.seq_leader[qb] = 0xffffffffu;
         sq.seq_nd[qb] = 0;
@@ -74,6 +83,7 @@ __global__ void k_seq_init(u32 H, u32 r0, const u32* hap_group, const u32* leade
     for (u32 h = threadIdx.x; h < H; h += blockDim.x) {
         if (leader[(size_t)r * H + h] == h) {
             u64 q = qb + hap_group[(size_t)r * H + h];
+            if (q >= sq.n_seq) continue;  // more sequences than the scratch holds: the run is repeated (need_seq)
             sq.seq_region[q] = r;
             sq.seq_leader[q] = h;
             sq.seq_nd[q] = nd_in[(size_t)r * H + h];
@@ -102,30 +112,18 @@ __device__ __forceinline__ void report(DevStatus* st, u64 q, i64 relpos, u32 cod
     atomicMin(&st->err_key, key);
 }
 
-// Thread per sequence: gathers the carried in-window diffs (haplotype.rs:95), sorts them (:96) and walks
-// them exactly like next_chunk (:98-153), emitting segments instead of bases.
-__global__ void k_walk(DevBlock b, DevSeqs sq, DevStatus* st) {
-    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= sq.n_seq) return;
-    u32 r = sq.seq_region[q];
-    u32 h = sq.seq_leader[q];
-    u64 doff = sq.seq_doff[q];
-    u32* dl = sq.dlist + doff;
-    Seg* sg = sq.segs + 2 * doff + 2 * (u64)q;
-    i64 start = b.region_start[r], end = b.region_end[r];
-    u64 ro = b.ref_off[r];
-    i64 n_ref = (i64)(b.ref_off[r + 1] - ro);
-    i64 avail_end = start + n_ref - 1;
-    u32 nd = 0;
-    if (h != 0xffffffffu) {
-        for (u32 v = b.var_off[r]; v < b.var_off[r + 1]; ++v)
-            if (b.var_inwin[v] && carries(b, v, h)) {
-                // insertion sort; records come sorted by position, so this is nearly linear
-                u32 k = nd++;
-                while (k > 0 && diff_less(b, v, dl[k - 1])) { dl[k] = dl[k - 1]; --k; }
-                dl[k] = v;
-            }
-    }
+// patch_haplotype (haplotype.rs:98-153) over the sorted diff list dl[0, nd): the same cases in the same order, emitting segments
+// instead of bases.  Returns the number of segments (the terminator is written behind them); st == NULL: panics are not
+// reported (a configuration replays diffs whose haplotype has already reported them).
+struct WalkOut {
+    u32 ns, len, ntake;
+    bool trunc;
+};
+__device__ __forceinline__ WalkOut walk_diffs(const DevBlock& b, u32 r, const u32* dl, u32 nd, Seg* sg, DevStatus* st, u64 q_report) {
+    const i64 start = b.region_start[r], end = b.region_end[r];
+    const u64 ro = b.ref_off[r];
+    const i64 n_ref = (i64)(b.ref_off[r + 1] - ro);
+    const i64 avail_end = start + n_ref - 1;
     u32 out = 0, ns = 0;
     bool trunc = false;
     i64 rp = start;
@@ -149,7 +147,7 @@ __global__ void k_walk(DevBlock b, DevSeqs sq, DevStatus* st) {
             rp = d.pos;
         } else if (d.pos == rp && d.ref_len == 1) {  // :115-135 SNV or insertion
             u8 at = (rp >= start && rp <= avail_end) ? b.ref_codes[ro + (u64)(rp - start)] : (u8)4;
-            if (b.allele_codes[d.ref_off] != at) { report(st, q, rp - start, DEV_REF_MISMATCH); break; }
+            if (b.allele_codes[d.ref_off] != at) { if (st) report(st, q_report, rp - start, DEV_REF_MISMATCH); break; }
             sg[ns++] = Seg{out, d.alt_off, (int)(rp - start), 1u};
             out += d.alt_len;
             rp += 1;
@@ -160,23 +158,51 @@ __global__ void k_walk(DevBlock b, DevSeqs sq, DevStatus* st) {
             rp += d.ref_len;
             ++k;
         } else if (d.pos == rp) {  // :141-143
-            report(st, q, rp - start, DEV_MISSING_CASE);
+            if (st) report(st, q_report, rp - start, DEV_MISSING_CASE);
             break;
         } else if (rp >= end) {  // :144-146
             trunc = true;
             emit_ref(rp, rp);
+            ++k;
             break;
         } else {  // :147-149
             trunc = true;
+            ++k;
             break;
         }
     }
     sg[ns] = Seg{out, 0u, 0, 2u};  // terminator
+    return WalkOut{ns, out, k, trunc};
+}
+
+// Thread per sequence: gathers the carried in-window diffs (haplotype.rs:95), sorts them (:96) and walks them.
+__global__ void k_walk(DevBlock b, DevSeqs sq, u64 d_cap, DevStatus* st) {
+    u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= seq_count(sq)) return;
+    u32 r = sq.seq_region[q];
+    u32 h = sq.seq_leader[q];
+    u64 doff = sq.seq_doff[q];
+    if (doff + sq.seq_nd[q] > d_cap) return;  // the diff lists do not fit: the run is repeated with more scratch (need_d says how much)
+    u32* dl = sq.dlist + doff;
+    Seg* sg = sq.segs + 2 * doff + 2 * (u64)q;
+    u32 nd = 0;
+    if (h != 0xffffffffu) {
+        for (u32 v = b.var_off[r]; v < b.var_off[r + 1]; ++v)
+            if (b.var_inwin[v] && carries(b, v, h)) {
+                // insertion sort; records come sorted by position, so this is nearly linear
+                u32 k = nd++;
+                while (k > 0 && diff_less(b, v, dl[k - 1])) { dl[k] = dl[k - 1]; --k; }
+                dl[k] = v;
+            }
+    }
+    const WalkOut w = walk_diffs(b, r, dl, nd, sg, st, q);
+    const u32 ns = w.ns;
     sq.seq_nseg[q] = ns;
-    sq.seq_len[q] = out;
-    sq.seq_flags[q] = trunc ? 1 : 0;
+    sq.seq_len[q] = w.len;
+    sq.seq_flags[q] = w.trunc ? 1 : 0;
+    sq.seq_ntake[q] = w.ntake;
     {   // hash of the (nuc, pos) vector from the segments
-        const u64* P = b.ref_prefix + ro + r;
+        const u64* P = b.ref_prefix + b.ref_off[r] + r;
         u64 hsh = 0;
         for (u32 s = 0; s < ns; ++s) {
             const u32 n = sg[s + 1].out_start - sg[s].out_start;
@@ -188,7 +214,7 @@ __global__ void k_walk(DevBlock b, DevSeqs sq, DevStatus* st) {
         }
         sq.seq_hash[q] = hsh;
     }
-    if (trunc) atomicAdd(&st->n_truncated, 1u);
+    if (w.trunc) atomicAdd(&st->n_truncated, 1u);
 }
 
 __device__ __forceinline__ u32 seg_find(const Seg* sg, u32 ns, u32 i) {  // last segment with out_start <= i
@@ -222,13 +248,14 @@ __global__ void k_ref_prefix(DevBlock b, u32 r0, u64* prefix) {
     }
 }
 
-__device__ __forceinline__ u32 seq_group(const DevSeqs& sq, u32 q) {  // group index of q inside its region
+__device__ __forceinline__ u32 seq_group(const DevSeqs& sq, u32 q) {  // group index of q inside its region (0 = the reference haplotype)
+    if (sq.n_ref) return q < sq.n_ref ? 0u : 1u;  // virtual sequences: only "reference or not" is meaningful
     return (u32)((u64)q + sq.gbase0 - sq.gbase[sq.seq_region[q]]);
 }
 
 __global__ void k_seq_insert(DevSeqs sq, u64* keys, u32* vals, u32 mask) {
     u32 q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= sq.n_seq) return;
+    if (q >= seq_count(sq)) return;
     u32 g = seq_group(sq, q);
     if (g == 0) return;  // the reference haplotype is not in the map (main.rs:129-147)
     u64 key = region_key(sq.seq_hash[q] + mix64(sq.seq_len[q]), sq.seq_region[q]);
@@ -250,7 +277,7 @@ __device__ __forceinline__ void base_at(const DevBlock& b, const DevSeqs& sq, u3
 // as the oracle).  The losers are dropped: their haplotypes stay in the reference set (main.rs:103-105).
 __global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32* vals, u32 mask, DevStatus* st) {
     u32 q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= sq.n_seq) return;
+    if (q >= seq_count(sq)) return;
     u32 g = seq_group(sq, q);
     if (g == 0) return;
     u64 key = region_key(sq.seq_hash[q] + mix64(sq.seq_len[q]), sq.seq_region[q]);
@@ -298,7 +325,7 @@ __global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32
 // hap_flags (audit only, else NULL): the flags of the haplotype's own diff list, taken before the redirect (TFBS_HAP_* bits).
 __global__ void k_redirect(u32 H, u32 r0, u32 nr, DevSeqs sq, u32* hap_group, u32* ref_used, u8* hap_flags) {
     u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (u64)nr * H) return;
+    if (idx >= (u64)nr * H || (sq.abort && *sq.abort)) return;
     u32 r = r0 + (u32)(idx / H), h = (u32)(idx % H);
     u32 g = hap_group[(size_t)r * H + h];
     const u8 fl = g ? sq.seq_flags[sq.gbase[r] - sq.gbase0 + g] : (u8)0;

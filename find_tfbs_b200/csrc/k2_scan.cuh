@@ -2,6 +2,7 @@
 // Part of the sm_100a kernels of the find-tfbs hot path; included through kernels.cuh (see the map there).
 #pragma once
 #include "k2_types.cuh"
+#include "k2c_configs.cuh"
 
 namespace tfbs {
 
@@ -19,9 +20,9 @@ __device__ __noinline__ u32 scan_on_hit(u64 hit, u32 t, u32 i, u32 item_index, C
     const Seg* sg = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
     const u32 r = sq.seq_region[q];
     const u32 g = seq_group(sq, q);
-    // 0 count every hit; 1 reference haplotype under delta scoring (count + remember the hit); 2 patched haplotype under delta
-    // scoring: count only windows that touch a variant, into the count vector of the (shared) item
-    const u32 mode = env->delta ? (g == 0 ? 1u : 2u) : 0u;
+    // 0 full scan: count every hit into the row of the haplotype's group; configuration path: 1 reference haplotype (count + remember
+    // the hit), 2 configuration: count only windows that touch one of its records, into its column of the difference matrix
+    const u32 mode = env->cf ? (g == 0 ? 1u : 2u) : 0u;
     const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
     const tfbs_inner_region* inner = b.inner + b.inner_off[r];
     const i64 region_start = b.region_start[r];
@@ -40,9 +41,13 @@ __device__ __noinline__ u32 scan_on_hit(u64 hit, u32 t, u32 i, u32 item_index, C
         i64 he = hs + L - 1;
         u32 pl = pt.pat_pid_index[pi];
         u32* crow;
-        if (mode == 2) {
-            crow = sq.item_cnt + sq.item_coff[item_index];
-            atomicAdd(&sq.item_hits[item_index], 1u);
+        u64 cstride = 1;
+        if (mode == 2) {  // a configuration: its column of the region's difference matrix D[key][configuration]
+            const DevConfigs& cf = *env->cf;
+            const u64 c = (u64)q - sq.n_ref;
+            crow = cf.D + cf.dbase[r] + (c - cf.cfgbase[r]);
+            cstride = cf.ncfg[r];
+            atomicAdd(&cf.cfg_net[c], 1);
         } else {
             crow = env->ct->C + (env->ct->cbase[r] - env->ct->cbase0) + (u64)g * pt.n_pid * nk;
             if (mode == 1) {
@@ -57,7 +62,7 @@ __device__ __noinline__ u32 scan_on_hit(u64 hit, u32 t, u32 i, u32 item_index, C
         for (u32 k = 0; k < nk; ++k) {
             i64 is = inner[k].start - region_start, ie = inner[k].end - region_start;
             bool ov = (hs >= is && hs <= ie) || (he >= is && he <= ie);  // inner.overlaps(match.range), range.rs:18-21
-            if (ov) atomicAdd(&crow[(size_t)pl * nk + k], inner[k].multiplicity);
+            if (ov) atomicAdd(&crow[((size_t)pl * nk + k) * cstride], inner[k].multiplicity);
         }
         if (env->mt->enabled) {
             u64 slot = atomicAdd(&st->n_matches, 1ULL);
@@ -121,7 +126,9 @@ template <int FIELDS>
 __global__ void __launch_bounds__(SCAN_CTA, 1)
     k_scan(const __grid_constant__ DevBlock b, const __grid_constant__ DevSeqs sq, const __grid_constant__ DevPatterns pt,
            const __grid_constant__ DevCounts ct, const __grid_constant__ DevMatches mt, const __grid_constant__ DevRefHits rh,
-           const u32* list, const u64* n_list_ptr, u32 per_grab, DevStatus* st, u32 chunk, int delta) {
+           const __grid_constant__ DevConfigs cf, int use_cf, const u32* list, const u64* n_list_ptr, u32 per_grab,
+           const u64* n_long_ptr, DevStatus* st, u32 chunk) {
+    if (use_cf && cf.plan->abort) return;  // an earlier stage ran out of scratch: the host repeats the run
     TFBS_DYNAMIC_SHARED(smem_raw);
     CtaShared* cs = reinterpret_cast<CtaShared*>(smem_raw);
     WarpShared* ws = reinterpret_cast<WarpShared*>(smem_raw + sizeof(CtaShared)) + (threadIdx.x >> 5);
@@ -139,15 +146,19 @@ __global__ void __launch_bounds__(SCAN_CTA, 1)
     __syncthreads();
     const u32 n_runs = cs->n_runs;
     const u64 n_list = *n_list_ptr;
-    const ScanEnv env{&b, &sq, &pt, &ct, &mt, &rh, st, delta};
+    const ScanEnv env{use_cf ? &cf : nullptr, &b, &sq, &pt, &ct, &mt, &rh, st};
 
+    // the first n_long entries are long items (whole reference haplotypes): one per trip to the work counter, so that the warps
+    // that draw them do not end up with `per_grab` times the work of the others; short items follow, per_grab at a time
+    u64 n_long = n_long_ptr ? *n_long_ptr : 0;
+    if (n_long > n_list) n_long = n_list;
     for (;;) {
         u32 w = 0;
         if (lane == 0) w = atomicAdd(&st->work_counter, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
-        u64 li = (u64)w * per_grab;
+        u64 li = w < n_long ? (u64)w : n_long + ((u64)w - n_long) * per_grab;
         if (li >= n_list) break;
-        const u64 lend = li + per_grab < n_list ? li + per_grab : n_list;
+        const u64 lend = w < n_long ? li + 1 : (li + per_grab < n_list ? li + per_grab : n_list);
         u32 done_in_item = 0;  // starts of entry li already scored
         u32 n_counted = 0;
         while (li < lend) {

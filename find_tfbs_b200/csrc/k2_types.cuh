@@ -101,7 +101,9 @@ template <>
 struct HitMask<2> { static constexpr u64 value = (1ULL << 31) | (1ULL << 63); };
 
 // Everything the rare path needs, passed by pointer (the structs are __grid_constant__ kernel parameters).
+struct DevConfigs;
 struct ScanEnv {
+    const DevConfigs* cf;   // configuration path (virtual sequences) or NULL
     const DevBlock* b;
     const DevSeqs* sq;
     const DevPatterns* pt;
@@ -109,7 +111,6 @@ struct ScanEnv {
     const DevMatches* mt;
     const DevRefHits* rh;
     DevStatus* st;
-    int delta;
 };
 
 }  // namespace tfbs

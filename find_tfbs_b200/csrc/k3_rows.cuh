@@ -1,4 +1,4 @@
-// k3_rows.cuh -- K3: fan-out to samples, min/max filter, row compaction, nominal cells
+// k3_rows.cuh -- K3 of the full scan (dense count rows per group): fan-out to samples, min/max filter, row compaction; nominal cells
 // Part of the sm_100a kernels of the find-tfbs hot path; included through kernels.cuh (see the map there).
 #pragma once
 #include "k2_types.cuh"
@@ -12,7 +12,7 @@ namespace tfbs {
 // One CTA per region, one thread per key (pid, inner): v[s] = C[group(left)] + C[group(right)]
 // (main.rs:441-448), min and max over samples (:450-451).  flag: 1 = row is emitted.
 __global__ void k_rows_minmax(DevBlock b, u32 r0, const u32* hap_group, DevCounts ct, const u64* gbase, u32 n_pid, const u64* kbase,
-                              u64 kbase0, int rows_mode, int delta, u32* vmin, u32* vmax, u32* flag, u32* max_count) {
+                              u64 kbase0, int rows_mode, u32* vmin, u32* vmax, u32* flag, u32* max_count) {
     u32 r = r0 + blockIdx.x;
     u32 row_max = 0;
     u32 nk = b.inner_off[r + 1] - b.inner_off[r];
@@ -23,11 +23,9 @@ __global__ void k_rows_minmax(DevBlock b, u32 r0, const u32* hap_group, DevCount
     (void)gbase;
     for (u32 key = threadIdx.x; key < nkeys; key += blockDim.x) {
         u32 lo = 0xffffffffu, hi = 0;
-        // under delta scoring the rows of patched haplotypes hold differences to the reference row (wrapping u32)
-        const u32 base = delta ? C[key] : 0u;
         for (u32 s = 0; s < b.S; ++s) {
             u32 g0 = hg[2 * s], g1 = hg[2 * s + 1];
-            u32 v = C[(size_t)g0 * nkeys + key] + C[(size_t)g1 * nkeys + key] + (g0 ? base : 0u) + (g1 ? base : 0u);
+            u32 v = C[(size_t)g0 * nkeys + key] + C[(size_t)g1 * nkeys + key];
             lo = min(lo, v);
             hi = max(hi, v);
         }
@@ -58,7 +56,7 @@ struct DevRows {
 template <class T>
 __global__ void k_rows_write(DevBlock b, u32 r0, u32 nr, const u32* hap_group, DevCounts ct, u32 n_pid, const u16* pid_list,
                              const u64* kbase, u64 kbase0, u64 n_keys, const u32* vmin, const u32* vmax, const u32* flag,
-                             const u64* rowidx, DevRows rows, u64 row_base, int delta) {
+                             const u64* rowidx, DevRows rows, u64 row_base) {
     u64 key = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     u32 lane = threadIdx.x & 31;
     if (key >= n_keys || !flag[key]) return;
@@ -83,13 +81,12 @@ __global__ void k_rows_write(DevBlock b, u32 r0, u32 nr, const u32* hap_group, D
     }
     const u32* C = ct.C + (ct.cbase[r] - ct.cbase0);
     const u32* hg = hap_group + (size_t)r * b.H;
-    const u32 base = delta ? C[kk] : 0u;
     T* left = reinterpret_cast<T*>(rows.left) + row * b.S;
     T* right = reinterpret_cast<T*>(rows.right) + row * b.S;
     for (u32 s = lane; s < b.S; s += 32) {
         u32 g0 = hg[2 * s], g1 = hg[2 * s + 1];
-        left[s] = (T)(C[(size_t)g0 * nkeys + kk] + (g0 ? base : 0u));
-        right[s] = (T)(C[(size_t)g1 * nkeys + kk] + (g1 ? base : 0u));
+        left[s] = (T)C[(size_t)g0 * nkeys + kk];
+        right[s] = (T)C[(size_t)g1 * nkeys + kk];
     }
 }
 
@@ -97,7 +94,7 @@ __global__ void k_rows_write(DevBlock b, u32 r0, u32 nr, const u32* hap_group, D
 __global__ void k_nominal(DevBlock b, u32 r0, u32 nr, const u32* hap_group, DevSeqs sq, DevPatterns pt, DevStatus* st) {
     u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     u64 cells = 0;
-    if (idx < (u64)nr * b.H) {
+    if (idx < (u64)nr * b.H && !(sq.abort && *sq.abort)) {
         u32 r = r0 + (u32)(idx / b.H), h = (u32)(idx % b.H);
         u32 len = sq.seq_len[sq.gbase[r] - sq.gbase0 + hap_group[(size_t)r * b.H + h]];
         if (len >= pt.max_len) cells = (u64)(len + 1) * pt.sum_len - (pt.sum_len_sq + pt.sum_len);

@@ -20,6 +20,8 @@
 #include "k1_build.cuh"
 #include "k2_types.cuh"
 #include "k2_worklist.cuh"
+#include "k2c_configs.cuh"
 #include "k2_scan.cuh"
 #include "k2_finish.cuh"
 #include "k3_rows.cuh"
+#include "k3_fanout.cuh"

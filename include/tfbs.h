@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TFBS_ABI_VERSION 1
+#define TFBS_ABI_VERSION 2
 
 /* Nucleotide codes: enum Nucleotide { A, C, G, T, N } (src/types.rs:5-8). */
 enum { TFBS_NUC_A = 0, TFBS_NUC_C = 1, TFBS_NUC_G = 2, TFBS_NUC_T = 3, TFBS_NUC_N = 4 };
@@ -129,7 +129,7 @@ typedef struct tfbs_block {
  * count_matches_by_sample (src/main.rs:500-534) that survives the filter.  left/right are the
  * reference's (Vec<u32>, Vec<u32>) value.  Rows come in a deterministic order: by region,
  * then pattern_id ascending, then inner index.  Pointers stay valid until the next
- * tfbs_submit_block / tfbs_run_resident / tfbs_destroy on the same context.
+ * tfbs_collect / tfbs_collect_grouped, the second-next tfbs_submit_block / tfbs_run_resident, or tfbs_destroy on the same context.
  */
 typedef struct tfbs_rows {
     uint64_t n_rows;
@@ -144,6 +144,36 @@ typedef struct tfbs_rows {
     const uint32_t* left;          /* [n_rows * n_samples] elements of count_bytes bytes (uint32_t by default) */
     const uint32_t* right;         /* [n_rows * n_samples] */
 } tfbs_rows;
+
+/*
+ * The same rows with identical count vectors stored once ("grouped rows"): haplotypes that carry the same records in a region
+ * (group_by_diffs, src/haplotype.rs:65-75) have the same count for every key, so a row holds one count per GROUP of the region and
+ * the haplotype -> group map is returned once per region.  A sample's (left, right) of count_matches_by_sample (src/main.rs:500-534)
+ * is (count[hap_group[2 * sample]], count[hap_group[2 * sample + 1]]); tfbs_expand_rows does exactly that.  Counts are packed as
+ * `bits`-wide offsets from the row's smallest count (bits = 0: every group has the count `base`).  This is what crosses PCIe for
+ * large cohorts: about 1/10 of the dense rows.
+ */
+typedef struct tfbs_grouped_rows {
+    uint64_t n_rows;
+    uint32_t n_samples;
+    uint32_t n_regions;
+    const uint32_t* region;        /* [n_rows] as in tfbs_rows */
+    const uint32_t* inner;         /* [n_rows] */
+    const uint16_t* pattern_id;    /* [n_rows] */
+    const uint32_t* vmin;          /* [n_rows] */
+    const uint32_t* vmax;          /* [n_rows] */
+    const uint32_t* base;          /* [n_rows] smallest per-haplotype count of the row */
+    const uint8_t* bits;           /* [n_rows] width of a packed entry: 0, 1, 2, 4, 8, 16 or 32 */
+    const uint64_t* offset;        /* [n_rows] first 32-bit word of the row in `packed` */
+    const uint32_t* packed;        /* per row ceil(n_groups[region] * bits / 32) words, little-endian bit order: entry g = count of
+                                      group g minus base, at bits [g * bits, (g + 1) * bits) of the row */
+    uint64_t packed_words;
+    const uint32_t* n_groups;      /* [n_regions] distinct haplotypes of the region incl. the reference haplotype (group 0) */
+    const void* hap_group;         /* [n_regions * 2 * n_samples] group of haplotype h = 2 * sample + side in its region, as uint16_t
+                                      or uint32_t (hap_group_bytes); 0 = the reference haplotype (main.rs:103-105,129-131) */
+    uint32_t hap_group_bytes;      /* 2 or 4 */
+    uint32_t reserved;
+} tfbs_grouped_rows;
 
 /* Individual hits (struct Match, src/types.rs:32-37), for debugging and parity tests. */
 typedef struct tfbs_matches {
@@ -238,7 +268,8 @@ const char* tfbs_last_error(const tfbs_ctx* ctx);
  * match buffer), "verify_groups" (0/1, exact check of hash-grouped haplotypes, default 1),
  * "scan_format" (0 auto, 1 force 32-bit tables), "delta" (default 1: score a patched haplotype only where its windows
  * touch a variant and inherit every other hit from the region's reference haplotype -- exact, scores are integers; 0: score
- * every distinct haplotype in full like the reference does; forced to 0 while "record_matches" is on), "scratch_mb",
+ * every distinct haplotype in full like the reference does; forced to 0 while "record_matches" is on), "scratch_mb" (upper bound of
+ * the device scratch a block may use; a block that needs more fails with TFBS_ERR_INVALID_ARGUMENT: submit fewer regions at a time),
  * "table_budget_kb", "rows_width" (32 = counts come back as uint32_t, the reference's Vec<u32>; 0 = the narrowest of 8/16/32 bits
  * that holds every count of the block, see tfbs_rows.count_bytes -- result rows are the dominant PCIe traffic of large cohorts). */
 int tfbs_set_option(tfbs_ctx* ctx, const char* key, int64_t value);
@@ -246,12 +277,23 @@ int tfbs_set_option(tfbs_ctx* ctx, const char* key, int64_t value);
 /* Replace the pattern list (the reference's pwm_list, src/main.rs:237). */
 int tfbs_set_patterns(tfbs_ctx* ctx, const tfbs_pattern* patterns, uint32_t n_patterns);
 
-/* Host-buffer path: copy the block to the device and launch the whole pipeline
- * asynchronously.  The caller's buffers may be reused after this returns. */
+/* Host-buffer path: enqueue the copy of the block to the device and the whole pipeline, then return -- nothing is waited for
+ * (default scoring mode; with "delta" = 0 or "record_matches" the call runs the block to completion).  Up to TWO blocks may be in
+ * flight per context: the copies of block i + 1 overlap the kernels of block i, the rows of block i travel back while block i + 1
+ * is computed.  A third tfbs_submit_block before a tfbs_collect fails with TFBS_ERR_STATE.  The caller's buffers must stay valid and
+ * unchanged until the tfbs_collect that returns this block's rows (they are read by asynchronous copies when page-locked). */
 int tfbs_submit_block(tfbs_ctx* ctx, const tfbs_block* block);
 
-/* Wait for the submitted block and expose its rows (device -> host copy included). */
+/* Wait for the OLDEST block in flight -- the only place the host waits for the device -- and expose its rows as the reference's
+ * (left, right) vectors (expanded on the device, then copied). */
 int tfbs_collect(tfbs_ctx* ctx, tfbs_rows* out);
+
+/* Same, but the rows come back grouped (see tfbs_grouped_rows): the compact form for large cohorts.  Default scoring mode only. */
+int tfbs_collect_grouped(tfbs_ctx* ctx, tfbs_grouped_rows* out);
+
+/* Host side of grouped rows: (left, right) of rows [first_row, first_row + n_rows), n_rows * n_samples uint32_t each.  Pure host
+ * code, no CUDA call; thread-safe. */
+int tfbs_expand_rows(const tfbs_grouped_rows* rows, uint64_t first_row, uint64_t n_rows, uint32_t* left, uint32_t* right);
 
 /* Matches of the last run when "record_matches" was on (call after tfbs_collect). */
 int tfbs_get_matches(tfbs_ctx* ctx, tfbs_matches* out);
@@ -264,7 +306,7 @@ int tfbs_audit_block(tfbs_ctx* ctx, tfbs_audit* out);
 
 /* Device-resident path for benchmarking: upload once, run the device pipeline on the
  * resident block any number of times.  tfbs_run_resident returns after the device work of
- * this run has been enqueued and its row count is known; tfbs_collect then fetches rows. */
+ * this run has been enqueued (two runs may be in flight, like tfbs_submit_block); tfbs_collect then fetches rows. */
 int tfbs_upload_block(tfbs_ctx* ctx, const tfbs_block* block);
 int tfbs_run_resident(tfbs_ctx* ctx);
 

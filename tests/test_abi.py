@@ -28,7 +28,7 @@ def test_header_functions_are_exported():
     for n in names:
         assert hasattr(L, n), n
     L.tfbs_abi_version.restype = C.c_int
-    assert L.tfbs_abi_version() == 1
+    assert L.tfbs_abi_version() == 2
 
 
 def test_no_gpu_fails_loudly():

@@ -482,3 +482,48 @@ def test_narrow_row_counts():
             g = hp.run_gpu(ps, blk, options=opts)
             assert g["count_bytes"] == width, (g["count_bytes"], int(base["vmax"].max()))
             hp.assert_rows_equal(g, base)
+
+
+def test_grouped_rows_two_blocks_in_flight_and_scratch_growth():
+    """The default path end to end: (i) started with minimal scratch (option tiny_caps) every capacity overflows once and the block is
+    repeated until it fits -- same rows; (ii) two blocks in flight on one context (a third submit is refused), rows collected in
+    submission order as GROUPED rows (one count per distinct haplotype + the haplotype -> group map per region) and expanded on the
+    host by tfbs_expand_rows -- equal to the oracle's (left, right) vectors; (iii) two resident runs in flight, one collected dense
+    (expanded on the device), one grouped."""
+    for seed in (1, 2, 3):
+        pats = synth.make_pwms(6, seed=seed)
+        lmax = max(p["weights"].shape[0] for p in pats)
+        blk = synth.make_cohort(12, 10, seed=seed, lmax_pattern=lmax, region_len=(200, 600), two_beds=True, n_runs=2, same_pos_frac=0.1,
+                                frac_ins=0.15, frac_del=0.15)
+        ps = PatternSet(pats)
+        for mode in (binding.ROWS_VARYING, binding.ROWS_ALL_KEYS):
+            o = hp.run_oracle(ps, blk, mode, False)
+            d = hp.run_gpu(ps, blk, mode, False, {"tiny_caps": 1})
+            hp.assert_rows_equal(d, o)
+            hp.check_stats(d["stats"], o)
+            ctx = binding.Context(0)
+            try:
+                ctx.set_option("rows_mode", mode)
+                ctx.set_patterns(ps)
+                half = blk.n_regions // 2
+                b1, b2 = blk.slice(0, half), blk.slice(half, blk.n_regions)
+                ctx.submit_block(b1)
+                ctx.submit_block(b2)
+                with pytest.raises(binding.TfbsError) as e:
+                    ctx.submit_block(b1)
+                assert e.value.code == binding.ERR_STATE
+                g1 = ctx.collect_grouped(expand=True)
+                g1 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in g1.items()}
+                g2 = ctx.collect_grouped(expand=True)
+                hp.assert_rows_equal(g1, hp.run_oracle(ps, b1, mode, False))
+                hp.assert_rows_equal(g2, hp.run_oracle(ps, b2, mode, False))
+                assert set(np.unique(g2["bits"]).tolist()) <= {0, 1, 2, 4, 8, 16, 32}
+                ctx.upload_block(blk)
+                ctx.run_resident()
+                ctx.run_resident()
+                hp.assert_rows_equal(ctx.collect(), o)
+                hp.assert_rows_equal(ctx.collect_grouped(expand=True), o)
+                with pytest.raises(binding.TfbsError):
+                    ctx.collect()  # nothing in flight any more
+            finally:
+                ctx.close()
