@@ -22,7 +22,7 @@ DIR_P, DIR_N = 0, 1
 
 EXPORTS = ["tfbs_abi_version", "tfbs_create", "tfbs_destroy", "tfbs_last_error", "tfbs_set_option", "tfbs_set_patterns",
            "tfbs_submit_block", "tfbs_collect", "tfbs_get_matches", "tfbs_upload_block", "tfbs_run_resident", "tfbs_get_stats",
-           "tfbs_stream", "tfbs_host_register", "tfbs_host_unregister", "tfbs_audit_block", "tfbs_collect_grouped", "tfbs_expand_rows"]
+           "tfbs_stream", "tfbs_host_register", "tfbs_host_unregister", "tfbs_audit_block", "tfbs_collect_grouped", "tfbs_expand_rows", "tfbs_set_result_arena"]
 
 
 class TfbsPattern(C.Structure):
@@ -63,6 +63,56 @@ class TfbsGroupedRows(C.Structure):
                 ("bits", C.POINTER(C.c_uint8)), ("offset", C.POINTER(C.c_uint64)), ("packed", C.POINTER(C.c_uint32)),
                 ("packed_words", C.c_uint64), ("n_groups", C.POINTER(C.c_uint32)), ("hap_group", C.c_void_p),
                 ("hap_group_bytes", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class TfbsArenaHeader(C.Structure):
+    _fields_ = [("magic", C.c_uint64), ("sequence", C.c_uint64), ("n_rows", C.c_uint64), ("packed_words", C.c_uint64),
+                ("n_samples", C.c_uint32), ("n_regions", C.c_uint32), ("hap_group_bytes", C.c_uint32), ("reserved", C.c_uint32),
+                ("off_region", C.c_uint64), ("off_inner", C.c_uint64), ("off_pattern_id", C.c_uint64), ("off_vmin", C.c_uint64),
+                ("off_vmax", C.c_uint64), ("off_base", C.c_uint64), ("off_bits", C.c_uint64), ("off_offset", C.c_uint64),
+                ("off_packed", C.c_uint64), ("off_n_groups", C.c_uint64), ("off_hap_group", C.c_uint64), ("bytes_used", C.c_uint64)]
+
+
+ARENA_MAGIC = 0x3152415342465400
+
+
+def read_arena(buf, half, expand=False):
+    """Grouped rows of the block most recently completed in one half of a result arena (tfbs_set_result_arena), e.g. through a
+    shared-memory mapping in ANOTHER process than the one that owns the context.  buf: writable/readable uint8 numpy array (or
+    np.memmap) over the whole arena."""
+    base = (len(buf) // 2) * half
+    h = TfbsArenaHeader.from_buffer_copy(bytes(buf[base:base + C.sizeof(TfbsArenaHeader)]))
+    if h.magic != ARENA_MAGIC:
+        return None
+    n, S, R = h.n_rows, h.n_samples, h.n_regions
+
+    def arr(off, cnt, dt):
+        return np.frombuffer(buf, dtype=dt, count=cnt, offset=base + off) if cnt else np.zeros(0, dtype=dt)
+
+    hg_dt = np.uint16 if h.hap_group_bytes == 2 else np.uint32
+    out = {"sequence": h.sequence, "n_rows": n, "n_samples": S, "n_regions": R, "region": arr(h.off_region, n, np.uint32),
+           "inner": arr(h.off_inner, n, np.uint32), "pattern_id": arr(h.off_pattern_id, n, np.uint16), "vmin": arr(h.off_vmin, n, np.uint32),
+           "vmax": arr(h.off_vmax, n, np.uint32), "base": arr(h.off_base, n, np.uint32), "bits": arr(h.off_bits, n, np.uint8),
+           "offset": arr(h.off_offset, n, np.uint64), "packed": arr(h.off_packed, h.packed_words, np.uint32),
+           "n_groups": arr(h.off_n_groups, R, np.uint32), "hap_group": arr(h.off_hap_group, R * 2 * S, hg_dt).reshape(R, 2 * S),
+           "bytes": int(h.bytes_used)}
+    if expand:
+        g = TfbsGroupedRows()
+        g.n_rows, g.n_samples, g.n_regions, g.packed_words, g.hap_group_bytes = n, S, R, h.packed_words, h.hap_group_bytes
+        keep = []
+        for name, ct in (("region", C.c_uint32), ("inner", C.c_uint32), ("pattern_id", C.c_uint16), ("vmin", C.c_uint32), ("vmax", C.c_uint32),
+                         ("base", C.c_uint32), ("bits", C.c_uint8), ("offset", C.c_uint64), ("packed", C.c_uint32), ("n_groups", C.c_uint32)):
+            a = np.ascontiguousarray(out[name])
+            keep.append(a)
+            setattr(g, name, a.ctypes.data_as(C.POINTER(ct)))
+        hg = np.ascontiguousarray(out["hap_group"])
+        g.hap_group = hg.ctypes.data
+        left = np.zeros((n, S), dtype=np.uint32)
+        right = np.zeros((n, S), dtype=np.uint32)
+        if n and lib().tfbs_expand_rows(C.byref(g), 0, n, _ptr(left, C.c_uint32), _ptr(right, C.c_uint32)) != TFBS_OK:
+            raise TfbsError(ERR_INVALID_ARGUMENT, "tfbs_expand_rows failed on the arena")
+        out["left"], out["right"] = left, right
+    return out
 
 
 class TfbsMatches(C.Structure):
@@ -131,6 +181,7 @@ def lib():
         L.tfbs_collect.argtypes = [C.c_void_p, C.POINTER(TfbsRows)]
         L.tfbs_collect_grouped.argtypes = [C.c_void_p, C.POINTER(TfbsGroupedRows)]
         L.tfbs_expand_rows.argtypes = [C.POINTER(TfbsGroupedRows), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+        L.tfbs_set_result_arena.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.tfbs_get_matches.argtypes = [C.c_void_p, C.POINTER(TfbsMatches)]
         L.tfbs_get_stats.argtypes = [C.c_void_p, C.POINTER(TfbsStats)]
         L.tfbs_audit_block.argtypes = [C.c_void_p, C.POINTER(TfbsAudit)]
@@ -238,12 +289,30 @@ class Block:
         return sum(a.nbytes for a in (self.region_start, self.region_end, self.ref_off, self.ref_bases, self.inner_off, self.inner,
                                       self.var_off, self.variants, self.allele_bases, self.carriers))
 
-    def slice(self, r0, r1):
-        """Sub-block of regions [r0, r1) (variants keep their global carrier rows)."""
+    def slice(self, r0, r1, compact=False):
+        """Sub-block of regions [r0, r1).  compact=False: variants keep their global carrier rows and allele offsets (the shard
+        carries the whole carrier matrix); compact=True: only the carrier rows and allele bytes the shard's records use are kept
+        and the records are renumbered -- what a shard sent to another GPU should look like."""
         ro, io, vo = self.ref_off, self.inner_off, self.var_off
+        variants = self.variants[int(vo[r0]):int(vo[r1])]
+        alleles, carriers = self.allele_bases, self.carriers
+        if compact:
+            variants = variants.copy()
+            if len(variants):
+                rows, inv = np.unique(variants["carrier_row"], return_inverse=True)
+                carriers = np.ascontiguousarray(self.carriers[rows])
+                variants["carrier_row"] = inv.astype(np.uint32)
+                lo = int(min(variants["ref_off"].min(), variants["alt_off"].min()))
+                hi = int(max((variants["ref_off"] + variants["ref_len"]).max(), (variants["alt_off"] + variants["alt_len"]).max()))
+                alleles = np.ascontiguousarray(self.allele_bases[lo:hi])
+                variants["ref_off"] -= np.uint32(lo)
+                variants["alt_off"] -= np.uint32(lo)
+            else:
+                carriers = np.zeros((1, self.carriers.shape[1]), dtype=np.uint32)
+                alleles = np.zeros(0, dtype=np.uint8)
         return Block(self.n_samples, self.region_start[r0:r1], self.region_end[r0:r1], ro[r0:r1 + 1] - ro[r0],
                      self.ref_bases[int(ro[r0]):int(ro[r1])], io[r0:r1 + 1] - io[r0], self.inner[int(io[r0]):int(io[r1])],
-                     vo[r0:r1 + 1] - vo[r0], self.variants[int(vo[r0]):int(vo[r1])], self.allele_bases, self.carriers)
+                     vo[r0:r1 + 1] - vo[r0], variants, alleles, carriers)
 
 
 class Context:
@@ -312,6 +381,15 @@ class Context:
                 "pattern_id": arr(rows.pattern_id, n, np.uint16), "vmin": arr(rows.vmin, n, np.uint32),
                 "vmax": arr(rows.vmax, n, np.uint32), "left": counts(rows.left), "right": counts(rows.right),
                 "count_bytes": int(rows.count_bytes or 4)}
+
+    def set_result_arena(self, buf):
+        """tfbs_set_result_arena: grouped rows are copied by the device straight into `buf` (a uint8 numpy array / np.memmap, e.g.
+        over a POSIX shared-memory file that the process gathering the rows has mapped too).  None detaches it."""
+        self._arena = buf
+        if buf is None:
+            self._check(self._lib.tfbs_set_result_arena(self._h, None, 0))
+        else:
+            self._check(self._lib.tfbs_set_result_arena(self._h, buf.ctypes.data, buf.nbytes))
 
     def collect_grouped(self, expand=False):
         """tfbs_collect_grouped: the rows with one count per distinct haplotype (group) of the region.  Arrays are views of the

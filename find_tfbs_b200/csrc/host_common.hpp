@@ -42,11 +42,19 @@ struct DevBuf {
     template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
-struct HostBuf {  // pinned
+struct HostBuf {  // pinned; owned (cudaMallocHost) or bound to a piece of the caller's result arena
     void* p = nullptr;
     size_t cap = 0;
-    ~HostBuf() { if (p) cudaFreeHost(p); }
+    bool owned = true;
+    ~HostBuf() { if (p && owned) cudaFreeHost(p); }
+    void bind(void* q, size_t bytes) {
+        if (p && owned) cudaFreeHost(p);
+        p = q;
+        cap = bytes;
+        owned = false;
+    }
     cudaError_t reserve(size_t bytes, bool keep) {
+        if (!owned) { p = nullptr; cap = 0; owned = true; }  // leave the arena: back to an own allocation
         if (bytes <= cap) return cudaSuccess;
         void* np = nullptr;
         size_t want = bytes + bytes / 4 + 256;
@@ -154,6 +162,8 @@ struct tfbs_ctx {
     BlockDev resident;
     BlockDev* last_block = nullptr;  // block of the most recent submit / upload (tfbs_audit_block)
     Caps hint;                     // largest needs seen so far (+ 25 %): what the next block is given
+    uint8_t* arena = nullptr;      // tfbs_set_result_arena: grouped rows are copied straight into the caller's memory
+    size_t arena_bytes = 0;
 
     // scratch shared by consecutive blocks (their kernels are serialised on `stream`)
     DevBuf d_ref_codes, d_allele_codes, d_var_class, d_var_inwin, d_ref_prefix;
@@ -168,7 +178,7 @@ struct tfbs_ctx {
         d_cfg_net, d_mcount, d_moff, d_mfill, d_members, d_D, d_C0;
     DevBuf d_vq_region, d_vq_leader, d_vq_nd, d_vq_doff, d_vq_dlist, d_vq_segs, d_vq_nseg, d_vq_len, d_vq_flags, d_vq_ntake, d_vq_nitems,
         d_vq_item_off;
-    DevBuf d_vmin, d_vmax, d_flag, d_rowwords, d_rowidx, d_rowoff;
+    DevBuf d_vmin, d_vmax, d_flag, d_rowwords, d_kbits, d_keyflag, d_rowidx, d_rowoff;
     // full-scan path
     std::vector<uint32_t> h_ngroups, h_sum_nd;
     std::vector<uint64_t> h_gbase, h_cbase, h_kbase;

@@ -24,6 +24,7 @@ struct DevPlan {
     u32 need_capr, need_groups;
     u32 abort, cfg_collision;
     u64 unused;
+    u64 rowwords_alloc;  // packed row words handed out by the fan-out (an atomic cursor)
 };
 
 // A count becomes known: total (+ add) against the capacity its consumers were launched for.  Behind an earlier overflow nothing
@@ -76,6 +77,7 @@ struct DevConfigs {
     // counts
     u32* D;                // [region][key][configuration of the region]: difference to the reference haplotype's count (wrapping u32)
     u32* C0;               // [key] counts of the region's reference haplotype
+    u8* keyflag;           // [key] 1 once any hit or lost hit touched the key: the fan-out looks at nothing else
     DevPlan* plan;
 };
 
@@ -312,7 +314,10 @@ __global__ void k_cfg_lost(DevBlock b, DevSeqs vq, DevConfigs cf, DevRefHits rh)
         const i64 hs = h.relpos, he = hs + h.len - 1;
         for (u32 k = 0; k < nk; ++k) {
             i64 is = inner[k].start - rs, ie = inner[k].end - rs;
-            if ((hs >= is && hs <= ie) || (he >= is && he <= ie)) atomicSub(&col[((u64)h.pid * nk + k) * ncfg], inner[k].multiplicity);
+            if ((hs >= is && hs <= ie) || (he >= is && he <= ie)) {
+                atomicSub(&col[((u64)h.pid * nk + k) * ncfg], inner[k].multiplicity);
+                cf.keyflag[cf.kbase[r] + (u64)h.pid * nk + k] = 1;
+            }
         }
     }
     if (lost) atomicSub(&cf.cfg_net[c], lost);

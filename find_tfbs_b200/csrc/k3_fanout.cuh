@@ -22,10 +22,11 @@ struct DevFan {
     // per key
     u32* vmin;
     u32* vmax;
-    u32* flag;
-    u32* rowwords;          // packed words of the key's row (0 when it is not emitted)
-    const u64* rowidx;      // exclusive scans of flag / rowwords (second pass)
-    const u64* rowoff;
+    u32* flag;              // 1 = the key becomes a row
+    u32* k_base;            // smallest per-group count of the key's row
+    u8* k_bits;             // width of a packed entry
+    u64* k_off;             // first packed word of the row
+    const u64* rowidx;      // exclusive scan of flag (k_row_headers)
     // rows
     u64 rows_cap, words_cap;
     u32* o_region;
@@ -52,15 +53,20 @@ __device__ __forceinline__ u32 bits_for(u32 span) {  // width that holds 0..span
 }
 
 constexpr int FAN_WARPS = 8;
+constexpr u32 FAN_KEYS = 1024;  // keys looked at per round (the list of the active ones among them lives in shared memory)
 
-// One CTA per region, one warp per key at a time.  WRITE = false: vmin / vmax / flag / rowwords of every key; WRITE = true: the rows.
-template <bool WRITE>
+// One CTA per region.  Keys no hit ever touched (DevConfigs::keyflag, the large majority) are answered at once: nobody has a count.
+// The others are dealt to the warps: a warp builds the count of every group for its key, takes min / max over the samples and, when
+// the key becomes a row, writes the packed counts at a position it draws from an atomic cursor (the payload order is arbitrary, the
+// rows are numbered afterwards in key order by k_row_headers).
 __global__ void __launch_bounds__(FAN_WARPS * 32) k_fanout(DevBlock b, DevConfigs cf, DevFan fn) {
     TFBS_DYNAMIC_SHARED(smem_raw);
+    __shared__ u32 s_n;
     if (cf.plan->abort) return;
     const u32 r = blockIdx.x;
     const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    u32* val = reinterpret_cast<u32*>(smem_raw) + (size_t)wid * fn.groups_cap;
+    u32* active = reinterpret_cast<u32*>(smem_raw);
+    u32* val = active + FAN_KEYS + (size_t)wid * fn.groups_cap;
     const u32 ng = (u32)(fn.gbase[r + 1] - fn.gbase[r]);
     if (ng > fn.groups_cap) {  // more distinct haplotypes than the shared-memory vector holds: the host repeats the run
         if (threadIdx.x == 0) { atomicMax(&cf.plan->need_groups, ng); cf.plan->abort = 1; }
@@ -75,20 +81,19 @@ __global__ void __launch_bounds__(FAN_WARPS * 32) k_fanout(DevBlock b, DevConfig
     const u32* Dr = cf.D + cf.dbase[r];
     const u32* hg = fn.hap_group + (size_t)r * b.H;
     u32 row_max = 0;
-    for (u32 key = wid; key < nkeys; key += nw) {
-        if (WRITE && !fn.flag[kb + key]) continue;
-        const u32 ref = cf.C0[kb + key];
-        const u32* drow = Dr + (u64)key * ncfg;
-        // which configurations change this key?
-        bool any = false;
-        for (u32 c0 = 0; c0 < ncfg; c0 += 32) {
-            const u32 d = c0 + lane < ncfg ? drow[c0 + lane] : 0u;
-            if (__ballot_sync(0xffffffffu, d != 0)) { any = true; break; }
+    for (u32 k0 = 0; k0 < nkeys; k0 += FAN_KEYS) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        for (u32 key = k0 + threadIdx.x; key < nkeys && key < k0 + FAN_KEYS; key += blockDim.x) {
+            if (cf.keyflag[kb + key]) active[atomicAdd(&s_n, 1u)] = key;
+            else { fn.vmin[kb + key] = 0; fn.vmax[kb + key] = 0; fn.flag[kb + key] = 0; }
         }
-        u32 lo, hi, gmin = ref, gmax = ref;
-        if (!any) {
-            lo = hi = 2 * ref;  // every haplotype has the reference haplotype's count
-        } else {
+        __syncthreads();
+        const u32 n_active = s_n;
+        for (u32 a = wid; a < n_active; a += nw) {
+            const u32 key = active[a];
+            const u32 ref = cf.C0[kb + key];
+            const u32* drow = Dr + (u64)key * ncfg;
             for (u32 g = lane; g < ng; g += 32) val[g] = 0;
             __syncwarp();
             for (u32 c0 = 0; c0 < ncfg; c0 += 32) {
@@ -104,14 +109,14 @@ __global__ void __launch_bounds__(FAN_WARPS * 32) k_fanout(DevBlock b, DevConfig
                 }
             }
             // smallest / largest count over the groups (the packing base and width) ...
+            u32 gmin = ref, gmax = ref;
             for (u32 g = lane; g < ng; g += 32) {
                 const u32 c = ref + val[g];
                 gmin = min(gmin, c);
                 gmax = max(gmax, c);
             }
             // ... and min / max of left + right over the samples (main.rs:441-451)
-            lo = 0xffffffffu;
-            hi = 0;
+            u32 lo = 0xffffffffu, hi = 0;
             for (u32 s = lane; s < b.S; s += 32) {
                 const u32 v = 2 * ref + val[hg[2 * s]] + val[hg[2 * s + 1]];
                 lo = min(lo, v);
@@ -124,51 +129,63 @@ __global__ void __launch_bounds__(FAN_WARPS * 32) k_fanout(DevBlock b, DevConfig
                 gmin = min(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
                 gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
             }
-        }
-        const u32 bits = bits_for(gmax - gmin);
-        const u32 words = (u32)(((u64)ng * bits + 31) / 32);
-        if (!WRITE) {
             // keys exist once a hit of any scanned haplotype touched the inner region (main.rs:517-528): hi > 0
             const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING) ? (lo != hi ? 1u : 0u) : (hi > 0 ? 1u : 0u);
+            const u32 bits = bits_for(gmax - gmin);
+            const u32 words = (u32)(((u64)ng * bits + 31) / 32);
+            u64 off = 0;
+            if (f && lane == 0) off = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)words);
+            off = __shfl_sync(0xffffffffu, off, 0);
             if (lane == 0) {
                 fn.vmin[kb + key] = lo;
                 fn.vmax[kb + key] = hi;
                 fn.flag[kb + key] = f;
-                fn.rowwords[kb + key] = f ? words : 0u;
+                fn.k_base[kb + key] = gmin;
+                fn.k_bits[kb + key] = (u8)bits;
+                fn.k_off[kb + key] = off;
             }
-            if (f) row_max = max(row_max, hi);
-        } else {
-            const u64 row = fn.rowidx[kb + key];
-            const u64 off = fn.rowoff[kb + key];
-            if (row >= fn.rows_cap || off + words > fn.words_cap) continue;  // the gate in front of this pass has raised abort
-            if (lane == 0) {
-                fn.o_region[row] = r;
-                fn.o_inner[row] = b.inner_off[r] + key % nk;
-                fn.o_pid[row] = fn.pid_list[key / nk];
-                fn.o_vmin[row] = lo;
-                fn.o_vmax[row] = hi;
-                fn.o_base[row] = gmin;
-                fn.o_bits[row] = (u8)bits;
-                fn.o_off[row] = off;
-            }
-            if (bits) {
-                const u32 per = 32 / bits;
-                for (u32 w = lane; w < words; w += 32) {
-                    u32 word = 0;
-                    for (u32 x = 0; x < per; ++x) {
-                        const u32 g = w * per + x;
-                        if (g < ng) word |= (ref + (any ? val[g] : 0u) - gmin) << (x * bits);
+            if (f) {
+                row_max = max(row_max, hi);
+                if (bits && off + words <= fn.words_cap) {  // beyond the capacity: the gate behind this kernel raises abort
+                    const u32 per = 32 / bits;
+                    for (u32 w = lane; w < words; w += 32) {
+                        u32 word = 0;
+                        for (u32 x = 0; x < per; ++x) {
+                            const u32 g = w * per + x;
+                            if (g < ng) word |= (ref + val[g] - gmin) << (x * bits);
+                        }
+                        fn.o_packed[off + w] = word;
                     }
-                    fn.o_packed[off + w] = word;
                 }
             }
+            __syncwarp();
         }
-        __syncwarp();
+        __syncthreads();
     }
-    if (!WRITE) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) row_max = max(row_max, __shfl_xor_sync(0xffffffffu, row_max, o));
-        if (lane == 0 && row_max) atomicMax(fn.max_count, row_max);
+    for (int o = 16; o > 0; o >>= 1) row_max = max(row_max, __shfl_xor_sync(0xffffffffu, row_max, o));
+    if (lane == 0 && row_max) atomicMax(fn.max_count, row_max);
+}
+
+// Rows in key order = (region, pattern_id, inner): thread per key.
+__global__ void k_row_headers(DevBlock b, DevConfigs cf, DevFan fn, const u64* n_rows_ptr) {
+    if (cf.plan->abort) return;
+    const u32 r = blockIdx.x;
+    const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
+    const u32 nkeys = fn.n_pid * nk;
+    const u64 kb = cf.kbase[r];
+    for (u32 key = threadIdx.x; key < nkeys; key += blockDim.x) {
+        if (!fn.flag[kb + key]) continue;
+        const u64 row = fn.rowidx[kb + key];
+        if (row >= fn.rows_cap || row >= *n_rows_ptr) continue;
+        fn.o_region[row] = r;
+        fn.o_inner[row] = b.inner_off[r] + key % nk;
+        fn.o_pid[row] = fn.pid_list[key / nk];
+        fn.o_vmin[row] = fn.vmin[kb + key];
+        fn.o_vmax[row] = fn.vmax[kb + key];
+        fn.o_base[row] = fn.k_base[kb + key];
+        fn.o_bits[row] = fn.k_bits[kb + key];
+        fn.o_off[row] = fn.k_off[kb + key];
     }
 }
 

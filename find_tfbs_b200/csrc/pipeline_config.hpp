@@ -171,6 +171,8 @@ struct ConfigPipeline {
         RS(ctx->d_vmax, n_keys * 4);
         RS(ctx->d_flag, n_keys * 4);
         RS(ctx->d_rowwords, n_keys * 4);
+        RS(ctx->d_kbits, n_keys);
+        RS(ctx->d_keyflag, n_keys);
         RS(ctx->d_rowidx, (n_keys + 1) * 8);
         RS(ctx->d_rowoff, (n_keys + 1) * 8);
         RS(slot->d_o_region, c.rows * 4);
@@ -340,6 +342,7 @@ struct ConfigPipeline {
         cf.members = ctx->d_members.as<u32>();
         cf.D = ctx->d_D.as<u32>();
         cf.C0 = ctx->d_C0.as<u32>();
+        cf.keyflag = ctx->d_keyflag.as<u8>();
         cf.plan = plan;
         TFBS_LAUNCH(k_cluster, R, 128, 0, st)(db, cf);
         ++launches();
@@ -411,6 +414,7 @@ struct ConfigPipeline {
         TFBS_LAUNCH(k_zero_words, slot->stats.sm_count * 8, 256, 0, st)(cf.D, &plan->n_dwords, (u64)c.dwords);
         ++launches();
         if (n_keys) CK(cudaMemsetAsync(cf.C0, 0, n_keys * 4, st));
+        if (n_keys) CK(cudaMemsetAsync(cf.keyflag, 0, n_keys, st));
         CK(cudaMemsetAsync(ctx->d_refcnt.p, 0, (size_t)R * 4, st));
         DevRefHits drh{ctx->d_refhits.as<RefHit>(), ctx->d_refcnt.as<u32>(), c.capr, 0};
         DevCounts dc{cf.C0, cf.kbase, 0};
@@ -460,9 +464,10 @@ struct ConfigPipeline {
             fn.vmin = ctx->d_vmin.as<u32>();
             fn.vmax = ctx->d_vmax.as<u32>();
             fn.flag = ctx->d_flag.as<u32>();
-            fn.rowwords = ctx->d_rowwords.as<u32>();
+            fn.k_base = ctx->d_rowwords.as<u32>();
+            fn.k_bits = ctx->d_kbits.as<u8>();
+            fn.k_off = ctx->d_rowoff.as<u64>();
             fn.rowidx = ctx->d_rowidx.as<u64>();
-            fn.rowoff = ctx->d_rowoff.as<u64>();
             fn.rows_cap = c.rows;
             fn.words_cap = c.rowwords;
             fn.o_region = slot->d_o_region.as<u32>();
@@ -476,21 +481,19 @@ struct ConfigPipeline {
             fn.o_packed = slot->d_o_packed.as<u32>();
             fn.pid_list = ctx->d_pid_list.as<u16>();
             fn.max_count = &dst->max_count;
-            // one count vector per warp in shared memory: as many warps as fit
-            const size_t max_smem = std::min<size_t>(ctx->prop.sharedMemPerBlockOptin, 200 * 1024);
+            // one count vector per warp in shared memory (+ the list of active keys): as many warps as fit
+            const size_t max_smem = std::min<size_t>(ctx->prop.sharedMemPerBlockOptin, 200 * 1024) - FAN_KEYS * 4;
             int warps = (int)std::min<size_t>(FAN_WARPS, max_smem / std::max<size_t>(4, (size_t)c.groups * 4));
             if (warps < 1) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "a region has more distinct haplotypes than the fan-out kernel holds in shared memory (" +
                                                                          std::to_string(c.groups) + "): use sample blocks");
-            const int fan_smem = (int)((size_t)warps * c.groups * 4);
-            CK(cudaFuncSetAttribute(k_fanout<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, fan_smem));
-            CK(cudaFuncSetAttribute(k_fanout<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fan_smem));
-            TFBS_LAUNCH(k_fanout<false>, R, warps * 32, fan_smem, st)(db, cf, fn);
+            const int fan_smem = (int)(FAN_KEYS * 4 + (size_t)warps * c.groups * 4);
+            CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributeMaxDynamicSharedMemorySize, fan_smem));
+            TFBS_LAUNCH(k_fanout, R, warps * 32, fan_smem, st)(db, cf, fn);
             ++launches();
             if ((rc = scan(fn.flag, n_keys, nullptr, ctx->d_rowidx.as<u64>()))) return rc;
-            if ((rc = scan(fn.rowwords, n_keys, nullptr, ctx->d_rowoff.as<u64>()))) return rc;
             gate(ctx->d_rowidx.as<u64>() + n_keys, 0, c.rows, &plan->n_rows, &plan->need_rows);
-            gate(ctx->d_rowoff.as<u64>() + n_keys, 0, c.rowwords, &plan->n_rowwords, &plan->need_rowwords);
-            TFBS_LAUNCH(k_fanout<true>, R, warps * 32, fan_smem, st)(db, cf, fn);
+            gate(&plan->rowwords_alloc, 0, c.rowwords, &plan->n_rowwords, &plan->need_rowwords);
+            TFBS_LAUNCH(k_row_headers, R, 128, 0, st)(db, cf, fn, &plan->n_rows);
             ++launches();
         }
         return finish_enqueue();
@@ -579,9 +582,9 @@ struct ConfigPipeline {
     int publish(const DevStatus& hs, const DevPlan& hp) {
         tfbs_stats& s = slot->stats;
         float t;
-        CK(cudaEventElapsedTime(&t, slot->ev_t[0], slot->ev_t[1])); s.ms_group = t;
-        CK(cudaEventElapsedTime(&t, slot->ev_t[1], slot->ev_t[2])); s.ms_build = t;
         if (R && S) {
+            CK(cudaEventElapsedTime(&t, slot->ev_t[0], slot->ev_t[1])); s.ms_group = t;
+            CK(cudaEventElapsedTime(&t, slot->ev_t[1], slot->ev_t[2])); s.ms_build = t;
             CK(cudaEventElapsedTime(&t, slot->ev_t[2], slot->ev_t[5])); s.ms_scan = t;
             CK(cudaEventElapsedTime(&t, slot->ev_t[3], slot->ev_t[4])); s.ms_scan_kernel = t;
             CK(cudaEventElapsedTime(&t, slot->ev_t[5], slot->ev_t[6])); s.ms_count = t;
@@ -629,30 +632,76 @@ struct ConfigPipeline {
         return TFBS_OK;
     }
 
-    // grouped rows -> host (stream_out: the kernels of the next block keep running meanwhile)
+    // grouped rows -> host (stream_out: the kernels of the next block keep running meanwhile); into the caller's result arena if there is one
     int fetch_grouped() {
         Results& res = slot->res;
         if (res.have_grouped) return TFBS_OK;
         cudaStream_t so = ctx->stream_out;
         const uint64_t n = res.n_rows, w = res.packed_words;
-        int rc;
-        slot->stats.d2h_bytes = 0;
-        if ((rc = fetch_headers(so))) return rc;
-        CK(res.h_base.reserve(std::max<uint64_t>(1, n) * 4, false));
-        CK(res.h_bits.reserve(std::max<uint64_t>(1, n), false));
-        CK(res.h_off.reserve(std::max<uint64_t>(1, n) * 8, false));
-        CK(res.h_packed.reserve(std::max<uint64_t>(1, w) * 4, false));
-        CK(res.h_ngroups.reserve((size_t)(R + 1) * 8 + 8, false));
         res.hg_bytes = (uint64_t)H + 1 <= 65536 ? 2 : 4;
-        CK(res.h_hg.reserve(std::max<uint64_t>(1, RH) * res.hg_bytes, false));
+        const bool maps = R && S;
+        tfbs_arena_header* hdr = nullptr;
+        slot->stats.d2h_bytes = 0;
+        if (ctx->arena) {
+            uint8_t* half = ctx->arena + (size_t)(slot - ctx->slot) * (ctx->arena_bytes / 2);
+            hdr = reinterpret_cast<tfbs_arena_header*>(half);
+            tfbs_arena_header h = *hdr;
+            if (h.magic != TFBS_ARENA_MAGIC) { memset(&h, 0, sizeof h); h.magic = TFBS_ARENA_MAGIC; }
+            uint64_t off = 256;
+            auto place = [&](HostBuf& hb, uint64_t bytes, uint64_t* where) {
+                *where = off;
+                hb.bind(half + off, bytes);
+                off += (bytes + 63) & ~63ull;
+            };
+            place(res.h_region, n * 4, &h.off_region);
+            place(res.h_inner, n * 4, &h.off_inner);
+            place(res.h_pid, n * 2, &h.off_pattern_id);
+            place(res.h_vmin, n * 4, &h.off_vmin);
+            place(res.h_vmax, n * 4, &h.off_vmax);
+            place(res.h_base, n * 4, &h.off_base);
+            place(res.h_bits, n, &h.off_bits);
+            place(res.h_off, n * 8, &h.off_offset);
+            place(res.h_packed, w * 4, &h.off_packed);
+            place(res.h_ngroups, (uint64_t)(R + 1) * 8 + 8, &h.off_n_groups);
+            place(res.h_hg, RH * res.hg_bytes, &h.off_hap_group);
+            if (off > ctx->arena_bytes / 2)
+                return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "the result arena is too small: this block needs " + std::to_string(off) + " bytes, a half of the arena has " +
+                                                                std::to_string(ctx->arena_bytes / 2));
+            h.n_rows = n;
+            h.packed_words = w;
+            h.n_samples = S;
+            h.n_regions = R;
+            h.hap_group_bytes = res.hg_bytes;
+            h.bytes_used = off;
+            const uint64_t seq = h.sequence;
+            *hdr = h;
+            hdr->sequence = seq;  // bumped below, once the arrays are complete
+        } else {
+            CK(res.h_region.reserve(std::max<uint64_t>(1, n) * 4, false));
+            CK(res.h_inner.reserve(std::max<uint64_t>(1, n) * 4, false));
+            CK(res.h_pid.reserve(std::max<uint64_t>(1, n) * 2, false));
+            CK(res.h_vmin.reserve(std::max<uint64_t>(1, n) * 4, false));
+            CK(res.h_vmax.reserve(std::max<uint64_t>(1, n) * 4, false));
+            CK(res.h_base.reserve(std::max<uint64_t>(1, n) * 4, false));
+            CK(res.h_bits.reserve(std::max<uint64_t>(1, n), false));
+            CK(res.h_off.reserve(std::max<uint64_t>(1, n) * 8, false));
+            CK(res.h_packed.reserve(std::max<uint64_t>(1, w) * 4, false));
+            CK(res.h_ngroups.reserve((size_t)(R + 1) * 8 + 8, false));
+            CK(res.h_hg.reserve(std::max<uint64_t>(1, RH) * res.hg_bytes, false));
+        }
         if (n) {
+            CK(cudaMemcpyAsync(res.h_region.p, slot->d_o_region.p, n * 4, cudaMemcpyDeviceToHost, so));
+            CK(cudaMemcpyAsync(res.h_inner.p, slot->d_o_inner.p, n * 4, cudaMemcpyDeviceToHost, so));
+            CK(cudaMemcpyAsync(res.h_pid.p, slot->d_o_pid.p, n * 2, cudaMemcpyDeviceToHost, so));
+            CK(cudaMemcpyAsync(res.h_vmin.p, slot->d_o_vmin.p, n * 4, cudaMemcpyDeviceToHost, so));
+            CK(cudaMemcpyAsync(res.h_vmax.p, slot->d_o_vmax.p, n * 4, cudaMemcpyDeviceToHost, so));
             CK(cudaMemcpyAsync(res.h_base.p, slot->d_o_base.p, n * 4, cudaMemcpyDeviceToHost, so));
             CK(cudaMemcpyAsync(res.h_bits.p, slot->d_o_bits.p, n, cudaMemcpyDeviceToHost, so));
             CK(cudaMemcpyAsync(res.h_off.p, slot->d_o_off.p, n * 8, cudaMemcpyDeviceToHost, so));
             if (w) CK(cudaMemcpyAsync(res.h_packed.p, slot->d_o_packed.p, w * 4, cudaMemcpyDeviceToHost, so));
-            slot->stats.d2h_bytes += n * 13 + w * 4;
+            slot->stats.d2h_bytes += n * 31 + w * 4;
         }
-        if (R && S) {
+        if (maps) {
             // groups per region (from the prefix array) and the haplotype -> group map, narrowed to u16 when it fits
             CK(cudaMemcpyAsync(res.h_ngroups.p, slot->d_gbase.p, (size_t)(R + 1) * 8, cudaMemcpyDeviceToHost, so));
             if (res.hg_bytes == 2) {
@@ -666,10 +715,14 @@ struct ConfigPipeline {
             slot->stats.d2h_bytes += (uint64_t)R * 4 + RH * res.hg_bytes;
         }
         CK(cudaStreamSynchronize(so));
-        if (R && S) {  // prefix array -> counts, in place (u64 -> u32)
+        if (maps) {  // prefix array -> counts, in place (u64 -> u32)
             const uint64_t* gb = res.h_ngroups.as<uint64_t>();
             uint32_t* ng = res.h_ngroups.as<uint32_t>();
             for (uint32_t r = 0; r < R; ++r) ng[r] = (uint32_t)(gb[r + 1] - gb[r]);
+        }
+        if (hdr) {
+            __atomic_thread_fence(__ATOMIC_RELEASE);
+            hdr->sequence = hdr->sequence + 1;
         }
         res.have_grouped = true;
         return TFBS_OK;

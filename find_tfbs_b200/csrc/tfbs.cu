@@ -190,6 +190,7 @@ void tfbs_destroy(tfbs_ctx* ctx) {
         for (auto& ev : s.ev_t)
             if (ev) cudaEventDestroy(ev);
     }
+    if (ctx->arena) cudaHostUnregister(ctx->arena);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream_in);
     cudaStreamDestroy(ctx->stream_out);
@@ -321,6 +322,31 @@ int tfbs_collect_grouped(tfbs_ctx* ctx, tfbs_grouped_rows* out) {
     out->hap_group = res.h_hg.p;
     out->hap_group_bytes = res.hg_bytes;
     retire_oldest(ctx);
+    return TFBS_OK;
+}
+
+int tfbs_set_result_arena(tfbs_ctx* ctx, void* base, size_t bytes) {
+    if (!ctx) return TFBS_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    int rc = quiesce(ctx);
+    if (rc) return rc;
+    if (ctx->in_flight) return fail(ctx, TFBS_ERR_STATE, "tfbs_set_result_arena with blocks in flight: call tfbs_collect first");
+    if (ctx->arena) {
+        cudaHostUnregister(ctx->arena);
+        for (Slot& s : ctx->slot)
+            for (HostBuf* hb : {&s.res.h_region, &s.res.h_inner, &s.res.h_pid, &s.res.h_vmin, &s.res.h_vmax, &s.res.h_base, &s.res.h_bits, &s.res.h_off,
+                                &s.res.h_packed, &s.res.h_ngroups, &s.res.h_hg})
+                if (!hb->owned) hb->bind(nullptr, 0);
+        ctx->arena = nullptr;
+        ctx->arena_bytes = 0;
+    }
+    if (!base) return TFBS_OK;
+    if (bytes < 2 * 4096 || ((uintptr_t)base & 63)) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "the result arena must be 64-byte aligned and hold at least 8 KB");
+    CK(cudaHostRegister(base, bytes, cudaHostRegisterDefault));
+    ctx->arena = (uint8_t*)base;
+    ctx->arena_bytes = bytes;
+    memset(base, 0, sizeof(tfbs_arena_header));
+    memset((uint8_t*)base + bytes / 2, 0, sizeof(tfbs_arena_header));
     return TFBS_OK;
 }
 

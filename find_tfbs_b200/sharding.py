@@ -24,38 +24,65 @@ def region_ranges(costs, world):
     return [(cuts[k], cuts[k + 1]) for k in range(world)]
 
 
-def block_costs(block):
-    """Window length per region (the scan cost is ~ length x distinct haplotypes x sum of pattern lengths)."""
-    return (block.region_end - block.region_start + 1).astype(np.float64)
+def block_costs(block, lmax=30):
+    """Device work per region, in window starts the scan scores: the reference haplotype in full (the window length) plus about
+    1.4 configurations per record (measured on the synthetic cohorts) of 2 * Lmax starts each.  The bookkeeping kernels (grouping,
+    walk, fan-out) grow with the records of the region too, so this also balances them; the window length alone does not."""
+    w = (block.region_end - block.region_start + 1).astype(np.float64)
+    v = np.diff(block.var_off.astype(np.int64)).astype(np.float64)
+    return w + 1.4 * 2.0 * lmax * v
 
 
-def shard_block(block, world, rank):
-    r0, r1 = region_ranges(block_costs(block), world)[rank]
-    return block.slice(r0, r1), r0
+def shard_block(block, world, rank, lmax=30, compact=True):
+    """The rank's contiguous range of regions as a block of its own; returns (shard, first region, first inner index)."""
+    r0, r1 = region_ranges(block_costs(block, lmax), world)[rank]
+    return block.slice(r0, r1, compact=compact), r0, int(block.inner_off[r0])
 
 
 def merge_rows(parts, offsets):
-    """parts: per-rank row dicts (region indices relative to the shard), offsets: first region of each shard."""
+    """parts: per-rank row dicts with region / inner indices relative to the shard; offsets: (first region, first inner index) of
+    each shard, as shard_block returns them.  Rows come back block-wide, in the order of a single-process run."""
     out = {}
-    for k in ("region", "inner", "pattern_id", "vmin", "vmax", "left", "right"):
+    for k in ("pattern_id", "vmin", "vmax", "left", "right"):
         out[k] = np.concatenate([p[k] for p in parts]) if parts else np.zeros(0)
-    out["region"] = np.concatenate([p["region"].astype(np.int64) + o for p, o in zip(parts, offsets)]).astype(np.uint32) if parts else out["region"]
+    for k, j in (("region", 0), ("inner", 1)):
+        out[k] = (np.concatenate([p[k].astype(np.int64) + o[j] for p, o in zip(parts, offsets)]).astype(np.uint32) if parts
+                  else np.zeros(0, np.uint32))
     return out
 
 
 def gather_rows(rows, region_offset, inner_offset, group=None):
     """torch.distributed gather of the per-rank rows to rank 0 (host tensors; gloo or nccl object collectives).  Returns the merged
-    rows on rank 0 and None elsewhere.  `inner` indices are made block-wide with inner_offset."""
+    rows on rank 0 and None elsewhere."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
-    payload = dict(rows)
-    payload["inner"] = (rows["inner"].astype(np.int64) + inner_offset).astype(np.uint32)
     gathered = [None] * world if rank == 0 else None
-    dist.gather_object((payload, region_offset), gathered, dst=0, group=group)
+    dist.gather_object((dict(rows), (region_offset, inner_offset)), gathered, dst=0, group=group)
     if rank != 0:
         return None
     return merge_rows([g[0] for g in gathered], [g[1] for g in gathered])
+
+
+class SharedArena:
+    """The result arena of one rank as a file in /dev/shm: the rank's GPU copies its grouped rows straight into it
+    (tfbs_set_result_arena) and the gathering rank maps the same file -- the rows of all GPUs of the box end up in one process'
+    address space without a collective and without a host copy (regions are independent, reference main.rs:395-429)."""
+
+    def __init__(self, tag, rank, nbytes=None, create=False):
+        import os
+        self.path = "/dev/shm/tfbs_arena_%s_%d" % (tag, rank)
+        self.created = create
+        if create:
+            self.buf = np.memmap(self.path, dtype=np.uint8, mode="w+", shape=(int(nbytes),))
+        else:
+            self.buf = np.memmap(self.path, dtype=np.uint8, mode="r", shape=(os.path.getsize(self.path),))
+
+    def close(self):
+        import os
+        del self.buf
+        if self.created and os.path.exists(self.path):
+            os.unlink(self.path)
 
 
 # ---- sample-block sharding (BASELINE.json configs[3]: biobank-scale cohorts) -------------------------------------------

@@ -291,6 +291,32 @@ int tfbs_collect(tfbs_ctx* ctx, tfbs_rows* out);
 /* Same, but the rows come back grouped (see tfbs_grouped_rows): the compact form for large cohorts.  Default scoring mode only. */
 int tfbs_collect_grouped(tfbs_ctx* ctx, tfbs_grouped_rows* out);
 
+/*
+ * Result arena: caller-owned host memory that receives the grouped rows of every block DIRECTLY by the device -> host copies, e.g. a
+ * POSIX shared-memory segment that the process owning the VCF writer has mapped: with one process per GPU this is how the rows of
+ * all GPUs are gathered on one host without a collective (regions are independent, src/main.rs:395-429).  The library page-locks the
+ * memory.  It is used as two halves of bytes / 2 (blocks in flight alternate, first block -> first half); each half starts with a
+ * tfbs_arena_header, every array sits at the byte offset the header gives (relative to the header) and has the layout of the
+ * tfbs_grouped_rows member of the same name.  `sequence` is written last, after the copies have completed: a reader that sees it
+ * change finds a complete block.  tfbs_collect_grouped fails with TFBS_ERR_INVALID_ARGUMENT when a block does not fit its half.
+ * base == NULL goes back to the library's own buffers.
+ */
+#define TFBS_ARENA_MAGIC 0x3152415342465400ULL /* "\0TFBSAR1" */
+typedef struct tfbs_arena_header {
+    uint64_t magic;
+    uint64_t sequence;         /* number of blocks this half has received */
+    uint64_t n_rows;
+    uint64_t packed_words;
+    uint32_t n_samples;
+    uint32_t n_regions;
+    uint32_t hap_group_bytes;
+    uint32_t reserved;
+    uint64_t off_region, off_inner, off_pattern_id, off_vmin, off_vmax, off_base, off_bits, off_offset, off_packed, off_n_groups,
+        off_hap_group;
+    uint64_t bytes_used;       /* header + arrays */
+} tfbs_arena_header;
+int tfbs_set_result_arena(tfbs_ctx* ctx, void* base, size_t bytes);
+
 /* Host side of grouped rows: (left, right) of rows [first_row, first_row + n_rows), n_rows * n_samples uint32_t each.  Pure host
  * code, no CUDA call; thread-safe. */
 int tfbs_expand_rows(const tfbs_grouped_rows* rows, uint64_t first_row, uint64_t n_rows, uint32_t* left, uint32_t* right);

@@ -78,10 +78,12 @@ CONTRACT_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per
 
 def test_bench_control_flow_dry_run(emu_env):
     """bench.py end to end with torch.cuda stubbed and the emulated library (tests/cuda_emu/run_bench_emulated.py): the one JSON
-    line carries every contract key and internally consistent counters.  The numbers themselves mean nothing here."""
+    line carries every contract key and internally consistent counters: the north-star workload (configs[2], strong scaling), the
+    shared-memory gather of the grouped rows, the sustained run, the configs[1] secondary object.  The numbers themselves mean nothing."""
     import json
     r = subprocess.run([sys.executable, os.path.join(EMU, "run_bench_emulated.py"), "--scale", "0.001", "--steps", "2", "--warmup", "1",
-                        "--cpu-seconds", "0.5", "--no-full-scan"], cwd=ROOT, env=emu_env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+                        "--cpu-seconds", "0.5", "--no-full-scan", "--sustain-seconds", "0.01", "--no-driver"], cwd=ROOT, env=emu_env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
     assert len(lines) == 1, lines
@@ -89,12 +91,15 @@ def test_bench_control_flow_dry_run(emu_env):
     for k in CONTRACT_KEYS:
         assert k in d, k
     assert d["metric"] == "pwm_cells_per_s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["higher_is_better"] is True
+    assert d["scaling"] == "strong" and d["config"]["workload"].startswith("configs[2]") and d["config"]["samples"] == 2504
     rf = d["roofline"]
     for k in ("bound", "achieved", "peak", "unit", "frac", "traffic", "hbm"):
         assert k in rf, k
-    assert rf["hbm"]["algorithmic_bytes_per_launch"] > 0 and rf["cells_per_launch"] == d["evaluated_cells_per_step"]
+    assert rf["hbm"]["algorithmic_bytes_per_step"] > 0 and rf["cells_per_step"] == d["evaluated_cells_per_step"]
     assert d["nominal_cells_per_step"] >= d["executed_cells_per_step"] >= d["evaluated_cells_per_step"] > 0
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["gpu_launches"] > 0
+    assert d["e2e"]["gathered_on_rank0"]["rows_last_step"] == d["rows_per_step"]
+    assert d["sustained"]["steps"] >= 2 and d["secondary"]["config"]["workload"].startswith("configs[1]")
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
 
 

@@ -37,9 +37,9 @@ def _worker(rank, world, port, ret):
     pats = synth.make_pwms(4, seed=9, lmin=6, lmax=14)
     blk = synth.make_cohort(8, 30, seed=9, lmax_pattern=14, region_len=(60, 300), two_beds=True, variant_rate=0.05)
     ps = PatternSet(pats)
-    shard, r0 = sharding.shard_block(blk, world, rank)
+    shard, r0, i0 = sharding.shard_block(blk, world, rank, lmax=14)
     rows = hp.run_oracle(ps, shard, 0, False, 1)
-    merged = sharding.gather_rows(rows, r0, int(blk.inner_off[r0]))
+    merged = sharding.gather_rows(rows, r0, i0)
     if rank == 0:
         full = hp.run_oracle(ps, blk, 0, False, 2)
         ok = all(np.array_equal(merged[k], full[k]) for k in ("region", "inner", "pattern_id", "vmin", "vmax", "left", "right"))
