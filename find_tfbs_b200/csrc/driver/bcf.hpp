@@ -49,6 +49,10 @@ struct Record {
     uint32_t n_allele;
     std::string ref, alt;   // alleles[0], alleles[1]
     uint32_t carrier_row;   // row in Cohort::carriers (biallelic records only), else UINT32_MAX
+    // What the reference would panic with when this record is fetched for a region (haplotype.rs:21-32: alleles[1] of a record
+    // without ALT, a letter outside ACGTN in REF / ALT, a missing GT, a ploidy other than 2).  The reference only ever looks at
+    // records inside an extended peak, so the message is kept here and raised by build_block for such records only.
+    std::string problem;
 };
 
 struct Cohort {
@@ -100,10 +104,11 @@ void parse_bcf_header(Cursor& c, std::vector<std::string>* contigs, std::vector<
         if (dict[i] == "GT") *gt_key = (int)i;
 }
 
-void check_letters(const std::string& s) {  // util.rs:4-16
+std::string check_letters(const std::string& s) {  // util.rs:4-16; "" = fine
     for (unsigned char l : s)
         if (!(l == 65 || l == 97 || l == 67 || l == 99 || l == 71 || l == 103 || l == 84 || l == 116 || l == 78 || l == 110))
-            die("Unknown nucleotide " + std::to_string((int)l));
+            return "Unknown nucleotide " + std::to_string((int)l);
+    return "";
 }
 
 // Where the records of contig `rid` live in the BGZF file, from the CSI index next to the BCF (<bcf>.csi).  The reference reads
@@ -211,7 +216,7 @@ Cohort load_bcf(const Options& o) {
     if (first_record > raw.size()) die("truncated BCF");
     Cursor c{raw.data() + first_record, raw.data() + raw.size()};
     // pass 1 (serial, a few bytes per record): positions, alleles, carrier rows; the genotype blocks are only located
-    struct Pending { uint32_t row; const uint8_t* indiv; uint32_t l_indiv, n_fmt, n_sample; };
+    struct Pending { uint32_t row; const uint8_t* indiv; uint32_t l_indiv, n_fmt, n_sample; size_t rec; };
     std::vector<Pending> pending;
     while (c.p < c.e) {
         if (indexed) {
@@ -242,17 +247,15 @@ Cohort load_bcf(const Options& o) {
             continue;
         }
         s.tstr();
-        if (r.n_allele < 2) die("index out of bounds: the len is " + std::to_string(r.n_allele) + " but the index is 1");  // haplotype.rs:22
-        r.ref = s.tstr();
-        r.alt = s.tstr();
-        check_letters(r.ref);  // haplotype.rs:21-22 convert alleles[0] and [1] of every record
-        check_letters(r.alt);
+        if (r.n_allele >= 1) r.ref = s.tstr();
+        if (r.n_allele >= 2) r.alt = s.tstr();
+        if (r.n_allele < 2) r.problem = "index out of bounds: the len is " + std::to_string(r.n_allele) + " but the index is 1";  // haplotype.rs:22
+        if (r.problem.empty()) r.problem = check_letters(r.ref);  // haplotype.rs:21-22 convert alleles[0] and [1] of every fetched record
+        if (r.problem.empty()) r.problem = check_letters(r.alt);
         r.carrier_row = UINT32_MAX;
-        if (r.n_allele == 2) {
+        if (r.n_allele == 2 && r.problem.empty()) {
             r.carrier_row = (uint32_t)pending.size();
-            pending.push_back(Pending{r.carrier_row, indiv, l_indiv, n_fmt, n_sample});
-        } else {
-            printf("Unusual number of alleles: %u\n", r.n_allele);  // haplotype.rs:53-55
+            pending.push_back(Pending{r.carrier_row, indiv, l_indiv, n_fmt, n_sample, co.records.size()});
         }
         co.max_rlen = std::max(co.max_rlen, std::max(1, r.rlen));
         co.records.push_back(std::move(r));
@@ -272,6 +275,7 @@ Cohort load_bcf(const Options& o) {
                     Cursor d{pd.indiv, pd.indiv + pd.l_indiv};
                     uint32_t* row = co.carriers.data() + (size_t)pd.row * co.pitch;
                     bool have_gt = false;
+                    std::string& problem = co.records[pd.rec].problem;  // one thread per record: no race
                     for (uint32_t f = 0; f < pd.n_fmt; ++f) {
                         int kt, vt; uint32_t kl, vl;
                         d.desc(&kt, &kl);
@@ -281,18 +285,22 @@ Cohort load_bcf(const Options& o) {
                         d.need(bytes);
                         if (key == gt_key && vt >= 1 && vt <= 3) {
                             have_gt = true;
-                            if (vl != 2 && S) die("Inconsistent number of alleles");  // haplotype.rs:32
+                            if (vl != 2 && S) { problem = "Inconsistent number of alleles"; d.p += bytes; continue; }  // haplotype.rs:32
                             const size_t es = Cursor::tsize(vt);
                             for (uint32_t k = 0; k < S; ++k) {
                                 Cursor g{d.p + co.sample_positions[k] * 2 * es, d.p + bytes};
                                 int32_t g0 = g.tint(vt), g1 = g.tint(vt);
+                                // a vector shorter than the ploidy of the record is padded with END_OF_VECTOR (BCF2.2, 6.3.3); rust-htslib
+                                // trims it, so genotype.len() < 2 and the assertion of haplotype.rs:32 fires
+                                const int32_t vend = vt == 1 ? -127 : (vt == 2 ? -32767 : INT32_MIN + 1);
+                                if ((g0 == vend || g1 == vend) && problem.empty()) problem = "Inconsistent number of alleles";
                                 if (g0 == 4) row[(2 * k) >> 5] |= 1u << ((2 * k) & 31);          // Unphased(1), haplotype.rs:34-37
                                 if (g1 == 5) row[(2 * k + 1) >> 5] |= 1u << ((2 * k + 1) & 31);  // Phased(1),   haplotype.rs:38-41
                             }
                         }
                         d.p += bytes;
                     }
-                    if (!have_gt && S) die("called `Result::unwrap()` on an `Err` value: missing GT");  // haplotype.rs:24
+                    if (!have_gt && S && problem.empty()) problem = "called `Result::unwrap()` on an `Err` value: missing GT";  // haplotype.rs:24
                 }
             }
         } catch (const std::exception& e) {  // only under the test shim, where die() throws

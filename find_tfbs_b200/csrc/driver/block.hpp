@@ -71,6 +71,8 @@ void build_block(const std::vector<Range>& merged, size_t m0, size_t m1, const s
         for (auto it = lo; it != co.records.end() && it->pos <= we; ++it) {
             if (it->pos + std::max(1, it->rlen) <= ws) continue;
             ++nrec;
+            if (!it->problem.empty()) die(it->problem);  // the reference panics on such a record once a region fetches it (haplotype.rs:21-32)
+            if (it->n_allele != 2) printf("Unusual number of alleles: %u\n", it->n_allele);  // haplotype.rs:53-55
             if (it->carrier_row == UINT32_MAX) continue;  // not biallelic: counted, not used (haplotype.rs:27,53-55)
             tfbs_variant v;
             memset(&v, 0, sizeof v);

@@ -104,8 +104,12 @@ int main(int argc, char** argv) {
     for (auto& t : pre) t.join();
     const uint32_t S = (uint32_t)co.samples.size();
 
-    std::string chr = o.chromosome;  // main.rs:402
-    for (size_t p; (p = chr.find("chr")) != std::string::npos;) chr.erase(p, 3);
+    // main.rs:402 chromosome.replace("chr", ""): one left-to-right pass over non-overlapping matches
+    std::string chr;
+    for (size_t p = 0; p < o.chromosome.size();) {
+        if (o.chromosome.compare(p, 3, "chr") == 0) p += 3;
+        else chr += o.chromosome[p++];
+    }
 
     const std::string part = o.output + ".part";
     BgzfWriter* gz = o.plain_text ? nullptr : new BgzfWriter(part, o.threads);
@@ -119,8 +123,28 @@ int main(int argc, char** argv) {
     }
 
     const size_t n_chunks = (merged.size() + o.chunk - 1) / o.chunk;
-    struct ChunkOut { std::vector<std::string> rows; std::string audit; };
-    std::vector<ChunkOut> outs(n_chunks);
+    // The writer (main.rs:264-290 has a writer thread fed through a channel): chunks finish in any order on the devices and are
+    // written in chunk order as soon as every earlier chunk is there; a finished chunk's text is freed once written, so the
+    // memory in flight is a few chunks, not the chromosome.  POS is the reference's running counter (main.rs:329,424-425).
+    struct ChunkText { std::vector<std::string> rows; };
+    std::mutex out_mu;
+    std::map<size_t, ChunkText> done_chunks;
+    std::vector<std::string> audit_text(o.audit_file.empty() ? 0 : n_chunks);
+    size_t next_to_write = 0;
+    uint64_t fake_position = 1;
+    double secs_write = 0;
+    auto chunk_finished = [&](size_t c, ChunkText&& t) {
+        std::lock_guard<std::mutex> lk(out_mu);
+        done_chunks.emplace(c, std::move(t));
+        auto tw = std::chrono::steady_clock::now();
+        for (auto it = done_chunks.find(next_to_write); it != done_chunks.end(); it = done_chunks.find(next_to_write)) {
+            for (const std::string& row : it->second.rows) emit(chr + "\t" + std::to_string(fake_position++) + row);
+            done_chunks.erase(it);
+            ++next_to_write;
+        }
+        secs_write += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw).count();
+    };
+
     std::atomic<size_t> next{0};
     std::atomic<uint64_t> total_cells{0}, total_hits{0};
     std::atomic<uint64_t> us_wait{0}, us_gpu{0}, us_sort{0}, us_format{0};
@@ -128,7 +152,7 @@ int main(int argc, char** argv) {
         tfbs_ctx* ctx = ctxs[slot];
         // a builder thread prepares the next blocks (FASTA windows, inner regions, records) while the GPU works on the current one;
         // private readers per worker, like main.rs:345-346
-        struct Ready { size_t c; std::unique_ptr<BlockData> bd; };
+        struct Ready { size_t c = 0; std::unique_ptr<BlockData> bd; };
         std::mutex mu;
         std::condition_variable cv;
         std::deque<Ready> ready;
@@ -141,7 +165,7 @@ int main(int argc, char** argv) {
                 std::unique_ptr<BlockData> bd(new BlockData());
                 build_block(merged, c * o.chunk, std::min(merged.size(), (c + 1) * (size_t)o.chunk), peak_map, co, fa, largest, bd.get());
                 std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return ready.size() < 2; });
+                cv.wait(lk, [&] { return ready.size() < 3; });
                 ready.push_back(Ready{c, std::move(bd)});
                 cv.notify_all();
             }
@@ -149,31 +173,109 @@ int main(int argc, char** argv) {
             finished = true;
             cv.notify_all();
         });
-        for (;;) {
-            Ready item;
+        auto take_ready = [&](Ready* item, bool wait) -> bool {
             uint64_t tw = now_us();
-            {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return !ready.empty() || finished; });
-                if (ready.empty()) break;
-                item = std::move(ready.front());
-                ready.pop_front();
-                cv.notify_all();
-            }
-            const size_t c = item.c, m0 = c * o.chunk, m1 = std::min(merged.size(), m0 + o.chunk);
-            BlockData& bd = *item.bd;
+            std::unique_lock<std::mutex> lk(mu);
+            if (wait) cv.wait(lk, [&] { return !ready.empty() || finished; });
+            if (ready.empty()) return false;
+            *item = std::move(ready.front());
+            ready.pop_front();
+            cv.notify_all();
             us_wait += now_us() - tw;
-            uint64_t tg = now_us();
-            tfbs_block blk = bd.view(co);
-            if (o.audit_file.empty()) {
-                TF(tfbs_submit_block(ctx, &blk));
-            } else {
+            return true;
+        };
+        // rows of one block -> text, in the canonical order inside a region: (bed file, inner range, pattern_id); the reference's
+        // order is HashMap::drain().  `counts(i, l, r)` fills the (left, right) vectors of row i.
+        auto rows_to_text = [&](size_t c, const BlockData& bd, uint64_t n_rows, const uint32_t* region, const uint32_t* inner, const uint16_t* pid,
+                                const uint32_t* vmin, const uint32_t* vmax, const std::function<void(uint64_t, uint32_t*, uint32_t*)>& counts) {
+            uint64_t ts = now_us();
+            std::vector<uint64_t> order(n_rows);
+            for (uint64_t i = 0; i < n_rows; ++i) order[i] = i;
+            std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
+                if (region[a] != region[b]) return region[a] < region[b];
+                const tfbs_inner_region& ia = bd.inner[inner[a]];
+                const tfbs_inner_region& ib = bd.inner[inner[b]];
+                if (ia.bed_index != ib.bed_index) return ia.bed_index < ib.bed_index;
+                if (ia.start != ib.start) return ia.start < ib.start;
+                if (ia.end != ib.end) return ia.end < ib.end;
+                return pid[a] < pid[b];
+            });
+            us_sort += now_us() - ts;
+            uint64_t tf = now_us();
+            // row text on --threads host threads (the reference formats inside its worker threads, main.rs:415-425)
+            std::vector<std::string> text(order.size());
+            auto format_range = [&](size_t a, size_t b) {
+                std::vector<uint32_t> l(S), r(S);
+                for (size_t k = a; k < b; ++k) {
+                    const uint64_t i = order[k];
+                    counts(i, l.data(), r.data());
+                    RowText t = finalise_row(l.data(), r.data(), S, vmin[i], vmax[i], o.min_maf);
+                    if (!t.keep) continue;
+                    const tfbs_inner_region& ir = bd.inner[inner[i]];
+                    // POS is filled in by the writer (a running counter, main.rs:329,424-425)
+                    text[k] = "\t" + bed_names[ir.bed_index] + "," + pwm_name.at(pid[i]) + "," + std::to_string(ir.start) + "-" +
+                              std::to_string(ir.end) + "\t.\t.\t.\tPASS\t" + t.info + "\tGT:DS" + t.genotypes + "\n";
+                }
+            };
+            const size_t nt = std::max<size_t>(1, std::min<size_t>(o.threads, order.size() / 64 + 1));
+            if (nt == 1) format_range(0, order.size());
+            else {
+                std::vector<std::thread> ft;
+                for (size_t t = 0; t < nt; ++t) ft.emplace_back(format_range, order.size() * t / nt, order.size() * (t + 1) / nt);
+                for (auto& t : ft) t.join();
+            }
+            ChunkText ct;
+            for (std::string& row : text)
+                if (!row.empty()) ct.rows.push_back(std::move(row));
+            us_format += now_us() - tf;
+            chunk_finished(c, std::move(ct));
+        };
+        auto note_stats = [&](size_t c) {
+            tfbs_stats st;
+            tfbs_get_stats(ctx, &st);
+            total_cells += st.nominal_cells;
+            total_hits += st.n_hits;
+            if (o.verbose)
+                printf("\nChunk %zu/%zu\t%llu haplotypes\t%llu hits\n", c + 1, n_chunks, (unsigned long long)st.n_groups, (unsigned long long)st.n_hits);
+        };
+        if (o.audit_file.empty()) {
+            // two blocks in flight per device: the copies and the host work of one overlap the kernels of the other
+            std::deque<Ready> flying;
+            for (;;) {
+                while (flying.size() < 2) {
+                    Ready item;
+                    if (!take_ready(&item, flying.empty())) break;
+                    uint64_t tg = now_us();
+                    tfbs_block blk = item.bd->view(co);
+                    TF(tfbs_submit_block(ctx, &blk));
+                    us_gpu += now_us() - tg;
+                    flying.push_back(std::move(item));
+                }
+                if (flying.empty()) break;
+                Ready item = std::move(flying.front());
+                flying.pop_front();
+                uint64_t tg = now_us();
+                tfbs_grouped_rows g;
+                TF(tfbs_collect_grouped(ctx, &g));
+                us_gpu += now_us() - tg;
+                note_stats(item.c);
+                rows_to_text(item.c, *item.bd, g.n_rows, g.region, g.inner, g.pattern_id, g.vmin, g.vmax,
+                             [&](uint64_t i, uint32_t* l, uint32_t* r) { tfbs_expand_rows(&g, i, 1, l, r); });
+            }
+        } else {
+            for (;;) {
+                Ready item;
+                if (!take_ready(&item, true)) break;
+                const size_t c = item.c, m0 = c * o.chunk;
+                BlockData& bd = *item.bd;
+                uint64_t tg = now_us();
+                tfbs_block blk = bd.view(co);
                 // the audit scores the block twice (thresholds lowered by one, then as given) and leaves the rows of the normal run
                 TF(tfbs_upload_block(ctx, &blk));
                 tfbs_audit au;
                 TF(tfbs_audit_block(ctx, &au));
                 if (au.truncated) die("--audit: the match buffer overflowed; use a smaller --chunk");
-                std::string& out = outs[c].audit;
+                std::string& out = audit_text[c];
                 const uint32_t H = 2 * au.n_samples;
                 auto region_name = [&](uint32_t r) { return std::to_string(merged[m0 + r].start) + "-" + std::to_string(merged[m0 + r].end); };
                 for (uint64_t i = 0; i < au.n_ties; ++i) {
@@ -194,58 +296,17 @@ int main(int argc, char** argv) {
                         if (fl & TFBS_HAP_OVERWRITTEN)
                             out += "overwritten\t" + chr + "\t" + region_name(r) + "\t" + co.samples[h / 2] + (h % 2 ? ":R" : ":L") + "\n";
                     }
+                tfbs_rows rows;
+                TF(tfbs_collect(ctx, &rows));
+                us_gpu += now_us() - tg;
+                note_stats(c);
+                rows_to_text(c, bd, rows.n_rows, rows.region, rows.inner, rows.pattern_id, rows.vmin, rows.vmax, [&](uint64_t i, uint32_t* l, uint32_t* r) {
+                    for (uint32_t s = 0; s < S; ++s) {  // counts arrive in the narrowest type that holds them (tfbs_rows.count_bytes)
+                        l[s] = rows.count_bytes == 1 ? ((const uint8_t*)rows.left)[i * S + s] : rows.count_bytes == 2 ? ((const uint16_t*)rows.left)[i * S + s] : rows.left[i * S + s];
+                        r[s] = rows.count_bytes == 1 ? ((const uint8_t*)rows.right)[i * S + s] : rows.count_bytes == 2 ? ((const uint16_t*)rows.right)[i * S + s] : rows.right[i * S + s];
+                    }
+                });
             }
-            tfbs_rows rows;
-            TF(tfbs_collect(ctx, &rows));
-            us_gpu += now_us() - tg;
-            uint64_t ts = now_us();
-            tfbs_stats st;
-            tfbs_get_stats(ctx, &st);
-            total_cells += st.nominal_cells;
-            total_hits += st.n_hits;
-            // canonical order inside a region: (bed file, inner range, pattern_id); the reference's order is HashMap::drain()
-            std::vector<uint64_t> order(rows.n_rows);
-            for (uint64_t i = 0; i < rows.n_rows; ++i) order[i] = i;
-            std::stable_sort(order.begin(), order.end(), [&](uint64_t a, uint64_t b) {
-                if (rows.region[a] != rows.region[b]) return rows.region[a] < rows.region[b];
-                const tfbs_inner_region& ia = bd.inner[rows.inner[a]];
-                const tfbs_inner_region& ib = bd.inner[rows.inner[b]];
-                if (ia.bed_index != ib.bed_index) return ia.bed_index < ib.bed_index;
-                if (ia.start != ib.start) return ia.start < ib.start;
-                if (ia.end != ib.end) return ia.end < ib.end;
-                return rows.pattern_id[a] < rows.pattern_id[b];
-            });
-            us_sort += now_us() - ts;
-            uint64_t tf = now_us();
-            // row text on --threads host threads (the reference formats inside its worker threads, main.rs:415-425)
-            std::vector<std::string> text(order.size());
-            auto format_range = [&](size_t a, size_t b) {
-                for (size_t k = a; k < b; ++k) {
-                    const uint64_t i = order[k];
-                    // counts arrive in the narrowest type that holds them (option rows_width = 0, tfbs_rows.count_bytes)
-                    RowText t = rows.count_bytes == 1 ? finalise_row((const uint8_t*)rows.left + i * S, (const uint8_t*)rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf)
-                              : rows.count_bytes == 2 ? finalise_row((const uint16_t*)rows.left + i * S, (const uint16_t*)rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf)
-                                                      : finalise_row(rows.left + i * S, rows.right + i * S, S, rows.vmin[i], rows.vmax[i], o.min_maf);
-                    if (!t.keep) continue;
-                    const tfbs_inner_region& ir = bd.inner[rows.inner[i]];
-                    // POS is filled in by the writer (a running counter, main.rs:329,424-425)
-                    text[k] = "\t" + bed_names[ir.bed_index] + "," + pwm_name.at(rows.pattern_id[i]) + "," + std::to_string(ir.start) + "-" +
-                              std::to_string(ir.end) + "\t.\t.\t.\tPASS\t" + t.info + "\tGT:DS" + t.genotypes + "\n";
-                }
-            };
-            const size_t nt = std::max<size_t>(1, std::min<size_t>(o.threads, order.size() / 64 + 1));
-            if (nt == 1) format_range(0, order.size());
-            else {
-                std::vector<std::thread> ft;
-                for (size_t t = 0; t < nt; ++t) ft.emplace_back(format_range, order.size() * t / nt, order.size() * (t + 1) / nt);
-                for (auto& t : ft) t.join();
-            }
-            for (std::string& row : text)
-                if (!row.empty()) outs[c].rows.push_back(std::move(row));
-            us_format += now_us() - tf;
-            if (o.verbose)
-                printf("\nChunk %zu/%zu\tregions %zu-%zu\t%llu haplotypes\t%llu hits\n", c + 1, n_chunks, m0, m1, (unsigned long long)st.n_groups,
-                       (unsigned long long)st.n_hits);
         }
         builder.join();
         tfbs_destroy(ctx);
@@ -257,9 +318,7 @@ int main(int argc, char** argv) {
         for (auto& t : th) t.join();
     }
     const double t_after_gpu = since();
-    uint64_t fake_position = 1;
-    for (const ChunkOut& co2 : outs)
-        for (const std::string& row : co2.rows) emit(chr + "\t" + std::to_string(fake_position++) + row);
+    if (next_to_write != n_chunks) die("internal error: " + std::to_string(n_chunks - next_to_write) + " chunks were not written");
     if (gz) { gz->finish(); delete gz; } else plain.close();
     if (!o.audit_file.empty()) {
         // tie: a window scoring exactly min_score (not a hit, pattern.rs:151); truncated: haplotype.rs:144-149; overwritten: the
@@ -268,7 +327,7 @@ int main(int argc, char** argv) {
         std::ofstream af(o.audit_file, std::ios::binary);
         if (!af) die("Could not create audit file");
         af << "#tie\tCHROM\tREGION\tPWM\tSTRAND\tSTART\tMIN_SCORE\tGROUP\tHAPLOTYPES\n#truncated|overwritten\tCHROM\tREGION\tHAPLOTYPE\n";
-        for (const ChunkOut& co2 : outs) af << co2.audit;
+        for (const std::string& t : audit_text) af << t;
     }
     if (rename(part.c_str(), o.output.c_str()) != 0) die("Could not rename " + part + " into " + o.output);
     if (o.tabix) {
@@ -278,8 +337,8 @@ int main(int argc, char** argv) {
     }
     double secs = since();
     printf("phases: PWM+BED %.2f s, BCF %.2f s, blocks+GPU+rows %.2f s (context %.2f, waiting for blocks %.2f, submit+collect %.2f, sort %.2f, "
-           "row text %.2f; summed over devices), VCF write %.2f s\n", t_before_bcf, t_after_bcf - t_before_bcf, t_after_gpu - t_after_bcf,
-           us_create / 1e6, us_wait / 1e6, us_gpu / 1e6, us_sort / 1e6, us_format / 1e6, secs - t_after_gpu);
+           "row text %.2f; summed over devices; VCF write %.2f of it, overlapped), closing the file %.2f s\n", t_before_bcf, t_after_bcf - t_before_bcf, t_after_gpu - t_after_bcf,
+           us_create / 1e6, us_wait / 1e6, us_gpu / 1e6, us_sort / 1e6, us_format / 1e6, secs_write, secs - t_after_gpu);
     printf("%zu merged regions, %llu rows, %llu hits, %.3e nominal cells in %.2f s\nEnd of program.\n", merged.size(),
            (unsigned long long)(fake_position - 1), (unsigned long long)total_hits.load(), (double)total_cells.load(), secs);
     return 0;

@@ -11,7 +11,8 @@ namespace {
 struct Fasta {
     std::ifstream f;
     uint64_t len = 0, offset = 0, line_bases = 1, line_bytes = 1;
-    Fasta(const std::string& path, const std::string& chrom) : f(path, std::ios::binary) {
+    std::string chrom_;
+    Fasta(const std::string& path, const std::string& chrom) : f(path, std::ios::binary), chrom_(chrom) {
         if (!f) die("Error while opening the reference genome '" + path + "'");
         std::ifstream fai(path + ".fai");
         if (!fai) die("Error while opening the reference genome '" + path + "': missing .fai index");
@@ -30,8 +31,13 @@ struct Fasta {
         }
         if (!found) die("Error while seeking in reference genome file");
     }
-    void fetch(uint64_t start, uint64_t stop, std::vector<uint8_t>* out) {  // [start, stop), clipped at the contig end
-        stop = std::min(stop, len);
+    // [start, stop).  bio 0.28's IndexedReader::read refuses an interval that ends behind the contig ("FASTA read interval was out of
+    // bounds") and the reference panics through .expect (main.rs:157-159): a peak within Lmax - 1 of the contig end kills its worker
+    // there, and ends this program with the same message here.
+    void fetch(uint64_t start, uint64_t stop, std::vector<uint8_t>* out) {
+        if (stop > len || start > stop)
+            die("Error while reading in reference genome file " + chrom_ + ":" + std::to_string(start) + "-" + std::to_string(stop - 1) +
+                ": FASTA read interval was out of bounds");
         uint64_t pos = start;
         while (pos < stop) {
             uint64_t ln = pos / line_bases, col = pos % line_bases, take = std::min(stop - pos, line_bases - col);

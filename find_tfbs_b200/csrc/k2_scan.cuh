@@ -129,8 +129,8 @@ template <int FIELDS>
 __global__ void __launch_bounds__(SCAN_CTA, 1)
     k_scan(const __grid_constant__ DevBlock b, const __grid_constant__ DevSeqs sq, const __grid_constant__ DevPatterns pt,
            const __grid_constant__ DevCounts ct, const __grid_constant__ DevMatches mt, const __grid_constant__ DevRefHits rh,
-           const __grid_constant__ DevConfigs cf, int use_cf, const u32* list, const u64* n_list_ptr, u32 per_grab,
-           const u64* n_long_ptr, DevStatus* st, u32 chunk) {
+           const __grid_constant__ DevConfigs cf, int use_cf, const u32* list, const u64* n_list_ptr, u32 per_grab, DevStatus* st,
+           u32 chunk) {
     if (use_cf && cf.plan->abort) return;  // an earlier stage ran out of scratch: the host repeats the run
     TFBS_DYNAMIC_SHARED(smem_raw);
     CtaShared* cs = reinterpret_cast<CtaShared*>(smem_raw);
@@ -144,24 +144,24 @@ __global__ void __launch_bounds__(SCAN_CTA, 1)
         u32 n16 = (cd.tbl_words + 1) / 2;
         for (u32 k = tid; k < n16; k += SCAN_CTA) dst[k] = src[k];
         if (tid < cd.n_runs && tid < MAX_RUNS) cs->runs[tid] = pt.runs[cd.run_off + tid];
-        if (tid == 0) cs->n_runs = cd.n_runs;
+        if (tid == 0) {
+            cs->n_runs = cd.n_runs;
+            cs->per_grab = per_grab;
+            cs->n_list = *n_list_ptr;
+            cs->env = ScanEnv{use_cf ? &cf : nullptr, &b, &sq, &pt, &ct, &mt, &rh, st};
+        }
     }
     __syncthreads();
     const u32 n_runs = cs->n_runs;
-    const u64 n_list = *n_list_ptr;
-    const ScanEnv env{use_cf ? &cf : nullptr, &b, &sq, &pt, &ct, &mt, &rh, st};
+    const ScanEnv& env = cs->env;
 
-    // the first n_long entries are long items (whole reference haplotypes): one per trip to the work counter, so that the warps
-    // that draw them do not end up with `per_grab` times the work of the others; short items follow, per_grab at a time
-    u64 n_long = n_long_ptr ? *n_long_ptr : 0;
-    if (n_long > n_list) n_long = n_list;
     for (;;) {
         u32 w = 0;
         if (lane == 0) w = atomicAdd(&st->work_counter, 1u);
         w = __shfl_sync(0xffffffffu, w, 0);
-        u64 li = w < n_long ? (u64)w : n_long + ((u64)w - n_long) * per_grab;
-        if (li >= n_list) break;
-        const u64 lend = w < n_long ? li + 1 : (li + per_grab < n_list ? li + per_grab : n_list);
+        u64 li = (u64)w * cs->per_grab;
+        if (li >= cs->n_list) break;
+        const u64 lend = li + cs->per_grab < cs->n_list ? li + cs->per_grab : cs->n_list;
         u32 done_in_item = 0;  // starts of entry li already scored
         u32 n_counted = 0;
         while (li < lend) {

@@ -87,12 +87,6 @@ struct __align__(16) WarpShared {
     u32 n_pieces, pad[3];
 };
 
-struct __align__(16) CtaShared {
-    RunDesc runs[MAX_RUNS];
-    u32 n_runs;
-    u32 pad[3];
-};
-
 template <int FIELDS>
 struct HitMask;
 template <>
@@ -102,6 +96,7 @@ struct HitMask<2> { static constexpr u64 value = (1ULL << 31) | (1ULL << 63); };
 
 // Everything the rare path needs, passed by pointer (the structs are __grid_constant__ kernel parameters).
 struct DevConfigs;
+struct DevStatus;
 struct ScanEnv {
     const DevConfigs* cf;   // configuration path (virtual sequences) or NULL
     const DevBlock* b;
@@ -111,6 +106,16 @@ struct ScanEnv {
     const DevMatches* mt;
     const DevRefHits* rh;
     DevStatus* st;
+};
+
+// One per CTA: the runs of the chunk, the rare path's environment (the hot loop keeps none of it in registers) and the bounds of
+// the work list (read once per trip to the work counter).
+struct __align__(16) CtaShared {
+    RunDesc runs[MAX_RUNS];
+    u32 n_runs;
+    u32 per_grab;
+    u64 n_list;
+    ScanEnv env;
 };
 
 }  // namespace tfbs

@@ -235,6 +235,7 @@ __global__ void k_cfg_walk(DevBlock b, DevSeqs sq, DevConfigs cf, DevSeqs vq, u6
 // Work list over the virtual sequences: the reference haplotype of a region in full, a configuration only at the window starts
 // that touch one of its ALT segments ([a - Lmax + 1, e - 1] for a segment [a, e)): every other window lies inside one
 // reference-copy segment and has the bases and positions of the reference window there.
+constexpr u32 REF_PIECE = 128;
 template <bool FILL>
 __global__ void k_vitems(DevSeqs vq, u32 max_len, const u32* abort_flag) {
     if (*abort_flag) return;
@@ -250,7 +251,9 @@ __global__ void k_vitems(DevSeqs vq, u32 max_len, const u32* abort_flag) {
     if (len == 0) {
         n = 0;
     } else if (q < vq.n_ref) {
-        put(0u, len - 1);
+        // the reference haplotype in pieces of REF_PIECE starts: a trip to the scan's work counter then costs about the same
+        // whether it draws pieces of a reference haplotype or short items of configurations
+        for (u32 a = 0; a < len; a += REF_PIECE) put(a, (a + REF_PIECE < len ? a + REF_PIECE : len) - 1);
     } else {
         const Seg* sg = vq.segs + 2 * vq.seq_doff[q] + 2 * (u64)q;
         const u32 ns = vq.seq_nseg[q];

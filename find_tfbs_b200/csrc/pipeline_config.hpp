@@ -50,6 +50,7 @@ struct ConfigPipeline {
     DevStatus* dst = nullptr;
     DevPlan* plan = nullptr;
     DevBlock db{};
+    uint64_t ref_items = 0;  // work-list items of the reference haplotypes (pieces of REF_PIECE window starts)
 
     ConfigPipeline(tfbs_ctx* c, Slot* s)
         : ctx(c), slot(s), B(*s->in), st(c->stream), R(s->in->R), S(s->in->S), H(s->in->H), RH((uint64_t)s->in->R * s->in->H) {}
@@ -66,14 +67,20 @@ struct ConfigPipeline {
     static uint64_t up(uint64_t need) { return need + need / 4 + 16; }
     void choose_caps(bool first_attempt) {
         Caps& c = slot->caps;
-        if (!first_attempt) return;  // a repeated run keeps the capacities finalize() grew
         const Caps& h = ctx->hint;
         const uint64_t n_var = B.n_var;
         uint64_t ref_units = 0;
-        for (uint32_t r = 0; r < R; ++r) ref_units += (uint64_t)((B.h_region_end[r] - B.h_region_start[r] + 1 + 64) >> 5) + 2;
+        ref_items = 0;
+        for (uint32_t r = 0; r < R; ++r) {
+            const uint64_t w = (uint64_t)(B.h_region_end[r] - B.h_region_start[r] + 1);
+            const uint64_t pieces = w / REF_PIECE + 1;
+            ref_items += pieces;
+            ref_units += pieces * ((REF_PIECE + 64) / 32 + 2);
+        }
+        if (!first_attempt) return;  // a repeated run keeps the capacities finalize() grew
         if (ctx->tiny_caps) {  // testing: every growth path runs
             c = Caps{};
-            c.seq = R; c.d = 1; c.cfg = 1; c.vd = 1; c.items = R + 1; c.units = 1; c.dwords = 1; c.rows = 1; c.rowwords = 1; c.capr = 1; c.groups = 1;
+            c.seq = R; c.d = 1; c.cfg = 1; c.vd = 1; c.items = ref_items + 1; c.units = 1; c.dwords = 1; c.rows = 1; c.rowwords = 1; c.capr = 1; c.groups = 1;
             return;
         }
         // what the previous blocks needed (+ 25 %) when there is a history, else a guess from the shape of the block; a wrong guess
@@ -84,7 +91,7 @@ struct ConfigPipeline {
         c.d = pick(h.d, std::min<uint64_t>(2 * c.seq, ctx->scratch_bytes / 4 / 72));
         c.cfg = pick(h.cfg, 4 * n_var + R);
         c.vd = pick(h.vd, 2 * c.cfg);
-        c.items = R + c.vd;  // a configuration has at most one item per carried record
+        c.items = ref_items + c.vd;  // the reference haplotypes in pieces, a configuration has at most one item per carried record
         c.units = std::max<uint64_t>(pick(h.units, 0), ref_units + 8 * c.cfg);
         c.dwords = pick(h.dwords, c.cfg * (n_keys / std::max<uint32_t>(1, R) + 1));
         c.rows = std::min<uint64_t>(std::max<uint64_t>(1, n_keys), pick(h.rows, std::max<uint64_t>(4096, n_keys / 4)));
@@ -429,9 +436,8 @@ struct ConfigPipeline {
         CK(cudaEventRecord(slot->ev_t[3], st));
         for (uint32_t ch = 0; ch < cp.chunks.size(); ++ch) {
             CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
-            // the items of the first R virtual sequences are whole reference haplotypes: item_off[R] of them, one per grab
-            if (wide) TFBS_LAUNCH(k_scan<2>, scan_grid, SCAN_CTA, smem_bytes, st)(db, vq, ctx->dpat, dc, dm, drh, cf, 1, ctx->d_list.as<u32>(), &plan->n_items, (u32)SCAN_PER_GRAB, vq.item_off + R, dst, ch);
-            else TFBS_LAUNCH(k_scan<3>, scan_grid, SCAN_CTA, smem_bytes, st)(db, vq, ctx->dpat, dc, dm, drh, cf, 1, ctx->d_list.as<u32>(), &plan->n_items, (u32)SCAN_PER_GRAB, vq.item_off + R, dst, ch);
+            if (wide) TFBS_LAUNCH(k_scan<2>, scan_grid, SCAN_CTA, smem_bytes, st)(db, vq, ctx->dpat, dc, dm, drh, cf, 1, ctx->d_list.as<u32>(), &plan->n_items, (u32)SCAN_PER_GRAB, dst, ch);
+            else TFBS_LAUNCH(k_scan<3>, scan_grid, SCAN_CTA, smem_bytes, st)(db, vq, ctx->dpat, dc, dm, drh, cf, 1, ctx->d_list.as<u32>(), &plan->n_items, (u32)SCAN_PER_GRAB, dst, ch);
             ++launches();
             ++slot->stats.scan_launches;
         }
@@ -551,12 +557,13 @@ struct ConfigPipeline {
 
     void grow_caps(const DevPlan& hp) {
         Caps& c = slot->caps;
+        choose_caps(false);  // ref_items of this block
         auto g = [](uint64_t& cap, uint64_t need) { if (need > cap) cap = up(need); };
         g(c.seq, hp.need_seq);
         g(c.d, hp.need_d);
         g(c.cfg, hp.need_cfg);
         g(c.vd, hp.need_vd);
-        c.items = std::max<uint64_t>(c.items, R + c.vd);
+        c.items = std::max<uint64_t>(c.items, ref_items + c.vd);
         g(c.items, hp.need_items);
         g(c.units, hp.need_units);
         g(c.dwords, hp.need_dwords);

@@ -377,8 +377,8 @@ private:
         CK(cudaEventRecord(ctx->ev[8], st));
         for (uint32_t c = 0; c < ctx->cp.chunks.size() && b.n_list_host; ++c) {
             CK(cudaMemsetAsync(&dst->work_counter, 0, 4, st));
-            if (wide) TFBS_LAUNCH(k_scan<2>, scan_grid, SCAN_CTA, smem_bytes, st)(db, sq, ctx->dpat, b.dc, dm, b.drh, no_cf, 0, ctx->d_list.as<u32>(), b.d_n_items, 1u, nullptr, dst, c);
-            else TFBS_LAUNCH(k_scan<3>, scan_grid, SCAN_CTA, smem_bytes, st)(db, sq, ctx->dpat, b.dc, dm, b.drh, no_cf, 0, ctx->d_list.as<u32>(), b.d_n_items, 1u, nullptr, dst, c);
+            if (wide) TFBS_LAUNCH(k_scan<2>, scan_grid, SCAN_CTA, smem_bytes, st)(db, sq, ctx->dpat, b.dc, dm, b.drh, no_cf, 0, ctx->d_list.as<u32>(), b.d_n_items, 1u, dst, c);
+            else TFBS_LAUNCH(k_scan<3>, scan_grid, SCAN_CTA, smem_bytes, st)(db, sq, ctx->dpat, b.dc, dm, b.drh, no_cf, 0, ctx->d_list.as<u32>(), b.d_n_items, 1u, dst, c);
             ++launches();
             ++stats().scan_launches;
             table_bytes += (uint64_t)ctx->cp.chunks[c].tbl_words * 8 * scan_grid;
