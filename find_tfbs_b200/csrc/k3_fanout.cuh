@@ -94,6 +94,25 @@ __global__ void __launch_bounds__(FAN_WARPS * 32) k_fanout(DevBlock b, DevConfig
             const u32 key = active[a];
             const u32 ref = cf.C0[kb + key];
             const u32* drow = Dr + (u64)key * ncfg;
+            // does any configuration change this key?  (a hit that a configuration loses and finds again leaves its difference at 0)
+            bool any = false;
+            for (u32 c0 = 0; c0 < ncfg && !any; c0 += 32) {
+                const u32 d = c0 + lane < ncfg ? drow[c0 + lane] : 0u;
+                any = __ballot_sync(0xffffffffu, d != 0) != 0;
+            }
+            if (!any) {  // every haplotype has the reference haplotype's count: a row only when every key is asked for
+                const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING || ref == 0) ? 0u : 1u;
+                if (lane == 0) {
+                    fn.vmin[kb + key] = 2 * ref;
+                    fn.vmax[kb + key] = 2 * ref;
+                    fn.flag[kb + key] = f;
+                    fn.k_base[kb + key] = ref;
+                    fn.k_bits[kb + key] = 0;
+                    fn.k_off[kb + key] = 0;
+                }
+                if (f) row_max = max(row_max, 2 * ref);
+                continue;
+            }
             for (u32 g = lane; g < ng; g += 32) val[g] = 0;
             __syncwarp();
             for (u32 c0 = 0; c0 < ncfg; c0 += 32) {
