@@ -139,7 +139,7 @@ struct tfbs_ctx {
     int verify_groups = 1;
     int scan_format = 0;
     uint64_t scratch_bytes = 24ull << 30;
-    uint32_t table_budget = 96 * 1024;
+    uint32_t table_budget = 160 * 1024;  // measured on configs[2] (802 patterns): 96 KB -> 5 chunk launches, 0.763 of the roof; 160 KB -> 3, 0.796
     int scan_ctas_per_sm = 0;  // < 0: fixed grid size (debugging)
     int delta = 1;             // 1: configuration path (delta scoring); 0: every distinct haplotype scored in full
     int64_t refhit_cap_opt = 0; // testing: reference hits kept per region (0 = automatic)
@@ -169,7 +169,7 @@ struct tfbs_ctx {
     DevBuf d_ref_codes, d_allele_codes, d_var_class, d_var_inwin, d_ref_prefix;
     DevBuf d_sig, d_nd_in, d_leader, d_hap_group, d_ngroups, d_sum_nd, d_ref_used;
     DevBuf d_keys, d_vals, d_scanwork;
-    DevBuf d_kbase;
+    DevBuf d_kbase, d_hap_mask, d_mask_base, d_region_dups;
     // distinct haplotypes ("sequences")
     DevBuf d_seq_region, d_seq_leader, d_seq_nd, d_seq_doff, d_dlist, d_segs, d_seq_nseg, d_seq_len, d_seq_hash, d_seq_flags, d_seq_ntake,
         d_seq_nitems, d_item_off, d_items, d_list, d_ent_units, d_ent_uoff, d_pk, d_nm, d_refhits, d_refcnt;

@@ -20,10 +20,12 @@ __device__ __forceinline__ bool same_diff(const DevBlock& b, const tfbs_variant&
 
 // One CTA per region.  Two records with equal (pos, reference, alternative) are the same Diff value
 // for Vec<Diff> equality, so they share a class.
-__global__ void k_variant_prep(DevBlock b, u32 r0, u32* var_class, u8* var_inwin) {
+__global__ void k_variant_prep(DevBlock b, u32 r0, u32* var_class, u8* var_inwin, u32* region_dups) {
     u32 r = r0 + blockIdx.x;
     u32 v0 = b.var_off[r], v1 = b.var_off[r + 1];
     i64 s = b.region_start[r], e = b.region_end[r];
+    if (region_dups && threadIdx.x == 0) region_dups[r] = 0;
+    __syncthreads();
     for (u32 v = v0 + threadIdx.x; v < v1; v += blockDim.x) {
         tfbs_variant x = b.variants[v];
         var_inwin[v] = (x.pos >= s && x.pos <= e) ? 1 : 0;
@@ -31,7 +33,14 @@ __global__ void k_variant_prep(DevBlock b, u32 r0, u32* var_class, u8* var_inwin
         for (u32 u = v0; u < v; ++u)
             if (same_diff(b, b.variants[u], x)) { cls = u - v0; break; }
         var_class[v] = cls;
+        if (region_dups && cls != v - v0) region_dups[r] = 1;
     }
+}
+
+// words of carried-record masks per region: H * ceil(V / 32)
+__global__ void k_mask_words(DevBlock b, u32* words) {
+    const u32 r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < b.R) words[r] = b.H * ((b.var_off[r + 1] - b.var_off[r] + 31) / 32);
 }
 
 __device__ __forceinline__ bool carries(const DevBlock& b, u32 v, u32 h) {
@@ -46,12 +55,18 @@ __global__ void k_signatures(DevBlock b, u32 r0, u32 nr, u64 seed, u64* sig, u32
     u32 r = r0 + (u32)(idx / b.H), h = (u32)(idx % b.H);
     u64 s = seed;
     u32 carried = 0, inw = 0;
-    for (u32 v = b.var_off[r]; v < b.var_off[r + 1]; ++v)
+    const u32 v0 = b.var_off[r], v1 = b.var_off[r + 1];
+    u32* mask = b.hap_mask ? b.hap_mask + b.mask_base[r] + (u64)h * ((v1 - v0 + 31) / 32) : nullptr;
+    u32 word = 0;
+    for (u32 v = v0; v < v1; ++v) {
         if (carries(b, v, h)) {
             s = mix64(s + b.var_class[v] + 1) * 0x9e3779b97f4a7c15ULL + carried;
             ++carried;
             inw += b.var_inwin[v];
+            word |= 1u << ((v - v0) & 31);
         }
+        if (mask && (((v - v0) & 31) == 31 || v + 1 == v1)) { mask[(v - v0) >> 5] = word; word = 0; }
+    }
     sig[(size_t)r * b.H + h] = carried ? (mix64(s) | 1ULL) : 0ULL;
     nd_in[(size_t)r * b.H + h] = inw;
 }
@@ -100,6 +115,15 @@ __global__ void k_group_lookup(DevBlock b, u32 r0, u32 nr, const u64* sig, const
     leader[(size_t)r * b.H + h] = ld;
     if (ld == h) return;
     bool ok = ld < b.H;
+    if (ok && b.hap_mask) {  // equal masks = the same records = equal lists; different masks are different lists unless the region holds duplicates
+        const u32 nw = (b.var_off[r + 1] - b.var_off[r] + 31) / 32;
+        const u32* ma = b.hap_mask + b.mask_base[r] + (u64)h * nw;
+        const u32* mb = b.hap_mask + b.mask_base[r] + (u64)ld * nw;
+        bool same = true;
+        for (u32 w = 0; w < nw && same; ++w) same = ma[w] == mb[w];
+        if (same) return;
+        if (!b.region_dups[r]) { atomicAdd(&st->sig_collision, 1u); return; }
+    }
     if (ok) {
         u32 v1 = b.var_off[r + 1];
         u32 i = b.var_off[r], j = i;

@@ -186,14 +186,22 @@ __global__ void k_walk(DevBlock b, DevSeqs sq, u64 d_cap, DevStatus* st) {
     u32* dl = sq.dlist + doff;
     Seg* sg = sq.segs + 2 * doff + 2 * (u64)q;
     u32 nd = 0;
-    if (h != 0xffffffffu) {
-        for (u32 v = b.var_off[r]; v < b.var_off[r + 1]; ++v)
-            if (b.var_inwin[v] && carries(b, v, h)) {
-                // insertion sort; records come sorted by position, so this is nearly linear
-                u32 k = nd++;
-                while (k > 0 && diff_less(b, v, dl[k - 1])) { dl[k] = dl[k - 1]; --k; }
-                dl[k] = v;
+    auto take = [&](u32 v) {  // insertion sort; records come sorted by position, so this is nearly linear
+        u32 k = nd++;
+        while (k > 0 && diff_less(b, v, dl[k - 1])) { dl[k] = dl[k - 1]; --k; }
+        dl[k] = v;
+    };
+    if (h != 0xffffffffu && b.hap_mask) {  // the set bits of the leader's mask
+        const u32 v0 = b.var_off[r], nw = (b.var_off[r + 1] - v0 + 31) / 32;
+        const u32* mask = b.hap_mask + b.mask_base[r] + (u64)h * nw;
+        for (u32 w = 0; w < nw; ++w)
+            for (u32 m = mask[w]; m; m &= m - 1) {
+                const u32 v = v0 + 32 * w + (u32)__ffs((int)m) - 1;
+                if (b.var_inwin[v]) take(v);
             }
+    } else if (h != 0xffffffffu) {
+        for (u32 v = b.var_off[r]; v < b.var_off[r + 1]; ++v)
+            if (b.var_inwin[v] && carries(b, v, h)) take(v);
     }
     const WalkOut w = walk_diffs(b, r, dl, nd, sg, st, q);
     const u32 ns = w.ns;

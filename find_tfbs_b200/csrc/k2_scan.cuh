@@ -148,12 +148,11 @@ __global__ void __launch_bounds__(SCAN_CTA, 1)
             cs->n_runs = cd.n_runs;
             cs->per_grab = per_grab;
             cs->n_list = *n_list_ptr;
-            cs->env = ScanEnv{use_cf ? &cf : nullptr, &b, &sq, &pt, &ct, &mt, &rh, st};
         }
     }
     __syncthreads();
     const u32 n_runs = cs->n_runs;
-    const ScanEnv& env = cs->env;
+    const ScanEnv env{use_cf ? &cf : nullptr, &b, &sq, &pt, &ct, &mt, &rh, st};  // for the rare path: pointers to the kernel's own parameters
 
     for (;;) {
         u32 w = 0;

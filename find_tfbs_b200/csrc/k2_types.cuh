@@ -108,14 +108,12 @@ struct ScanEnv {
     DevStatus* st;
 };
 
-// One per CTA: the runs of the chunk, the rare path's environment (the hot loop keeps none of it in registers) and the bounds of
-// the work list (read once per trip to the work counter).
+// One per CTA: the runs of the chunk and the bounds of the work list (read once per trip to the work counter).
 struct __align__(16) CtaShared {
     RunDesc runs[MAX_RUNS];
     u32 n_runs;
     u32 per_grab;
     u64 n_list;
-    ScanEnv env;
 };
 
 }  // namespace tfbs

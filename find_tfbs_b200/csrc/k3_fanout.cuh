@@ -3,8 +3,7 @@
 //
 // count_matches_by_sample (main.rs:500-534) gives every sample the hits of its two haplotypes; here a haplotype's count for a key
 // (pattern_id, inner region) is the reference haplotype's count plus the differences of its live configurations.  One warp owns a key:
-// it builds the count of every distinct haplotype (group) of the region in its private shared-memory vector -- no atomics: the members
-// of one configuration are distinct groups, configurations are applied one after the other -- then takes min and max of
+// it builds the count of every distinct haplotype (group) of the region in a shared-memory vector, then takes min and max of
 // left + right over the samples (main.rs:441-451) and, if the key is kept (min != max, main.rs:456-458), writes ONE GROUPED ROW:
 // the count of every group, as `bits`-wide offsets from the row's smallest count.  The region's haplotype -> group map goes to the
 // host once per region, not once per row: identical count vectors are stored once.
@@ -52,27 +51,31 @@ __device__ __forceinline__ u32 bits_for(u32 span) {  // width that holds 0..span
     return 32;
 }
 
-constexpr int FAN_WARPS = 8;
-constexpr u32 FAN_KEYS = 1024;  // keys looked at per round (the list of the active ones among them lives in shared memory)
+constexpr int FAN_THREADS = 256;
+constexpr u32 FAN_KEYS = 1024;  // keys looked at per round (the list of the ones that need the count vector lives in shared memory)
 
-// One CTA per region.  Keys no hit ever touched (DevConfigs::keyflag, the large majority) are answered at once: nobody has a count.
-// The others are dealt to the warps: a warp builds the count of every group for its key, takes min / max over the samples and, when
-// the key becomes a row, writes the packed counts at a position it draws from an atomic cursor (the payload order is arbitrary, the
-// rows are numbered afterwards in key order by k_row_headers).
-__global__ void __launch_bounds__(FAN_WARPS * 32) k_fanout(DevBlock b, DevConfigs cf, DevFan fn) {
+// One CTA per region.  Thread per key first: a key no hit ever touched (DevConfigs::keyflag, the large majority) or whose differences
+// all cancelled has the reference haplotype's count for everybody and is answered at once.  The remaining keys are taken one at a
+// time by the whole CTA: the count of every group is built in ONE shared-memory vector (the warps apply different configurations at
+// the same time; two configurations of different clusters can meet in a group, hence shared-memory atomics), min / max over the
+// samples are reduced, and when the key becomes a row its packed counts are written at a position drawn from an atomic cursor (the
+// payload order is arbitrary; k_row_headers numbers the rows in key order afterwards).
+__global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs cf, DevFan fn) {
     TFBS_DYNAMIC_SHARED(smem_raw);
-    __shared__ u32 s_n;
+    __shared__ u32 s_n, s_red[4][FAN_THREADS / 32], s_bcast[4];
+    __shared__ unsigned long long s_off;
     if (cf.plan->abort) return;
     const u32 r = blockIdx.x;
-    const u32 lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    u32* active = reinterpret_cast<u32*>(smem_raw);
-    u32* val = active + FAN_KEYS + (size_t)wid * fn.groups_cap;
+    const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    constexpr u32 NW = FAN_THREADS / 32;
+    u32* heavy = reinterpret_cast<u32*>(smem_raw);
+    u32* val = heavy + FAN_KEYS;
     const u32 ng = (u32)(fn.gbase[r + 1] - fn.gbase[r]);
     if (ng > fn.groups_cap) {  // more distinct haplotypes than the shared-memory vector holds: the host repeats the run
-        if (threadIdx.x == 0) { atomicMax(&cf.plan->need_groups, ng); cf.plan->abort = 1; }
+        if (tid == 0) { atomicMax(&cf.plan->need_groups, ng); cf.plan->abort = 1; }
         return;
     }
-    if (threadIdx.x == 0) atomicMax(&cf.plan->need_groups, ng);
+    if (tid == 0) atomicMax(&cf.plan->need_groups, ng);
     const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
     const u32 nkeys = fn.n_pid * nk;
     const u64 kb = cf.kbase[r];
@@ -82,61 +85,50 @@ __global__ void __launch_bounds__(FAN_WARPS * 32) k_fanout(DevBlock b, DevConfig
     const u32* hg = fn.hap_group + (size_t)r * b.H;
     u32 row_max = 0;
     for (u32 k0 = 0; k0 < nkeys; k0 += FAN_KEYS) {
-        if (threadIdx.x == 0) s_n = 0;
+        if (tid == 0) s_n = 0;
         __syncthreads();
-        for (u32 key = k0 + threadIdx.x; key < nkeys && key < k0 + FAN_KEYS; key += blockDim.x) {
-            if (cf.keyflag[kb + key]) active[atomicAdd(&s_n, 1u)] = key;
-            else { fn.vmin[kb + key] = 0; fn.vmax[kb + key] = 0; fn.flag[kb + key] = 0; }
+        for (u32 key = k0 + tid; key < nkeys && key < k0 + FAN_KEYS; key += FAN_THREADS) {
+            bool any = false;
+            if (cf.keyflag[kb + key]) {
+                const u32* drow = Dr + (u64)key * ncfg;
+                for (u32 c = 0; c < ncfg && !any; ++c) any = drow[c] != 0;
+            }
+            if (any) { heavy[atomicAdd(&s_n, 1u)] = key; continue; }
+            // every haplotype has the reference haplotype's count: a row only when every key with a hit is asked for (main.rs:517-528)
+            const u32 ref = cf.C0[kb + key];
+            const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING || ref == 0) ? 0u : 1u;
+            fn.vmin[kb + key] = 2 * ref;
+            fn.vmax[kb + key] = 2 * ref;
+            fn.flag[kb + key] = f;
+            fn.k_base[kb + key] = ref;
+            fn.k_bits[kb + key] = 0;
+            fn.k_off[kb + key] = 0;
+            if (f) row_max = max(row_max, 2 * ref);
         }
         __syncthreads();
-        const u32 n_active = s_n;
-        for (u32 a = wid; a < n_active; a += nw) {
-            const u32 key = active[a];
+        const u32 n_heavy = s_n;
+        for (u32 a = 0; a < n_heavy; ++a) {
+            const u32 key = heavy[a];
             const u32 ref = cf.C0[kb + key];
             const u32* drow = Dr + (u64)key * ncfg;
-            // does any configuration change this key?  (a hit that a configuration loses and finds again leaves its difference at 0)
-            bool any = false;
-            for (u32 c0 = 0; c0 < ncfg && !any; c0 += 32) {
-                const u32 d = c0 + lane < ncfg ? drow[c0 + lane] : 0u;
-                any = __ballot_sync(0xffffffffu, d != 0) != 0;
+            for (u32 g = tid; g < ng; g += FAN_THREADS) val[g] = 0;
+            __syncthreads();
+            for (u32 c = wid; c < ncfg; c += NW) {  // a warp per configuration, lanes over its members
+                const u32 d = drow[c];
+                if (!d) continue;
+                const u64 m0 = cf.moff[cb + c], m1 = cf.moff[cb + c + 1];
+                for (u64 m = m0 + lane; m < m1; m += 32) atomicAdd(&val[cf.members[m]], d);
             }
-            if (!any) {  // every haplotype has the reference haplotype's count: a row only when every key is asked for
-                const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING || ref == 0) ? 0u : 1u;
-                if (lane == 0) {
-                    fn.vmin[kb + key] = 2 * ref;
-                    fn.vmax[kb + key] = 2 * ref;
-                    fn.flag[kb + key] = f;
-                    fn.k_base[kb + key] = ref;
-                    fn.k_bits[kb + key] = 0;
-                    fn.k_off[kb + key] = 0;
-                }
-                if (f) row_max = max(row_max, 2 * ref);
-                continue;
-            }
-            for (u32 g = lane; g < ng; g += 32) val[g] = 0;
-            __syncwarp();
-            for (u32 c0 = 0; c0 < ncfg; c0 += 32) {
-                const u32 d = c0 + lane < ncfg ? drow[c0 + lane] : 0u;
-                u32 nz = __ballot_sync(0xffffffffu, d != 0);
-                while (nz) {
-                    const u32 l = (u32)__ffs((int)nz) - 1;
-                    nz &= nz - 1;
-                    const u32 dl = __shfl_sync(0xffffffffu, d, (int)l);
-                    const u64 m0 = cf.moff[cb + c0 + l], m1 = cf.moff[cb + c0 + l + 1];
-                    for (u64 m = m0 + lane; m < m1; m += 32) val[cf.members[m]] += dl;  // distinct groups: no conflict
-                    __syncwarp();
-                }
-            }
-            // smallest / largest count over the groups (the packing base and width) ...
-            u32 gmin = ref, gmax = ref;
-            for (u32 g = lane; g < ng; g += 32) {
+            __syncthreads();
+            // smallest / largest count over the groups (the packing base and width) and min / max of left + right over the samples
+            // (main.rs:441-451)
+            u32 gmin = ref, gmax = ref, lo = 0xffffffffu, hi = 0;
+            for (u32 g = tid; g < ng; g += FAN_THREADS) {
                 const u32 c = ref + val[g];
                 gmin = min(gmin, c);
                 gmax = max(gmax, c);
             }
-            // ... and min / max of left + right over the samples (main.rs:441-451)
-            u32 lo = 0xffffffffu, hi = 0;
-            for (u32 s = lane; s < b.S; s += 32) {
+            for (u32 s = tid; s < b.S; s += FAN_THREADS) {
                 const u32 v = 2 * ref + val[hg[2 * s]] + val[hg[2 * s + 1]];
                 lo = min(lo, v);
                 hi = max(hi, v);
@@ -148,38 +140,50 @@ __global__ void __launch_bounds__(FAN_WARPS * 32) k_fanout(DevBlock b, DevConfig
                 gmin = min(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
                 gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
             }
-            // keys exist once a hit of any scanned haplotype touched the inner region (main.rs:517-528): hi > 0
-            const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING) ? (lo != hi ? 1u : 0u) : (hi > 0 ? 1u : 0u);
-            const u32 bits = bits_for(gmax - gmin);
-            const u32 words = (u32)(((u64)ng * bits + 31) / 32);
-            u64 off = 0;
-            if (f && lane == 0) off = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)words);
-            off = __shfl_sync(0xffffffffu, off, 0);
-            if (lane == 0) {
+            if (lane == 0) { s_red[0][wid] = lo; s_red[1][wid] = hi; s_red[2][wid] = gmin; s_red[3][wid] = gmax; }
+            __syncthreads();
+            if (tid == 0) {
+                for (u32 w = 1; w < NW; ++w) {
+                    lo = min(lo, s_red[0][w]);
+                    hi = max(hi, s_red[1][w]);
+                    gmin = min(gmin, s_red[2][w]);
+                    gmax = max(gmax, s_red[3][w]);
+                }
+                // keys exist once a hit of any scanned haplotype touched the inner region (main.rs:517-528): hi > 0
+                const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING) ? (lo != hi ? 1u : 0u) : (hi > 0 ? 1u : 0u);
+                const u32 bits = bits_for(gmax - gmin);
+                const u32 words = (u32)(((u64)ng * bits + 31) / 32);
+                unsigned long long off = 0;
+                if (f) off = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)words);
                 fn.vmin[kb + key] = lo;
                 fn.vmax[kb + key] = hi;
                 fn.flag[kb + key] = f;
                 fn.k_base[kb + key] = gmin;
                 fn.k_bits[kb + key] = (u8)bits;
                 fn.k_off[kb + key] = off;
+                if (f) row_max = max(row_max, hi);
+                s_bcast[0] = f;
+                s_bcast[1] = bits;
+                s_bcast[2] = gmin;
+                s_bcast[3] = words;
+                s_off = off;
             }
-            if (f) {
-                row_max = max(row_max, hi);
-                if (bits && off + words <= fn.words_cap) {  // beyond the capacity: the gate behind this kernel raises abort
-                    const u32 per = 32 / bits;
-                    for (u32 w = lane; w < words; w += 32) {
-                        u32 word = 0;
-                        for (u32 x = 0; x < per; ++x) {
-                            const u32 g = w * per + x;
-                            if (g < ng) word |= (ref + val[g] - gmin) << (x * bits);
-                        }
-                        fn.o_packed[off + w] = word;
+            __syncthreads();
+            const u32 bits = s_bcast[1], words = s_bcast[3];
+            if (s_bcast[0] && bits && s_off + words <= fn.words_cap) {  // beyond the capacity: the gate behind this kernel raises abort
+                const u32 per = 32 / bits, base = s_bcast[2];
+                const u64 off = s_off;
+                for (u32 w = tid; w < words; w += FAN_THREADS) {
+                    u32 word = 0;
+                    for (u32 x = 0; x < per; ++x) {
+                        const u32 g = w * per + x;
+                        if (g < ng) word |= (ref + val[g] - base) << (x * bits);
                     }
+                    fn.o_packed[off + w] = word;
                 }
             }
-            __syncwarp();
+            __syncthreads();
         }
-        __syncthreads();
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) row_max = max(row_max, __shfl_xor_sync(0xffffffffu, row_max, o));

@@ -124,6 +124,13 @@ struct ConfigPipeline {
         RS(ctx->d_sum_nd, (uint64_t)R * 4);
         RS(ctx->d_ref_used, (uint64_t)R * 4);
         RS(ctx->d_kbase, (uint64_t)(R + 1) * 8);
+        {
+            uint64_t mask_words = 0;  // H * sum over the regions of ceil(V / 32)
+            for (uint32_t r = 0; r < R; ++r) mask_words += (uint64_t)H * ((B.h_var_off[r + 1] - B.h_var_off[r] + 31) / 32);
+            RS(ctx->d_hap_mask, mask_words * 4);
+            RS(ctx->d_mask_base, (uint64_t)(R + 1) * 8);
+            RS(ctx->d_region_dups, (uint64_t)R * 4);
+        }
         RS(ctx->d_seq_region, c.seq * 4);
         RS(ctx->d_seq_leader, c.seq * 4);
         RS(ctx->d_seq_nd, c.seq * 4);
@@ -259,7 +266,13 @@ struct ConfigPipeline {
             ++launches();
         }
         db = dev_block(ctx, B);
-        TFBS_LAUNCH(k_variant_prep, R, 128, 0, st)(db, 0, ctx->d_var_class.as<u32>(), ctx->d_var_inwin.as<u8>());
+        db.hap_mask = ctx->d_hap_mask.as<u32>();
+        db.mask_base = ctx->d_mask_base.as<u64>();
+        db.region_dups = ctx->d_region_dups.as<u32>();
+        TFBS_LAUNCH(k_mask_words, grid_for(R, 256), 256, 0, st)(db, ctx->d_dwords.as<u32>());
+        ++launches();
+        if ((rc = scan(ctx->d_dwords.as<u32>(), R, nullptr, ctx->d_mask_base.as<u64>()))) return rc;
+        TFBS_LAUNCH(k_variant_prep, R, 128, 0, st)(db, 0, ctx->d_var_class.as<u32>(), ctx->d_var_inwin.as<u8>(), ctx->d_region_dups.as<u32>());
         TFBS_LAUNCH(k_ref_prefix, R, SCAN_THREADS, 0, st)(db, 0, ctx->d_ref_prefix.as<u64>());
         TFBS_LAUNCH(k_region_keys, grid_for(R, 256), 256, 0, st)(db, n_pid, ctx->d_dwords.as<u32>());
         launches() += 3;
@@ -487,14 +500,15 @@ struct ConfigPipeline {
             fn.o_packed = slot->d_o_packed.as<u32>();
             fn.pid_list = ctx->d_pid_list.as<u16>();
             fn.max_count = &dst->max_count;
-            // one count vector per warp in shared memory (+ the list of active keys): as many warps as fit
-            const size_t max_smem = std::min<size_t>(ctx->prop.sharedMemPerBlockOptin, 200 * 1024) - FAN_KEYS * 4;
-            int warps = (int)std::min<size_t>(FAN_WARPS, max_smem / std::max<size_t>(4, (size_t)c.groups * 4));
-            if (warps < 1) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "a region has more distinct haplotypes than the fan-out kernel holds in shared memory (" +
-                                                                         std::to_string(c.groups) + "): use sample blocks");
-            const int fan_smem = (int)(FAN_KEYS * 4 + (size_t)warps * c.groups * 4);
-            CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributeMaxDynamicSharedMemorySize, fan_smem));
-            TFBS_LAUNCH(k_fanout, R, warps * 32, fan_smem, st)(db, cf, fn);
+            // one count vector per CTA in shared memory (+ the list of the keys that need it)
+            const size_t max_smem = std::min<size_t>(ctx->prop.sharedMemPerBlockOptin, 220 * 1024);
+            const size_t fan_smem = (size_t)FAN_KEYS * 4 + (size_t)c.groups * 4;
+            if (fan_smem > max_smem)
+                return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "a region has more distinct haplotypes than the fan-out kernel holds in shared memory (" +
+                                                                std::to_string(c.groups) + "): use sample blocks");
+            CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fan_smem));
+            CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+            TFBS_LAUNCH(k_fanout, R, FAN_THREADS, fan_smem, st)(db, cf, fn);
             ++launches();
             if ((rc = scan(fn.flag, n_keys, nullptr, ctx->d_rowidx.as<u64>()))) return rc;
             gate(ctx->d_rowidx.as<u64>() + n_keys, 0, c.rows, &plan->n_rows, &plan->need_rows);

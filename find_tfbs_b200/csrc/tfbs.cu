@@ -171,7 +171,6 @@ int tfbs_create(int device, tfbs_ctx** out) {
         cudaEventCreate(&s.ev_done);
         for (auto& ev : s.ev_t) cudaEventCreate(&ev);
     }
-    ctx->table_budget = 96 * 1024;
     *out = ctx;
     return TFBS_OK;
 }

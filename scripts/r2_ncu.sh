@@ -31,8 +31,10 @@ tail -3 $O/ncu_full.log
 for name in cfg1 cfg2; do
   [ -f scratch_data/$name/args.txt ] || continue
   for t in 16 64; do
-    /usr/bin/time -f "%e s wall, %M KB max RSS" -o $O/driver_${name}_t$t.time find_tfbs_b200/find-tfbs-b200 $(cat scratch_data/$name/args.txt) --output /tmp/out_$name.vcf.gz --threads $t > $O/driver_${name}_t$t.log 2>&1
-    echo "$name threads=$t: $(cat $O/driver_${name}_t$t.time | tr '\n' ' ') $(tail -3 $O/driver_${name}_t$t.log | head -2 | tr '\n' ' ')"
+    T0=$(date +%s.%N)
+    find_tfbs_b200/find-tfbs-b200 $(cat scratch_data/$name/args.txt) --output /tmp/out_$name.vcf.gz --threads $t > $O/driver_${name}_t$t.log 2>&1
+    T1=$(date +%s.%N)
+    echo "$name threads=$t: $(echo "$T1 - $T0" | bc) s wall | $(tail -3 $O/driver_${name}_t$t.log | head -2 | tr '\n' ' ')"
   done
   ls -la /tmp/out_$name.vcf.gz | awk '{print $5 " bytes"}'
 done

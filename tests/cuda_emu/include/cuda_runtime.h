@@ -306,7 +306,7 @@ struct emuEvent { std::chrono::steady_clock::time_point t; };
 typedef emuEvent* cudaEvent_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
 enum { cudaStreamNonBlocking = 1, cudaHostRegisterDefault = 0 };
-enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8, cudaFuncAttributePreferredSharedMemoryCarveout = 9 };
 struct cudaDeviceProp {
     char name[256];
     int major, minor, multiProcessorCount;

@@ -361,10 +361,9 @@ def test_config2_slice_properties():
 
 
 def test_config2_full_size_properties():
-    """BASELINE.json configs[1] at FULL size (the bench workload: 100 samples x 10,000 regions x 50 PWMs, both strands): the oracle
-    would need minutes for all of it, so the check is through properties that do not depend on size -- the two scan modes (every
-    distinct haplotype scored in full / delta scoring with shared items) must agree row for row and counter for counter, row
-    min / max and ordering must be consistent, and random slices of regions must equal the oracle's rows for those regions."""
+    """BASELINE.json configs[1] at FULL size (100 samples x 10,000 regions x 50 PWMs, both strands): the two scan modes (every distinct
+    haplotype scored in full / configurations) must agree row for row and counter for counter, row min / max and ordering must be
+    consistent, and EVERY region of the block must equal the oracle's rows (about a hundred seconds of CPU on the box's cores)."""
     import os
     scale = float(os.environ.get("TFBS_TEST_SCALE", "1.0"))  # the emulated run of this file uses a small fraction
     pats, blk = synth.config2(scale=scale)
@@ -380,15 +379,51 @@ def test_config2_full_size_properties():
     assert np.array_equal(v.min(axis=1), d["vmin"]) and np.array_equal(v.max(axis=1), d["vmax"]) and np.all(d["vmin"] != d["vmax"])
     key = d["region"].astype(np.int64) * (1 << 32) + d["pattern_id"].astype(np.int64) * (1 << 16)
     assert np.all(np.diff(key) >= 0)
-    rng = np.random.default_rng(5)
-    for r0 in rng.integers(0, max(1, blk.n_regions - 8), size=4):
-        r0 = int(r0)
-        r1 = min(blk.n_regions, r0 + 8)
-        o = hp.run_oracle(ps, blk.slice(r0, r1))
-        m = (d["region"] >= r0) & (d["region"] < r1)
-        assert int(m.sum()) == len(o["region"])
-        assert np.array_equal(d["region"][m] - r0, o["region"]) and np.array_equal(d["pattern_id"][m], o["pattern_id"])
-        assert np.array_equal(d["left"][m], o["left"]) and np.array_equal(d["right"][m], o["right"])
+    o = hp.run_oracle(ps, blk, 0, False, os.cpu_count() or 4, 50)  # the whole block, chunks of 50 regions like main.rs:378
+    hp.assert_rows_equal(d, o)
+    hp.check_stats(d["stats"], o)
+
+
+def test_config3_full_size_random_regions_vs_oracle():
+    """BASELINE.json configs[2] at FULL size (the bench workload: 2,504 samples x 4,873 merged regions x 401 PWMs on both strands) in one
+    block through the default path, rows collected GROUPED and expanded on the host: 56 regions in four random places must equal the
+    oracle's rows (the oracle needs about half a minute of one core per region), min / max / ordering must be consistent everywhere."""
+    import os
+    pats, blk = synth.config3(scale=float(os.environ.get("TFBS_TEST_SCALE", "1.0")))
+    ps = PatternSet(pats)
+    ctx = binding.Context(0)
+    try:
+        ctx.set_patterns(ps)
+        ctx.submit_block(blk)
+        g = ctx.collect_grouped()
+        st = ctx.stats()
+        assert g["n_rows"] == st["n_rows"] > 0 and g["bytes"] < 0.4e9  # the rows of the whole chromosome cross PCIe in well under 0.4 GB
+        key = g["region"].astype(np.int64) * (1 << 32) + g["pattern_id"].astype(np.int64) * (1 << 16)
+        assert np.all(np.diff(key) >= 0) and np.all(g["vmin"] != g["vmax"])
+        rng = np.random.default_rng(7)
+        picked = 0
+        for r0 in sorted(int(x) for x in rng.integers(0, max(1, blk.n_regions - 14), size=4)):
+            r1 = min(blk.n_regions, r0 + 14)
+            picked += r1 - r0
+            o = hp.run_oracle(ps, blk.slice(r0, r1), 0, False, os.cpu_count() or 4, 1)
+            rows = np.nonzero((g["region"] >= r0) & (g["region"] < r1))[0]
+            assert len(rows) == len(o["region"]) and len(rows) > 0
+            first, n = int(rows[0]), len(rows)
+            assert np.array_equal(rows, np.arange(first, first + n))
+            left = np.zeros((n, blk.n_samples), dtype=np.uint32)
+            right = np.zeros((n, blk.n_samples), dtype=np.uint32)
+            import ctypes as C
+            assert binding.lib().tfbs_expand_rows(C.byref(g["_c"]), first, n, left.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                                  right.ctypes.data_as(C.POINTER(C.c_uint32))) == 0
+            assert np.array_equal(g["region"][rows] - r0, o["region"]) and np.array_equal(g["pattern_id"][rows], o["pattern_id"])
+            assert np.array_equal(g["inner"][rows] - int(blk.inner_off[r0]), o["inner"])
+            assert np.array_equal(g["vmin"][rows], o["vmin"]) and np.array_equal(g["vmax"][rows], o["vmax"])
+            assert np.array_equal(left, o["left"]) and np.array_equal(right, o["right"])
+            v = left.astype(np.int64) + right
+            assert np.array_equal(v.min(axis=1), o["vmin"]) and np.array_equal(v.max(axis=1), o["vmax"])
+        assert picked >= 50
+    finally:
+        ctx.close()
 
 
 def test_region_sharding_on_device():

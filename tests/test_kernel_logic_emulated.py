@@ -63,7 +63,7 @@ def test_emulator_selftest(tmp_path):
 def test_parity_suite_on_emulated_kernels(emu_env):
     """Every parity case except the two large ones (minutes under emulation): rows, hit lists, groupings and counters of the
     emulated kernels equal the oracle's, in both scan modes."""
-    out = run_marked_gpu_tests(emu_env, "tests/test_gpu_parity.py", "not config2_slice and not config3_like")
+    out = run_marked_gpu_tests(emu_env, "tests/test_gpu_parity.py", "not config2_slice and not config3_like and not config3_full")
     assert "23 passed" in out or " passed" in out
 
 
