@@ -36,8 +36,8 @@ struct DevBlock {
     const u32* var_class;       // index (inside the region) of the first record with the same Diff
     const u8* var_inwin;        // region_start <= pos <= region_end (haplotype.rs:95)
     const u64* ref_prefix;      // polynomial prefix hash of every window: entry ref_off[r] + r + j = sum_{t<j} val(code_t, t) * B^t
-    // carried-record masks (NULL = not kept): haplotype h of region r owns the ceil(V_r / 32) words at mask_base[r] + h * ceil(V_r / 32),
-    // bit v = it carries record var_off[r] + v.  Written by k_signatures; they make the exact check of a group and the gather of a
+    // carried-record masks (NULL = not kept): word w of haplotype h of region r sits at mask_base[r] + w * H + h (ceil(V_r / 32) words per
+    // haplotype), bit v of the mask = it carries record var_off[r] + v.  Written by k_signatures; they make the exact check of a group and the gather of a
     // haplotype's diffs cost a few words instead of a walk over every record of the region.
     u32* hap_mask;
     const u64* mask_base;

@@ -56,7 +56,7 @@ __global__ void k_signatures(DevBlock b, u32 r0, u32 nr, u64 seed, u64* sig, u32
     u64 s = seed;
     u32 carried = 0, inw = 0;
     const u32 v0 = b.var_off[r], v1 = b.var_off[r + 1];
-    u32* mask = b.hap_mask ? b.hap_mask + b.mask_base[r] + (u64)h * ((v1 - v0 + 31) / 32) : nullptr;
+    u32* mask = b.hap_mask ? b.hap_mask + b.mask_base[r] + h : nullptr;  // word w of haplotype h sits at w * H + h: a warp writes 32 consecutive words
     u32 word = 0;
     for (u32 v = v0; v < v1; ++v) {
         if (carries(b, v, h)) {
@@ -65,7 +65,7 @@ __global__ void k_signatures(DevBlock b, u32 r0, u32 nr, u64 seed, u64* sig, u32
             inw += b.var_inwin[v];
             word |= 1u << ((v - v0) & 31);
         }
-        if (mask && (((v - v0) & 31) == 31 || v + 1 == v1)) { mask[(v - v0) >> 5] = word; word = 0; }
+        if (mask && (((v - v0) & 31) == 31 || v + 1 == v1)) { mask[(u64)((v - v0) >> 5) * b.H] = word; word = 0; }
     }
     sig[(size_t)r * b.H + h] = carried ? (mix64(s) | 1ULL) : 0ULL;
     nd_in[(size_t)r * b.H + h] = inw;
@@ -117,10 +117,9 @@ __global__ void k_group_lookup(DevBlock b, u32 r0, u32 nr, const u64* sig, const
     bool ok = ld < b.H;
     if (ok && b.hap_mask) {  // equal masks = the same records = equal lists; different masks are different lists unless the region holds duplicates
         const u32 nw = (b.var_off[r + 1] - b.var_off[r] + 31) / 32;
-        const u32* ma = b.hap_mask + b.mask_base[r] + (u64)h * nw;
-        const u32* mb = b.hap_mask + b.mask_base[r] + (u64)ld * nw;
+        const u32* mr = b.hap_mask + b.mask_base[r];
         bool same = true;
-        for (u32 w = 0; w < nw && same; ++w) same = ma[w] == mb[w];
+        for (u32 w = 0; w < nw && same; ++w) same = mr[(u64)w * b.H + h] == mr[(u64)w * b.H + ld];
         if (same) return;
         if (!b.region_dups[r]) { atomicAdd(&st->sig_collision, 1u); return; }
     }

@@ -193,9 +193,9 @@ __global__ void k_walk(DevBlock b, DevSeqs sq, u64 d_cap, DevStatus* st) {
     };
     if (h != 0xffffffffu && b.hap_mask) {  // the set bits of the leader's mask
         const u32 v0 = b.var_off[r], nw = (b.var_off[r + 1] - v0 + 31) / 32;
-        const u32* mask = b.hap_mask + b.mask_base[r] + (u64)h * nw;
+        const u32* mask = b.hap_mask + b.mask_base[r] + h;
         for (u32 w = 0; w < nw; ++w)
-            for (u32 m = mask[w]; m; m &= m - 1) {
+            for (u32 m = mask[(u64)w * b.H]; m; m &= m - 1) {
                 const u32 v = v0 + 32 * w + (u32)__ffs((int)m) - 1;
                 if (b.var_inwin[v]) take(v);
             }

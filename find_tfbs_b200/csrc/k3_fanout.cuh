@@ -39,6 +39,7 @@ struct DevFan {
     u32* o_packed;
     const u16* pid_list;
     u32* max_count;         // largest left + right of an emitted row
+    u32 hg16;               // 1 = the region's haplotype -> group map is kept in shared memory as u16
 };
 
 __device__ __forceinline__ u32 bits_for(u32 span) {  // width that holds 0..span: 0, 1, 2, 4, 8, 16 or 32
@@ -52,30 +53,47 @@ __device__ __forceinline__ u32 bits_for(u32 span) {  // width that holds 0..span
 }
 
 constexpr int FAN_THREADS = 256;
-constexpr u32 FAN_KEYS = 1024;  // keys looked at per round (the list of the ones that need the count vector lives in shared memory)
+constexpr u32 FAN_TRIPLES = 1024;  // (configuration, difference) pairs of a round of FAN_THREADS keys kept in shared memory
+constexpr u32 FAN_STAGE = 2048;    // packed row words staged in shared memory before they are copied out in one piece
+constexpr u32 FAN_STAGE_ROWS = 64;
 
-// One CTA per region.  Thread per key first: a key no hit ever touched (DevConfigs::keyflag, the large majority) or whose differences
-// all cancelled has the reference haplotype's count for everybody and is answered at once.  The remaining keys are taken one at a
-// time by the whole CTA: the count of every group is built in ONE shared-memory vector (the warps apply different configurations at
-// the same time; two configurations of different clusters can meet in a group, hence shared-memory atomics), min / max over the
-// samples are reduced, and when the key becomes a row its packed counts are written at a position drawn from an atomic cursor (the
-// payload order is arbitrary; k_row_headers numbers the rows in key order afterwards).
+struct FanPair { u32 cfg, d; };
+
+// Dynamic shared memory of k_fanout: val[groups_cap] | pairs[FAN_TRIPLES] | stage[FAN_STAGE] | hg16[H] (if DevFan::hg16)
+__host__ __device__ inline size_t fan_smem_bytes(u32 groups_cap, u32 H, bool hg16) {
+    return (size_t)groups_cap * 4 + (size_t)FAN_TRIPLES * sizeof(FanPair) + (size_t)FAN_STAGE * 4 + (hg16 ? (((size_t)H * 2 + 15) & ~(size_t)15) : 0);
+}
+
+// One CTA per region, rounds of FAN_THREADS keys.
+//  A. thread per key: a key no hit ever touched (DevConfigs::keyflag, the large majority) or whose differences all cancelled has
+//     the reference haplotype's count for everybody and is answered at once; the non-zero (configuration, difference) pairs of
+//     the other keys go to shared memory, key by key (one block scan orders them).
+//  B. the remaining keys one at a time, the whole CTA on each: the count of every group is built in ONE shared-memory vector (a warp
+//     per configuration, lanes over its member groups; two configurations of different clusters can meet in a group, hence
+//     shared-memory atomics), min / max of left + right over the samples are reduced (main.rs:441-451), and when the key becomes a
+//     row (min != max, main.rs:456-458) its packed counts are appended to a staging buffer in shared memory.  The staging buffer is
+//     copied out in one piece at a position drawn from an atomic cursor -- one global atomic per few dozen rows; the payload order
+//     is arbitrary, k_row_headers numbers the rows in key order afterwards.
 __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs cf, DevFan fn) {
     TFBS_DYNAMIC_SHARED(smem_raw);
-    __shared__ u32 s_n, s_red[4][FAN_THREADS / 32], s_bcast[4];
-    __shared__ unsigned long long s_off;
+    constexpr u32 NW = FAN_THREADS / 32;
+    __shared__ u32 s_scan[2][NW], s_red[4][NW], s_bcast[4];
+    __shared__ u32 s_hkey[FAN_THREADS], s_hfirst[FAN_THREADS], s_hcnt[FAN_THREADS];
+    __shared__ u32 s_stage_used, s_stage_rows, s_stage_key[FAN_STAGE_ROWS], s_stage_rel[FAN_STAGE_ROWS];
+    __shared__ unsigned long long s_base;
     if (cf.plan->abort) return;
     const u32 r = blockIdx.x;
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    constexpr u32 NW = FAN_THREADS / 32;
-    u32* heavy = reinterpret_cast<u32*>(smem_raw);
-    u32* val = heavy + FAN_KEYS;
     const u32 ng = (u32)(fn.gbase[r + 1] - fn.gbase[r]);
     if (ng > fn.groups_cap) {  // more distinct haplotypes than the shared-memory vector holds: the host repeats the run
         if (tid == 0) { atomicMax(&cf.plan->need_groups, ng); cf.plan->abort = 1; }
         return;
     }
     if (tid == 0) atomicMax(&cf.plan->need_groups, ng);
+    u32* val = reinterpret_cast<u32*>(smem_raw);
+    FanPair* pairs = reinterpret_cast<FanPair*>(val + fn.groups_cap);
+    u32* stage = reinterpret_cast<u32*>(pairs + FAN_TRIPLES);
+    u16* hg16 = reinterpret_cast<u16*>(stage + FAN_STAGE);
     const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
     const u32 nkeys = fn.n_pid * nk;
     const u64 kb = cf.kbase[r];
@@ -83,17 +101,37 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
     const u64 cb = cf.cfgbase[r];
     const u32* Dr = cf.D + cf.dbase[r];
     const u32* hg = fn.hap_group + (size_t)r * b.H;
+    if (fn.hg16)
+        for (u32 h = tid; h < b.H; h += FAN_THREADS) hg16[h] = (u16)hg[h];
+    if (tid == 0) { s_stage_used = 0; s_stage_rows = 0; }
     u32 row_max = 0;
-    for (u32 k0 = 0; k0 < nkeys; k0 += FAN_KEYS) {
-        if (tid == 0) s_n = 0;
+
+    // copies the staged rows out (all threads); the keys of the staged rows learn their offset
+    auto flush = [&]() {
         __syncthreads();
-        for (u32 key = k0 + tid; key < nkeys && key < k0 + FAN_KEYS; key += FAN_THREADS) {
-            bool any = false;
-            if (cf.keyflag[kb + key]) {
-                const u32* drow = Dr + (u64)key * ncfg;
-                for (u32 c = 0; c < ncfg && !any; ++c) any = drow[c] != 0;
-            }
-            if (any) { heavy[atomicAdd(&s_n, 1u)] = key; continue; }
+        const u32 used = s_stage_used, rows = s_stage_rows;
+        if (rows) {
+            if (tid == 0) s_base = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)used);
+            __syncthreads();
+            const u64 base = s_base;
+            if (base + used <= fn.words_cap)  // beyond the capacity: the gate behind this kernel raises abort
+                for (u32 w = tid; w < used; w += FAN_THREADS) fn.o_packed[base + w] = stage[w];
+            for (u32 i = tid; i < rows; i += FAN_THREADS) fn.k_off[kb + s_stage_key[i]] = base + s_stage_rel[i];
+            __syncthreads();
+            if (tid == 0) { s_stage_used = 0; s_stage_rows = 0; }
+        }
+        __syncthreads();
+    };
+
+    for (u32 k0 = 0; k0 < nkeys; k0 += FAN_THREADS) {
+        // ---- A: thread per key ----
+        const u32 key = k0 + tid;
+        u32 cnt = 0;
+        if (key < nkeys && cf.keyflag[kb + key]) {
+            const u32* drow = Dr + (u64)key * ncfg;
+            for (u32 c = 0; c < ncfg; ++c) cnt += drow[c] != 0 ? 1u : 0u;
+        }
+        if (key < nkeys && cnt == 0) {
             // every haplotype has the reference haplotype's count: a row only when every key with a hit is asked for (main.rs:517-528)
             const u32 ref = cf.C0[kb + key];
             const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING || ref == 0) ? 0u : 1u;
@@ -105,33 +143,74 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
             fn.k_off[kb + key] = 0;
             if (f) row_max = max(row_max, 2 * ref);
         }
+        // exclusive block scans: pairs before this key, heavy keys before this key
+        u32 x = cnt, y = cnt ? 1u : 0u;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 xv = __shfl_up_sync(0xffffffffu, x, o), yv = __shfl_up_sync(0xffffffffu, y, o);
+            if (lane >= (u32)o) { x += xv; y += yv; }
+        }
+        if (lane == 31) { s_scan[0][wid] = x; s_scan[1][wid] = y; }
         __syncthreads();
-        const u32 n_heavy = s_n;
-        for (u32 a = 0; a < n_heavy; ++a) {
-            const u32 key = heavy[a];
-            const u32 ref = cf.C0[kb + key];
+        u32 xoff = 0, yoff = 0, n_heavy = 0;
+        for (u32 w = 0; w < NW; ++w) {
+            if (w < wid) { xoff += s_scan[0][w]; yoff += s_scan[1][w]; }
+            n_heavy += s_scan[1][w];
+        }
+        if (cnt) {
+            const u32 first = xoff + x - cnt, hpos = yoff + y - 1;
+            s_hkey[hpos] = key;
+            s_hfirst[hpos] = first;
+            s_hcnt[hpos] = cnt;
             const u32* drow = Dr + (u64)key * ncfg;
+            u32 o = first;
+            for (u32 c = 0; c < ncfg; ++c) {
+                const u32 d = drow[c];
+                if (d) { if (o < FAN_TRIPLES) pairs[o] = FanPair{c, d}; ++o; }
+            }
+        }
+        __syncthreads();
+        // ---- B: the whole CTA per key that needs the count vector ----
+        for (u32 a = 0; a < n_heavy; ++a) {
+            const u32 hkey = s_hkey[a], first = s_hfirst[a], hcnt = s_hcnt[a];
+            const u32 ref = cf.C0[kb + hkey];
             for (u32 g = tid; g < ng; g += FAN_THREADS) val[g] = 0;
             __syncthreads();
-            for (u32 c = wid; c < ncfg; c += NW) {  // a warp per configuration, lanes over its members
-                const u32 d = drow[c];
-                if (!d) continue;
-                const u64 m0 = cf.moff[cb + c], m1 = cf.moff[cb + c + 1];
-                for (u64 m = m0 + lane; m < m1; m += 32) atomicAdd(&val[cf.members[m]], d);
+            if (first + hcnt <= FAN_TRIPLES) {
+                for (u32 j = wid; j < hcnt; j += NW) {  // a warp per configuration, lanes over its members
+                    const FanPair pr = pairs[first + j];
+                    const u64 m0 = cf.moff[cb + pr.cfg], m1 = cf.moff[cb + pr.cfg + 1];
+                    for (u64 m = m0 + lane; m < m1; m += 32) atomicAdd(&val[cf.members[m]], pr.d);
+                }
+            } else {  // more pairs in this round than shared memory holds: this key reads its row again
+                const u32* drow = Dr + (u64)hkey * ncfg;
+                for (u32 c = wid; c < ncfg; c += NW) {
+                    const u32 d = drow[c];
+                    if (!d) continue;
+                    const u64 m0 = cf.moff[cb + c], m1 = cf.moff[cb + c + 1];
+                    for (u64 m = m0 + lane; m < m1; m += 32) atomicAdd(&val[cf.members[m]], d);
+                }
             }
             __syncthreads();
-            // smallest / largest count over the groups (the packing base and width) and min / max of left + right over the samples
-            // (main.rs:441-451)
+            // smallest / largest count over the groups (the packing base and width), min / max of left + right over the samples
             u32 gmin = ref, gmax = ref, lo = 0xffffffffu, hi = 0;
             for (u32 g = tid; g < ng; g += FAN_THREADS) {
                 const u32 c = ref + val[g];
                 gmin = min(gmin, c);
                 gmax = max(gmax, c);
             }
-            for (u32 s = tid; s < b.S; s += FAN_THREADS) {
-                const u32 v = 2 * ref + val[hg[2 * s]] + val[hg[2 * s + 1]];
-                lo = min(lo, v);
-                hi = max(hi, v);
+            if (fn.hg16) {
+                for (u32 s = tid; s < b.S; s += FAN_THREADS) {
+                    const u32 v = 2 * ref + val[hg16[2 * s]] + val[hg16[2 * s + 1]];
+                    lo = min(lo, v);
+                    hi = max(hi, v);
+                }
+            } else {
+                for (u32 s = tid; s < b.S; s += FAN_THREADS) {
+                    const u32 v = 2 * ref + val[hg[2 * s]] + val[hg[2 * s + 1]];
+                    lo = min(lo, v);
+                    hi = max(hi, v);
+                }
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -142,49 +221,66 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
             }
             if (lane == 0) { s_red[0][wid] = lo; s_red[1][wid] = hi; s_red[2][wid] = gmin; s_red[3][wid] = gmax; }
             __syncthreads();
-            if (tid == 0) {
-                for (u32 w = 1; w < NW; ++w) {
-                    lo = min(lo, s_red[0][w]);
-                    hi = max(hi, s_red[1][w]);
-                    gmin = min(gmin, s_red[2][w]);
-                    gmax = max(gmax, s_red[3][w]);
-                }
-                // keys exist once a hit of any scanned haplotype touched the inner region (main.rs:517-528): hi > 0
-                const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING) ? (lo != hi ? 1u : 0u) : (hi > 0 ? 1u : 0u);
-                const u32 bits = bits_for(gmax - gmin);
-                const u32 words = (u32)(((u64)ng * bits + 31) / 32);
-                unsigned long long off = 0;
-                if (f) off = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)words);
-                fn.vmin[kb + key] = lo;
-                fn.vmax[kb + key] = hi;
-                fn.flag[kb + key] = f;
-                fn.k_base[kb + key] = gmin;
-                fn.k_bits[kb + key] = (u8)bits;
-                fn.k_off[kb + key] = off;
-                if (f) row_max = max(row_max, hi);
-                s_bcast[0] = f;
-                s_bcast[1] = bits;
-                s_bcast[2] = gmin;
-                s_bcast[3] = words;
-                s_off = off;
+            for (u32 w = 0; w < NW; ++w) {  // every thread reduces the eight partial results: no second broadcast needed
+                lo = min(lo, s_red[0][w]);
+                hi = max(hi, s_red[1][w]);
+                gmin = min(gmin, s_red[2][w]);
+                gmax = max(gmax, s_red[3][w]);
             }
-            __syncthreads();
-            const u32 bits = s_bcast[1], words = s_bcast[3];
-            if (s_bcast[0] && bits && s_off + words <= fn.words_cap) {  // beyond the capacity: the gate behind this kernel raises abort
-                const u32 per = 32 / bits, base = s_bcast[2];
-                const u64 off = s_off;
-                for (u32 w = tid; w < words; w += FAN_THREADS) {
-                    u32 word = 0;
-                    for (u32 x = 0; x < per; ++x) {
-                        const u32 g = w * per + x;
-                        if (g < ng) word |= (ref + val[g] - base) << (x * bits);
+            // keys exist once a hit of any scanned haplotype touched the inner region (main.rs:517-528): hi > 0
+            const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING) ? (lo != hi ? 1u : 0u) : (hi > 0 ? 1u : 0u);
+            const u32 bits = bits_for(gmax - gmin);
+            const u32 words = (u32)(((u64)ng * bits + 31) / 32);
+            if (tid == 0) {
+                fn.vmin[kb + hkey] = lo;
+                fn.vmax[kb + hkey] = hi;
+                fn.flag[kb + hkey] = f;
+                fn.k_base[kb + hkey] = gmin;
+                fn.k_bits[kb + hkey] = (u8)bits;
+                fn.k_off[kb + hkey] = 0;
+            }
+            if (f) row_max = max(row_max, hi);
+            if (f && bits) {
+                const u32 per = 32 / bits;
+                if (words > FAN_STAGE) {  // a row larger than the staging buffer goes out directly
+                    __syncthreads();
+                    if (tid == 0) s_base = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)words);
+                    __syncthreads();
+                    const u64 base = s_base;
+                    if (tid == 0) fn.k_off[kb + hkey] = base;
+                    if (base + words <= fn.words_cap)
+                        for (u32 w = tid; w < words; w += FAN_THREADS) {
+                            u32 word = 0;
+                            for (u32 xx = 0; xx < per; ++xx) {
+                                const u32 g = w * per + xx;
+                                if (g < ng) word |= (ref + val[g] - gmin) << (xx * bits);
+                            }
+                            fn.o_packed[base + w] = word;
+                        }
+                } else {
+                    if (s_stage_used + words > FAN_STAGE || s_stage_rows == FAN_STAGE_ROWS) flush();  // uniform: every thread reads the same counters
+                    const u32 rel = s_stage_used;
+                    for (u32 w = tid; w < words; w += FAN_THREADS) {
+                        u32 word = 0;
+                        for (u32 xx = 0; xx < per; ++xx) {
+                            const u32 g = w * per + xx;
+                            if (g < ng) word |= (ref + val[g] - gmin) << (xx * bits);
+                        }
+                        stage[rel + w] = word;
                     }
-                    fn.o_packed[off + w] = word;
+                    __syncthreads();
+                    if (tid == 0) {
+                        s_stage_key[s_stage_rows] = hkey;
+                        s_stage_rel[s_stage_rows] = rel;
+                        s_stage_rows += 1;
+                        s_stage_used = rel + words;
+                    }
                 }
             }
             __syncthreads();
         }
     }
+    flush();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) row_max = max(row_max, __shfl_xor_sync(0xffffffffu, row_max, o));
     if (lane == 0 && row_max) atomicMax(fn.max_count, row_max);

@@ -500,9 +500,10 @@ struct ConfigPipeline {
             fn.o_packed = slot->d_o_packed.as<u32>();
             fn.pid_list = ctx->d_pid_list.as<u16>();
             fn.max_count = &dst->max_count;
-            // one count vector per CTA in shared memory (+ the list of the keys that need it)
+            // one count vector per CTA in shared memory, next to the pairs of a round, the staged rows and (when it fits) the haplotype -> group map
             const size_t max_smem = std::min<size_t>(ctx->prop.sharedMemPerBlockOptin, 220 * 1024);
-            const size_t fan_smem = (size_t)FAN_KEYS * 4 + (size_t)c.groups * 4;
+            fn.hg16 = ((uint64_t)H + 1 <= 65536 && fan_smem_bytes(c.groups, H, true) <= 64 * 1024) ? 1u : 0u;
+            const size_t fan_smem = fan_smem_bytes(c.groups, H, fn.hg16 != 0);
             if (fan_smem > max_smem)
                 return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "a region has more distinct haplotypes than the fan-out kernel holds in shared memory (" +
                                                                 std::to_string(c.groups) + "): use sample blocks");

@@ -71,6 +71,7 @@ def test_driver_on_emulated_kernels(emu_env):
     """The C++ driver end to end on the CPU: the reference's two integration outputs (main.rs:548-568) and the synthetic file sets."""
     run_marked_gpu_tests(emu_env, "tests/test_driver.py", "", workers=2)
     run_marked_gpu_tests(emu_env, "tests/test_bcf_edge_cases.py", "", workers=2)
+    run_marked_gpu_tests(emu_env, "tests/test_multi_gpu.py", "", workers=2)  # two processes, shared-memory arenas; --devices 0,0
 
 
 CONTRACT_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
