@@ -401,7 +401,8 @@ def main():
            "cells": "nominal = every haplotype of every sample x every pattern; executed = distinct haplotypes only (what the reference scans); "
                     "evaluated = what k_scan scored (a patched haplotype is scored only where a window touches one of its records)",
            "rank0": {"stages_ms": stages, "groups": st["n_groups"], "hits": st["n_hits"], "rows": st["n_rows"], "scan_items": st["n_scan_items"],
-                     "groups_dropped": st["n_dropped"], "haplotypes_truncated": st["n_truncated"], "launches_per_step": st["total_launches"]},
+                     "groups_dropped": st["n_dropped"], "haplotypes_truncated": st["n_truncated"], "launches_per_step": st["total_launches"],
+                     "fanout_count_vectors": st["reserved"]},
            "roofline": roofline, "e2e": e2e, "e2e_dense_rows": e2e_dense, "sustained": sustained, "gpu_launches": launches, "clocks": clocks}
 
     ctx.close()

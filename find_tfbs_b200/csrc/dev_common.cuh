@@ -40,6 +40,8 @@ struct DevBlock {
     // haplotype), bit v of the mask = it carries record var_off[r] + v.  Written by k_signatures; they make the exact check of a group and the gather of a
     // haplotype's diffs cost a few words instead of a walk over every record of the region.
     u32* hap_mask;
+    const u32* var_row;         // carrier row of every record, contiguous (a copy of tfbs_variant::carrier_row)
+    u32* var_row_out;           // the same array, written by k_variant_prep
     const u64* mask_base;
     const u32* region_dups;     // 1 = the region holds two records with the same Diff value (equal lists may then have different masks)
 };

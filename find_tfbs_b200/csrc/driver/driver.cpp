@@ -128,21 +128,40 @@ int main(int argc, char** argv) {
     // memory in flight is a few chunks, not the chromosome.  POS is the reference's running counter (main.rs:329,424-425).
     struct ChunkText { std::vector<std::string> rows; };
     std::mutex out_mu;
+    std::condition_variable out_cv;
     std::map<size_t, ChunkText> done_chunks;
     std::vector<std::string> audit_text(o.audit_file.empty() ? 0 : n_chunks);
     size_t next_to_write = 0;
     uint64_t fake_position = 1;
     double secs_write = 0;
-    auto chunk_finished = [&](size_t c, ChunkText&& t) {
-        std::lock_guard<std::mutex> lk(out_mu);
-        done_chunks.emplace(c, std::move(t));
-        auto tw = std::chrono::steady_clock::now();
-        for (auto it = done_chunks.find(next_to_write); it != done_chunks.end(); it = done_chunks.find(next_to_write)) {
-            for (const std::string& row : it->second.rows) emit(chr + "\t" + std::to_string(fake_position++) + row);
-            done_chunks.erase(it);
-            ++next_to_write;
+    // the writer thread: takes the chunks in order, numbers the rows and feeds the BGZF writer while the workers go on
+    std::thread writer([&] {
+        for (;;) {
+            ChunkText t;
+            {
+                std::unique_lock<std::mutex> lk(out_mu);
+                out_cv.wait(lk, [&] { return next_to_write == n_chunks || done_chunks.count(next_to_write); });
+                if (next_to_write == n_chunks) return;
+                auto it = done_chunks.find(next_to_write);
+                t = std::move(it->second);
+                done_chunks.erase(it);
+            }
+            auto tw = std::chrono::steady_clock::now();
+            for (const std::string& row : t.rows) emit(chr + "\t" + std::to_string(fake_position++) + row);
+            secs_write += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw).count();
+            {
+                std::lock_guard<std::mutex> lk(out_mu);
+                ++next_to_write;
+            }
+            out_cv.notify_all();
         }
-        secs_write += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw).count();
+    });
+    // a worker hands a finished chunk over; it waits while the writer is more than a few chunks behind (bounded memory)
+    auto chunk_finished = [&](size_t c, ChunkText&& t) {
+        std::unique_lock<std::mutex> lk(out_mu);
+        out_cv.wait(lk, [&] { return c < next_to_write + 8 + 2 * o.devices.size(); });
+        done_chunks.emplace(c, std::move(t));
+        out_cv.notify_all();
     };
 
     std::atomic<size_t> next{0};
@@ -318,6 +337,7 @@ int main(int argc, char** argv) {
         for (auto& t : th) t.join();
     }
     const double t_after_gpu = since();
+    writer.join();
     if (next_to_write != n_chunks) die("internal error: " + std::to_string(n_chunks - next_to_write) + " chunks were not written");
     if (gz) { gz->finish(); delete gz; } else plain.close();
     if (!o.audit_file.empty()) {
@@ -337,7 +357,7 @@ int main(int argc, char** argv) {
     }
     double secs = since();
     printf("phases: PWM+BED %.2f s, BCF %.2f s, blocks+GPU+rows %.2f s (context %.2f, waiting for blocks %.2f, submit+collect %.2f, sort %.2f, "
-           "row text %.2f; summed over devices; VCF write %.2f of it, overlapped), closing the file %.2f s\n", t_before_bcf, t_after_bcf - t_before_bcf, t_after_gpu - t_after_bcf,
+           "row text %.2f; summed over devices), VCF writer thread %.2f s (overlapped), closing the file %.2f s\n", t_before_bcf, t_after_bcf - t_before_bcf, t_after_gpu - t_after_bcf,
            us_create / 1e6, us_wait / 1e6, us_gpu / 1e6, us_sort / 1e6, us_format / 1e6, secs_write, secs - t_after_gpu);
     printf("%zu merged regions, %llu rows, %llu hits, %.3e nominal cells in %.2f s\nEnd of program.\n", merged.size(),
            (unsigned long long)(fake_position - 1), (unsigned long long)total_hits.load(), (double)total_cells.load(), secs);

@@ -169,7 +169,7 @@ struct tfbs_ctx {
     DevBuf d_ref_codes, d_allele_codes, d_var_class, d_var_inwin, d_ref_prefix;
     DevBuf d_sig, d_nd_in, d_leader, d_hap_group, d_ngroups, d_sum_nd, d_ref_used;
     DevBuf d_keys, d_vals, d_scanwork;
-    DevBuf d_kbase, d_hap_mask, d_mask_base, d_region_dups;
+    DevBuf d_kbase, d_hap_mask, d_mask_base, d_region_dups, d_var_row;
     // distinct haplotypes ("sequences")
     DevBuf d_seq_region, d_seq_leader, d_seq_nd, d_seq_doff, d_dlist, d_segs, d_seq_nseg, d_seq_len, d_seq_hash, d_seq_flags, d_seq_ntake,
         d_seq_nitems, d_item_off, d_items, d_list, d_ent_units, d_ent_uoff, d_pk, d_nm, d_refhits, d_refcnt;
@@ -178,7 +178,7 @@ struct tfbs_ctx {
         d_cfg_net, d_mcount, d_moff, d_mfill, d_members, d_D, d_C0;
     DevBuf d_vq_region, d_vq_leader, d_vq_nd, d_vq_doff, d_vq_dlist, d_vq_segs, d_vq_nseg, d_vq_len, d_vq_flags, d_vq_ntake, d_vq_nitems,
         d_vq_item_off;
-    DevBuf d_vmin, d_vmax, d_flag, d_rowwords, d_kbits, d_keyflag, d_rowidx, d_rowoff;
+    DevBuf d_vmin, d_vmax, d_flag, d_rowwords, d_kbits, d_rowidx, d_rowoff;
     // full-scan path
     std::vector<uint32_t> h_ngroups, h_sum_nd;
     std::vector<uint64_t> h_gbase, h_cbase, h_kbase;

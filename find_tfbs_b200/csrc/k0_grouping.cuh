@@ -34,6 +34,7 @@ __global__ void k_variant_prep(DevBlock b, u32 r0, u32* var_class, u8* var_inwin
             if (same_diff(b, b.variants[u], x)) { cls = u - v0; break; }
         var_class[v] = cls;
         if (region_dups && cls != v - v0) region_dups[r] = 1;
+        if (b.var_row_out) b.var_row_out[v] = x.carrier_row;
     }
 }
 
@@ -56,16 +57,31 @@ __global__ void k_signatures(DevBlock b, u32 r0, u32 nr, u64 seed, u64* sig, u32
     u64 s = seed;
     u32 carried = 0, inw = 0;
     const u32 v0 = b.var_off[r], v1 = b.var_off[r + 1];
-    u32* mask = b.hap_mask ? b.hap_mask + b.mask_base[r] + h : nullptr;  // word w of haplotype h sits at w * H + h: a warp writes 32 consecutive words
-    u32 word = 0;
-    for (u32 v = v0; v < v1; ++v) {
-        if (carries(b, v, h)) {
-            s = mix64(s + b.var_class[v] + 1) * 0x9e3779b97f4a7c15ULL + carried;
-            ++carried;
-            inw += b.var_inwin[v];
-            word |= 1u << ((v - v0) & 31);
+    if (b.hap_mask) {
+        // first the mask, 32 records per word (the loads are the same for the 32 haplotypes of a warp: one carrier word per record),
+        // then the hash over its set bits: a haplotype carries a few records out of dozens
+        u32* mask = b.hap_mask + b.mask_base[r] + h;  // word w of haplotype h sits at w * H + h: a warp writes 32 consecutive words
+        const u32 hw = h >> 5, hb = h & 31;
+        for (u32 vb = v0, w = 0; vb < v1; vb += 32, ++w) {
+            const u32 ve = vb + 32 < v1 ? vb + 32 : v1;
+            u32 word = 0;
+            for (u32 v = vb; v < ve; ++v)
+                word |= ((b.carriers[(size_t)b.var_row[v] * b.pitch + hw] >> hb) & 1u) << (v - vb);
+            mask[(u64)w * b.H] = word;
+            for (u32 m = word; m; m &= m - 1) {
+                const u32 v = vb + (u32)__ffs((int)m) - 1;
+                s = mix64(s + b.var_class[v] + 1) * 0x9e3779b97f4a7c15ULL + carried;
+                ++carried;
+                inw += b.var_inwin[v];
+            }
         }
-        if (mask && (((v - v0) & 31) == 31 || v + 1 == v1)) { mask[(u64)((v - v0) >> 5) * b.H] = word; word = 0; }
+    } else {
+        for (u32 v = v0; v < v1; ++v)
+            if (carries(b, v, h)) {
+                s = mix64(s + b.var_class[v] + 1) * 0x9e3779b97f4a7c15ULL + carried;
+                ++carried;
+                inw += b.var_inwin[v];
+            }
     }
     sig[(size_t)r * b.H + h] = carried ? (mix64(s) | 1ULL) : 0ULL;
     nd_in[(size_t)r * b.H + h] = inw;

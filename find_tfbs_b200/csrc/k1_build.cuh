@@ -330,16 +330,38 @@ __global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32
     }
 }
 
+// cells a haplotype of `len` bases costs: sum over the patterns of max(0, len - L + 1) * L (pattern.rs:147-150)
+__device__ __forceinline__ u64 cells_of_length(u32 len, u32 max_len, u32 sum_len, u64 sum_len_sq, u32 n_patterns, const u32* pat_len) {
+    if (len >= max_len) return (u64)(len + 1) * sum_len - (sum_len_sq + sum_len);
+    u64 cells = 0;
+    for (u32 p = 0; p < n_patterns; ++p) {
+        const u32 L = pat_len[p];
+        if (L && len >= L) cells += (u64)(len - L + 1) * L;
+    }
+    return cells;
+}
+
 // hap_flags (audit only, else NULL): the flags of the haplotype's own diff list, taken before the redirect (TFBS_HAP_* bits).
-__global__ void k_redirect(u32 H, u32 r0, u32 nr, DevSeqs sq, u32* hap_group, u32* ref_used, u8* hap_flags) {
+// nominal (else NULL): the nominal cells -- every haplotype of every sample scanned on its own sequence (BASELINE.md "Unit of
+// work") -- are added up here, in the pass that visits every haplotype anyway.
+__global__ void k_redirect(u32 H, u32 r0, u32 nr, DevSeqs sq, u32* hap_group, u32* ref_used, u8* hap_flags, u64* nominal, u32 max_len,
+                           u32 sum_len, u64 sum_len_sq, u32 n_patterns, const u32* pat_len) {
     u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (u64)nr * H || (sq.abort && *sq.abort)) return;
-    u32 r = r0 + (u32)(idx / H), h = (u32)(idx % H);
-    u32 g = hap_group[(size_t)r * H + h];
-    const u8 fl = g ? sq.seq_flags[sq.gbase[r] - sq.gbase0 + g] : (u8)0;
-    if (hap_flags) hap_flags[(size_t)r * H + h] = fl;
-    if (fl & 2) { g = 0; hap_group[(size_t)r * H + h] = 0; }
-    if (g == 0) ref_used[r] = 1;
+    u64 cells = 0;
+    if (idx < (u64)nr * H && !(sq.abort && *sq.abort)) {
+        u32 r = r0 + (u32)(idx / H), h = (u32)(idx % H);
+        u32 g = hap_group[(size_t)r * H + h];
+        const u8 fl = g ? sq.seq_flags[sq.gbase[r] - sq.gbase0 + g] : (u8)0;
+        if (hap_flags) hap_flags[(size_t)r * H + h] = fl;
+        if (fl & 2) { g = 0; hap_group[(size_t)r * H + h] = 0; }
+        if (g == 0) ref_used[r] = 1;
+        if (nominal) cells = cells_of_length(sq.seq_len[sq.gbase[r] - sq.gbase0 + g], max_len, sum_len, sum_len_sq, n_patterns, pat_len);
+    }
+    if (nominal) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) cells += __shfl_xor_sync(0xffffffffu, cells, o);
+        if ((threadIdx.x & 31) == 0 && cells) atomicAdd((unsigned long long*)nominal, (unsigned long long)cells);
+    }
 }
 
 }  // namespace tfbs

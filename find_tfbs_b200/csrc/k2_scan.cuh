@@ -62,10 +62,7 @@ __device__ __noinline__ u32 scan_on_hit(u64 hit, u32 t, u32 i, u32 item_index, C
         for (u32 k = 0; k < nk; ++k) {
             i64 is = inner[k].start - region_start, ie = inner[k].end - region_start;
             bool ov = (hs >= is && hs <= ie) || (he >= is && he <= ie);  // inner.overlaps(match.range), range.rs:18-21
-            if (ov) {
-                atomicAdd(&crow[((size_t)pl * nk + k) * cstride], inner[k].multiplicity);
-                if (env->cf) env->cf->keyflag[env->cf->kbase[r] + (size_t)pl * nk + k] = 1;
-            }
+            if (ov) atomicAdd(&crow[((size_t)pl * nk + k) * cstride], inner[k].multiplicity);
         }
         if (env->mt->enabled) {
             u64 slot = atomicAdd(&st->n_matches, 1ULL);

@@ -25,6 +25,7 @@ struct DevPlan {
     u32 abort, cfg_collision;
     u64 unused;
     u64 rowwords_alloc;  // packed row words handed out by the fan-out (an atomic cursor)
+    u64 fan_keys;        // keys the fan-out built a count vector for
 };
 
 // A count becomes known: total (+ add) against the capacity its consumers were launched for.  Behind an earlier overflow nothing
@@ -77,7 +78,6 @@ struct DevConfigs {
     // counts
     u32* D;                // [region][key][configuration of the region]: difference to the reference haplotype's count (wrapping u32)
     u32* C0;               // [key] counts of the region's reference haplotype
-    u8* keyflag;           // [key] 1 once any hit or lost hit touched the key: the fan-out looks at nothing else
     DevPlan* plan;
 };
 
@@ -317,10 +317,7 @@ __global__ void k_cfg_lost(DevBlock b, DevSeqs vq, DevConfigs cf, DevRefHits rh)
         const i64 hs = h.relpos, he = hs + h.len - 1;
         for (u32 k = 0; k < nk; ++k) {
             i64 is = inner[k].start - rs, ie = inner[k].end - rs;
-            if ((hs >= is && hs <= ie) || (he >= is && he <= ie)) {
-                atomicSub(&col[((u64)h.pid * nk + k) * ncfg], inner[k].multiplicity);
-                cf.keyflag[cf.kbase[r] + (u64)h.pid * nk + k] = 1;
-            }
+            if ((hs >= is && hs <= ie) || (he >= is && he <= ie)) atomicSub(&col[((u64)h.pid * nk + k) * ncfg], inner[k].multiplicity);
         }
     }
     if (lost) atomicSub(&cf.cfg_net[c], lost);
@@ -334,24 +331,32 @@ __global__ void k_refhit_need(DevRefHits rh, u32 nr, DevPlan* plan) {
     atomicMax(&plan->need_capr, n);
 }
 
-// Members of the configurations (thread per distinct haplotype, twice: count, then fill) and the hit total of the scanned haplotypes:
-// a haplotype has the reference haplotype's hits plus the net hits of its live configurations.
+// Members of the configurations (thread per distinct haplotype, twice: count, then fill).  The fill pass also adds up the work
+// counters of the scanned haplotypes: hits (the reference haplotype's hits plus the net hits of the live configurations), executed
+// cells (pattern.rs:147-150 on the haplotype's length) and their number.
 template <bool FILL>
-__global__ void k_members(DevSeqs sq, DevConfigs cf, DevRefHits rh, const u32* ref_used, u64 d_cap, DevStatus* st) {
-    __shared__ unsigned long long s_hits;
+__global__ void k_members(DevSeqs sq, DevConfigs cf, DevRefHits rh, const u32* ref_used, u64 d_cap, DevPatterns pt, DevStatus* st) {
+    __shared__ unsigned long long s_hits, s_cells;
+    __shared__ u32 s_scanned;
     if (FILL) {
-        if (threadIdx.x == 0) s_hits = 0;
+        if (threadIdx.x == 0) { s_hits = 0; s_cells = 0; s_scanned = 0; }
         __syncthreads();
     }
     const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     long long hits = 0;
+    u64 cells = 0;
+    u32 scanned = 0;
     if (!cf.plan->abort && q < seq_count(sq)) {
         const u64 doff = sq.seq_doff[q];
         const u32 nd = sq.seq_nd[q];
         const u32 r = sq.seq_region[q];
         const u32 g = seq_group(sq, q);
         if (doff + nd <= d_cap) {
-            if (FILL && seq_is_scanned(sq, q, ref_used)) hits = (long long)min(rh.cnt[r - rh.r0], rh.capr);
+            if (FILL && seq_is_scanned(sq, q, ref_used)) {
+                hits = (long long)min(rh.cnt[r - rh.r0], rh.capr);
+                scanned = 1;
+                cells = cells_of_length(sq.seq_len[q], pt.max_len, pt.sum_len, pt.sum_len_sq, pt.n_patterns, pt.pat_len);
+            }
             for (u32 k = 0; k < nd; ++k) {
                 const u64 e = doff + k;
                 if (!cf.run_len[e]) continue;
@@ -367,10 +372,22 @@ __global__ void k_members(DevSeqs sq, DevConfigs cf, DevRefHits rh, const u32* r
     }
     if (FILL) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) hits += __shfl_xor_sync(0xffffffffu, hits, o);
-        if ((threadIdx.x & 31) == 0 && hits) atomicAdd(&s_hits, (unsigned long long)hits);
+        for (int o = 16; o > 0; o >>= 1) {
+            hits += __shfl_xor_sync(0xffffffffu, hits, o);
+            cells += __shfl_xor_sync(0xffffffffu, cells, o);
+            scanned += __shfl_xor_sync(0xffffffffu, scanned, o);
+        }
+        if ((threadIdx.x & 31) == 0) {
+            if (hits) atomicAdd(&s_hits, (unsigned long long)hits);
+            if (cells) atomicAdd(&s_cells, (unsigned long long)cells);
+            if (scanned) atomicAdd(&s_scanned, scanned);
+        }
         __syncthreads();
-        if (threadIdx.x == 0 && s_hits) atomicAdd(&st->n_hits, s_hits);
+        if (threadIdx.x == 0) {
+            if (s_hits) atomicAdd(&st->n_hits, s_hits);
+            if (s_cells) atomicAdd(&st->executed_cells, s_cells);
+            if (s_scanned) atomicAdd(&st->n_scanned, (u64)s_scanned);
+        }
     }
 }
 

@@ -53,33 +53,34 @@ __device__ __forceinline__ u32 bits_for(u32 span) {  // width that holds 0..span
 }
 
 constexpr int FAN_THREADS = 256;
-constexpr u32 FAN_TRIPLES = 1024;  // (configuration, difference) pairs of a round of FAN_THREADS keys kept in shared memory
+constexpr u32 FAN_PAIRS = 1024;    // non-zero (configuration, difference) pairs of a round of FAN_THREADS keys kept in shared memory
 constexpr u32 FAN_STAGE = 2048;    // packed row words staged in shared memory before they are copied out in one piece
 constexpr u32 FAN_STAGE_ROWS = 64;
 
-struct FanPair { u32 cfg, d; };
+struct FanPair { u32 m0, n, d; };  // members [m0, m0 + n) of the region's member list get the difference d
 
-// Dynamic shared memory of k_fanout: val[groups_cap] | pairs[FAN_TRIPLES] | stage[FAN_STAGE] | hg16[H] (if DevFan::hg16)
+// Dynamic shared memory of k_fanout: val[groups_cap] | pairs[FAN_PAIRS] | stage[FAN_STAGE] | hg16[H] (if DevFan::hg16)
 __host__ __device__ inline size_t fan_smem_bytes(u32 groups_cap, u32 H, bool hg16) {
-    return (size_t)groups_cap * 4 + (size_t)FAN_TRIPLES * sizeof(FanPair) + (size_t)FAN_STAGE * 4 + (hg16 ? (((size_t)H * 2 + 15) & ~(size_t)15) : 0);
+    return (size_t)groups_cap * 4 + (size_t)FAN_PAIRS * sizeof(FanPair) + (size_t)FAN_STAGE * 4 + (hg16 ? (((size_t)H * 2 + 15) & ~(size_t)15) : 0);
 }
 
 // One CTA per region, rounds of FAN_THREADS keys.
-//  A. thread per key: a key no hit ever touched (DevConfigs::keyflag, the large majority) or whose differences all cancelled has
-//     the reference haplotype's count for everybody and is answered at once; the non-zero (configuration, difference) pairs of
-//     the other keys go to shared memory, key by key (one block scan orders them).
+//  A. the round's slab of the difference matrix (FAN_THREADS keys x configurations) is read once, coalesced; the few non-zero
+//     entries are counted per key, one block scan gives every key its place, a second pass over the (now cached) slab files the
+//     pairs key by key into shared memory.  A key without a non-zero entry -- the large majority: no hit touched it, or what a
+//     configuration lost it found again -- has the reference haplotype's count for everybody and is answered at once.
 //  B. the remaining keys one at a time, the whole CTA on each: the count of every group is built in ONE shared-memory vector (a warp
 //     per configuration, lanes over its member groups; two configurations of different clusters can meet in a group, hence
 //     shared-memory atomics), min / max of left + right over the samples are reduced (main.rs:441-451), and when the key becomes a
-//     row (min != max, main.rs:456-458) its packed counts are appended to a staging buffer in shared memory.  The staging buffer is
-//     copied out in one piece at a position drawn from an atomic cursor -- one global atomic per few dozen rows; the payload order
-//     is arbitrary, k_row_headers numbers the rows in key order afterwards.
+//     row (min != max, main.rs:456-458) its packed counts are appended to a staging buffer in shared memory while the vector is
+//     cleared for the next key.  The staging buffer is copied out in one piece at a position drawn from an atomic cursor -- one
+//     global atomic per few dozen rows; the payload order is arbitrary, k_row_headers numbers the rows in key order afterwards.
 __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs cf, DevFan fn) {
     TFBS_DYNAMIC_SHARED(smem_raw);
     constexpr u32 NW = FAN_THREADS / 32;
-    __shared__ u32 s_scan[2][NW], s_red[4][NW], s_bcast[4];
-    __shared__ u32 s_hkey[FAN_THREADS], s_hfirst[FAN_THREADS], s_hcnt[FAN_THREADS];
-    __shared__ u32 s_stage_used, s_stage_rows, s_stage_key[FAN_STAGE_ROWS], s_stage_rel[FAN_STAGE_ROWS];
+    __shared__ u32 s_scan[2][NW], s_red[4][NW];
+    __shared__ u32 s_cnt[FAN_THREADS], s_fill[FAN_THREADS], s_hkey[FAN_THREADS], s_hfirst[FAN_THREADS], s_hcnt[FAN_THREADS], s_href[FAN_THREADS];
+    __shared__ u32 s_stage_key[FAN_STAGE_ROWS], s_stage_rel[FAN_STAGE_ROWS];
     __shared__ unsigned long long s_base;
     if (cf.plan->abort) return;
     const u32 r = blockIdx.x;
@@ -92,7 +93,7 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
     if (tid == 0) atomicMax(&cf.plan->need_groups, ng);
     u32* val = reinterpret_cast<u32*>(smem_raw);
     FanPair* pairs = reinterpret_cast<FanPair*>(val + fn.groups_cap);
-    u32* stage = reinterpret_cast<u32*>(pairs + FAN_TRIPLES);
+    u32* stage = reinterpret_cast<u32*>(pairs + FAN_PAIRS);
     u16* hg16 = reinterpret_cast<u16*>(stage + FAN_STAGE);
     const u32 nk = b.inner_off[r + 1] - b.inner_off[r];
     const u32 nkeys = fn.n_pid * nk;
@@ -101,49 +102,56 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
     const u64 cb = cf.cfgbase[r];
     const u32* Dr = cf.D + cf.dbase[r];
     const u32* hg = fn.hap_group + (size_t)r * b.H;
+    const u64 mbase = cf.moff[cb];
+    const u32* members = cf.members + mbase;
     if (fn.hg16)
         for (u32 h = tid; h < b.H; h += FAN_THREADS) hg16[h] = (u16)hg[h];
-    if (tid == 0) { s_stage_used = 0; s_stage_rows = 0; }
+    for (u32 g = tid; g < ng; g += FAN_THREADS) val[g] = 0;
     u32 row_max = 0;
+    u32 stage_used = 0, stage_rows = 0;  // the same in every thread: every decision about the staging buffer is uniform
 
     // copies the staged rows out (all threads); the keys of the staged rows learn their offset
     auto flush = [&]() {
         __syncthreads();
-        const u32 used = s_stage_used, rows = s_stage_rows;
-        if (rows) {
-            if (tid == 0) s_base = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)used);
+        if (stage_rows) {
+            if (tid == 0) s_base = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)stage_used);
             __syncthreads();
             const u64 base = s_base;
-            if (base + used <= fn.words_cap)  // beyond the capacity: the gate behind this kernel raises abort
-                for (u32 w = tid; w < used; w += FAN_THREADS) fn.o_packed[base + w] = stage[w];
-            for (u32 i = tid; i < rows; i += FAN_THREADS) fn.k_off[kb + s_stage_key[i]] = base + s_stage_rel[i];
+            if (base + stage_used <= fn.words_cap)  // beyond the capacity: the gate behind this kernel raises abort
+                for (u32 w = tid; w < stage_used; w += FAN_THREADS) fn.o_packed[base + w] = stage[w];
+            for (u32 i = tid; i < stage_rows; i += FAN_THREADS) fn.k_off[kb + s_stage_key[i]] = base + s_stage_rel[i];
             __syncthreads();
-            if (tid == 0) { s_stage_used = 0; s_stage_rows = 0; }
         }
-        __syncthreads();
+        stage_used = 0;
+        stage_rows = 0;
     };
 
     for (u32 k0 = 0; k0 < nkeys; k0 += FAN_THREADS) {
-        // ---- A: thread per key ----
+        // ---- A: the round's slab of D, coalesced ----
+        const u32 nround = nkeys - k0 < (u32)FAN_THREADS ? nkeys - k0 : (u32)FAN_THREADS;
+        const u32* slab = Dr + (u64)k0 * ncfg;
+        const u32 nwords = nround * ncfg;
+        s_cnt[tid] = 0;
+        s_fill[tid] = 0;
+        __syncthreads();
+        for (u32 i = tid; i < nwords; i += FAN_THREADS)
+            if (slab[i]) atomicAdd(&s_cnt[i / ncfg], 1u);
+        __syncthreads();
         const u32 key = k0 + tid;
-        u32 cnt = 0;
-        if (key < nkeys && cf.keyflag[kb + key]) {
-            const u32* drow = Dr + (u64)key * ncfg;
-            for (u32 c = 0; c < ncfg; ++c) cnt += drow[c] != 0 ? 1u : 0u;
-        }
-        if (key < nkeys && cnt == 0) {
+        const u32 cnt = tid < nround ? s_cnt[tid] : 0u;
+        const u32 ref_mine = tid < nround ? cf.C0[kb + key] : 0u;
+        if (tid < nround && cnt == 0) {
             // every haplotype has the reference haplotype's count: a row only when every key with a hit is asked for (main.rs:517-528)
-            const u32 ref = cf.C0[kb + key];
-            const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING || ref == 0) ? 0u : 1u;
-            fn.vmin[kb + key] = 2 * ref;
-            fn.vmax[kb + key] = 2 * ref;
+            const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING || ref_mine == 0) ? 0u : 1u;
+            fn.vmin[kb + key] = 2 * ref_mine;
+            fn.vmax[kb + key] = 2 * ref_mine;
             fn.flag[kb + key] = f;
-            fn.k_base[kb + key] = ref;
+            fn.k_base[kb + key] = ref_mine;
             fn.k_bits[kb + key] = 0;
             fn.k_off[kb + key] = 0;
-            if (f) row_max = max(row_max, 2 * ref);
+            if (f) row_max = max(row_max, 2 * ref_mine);
         }
-        // exclusive block scans: pairs before this key, heavy keys before this key
+        // exclusive block scans: pairs before this key, keys with pairs before this key
         u32 x = cnt, y = cnt ? 1u : 0u;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -157,30 +165,36 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
             if (w < wid) { xoff += s_scan[0][w]; yoff += s_scan[1][w]; }
             n_heavy += s_scan[1][w];
         }
-        if (cnt) {
-            const u32 first = xoff + x - cnt, hpos = yoff + y - 1;
-            s_hkey[hpos] = key;
-            s_hfirst[hpos] = first;
-            s_hcnt[hpos] = cnt;
-            const u32* drow = Dr + (u64)key * ncfg;
-            u32 o = first;
-            for (u32 c = 0; c < ncfg; ++c) {
-                const u32 d = drow[c];
-                if (d) { if (o < FAN_TRIPLES) pairs[o] = FanPair{c, d}; ++o; }
+        s_hfirst[tid] = 0xffffffffu;  // indexed by key here; re-indexed by heavy position below
+        __syncthreads();
+        u32 my_first = xoff + x - cnt, my_hpos = yoff + y - 1;
+        s_cnt[tid] = my_first;  // first pair of the key (indexed by key - k0), for the filing pass
+        __syncthreads();
+        for (u32 i = tid; i < nwords; i += FAN_THREADS) {
+            const u32 d = slab[i];
+            if (!d) continue;
+            const u32 kk = i / ncfg, c = i - kk * ncfg;
+            const u32 o = s_cnt[kk] + atomicAdd(&s_fill[kk], 1u);
+            if (o < FAN_PAIRS) {
+                const u64 m0 = cf.moff[cb + c], m1 = cf.moff[cb + c + 1];
+                pairs[o] = FanPair{(u32)(m0 - mbase), (u32)(m1 - m0), d};
             }
         }
+        if (cnt) {
+            s_hkey[my_hpos] = key;
+            s_hfirst[my_hpos] = my_first;
+            s_hcnt[my_hpos] = cnt;
+            s_href[my_hpos] = ref_mine;
+        }
+        if (tid == 0 && n_heavy) atomicAdd((unsigned long long*)&cf.plan->fan_keys, (unsigned long long)n_heavy);
         __syncthreads();
-        // ---- B: the whole CTA per key that needs the count vector ----
+        // ---- B: the whole CTA per key that needs the count vector (val is all zero on entry) ----
         for (u32 a = 0; a < n_heavy; ++a) {
-            const u32 hkey = s_hkey[a], first = s_hfirst[a], hcnt = s_hcnt[a];
-            const u32 ref = cf.C0[kb + hkey];
-            for (u32 g = tid; g < ng; g += FAN_THREADS) val[g] = 0;
-            __syncthreads();
-            if (first + hcnt <= FAN_TRIPLES) {
+            const u32 hkey = s_hkey[a], first = s_hfirst[a], hcnt = s_hcnt[a], ref = s_href[a];
+            if (first + hcnt <= FAN_PAIRS) {
                 for (u32 j = wid; j < hcnt; j += NW) {  // a warp per configuration, lanes over its members
                     const FanPair pr = pairs[first + j];
-                    const u64 m0 = cf.moff[cb + pr.cfg], m1 = cf.moff[cb + pr.cfg + 1];
-                    for (u64 m = m0 + lane; m < m1; m += 32) atomicAdd(&val[cf.members[m]], pr.d);
+                    for (u32 m = lane; m < pr.n; m += 32) atomicAdd(&val[members[pr.m0 + m]], pr.d);
                 }
             } else {  // more pairs in this round than shared memory holds: this key reads its row again
                 const u32* drow = Dr + (u64)hkey * ncfg;
@@ -201,7 +215,8 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
             }
             if (fn.hg16) {
                 for (u32 s = tid; s < b.S; s += FAN_THREADS) {
-                    const u32 v = 2 * ref + val[hg16[2 * s]] + val[hg16[2 * s + 1]];
+                    const u32 two = reinterpret_cast<const u32*>(hg16)[s];  // both haplotypes of the sample
+                    const u32 v = 2 * ref + val[two & 0xffffu] + val[two >> 16];
                     lo = min(lo, v);
                     hi = max(hi, v);
                 }
@@ -240,42 +255,37 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
                 fn.k_off[kb + hkey] = 0;
             }
             if (f) row_max = max(row_max, hi);
-            if (f && bits) {
-                const u32 per = 32 / bits;
-                if (words > FAN_STAGE) {  // a row larger than the staging buffer goes out directly
-                    __syncthreads();
-                    if (tid == 0) s_base = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)words);
-                    __syncthreads();
-                    const u64 base = s_base;
-                    if (tid == 0) fn.k_off[kb + hkey] = base;
-                    if (base + words <= fn.words_cap)
-                        for (u32 w = tid; w < words; w += FAN_THREADS) {
-                            u32 word = 0;
-                            for (u32 xx = 0; xx < per; ++xx) {
-                                const u32 g = w * per + xx;
-                                if (g < ng) word |= (ref + val[g] - gmin) << (xx * bits);
-                            }
-                            fn.o_packed[base + w] = word;
-                        }
-                } else {
-                    if (s_stage_used + words > FAN_STAGE || s_stage_rows == FAN_STAGE_ROWS) flush();  // uniform: every thread reads the same counters
-                    const u32 rel = s_stage_used;
-                    for (u32 w = tid; w < words; w += FAN_THREADS) {
-                        u32 word = 0;
-                        for (u32 xx = 0; xx < per; ++xx) {
-                            const u32 g = w * per + xx;
-                            if (g < ng) word |= (ref + val[g] - gmin) << (xx * bits);
-                        }
-                        stage[rel + w] = word;
+            if (f && bits && words <= FAN_STAGE) {
+                // pack the row into the staging buffer and clear the vector in the same pass
+                if (stage_used + words > FAN_STAGE || stage_rows == FAN_STAGE_ROWS) flush();
+                const u32 per = 32 / bits, rel = stage_used;
+                for (u32 w = tid; w < words; w += FAN_THREADS) {
+                    u32 word = 0;
+                    for (u32 xx = 0; xx < per; ++xx) {
+                        const u32 g = w * per + xx;
+                        if (g < ng) { word |= (ref + val[g] - gmin) << (xx * bits); val[g] = 0; }
                     }
-                    __syncthreads();
-                    if (tid == 0) {
-                        s_stage_key[s_stage_rows] = hkey;
-                        s_stage_rel[s_stage_rows] = rel;
-                        s_stage_rows += 1;
-                        s_stage_used = rel + words;
-                    }
+                    stage[rel + w] = word;
                 }
+                if (tid == 0) { s_stage_key[stage_rows] = hkey; s_stage_rel[stage_rows] = rel; }
+                stage_used = rel + words;
+                stage_rows += 1;
+            } else if (f && bits) {  // a row larger than the staging buffer goes out directly
+                const u32 per = 32 / bits;
+                if (tid == 0) s_base = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)words);
+                __syncthreads();
+                const u64 base = s_base;
+                if (tid == 0) fn.k_off[kb + hkey] = base;
+                for (u32 w = tid; w < words; w += FAN_THREADS) {
+                    u32 word = 0;
+                    for (u32 xx = 0; xx < per; ++xx) {
+                        const u32 g = w * per + xx;
+                        if (g < ng) { word |= (ref + val[g] - gmin) << (xx * bits); val[g] = 0; }
+                    }
+                    if (base + words <= fn.words_cap) fn.o_packed[base + w] = word;
+                }
+            } else {
+                for (u32 g = tid; g < ng; g += FAN_THREADS) val[g] = 0;
             }
             __syncthreads();
         }

@@ -130,6 +130,7 @@ struct ConfigPipeline {
             RS(ctx->d_hap_mask, mask_words * 4);
             RS(ctx->d_mask_base, (uint64_t)(R + 1) * 8);
             RS(ctx->d_region_dups, (uint64_t)R * 4);
+            RS(ctx->d_var_row, B.n_var * 4);
         }
         RS(ctx->d_seq_region, c.seq * 4);
         RS(ctx->d_seq_leader, c.seq * 4);
@@ -186,7 +187,6 @@ struct ConfigPipeline {
         RS(ctx->d_flag, n_keys * 4);
         RS(ctx->d_rowwords, n_keys * 4);
         RS(ctx->d_kbits, n_keys);
-        RS(ctx->d_keyflag, n_keys);
         RS(ctx->d_rowidx, (n_keys + 1) * 8);
         RS(ctx->d_rowoff, (n_keys + 1) * 8);
         RS(slot->d_o_region, c.rows * 4);
@@ -269,6 +269,7 @@ struct ConfigPipeline {
         db.hap_mask = ctx->d_hap_mask.as<u32>();
         db.mask_base = ctx->d_mask_base.as<u64>();
         db.region_dups = ctx->d_region_dups.as<u32>();
+        db.var_row = db.var_row_out = ctx->d_var_row.as<u32>();
         TFBS_LAUNCH(k_mask_words, grid_for(R, 256), 256, 0, st)(db, ctx->d_dwords.as<u32>());
         ++launches();
         if ((rc = scan(ctx->d_dwords.as<u32>(), R, nullptr, ctx->d_mask_base.as<u64>()))) return rc;
@@ -334,7 +335,8 @@ struct ConfigPipeline {
             CK(cudaMemsetAsync(ctx->d_ref_used.p, 0, (size_t)R * 4, st));
             TFBS_LAUNCH(k_seq_insert, grid_for(c.seq, 256), 256, 0, st)(sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), mask);
             TFBS_LAUNCH(k_seq_resolve, grid_for(c.seq, 128), 128, 0, st)(db, sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), mask, dst);
-            TFBS_LAUNCH(k_redirect, grid_for(RH, 256), 256, 0, st)(H, 0, R, sq, hap_group, ctx->d_ref_used.as<u32>(), (u8*)nullptr);
+            TFBS_LAUNCH(k_redirect, grid_for(RH, 256), 256, 0, st)(H, 0, R, sq, hap_group, ctx->d_ref_used.as<u32>(), (u8*)nullptr, (u64*)&dst->nominal_cells,
+                                                                   ctx->dpat.max_len, ctx->dpat.sum_len, (u64)ctx->dpat.sum_len_sq, ctx->dpat.n_patterns, ctx->dpat.pat_len);
             launches() += 3;
         }
         CK(cudaEventRecord(slot->ev_t[2], st));
@@ -362,7 +364,6 @@ struct ConfigPipeline {
         cf.members = ctx->d_members.as<u32>();
         cf.D = ctx->d_D.as<u32>();
         cf.C0 = ctx->d_C0.as<u32>();
-        cf.keyflag = ctx->d_keyflag.as<u8>();
         cf.plan = plan;
         TFBS_LAUNCH(k_cluster, R, 128, 0, st)(db, cf);
         ++launches();
@@ -434,7 +435,6 @@ struct ConfigPipeline {
         TFBS_LAUNCH(k_zero_words, slot->stats.sm_count * 8, 256, 0, st)(cf.D, &plan->n_dwords, (u64)c.dwords);
         ++launches();
         if (n_keys) CK(cudaMemsetAsync(cf.C0, 0, n_keys * 4, st));
-        if (n_keys) CK(cudaMemsetAsync(cf.keyflag, 0, n_keys, st));
         CK(cudaMemsetAsync(ctx->d_refcnt.p, 0, (size_t)R * 4, st));
         DevRefHits drh{ctx->d_refhits.as<RefHit>(), ctx->d_refcnt.as<u32>(), c.capr, 0};
         DevCounts dc{cf.C0, cf.kbase, 0};
@@ -462,14 +462,12 @@ struct ConfigPipeline {
         launches() += 2;
         CK(cudaMemsetAsync(cf.mcount, 0, c.cfg * 4, st));
         CK(cudaMemsetAsync(cf.mfill, 0, c.cfg * 4, st));
-        TFBS_LAUNCH(k_members<false>, grid_for(c.seq, 128), 128, 0, st)(sq, cf, drh, ctx->d_ref_used.as<u32>(), (u64)c.d, dst);
+        TFBS_LAUNCH(k_members<false>, grid_for(c.seq, 128), 128, 0, st)(sq, cf, drh, ctx->d_ref_used.as<u32>(), (u64)c.d, ctx->dpat, dst);
         ++launches();
         if ((rc = scan(cf.mcount, c.cfg, &plan->n_cfg, cf.moff))) return rc;
         TFBS_LAUNCH(k_gate_at, 1, 1, 0, st)(cf.moff, &plan->n_cfg, (u64)c.d, &plan->n_members, &plan->need_members, &plan->abort);
-        TFBS_LAUNCH(k_members<true>, grid_for(c.seq, 128), 128, 0, st)(sq, cf, drh, ctx->d_ref_used.as<u32>(), (u64)c.d, dst);
-        TFBS_LAUNCH(k_nominal, grid_for(RH, 256), 256, 0, st)(db, 0, R, hap_group, sq, ctx->dpat, dst);
-        TFBS_LAUNCH(k_seq_stats, grid_for(c.seq, 256), 256, 0, st)(sq, ctx->dpat, ctx->d_ref_used.as<u32>(), dst);
-        launches() += 4;
+        TFBS_LAUNCH(k_members<true>, grid_for(c.seq, 128), 128, 0, st)(sq, cf, drh, ctx->d_ref_used.as<u32>(), (u64)c.d, ctx->dpat, dst);
+        launches() += 2;
         CK(cudaEventRecord(slot->ev_t[5], st));
 
         // ---- K3: fan-out, min / max filter, grouped rows ----
@@ -623,6 +621,7 @@ struct ConfigPipeline {
         s.n_scan_items = hp.n_items;
         s.n_dropped = hs.n_dropped;
         s.n_truncated = hs.n_truncated;
+        s.reserved = (uint32_t)std::min<uint64_t>(hp.fan_keys, 0xffffffffu);
         uint64_t table_bytes = 0;
         for (const ChunkDesc& cd : ctx->cp.chunks) table_bytes += (uint64_t)cd.tbl_words * 8 * s.scan_ctas;
         s.scan_input_bytes = (R && S) ? hp.n_units * 12 * ctx->cp.chunks.size() + table_bytes : 0;

@@ -245,7 +245,8 @@ typedef struct tfbs_stats {
     float ms_scan_kernel;       /* device time of the k_scan launches alone (CUDA events around them), summed over batches */
     uint32_t n_dropped;         /* groups overwritten in the sequence-keyed map (haplotype.rs:84) */
     uint32_t n_truncated;       /* haplotypes truncated by an overlapping variant (haplotype.rs:144-149) */
-    uint32_t reserved;
+    uint32_t reserved;          /* default path: keys for which the per-group count vector had to be built (the others have the
+                                   reference haplotype's count for everybody) */
     uint64_t scan_input_bytes;  /* algorithmic HBM bytes the scan launches read: 12 B per 32 packed bases (2 bit + N mask) of every
                                    scored entry, once per pattern chunk, plus the chunk's tables once per CTA */
 } tfbs_stats;
