@@ -52,6 +52,18 @@ __device__ __forceinline__ u32 bits_for(u32 span) {  // width that holds 0..span
     return 32;
 }
 
+// Packs the counts of the 32 consecutive groups [g0, g0 + 32) held by the lanes of a warp (lane l: value v of group g0 + l, 0 behind
+// the last group) as `bits`-wide fields: they fill `bits` consecutive words starting at word g0 * bits / 32; word k of them is the OR
+// over the 32 / bits lanes whose group lives in it (REDUX), written by lane k.
+__device__ __forceinline__ void pack_32_groups(u32 v, u32 bits, u32 lane, u32* out, u32 n_out) {  // n_out: words of the row left from `out` on
+    if (bits == 32) { if (lane < n_out) out[lane] = v; return; }
+    const u32 per = 32 / bits, mine = lane / per, x = v << ((lane % per) * bits);
+    for (u32 k = 0; k < bits; ++k) {
+        const u32 word = __reduce_or_sync(0xffffffffu, mine == k ? x : 0u);
+        if (lane == k && k < n_out) out[k] = word;
+    }
+}
+
 constexpr int FAN_THREADS = 256;
 constexpr u32 FAN_PAIRS = 1024;    // non-zero (configuration, difference) pairs of a round of FAN_THREADS keys kept in shared memory
 constexpr u32 FAN_STAGE = 2048;    // packed row words staged in shared memory before they are copied out in one piece
@@ -255,34 +267,31 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
                 fn.k_off[kb + hkey] = 0;
             }
             if (f) row_max = max(row_max, hi);
+            // the row is packed a warp at a time (32 consecutive groups fill `bits` whole words) while the vector is cleared for the next key
+            const u32 ng32 = (ng + 31) & ~31u;
             if (f && bits && words <= FAN_STAGE) {
-                // pack the row into the staging buffer and clear the vector in the same pass
                 if (stage_used + words > FAN_STAGE || stage_rows == FAN_STAGE_ROWS) flush();
-                const u32 per = 32 / bits, rel = stage_used;
-                for (u32 w = tid; w < words; w += FAN_THREADS) {
-                    u32 word = 0;
-                    for (u32 xx = 0; xx < per; ++xx) {
-                        const u32 g = w * per + xx;
-                        if (g < ng) { word |= (ref + val[g] - gmin) << (xx * bits); val[g] = 0; }
-                    }
-                    stage[rel + w] = word;
+                const u32 rel = stage_used;
+                for (u32 g = tid; g < ng32; g += FAN_THREADS) {
+                    u32 v = 0;
+                    if (g < ng) { v = ref + val[g] - gmin; val[g] = 0; }
+                    const u32 w0 = (g - lane) / 32 * bits;
+                    pack_32_groups(v, bits, lane, stage + rel + w0, words - w0);
                 }
                 if (tid == 0) { s_stage_key[stage_rows] = hkey; s_stage_rel[stage_rows] = rel; }
                 stage_used = rel + words;
                 stage_rows += 1;
             } else if (f && bits) {  // a row larger than the staging buffer goes out directly
-                const u32 per = 32 / bits;
                 if (tid == 0) s_base = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)words);
                 __syncthreads();
                 const u64 base = s_base;
                 if (tid == 0) fn.k_off[kb + hkey] = base;
-                for (u32 w = tid; w < words; w += FAN_THREADS) {
-                    u32 word = 0;
-                    for (u32 xx = 0; xx < per; ++xx) {
-                        const u32 g = w * per + xx;
-                        if (g < ng) { word |= (ref + val[g] - gmin) << (xx * bits); val[g] = 0; }
-                    }
-                    if (base + words <= fn.words_cap) fn.o_packed[base + w] = word;
+                const bool fits = base + words <= fn.words_cap;
+                for (u32 g = tid; g < ng32; g += FAN_THREADS) {
+                    u32 v = 0;
+                    if (g < ng) { v = ref + val[g] - gmin; val[g] = 0; }
+                    const u32 w0 = (g - lane) / 32 * bits;
+                    if (fits) pack_32_groups(v, bits, lane, fn.o_packed + base + w0, words - w0);
                 }
             } else {
                 for (u32 g = tid; g < ng; g += FAN_THREADS) val[g] = 0;

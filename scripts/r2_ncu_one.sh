@@ -10,5 +10,5 @@ timeout 600 ncu --set full --clock-control none --import-source on -k "regex:$K"
 ncu -i $O/one.ncu-rep --page raw --csv > $O/one_raw.csv 2> /dev/null
 ncu -i $O/one.ncu-rep --page source --csv > $O/one_source.csv 2> /dev/null
 ncu -i $O/one.ncu-rep --page details > $O/one_details.txt 2> /dev/null
-rm -f $O/one.ncu-rep
+ls -la $O/one.ncu-rep
 tail -2 $O/ncu.log

@@ -274,6 +274,17 @@ inline unsigned __ballot_sync(unsigned m, int pred) {
     emu::mask_barrier_wait(m);
     return out;
 }
+inline unsigned __reduce_or_sync(unsigned m, unsigned v) {
+    emu::State& s = emu::S();
+    const unsigned w = emu::warp_id();
+    s.warp_slot[w][emu::lane_id()] = v;
+    emu::mask_barrier_wait(m);
+    unsigned out = 0;
+    for (unsigned l = 0; l < 32; ++l)
+        if (((m & s.alive_mask[w]) >> l) & 1u) out |= (unsigned)s.warp_slot[w][l];
+    emu::mask_barrier_wait(m);
+    return out;
+}
 inline unsigned __activemask() { return emu::S().alive_mask[emu::warp_id()]; }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 inline int __ffs(int x) { return __builtin_ffs(x); }
