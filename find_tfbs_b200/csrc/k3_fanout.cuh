@@ -64,9 +64,18 @@ __device__ __forceinline__ void pack_32_groups(u32 v, u32 bits, u32 lane, u32* o
     }
 }
 
-constexpr int FAN_THREADS = 256;
-constexpr u32 FAN_PAIRS = 1024;    // non-zero (configuration, difference) pairs of a round of FAN_THREADS keys kept in shared memory
-constexpr u32 FAN_STAGE = 2048;    // packed row words staged in shared memory before they are copied out in one piece
+#ifndef TFBS_FAN_THREADS
+#define TFBS_FAN_THREADS 512   /* measured on configs[2]: 128 -> 8.7 ms, 256 -> 7.3 ms, 512 -> 6.7 ms for the count stage */
+#endif
+#ifndef TFBS_FAN_PAIRS
+#define TFBS_FAN_PAIRS 1024
+#endif
+#ifndef TFBS_FAN_STAGE
+#define TFBS_FAN_STAGE 2048
+#endif
+constexpr int FAN_THREADS = TFBS_FAN_THREADS;
+constexpr u32 FAN_PAIRS = TFBS_FAN_PAIRS;    // non-zero (configuration, difference) pairs of a round of FAN_THREADS keys kept in shared memory
+constexpr u32 FAN_STAGE = TFBS_FAN_STAGE;    // packed row words staged in shared memory before they are copied out in one piece
 constexpr u32 FAN_STAGE_ROWS = 64;
 
 struct FanPair { u32 m0, n, d; };  // members [m0, m0 + n) of the region's member list get the difference d
