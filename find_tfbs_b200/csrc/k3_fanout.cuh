@@ -65,27 +65,31 @@ __device__ __forceinline__ void pack_32_groups(u32 v, u32 bits, u32 lane, u32* o
 }
 
 #ifndef TFBS_FAN_THREADS
-#define TFBS_FAN_THREADS 512   /* measured on configs[2]: 128 -> 8.7 ms, 256 -> 7.3 ms, 512 -> 6.7 ms for the count stage */
+#define TFBS_FAN_THREADS 256
 #endif
 #ifndef TFBS_FAN_PAIRS
-#define TFBS_FAN_PAIRS 1024
+#define TFBS_FAN_PAIRS 512
 #endif
 #ifndef TFBS_FAN_STAGE
-#define TFBS_FAN_STAGE 2048
+#define TFBS_FAN_STAGE 1024
 #endif
 constexpr int FAN_THREADS = TFBS_FAN_THREADS;
 constexpr u32 FAN_PAIRS = TFBS_FAN_PAIRS;    // non-zero (configuration, difference) pairs of a round of FAN_THREADS keys kept in shared memory
 constexpr u32 FAN_STAGE = TFBS_FAN_STAGE;    // packed row words staged in shared memory before they are copied out in one piece
-constexpr u32 FAN_STAGE_ROWS = 64;
+constexpr u32 FAN_STAGE_ROWS = 32;
+#ifndef TFBS_FAN_SPLIT
+#define TFBS_FAN_SPLIT 4
+#endif
+constexpr u32 FAN_SPLIT = TFBS_FAN_SPLIT;      // CTAs per region: CTA j takes the rounds j, j + FAN_SPLIT, ... of FAN_THREADS keys
 
-struct FanPair { u32 m0, n, d; };  // members [m0, m0 + n) of the region's member list get the difference d
+struct FanPair { u32 m0, n, d, cum; };  // members [m0, m0 + n) of the region's member list get the difference d; cum = members of the key's earlier pairs
 
 // Dynamic shared memory of k_fanout: val[groups_cap] | pairs[FAN_PAIRS] | stage[FAN_STAGE] | hg16[H] (if DevFan::hg16)
 __host__ __device__ inline size_t fan_smem_bytes(u32 groups_cap, u32 H, bool hg16) {
     return (size_t)groups_cap * 4 + (size_t)FAN_PAIRS * sizeof(FanPair) + (size_t)FAN_STAGE * 4 + (hg16 ? (((size_t)H * 2 + 15) & ~(size_t)15) : 0);
 }
 
-// One CTA per region, rounds of FAN_THREADS keys.
+// FAN_SPLIT CTAs per region, each takes every FAN_SPLIT-th round of FAN_THREADS keys.
 //  A. the round's slab of the difference matrix (FAN_THREADS keys x configurations) is read once, coalesced; the few non-zero
 //     entries are counted per key, one block scan gives every key its place, a second pass over the (now cached) slab files the
 //     pairs key by key into shared memory.  A key without a non-zero entry -- the large majority: no hit touched it, or what a
@@ -99,13 +103,14 @@ __host__ __device__ inline size_t fan_smem_bytes(u32 groups_cap, u32 H, bool hg1
 __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs cf, DevFan fn) {
     TFBS_DYNAMIC_SHARED(smem_raw);
     constexpr u32 NW = FAN_THREADS / 32;
-    __shared__ u32 s_scan[2][NW], s_red[4][NW];
-    __shared__ u32 s_cnt[FAN_THREADS], s_fill[FAN_THREADS], s_hkey[FAN_THREADS], s_hfirst[FAN_THREADS], s_hcnt[FAN_THREADS], s_href[FAN_THREADS];
+    __shared__ u32 s_scan[2][NW], s_red[4][NW], s_fin[4];
+    __shared__ u32 s_cnt[FAN_THREADS], s_fill[FAN_THREADS], s_hkey[FAN_THREADS], s_hfirst[FAN_THREADS], s_hcnt[FAN_THREADS], s_href[FAN_THREADS], s_htot[FAN_THREADS];
     __shared__ u32 s_stage_key[FAN_STAGE_ROWS], s_stage_rel[FAN_STAGE_ROWS];
     __shared__ unsigned long long s_base;
     if (cf.plan->abort) return;
     const u32 r = blockIdx.x;
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if ((u64)blockIdx.y * FAN_THREADS >= (u64)fn.n_pid * (b.inner_off[r + 1] - b.inner_off[r])) return;  // no round for this CTA
     const u32 ng = (u32)(fn.gbase[r + 1] - fn.gbase[r]);
     if (ng > fn.groups_cap) {  // more distinct haplotypes than the shared-memory vector holds: the host repeats the run
         if (tid == 0) { atomicMax(&cf.plan->need_groups, ng); cf.plan->abort = 1; }
@@ -147,7 +152,7 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
         stage_rows = 0;
     };
 
-    for (u32 k0 = 0; k0 < nkeys; k0 += FAN_THREADS) {
+    for (u32 k0 = blockIdx.y * FAN_THREADS; k0 < nkeys; k0 += FAN_SPLIT * FAN_THREADS) {
         // ---- A: the round's slab of D, coalesced ----
         const u32 nround = nkeys - k0 < (u32)FAN_THREADS ? nkeys - k0 : (u32)FAN_THREADS;
         const u32* slab = Dr + (u64)k0 * ncfg;
@@ -198,7 +203,7 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
             const u32 o = s_cnt[kk] + atomicAdd(&s_fill[kk], 1u);
             if (o < FAN_PAIRS) {
                 const u64 m0 = cf.moff[cb + c], m1 = cf.moff[cb + c + 1];
-                pairs[o] = FanPair{(u32)(m0 - mbase), (u32)(m1 - m0), d};
+                pairs[o] = FanPair{(u32)(m0 - mbase), (u32)(m1 - m0), d, 0u};
             }
         }
         if (cnt) {
@@ -209,13 +214,26 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
         }
         if (tid == 0 && n_heavy) atomicAdd((unsigned long long*)&cf.plan->fan_keys, (unsigned long long)n_heavy);
         __syncthreads();
+        if (tid < n_heavy && s_hfirst[tid] + s_hcnt[tid] <= FAN_PAIRS) {  // members before every pair of the key: the scatter below is flat
+            u32 cum = 0;
+            for (u32 j = 0; j < s_hcnt[tid]; ++j) {
+                pairs[s_hfirst[tid] + j].cum = cum;
+                cum += pairs[s_hfirst[tid] + j].n;
+            }
+            s_htot[tid] = cum;
+        }
+        __syncthreads();
         // ---- B: the whole CTA per key that needs the count vector (val is all zero on entry) ----
         for (u32 a = 0; a < n_heavy; ++a) {
             const u32 hkey = s_hkey[a], first = s_hfirst[a], hcnt = s_hcnt[a], ref = s_href[a];
             if (first + hcnt <= FAN_PAIRS) {
-                for (u32 j = wid; j < hcnt; j += NW) {  // a warp per configuration, lanes over its members
+                // a thread per (configuration, member group) of the key: two configurations of different clusters can meet in a group
+                const u32 tot = s_htot[a];
+                for (u32 x = tid; x < tot; x += FAN_THREADS) {
+                    u32 j = 0;
+                    while (j + 1 < hcnt && pairs[first + j + 1].cum <= x) ++j;
                     const FanPair pr = pairs[first + j];
-                    for (u32 m = lane; m < pr.n; m += 32) atomicAdd(&val[members[pr.m0 + m]], pr.d);
+                    atomicAdd(&val[members[pr.m0 + (x - pr.cum)]], pr.d);
                 }
             } else {  // more pairs in this round than shared memory holds: this key reads its row again
                 const u32* drow = Dr + (u64)hkey * ncfg;
@@ -257,12 +275,25 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
             }
             if (lane == 0) { s_red[0][wid] = lo; s_red[1][wid] = hi; s_red[2][wid] = gmin; s_red[3][wid] = gmax; }
             __syncthreads();
-            for (u32 w = 0; w < NW; ++w) {  // every thread reduces the eight partial results: no second broadcast needed
-                lo = min(lo, s_red[0][w]);
-                hi = max(hi, s_red[1][w]);
-                gmin = min(gmin, s_red[2][w]);
-                gmax = max(gmax, s_red[3][w]);
+            if (wid == 0) {  // the first warp reduces the partial results of the warps and publishes the four values
+                lo = lane < NW ? s_red[0][lane] : 0xffffffffu;
+                hi = lane < NW ? s_red[1][lane] : 0u;
+                gmin = lane < NW ? s_red[2][lane] : 0xffffffffu;
+                gmax = lane < NW ? s_red[3][lane] : 0u;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+                    hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+                    gmin = min(gmin, __shfl_xor_sync(0xffffffffu, gmin, o));
+                    gmax = max(gmax, __shfl_xor_sync(0xffffffffu, gmax, o));
+                }
+                if (lane == 0) { s_fin[0] = lo; s_fin[1] = hi; s_fin[2] = gmin; s_fin[3] = gmax; }
             }
+            __syncthreads();
+            lo = s_fin[0];
+            hi = s_fin[1];
+            gmin = s_fin[2];
+            gmax = s_fin[3];
             // keys exist once a hit of any scanned haplotype touched the inner region (main.rs:517-528): hi > 0
             const u32 f = (fn.rows_mode == TFBS_ROWS_VARYING) ? (lo != hi ? 1u : 0u) : (hi > 0 ? 1u : 0u);
             const u32 bits = bits_for(gmax - gmin);

@@ -507,7 +507,7 @@ struct ConfigPipeline {
                                                                 std::to_string(c.groups) + "): use sample blocks");
             CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fan_smem));
             CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            TFBS_LAUNCH(k_fanout, R, FAN_THREADS, fan_smem, st)(db, cf, fn);
+            TFBS_LAUNCH(k_fanout, dim3(R, FAN_SPLIT), FAN_THREADS, fan_smem, st)(db, cf, fn);
             ++launches();
             if ((rc = scan(fn.flag, n_keys, nullptr, ctx->d_rowidx.as<u64>()))) return rc;
             gate(ctx->d_rowidx.as<u64>() + n_keys, 0, c.rows, &plan->n_rows, &plan->need_rows);
