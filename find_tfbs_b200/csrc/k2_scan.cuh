@@ -143,8 +143,12 @@ __global__ void __launch_bounds__(SCAN_CTA, 1)
         if (tid < cd.n_runs && tid < MAX_RUNS) cs->runs[tid] = pt.runs[cd.run_off + tid];
         if (tid == 0) {
             cs->n_runs = cd.n_runs;
-            cs->per_grab = per_grab;
-            cs->n_list = *n_list_ptr;
+            // entries per trip to the work counter: `per_grab` when the list is long, fewer when every warp would otherwise get only
+            // one or two trips (a short list, e.g. one rank's shard of a strong-scaled block): the last trips decide the tail
+            const u64 n_list = *n_list_ptr;
+            const u64 per_warp = n_list / ((u64)gridDim.x * SCAN_WARPS * 6) + 1;
+            cs->per_grab = per_warp < per_grab ? (u32)per_warp : per_grab;
+            cs->n_list = n_list;
         }
     }
     __syncthreads();
