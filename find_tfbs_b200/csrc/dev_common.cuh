@@ -12,7 +12,7 @@ namespace tfbs {
 // One output segment of a patched haplotype: bases [out_start, next.out_start) come either from the
 // reference window (kind 0: window index src, ref position region_start + relpos + k) or from an ALT
 // allele (kind 1: allele_codes[src + k], every base at region_start + relpos, haplotype.rs:130-132).
-struct Seg {
+struct __align__(16) Seg {  // one 128-bit load / store
     u32 out_start;
     u32 src;
     int relpos;

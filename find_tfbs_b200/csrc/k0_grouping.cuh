@@ -107,27 +107,31 @@ __device__ __forceinline__ u32 table_find(const u64* keys, u32 mask, u64 key) {
 
 __device__ __forceinline__ u64 region_key(u64 h, u32 r) { return mix64(h ^ ((u64)(r + 1) * 0xd6e8feb86659fd93ULL)) | 1ULL; }
 
-__global__ void k_group_insert(u32 H, u32 r0, u32 nr, const u64* sig, u64* keys, u32* vals, u32 mask) {
+// seg > 0: the table is cut into one segment of `seg` slots (a power of two >= 2 * H) per region of the batch, so that the slots a
+// region touches stay in L2 while its haplotypes are inserted and looked up; seg == 0: one table of mask + 1 slots for the batch.
+__global__ void k_group_insert(u32 H, u32 r0, u32 nr, const u64* sig, u64* keys, u32* vals, u32 mask, u32 seg) {
     u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (u64)nr * H) return;
     u32 r = r0 + (u32)(idx / H), h = (u32)(idx % H);
     u64 s = sig[(size_t)r * H + h];
     if (!s) return;
-    u32 slot = table_find_or_insert(keys, mask, region_key(s, r));
-    atomicMin(&vals[slot], h);
+    const u64 base = seg ? (u64)(r - r0) * seg : 0;
+    u32 slot = table_find_or_insert(keys + base, seg ? seg - 1 : mask, region_key(s, r));
+    atomicMin(&vals[base + slot], h);
 }
 
 // leader[r,h] = smallest haplotype with the same signature; the class lists are compared exactly so
 // that a hash collision is detected (and retried with another seed) instead of merging two groups.
-__global__ void k_group_lookup(DevBlock b, u32 r0, u32 nr, const u64* sig, const u64* keys, const u32* vals, u32 mask, u32* leader,
+__global__ void k_group_lookup(DevBlock b, u32 r0, u32 nr, const u64* sig, const u64* keys, const u32* vals, u32 mask, u32 seg, u32* leader,
                                DevStatus* st) {
     u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (u64)nr * b.H) return;
     u32 r = r0 + (u32)(idx / b.H), h = (u32)(idx % b.H);
     u64 s = sig[(size_t)r * b.H + h];
     if (!s) { leader[(size_t)r * b.H + h] = 0xffffffffu; return; }
-    u32 slot = table_find(keys, mask, region_key(s, r));
-    u32 ld = vals[slot];
+    const u64 base = seg ? (u64)(r - r0) * seg : 0;
+    u32 slot = table_find(keys + base, seg ? seg - 1 : mask, region_key(s, r));
+    u32 ld = vals[base + slot];
     leader[(size_t)r * b.H + h] = ld;
     if (ld == h) return;
     bool ok = ld < b.H;

@@ -13,7 +13,7 @@ namespace tfbs {
 
 // Window starts [p0, p1] of sequence q.  With delta scoring only the windows that touch a variant are scored for a patched
 // haplotype; every other window is identical (bases and positions) to a window of the reference haplotype.
-struct ScanItem {
+struct __align__(16) ScanItem {
     u32 q, p0, p1;
     u32 index;   // its own index in the work list
 };
@@ -261,14 +261,15 @@ __device__ __forceinline__ u32 seq_group(const DevSeqs& sq, u32 q) {  // group i
     return (u32)((u64)q + sq.gbase0 - sq.gbase[sq.seq_region[q]]);
 }
 
-__global__ void k_seq_insert(DevSeqs sq, u64* keys, u32* vals, u32 mask) {
+__global__ void k_seq_insert(DevSeqs sq, u64* keys, u32* vals, u32 mask, u32 seg, u32 r0) {  // seg, r0: see k_group_insert
     u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= seq_count(sq)) return;
     u32 g = seq_group(sq, q);
     if (g == 0) return;  // the reference haplotype is not in the map (main.rs:129-147)
     u64 key = region_key(sq.seq_hash[q] + mix64(sq.seq_len[q]), sq.seq_region[q]);
-    u32 slot = table_find_or_insert(keys, mask, key);
-    atomicMin(&vals[slot], g);
+    const u64 base = seg ? (u64)(sq.seq_region[q] - r0) * seg : 0;
+    u32 slot = table_find_or_insert(keys + base, seg ? seg - 1 : mask, key);
+    atomicMin(&vals[base + slot], g);
 }
 
 __device__ __forceinline__ void base_at(const DevBlock& b, const DevSeqs& sq, u32 q, u32 i, u8* c, int* rel) {
@@ -283,14 +284,15 @@ __device__ __forceinline__ void base_at(const DevBlock& b, const DevSeqs& sq, u3
 // A later insert with an equal key overwrites the earlier one in the reference (haplotype.rs:84); the
 // winner there depends on HashMap order, here the group with the smallest first haplotype wins (same rule
 // as the oracle).  The losers are dropped: their haplotypes stay in the reference set (main.rs:103-105).
-__global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32* vals, u32 mask, DevStatus* st) {
+__global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32* vals, u32 mask, u32 seg, u32 r0, DevStatus* st) {
     u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= seq_count(sq)) return;
     u32 g = seq_group(sq, q);
     if (g == 0) return;
     u64 key = region_key(sq.seq_hash[q] + mix64(sq.seq_len[q]), sq.seq_region[q]);
-    u32 slot = table_find(keys, mask, key);
-    u32 w = vals[slot];
+    const u64 base = seg ? (u64)(sq.seq_region[q] - r0) * seg : 0;
+    u32 slot = table_find(keys + base, seg ? seg - 1 : mask, key);
+    u32 w = vals[base + slot];
     if (w == g) return;
     u32 qw = q - g + w;
     bool same = sq.seq_len[qw] == sq.seq_len[q] && sq.seq_region[qw] == sq.seq_region[q];

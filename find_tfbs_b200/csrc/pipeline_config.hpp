@@ -101,8 +101,10 @@ struct ConfigPipeline {
     }
     uint64_t scratch_bytes_needed() const {
         const Caps& c = slot->caps;
-        uint64_t tbl = 1024;
-        while (tbl < 2 * std::max<uint64_t>(std::max<uint64_t>(c.seq, c.d), std::min<uint64_t>(RH, 1ull << 25))) tbl <<= 1;
+        uint64_t tbl = 1024, seg = 64;
+        while (tbl < 2 * c.d) tbl <<= 1;
+        while (seg < 2 * ((uint64_t)H + 1)) seg <<= 1;
+        tbl = std::max<uint64_t>(tbl, (uint64_t)R * seg);
         return RH * 20 + tbl * 12 + c.seq * 50 + c.d * (4 + 32 + 20 + 4) + c.seq * 32 + c.cfg * 32 + (R + c.cfg) * 60 + c.vd * 36 + c.items * 28 +
                c.units * 12 + c.dwords * 4 + n_keys * 36 + (uint64_t)c.capr * R * sizeof(RefHit) + c.rows * 34 + c.rowwords * 4;
     }
@@ -204,7 +206,15 @@ struct ConfigPipeline {
         return TFBS_OK;
     }
 
-    int table(uint64_t entries, uint32_t* mask) {  // the shared open-addressing table, emptied
+    int table_slots(uint64_t slots) {  // the shared open-addressing table with room for `slots` slots, emptied
+        int rc;
+        if ((rc = grow(ctx, ctx->d_keys, slots * 8))) return rc;
+        if ((rc = grow(ctx, ctx->d_vals, slots * 4))) return rc;
+        CK(cudaMemsetAsync(ctx->d_keys.p, 0, slots * 8, st));
+        CK(cudaMemsetAsync(ctx->d_vals.p, 0xff, slots * 4, st));
+        return TFBS_OK;
+    }
+    int table(uint64_t entries, uint32_t* mask) {  // the same as one table of a power-of-two number of slots >= 2 * entries
         uint64_t cap = 1024;
         while (cap < 2 * entries) cap <<= 1;
         if (cap > (1ull << 31)) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "block too large for the grouping table: submit fewer regions at a time");
@@ -281,17 +291,19 @@ struct ConfigPipeline {
 
         // ---- K0: grouping by Vec<Diff> (haplotype.rs:65-75) ----
         u32* hap_group = slot->d_hap_group.as<u32>();
+        // the tables of K0 and of the sequence-keyed map: one segment of `seg` slots per region (L2-resident while the region is worked on)
+        uint32_t seg = 64;
+        while (seg < 2 * ((uint64_t)H + 1)) seg <<= 1;
         {
             const uint64_t max_pairs = 1ull << 25;
             const uint32_t regions_per_super = (uint32_t)std::max<uint64_t>(1, max_pairs / std::max<uint32_t>(1, H));
             for (uint32_t r0 = 0; r0 < R; r0 += regions_per_super) {
                 const uint32_t nr = std::min(regions_per_super, R - r0);
                 const uint64_t pairs = (uint64_t)nr * H;
-                uint32_t mask;
-                if ((rc = table(pairs, &mask))) return rc;
+                if ((rc = table_slots((uint64_t)nr * seg))) return rc;
                 TFBS_LAUNCH(k_signatures, grid_for(pairs, 256), 256, 0, st)(db, r0, nr, slot->seed, ctx->d_sig.as<u64>(), ctx->d_nd_in.as<u32>());
-                TFBS_LAUNCH(k_group_insert, grid_for(pairs, 256), 256, 0, st)(H, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), mask);
-                TFBS_LAUNCH(k_group_lookup, grid_for(pairs, 256), 256, 0, st)(db, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), mask,
+                TFBS_LAUNCH(k_group_insert, grid_for(pairs, 256), 256, 0, st)(H, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), 0u, seg);
+                TFBS_LAUNCH(k_group_lookup, grid_for(pairs, 256), 256, 0, st)(db, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), 0u, seg,
                                                                      ctx->d_leader.as<u32>(), dst);
                 TFBS_LAUNCH(k_group_rank, nr, 256, 0, st)(H, r0, ctx->d_leader.as<u32>(), ctx->d_nd_in.as<u32>(), hap_group, ctx->d_ngroups.as<u32>(),
                                                  ctx->d_sum_nd.as<u32>());
@@ -330,11 +342,10 @@ struct ConfigPipeline {
         TFBS_LAUNCH(k_walk, grid_for(c.seq, 128), 128, 0, st)(db, sq, (u64)c.d, dst);
         ++launches();
         {
-            uint32_t mask;
-            if ((rc = table(c.seq, &mask))) return rc;
+            if ((rc = table_slots((uint64_t)R * seg))) return rc;  // at most H + 1 distinct haplotypes per region
             CK(cudaMemsetAsync(ctx->d_ref_used.p, 0, (size_t)R * 4, st));
-            TFBS_LAUNCH(k_seq_insert, grid_for(c.seq, 256), 256, 0, st)(sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), mask);
-            TFBS_LAUNCH(k_seq_resolve, grid_for(c.seq, 128), 128, 0, st)(db, sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), mask, dst);
+            TFBS_LAUNCH(k_seq_insert, grid_for(c.seq, 256), 256, 0, st)(sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), 0u, seg, 0u);
+            TFBS_LAUNCH(k_seq_resolve, grid_for(c.seq, 128), 128, 0, st)(db, sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), 0u, seg, 0u, dst);
             TFBS_LAUNCH(k_redirect, grid_for(RH, 256), 256, 0, st)(H, 0, R, sq, hap_group, ctx->d_ref_used.as<u32>(), (u8*)nullptr, (u64*)&dst->nominal_cells,
                                                                    ctx->dpat.max_len, ctx->dpat.sum_len, (u64)ctx->dpat.sum_len_sq, ctx->dpat.n_patterns, ctx->dpat.pat_len);
             launches() += 3;
