@@ -159,6 +159,18 @@ def cpu_reference_rate(ps, blk, seconds, threads):
                       (n, blk.n_regions, 100.0 * n / max(1, blk.n_regions), blk.n_samples, threads, chunk)}
 
 
+def measured_traffic(workload, scale):
+    """DRAM bytes of the k_scan launches of one step, from the committed `ncu --set full` capture of this workload at full scale
+    (profiles/k_scan_traffic.json; not a live number).  None for any other workload or scale."""
+    p = os.path.join(ROOT, "profiles", "k_scan_traffic.json")
+    if scale != 1.0 or not os.path.exists(p):
+        return None, None
+    t = json.load(open(p)).get(workload)
+    if not t:
+        return None, None
+    return t["dram_bytes_per_step"], "profiles/k_scan_traffic.json: " + t["source"]
+
+
 def roofline_object(st, scan_ms, clocks, pk, traffic=None, traffic_source=None):
     scan_s = scan_ms * 1e-3
     achieved = st["evaluated_cells"] / scan_s
@@ -391,7 +403,7 @@ def main():
             ctx.close()
             return
 
-    roofline = roofline_object(st, scan_ms, clocks, pk)
+    roofline = roofline_object(st, scan_ms, clocks, pk, *(measured_traffic(args.workload, args.scale) if world == 1 else (None, None)))
     if full_scan:
         roofline["full_scan"] = full_scan
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -485,7 +497,7 @@ def secondary_configs1(args, binding, sharding, device, pk):
     ms_e2e = timed(lambda: pipelined(lambda: ctx.submit_block(blk), steps)) / steps
     st2 = ctx.stats()
     blk.unpin()
-    roof = roofline_object(st, sum(scan_ms) / len(scan_ms), None, pk)
+    roof = roofline_object(st, sum(scan_ms) / len(scan_ms), None, pk, *measured_traffic("configs1", args.scale))
     if not args.no_full_scan:
         roof["full_scan"] = full_scan_roofline(ctx, blk, pk, None)
     ctx.close()

@@ -53,8 +53,26 @@ def one_case(seed):
         opts["rows_width"] = 0
     if rng.random() < 0.2:
         opts["scan_format"] = 1
+    if rng.random() < 0.25:
+        opts["tiny_caps"] = 1  # the sync-free pipeline starts with minimal scratch: every capacity overflows once
     ps = binding.PatternSet(pats)
-    hp.check_parity(ps, blk, rows_mode=int(rng.integers(0, 2)), options=opts, resident=bool(rng.integers(0, 2)))
+    mode = int(rng.integers(0, 2))
+    hp.check_parity(ps, blk, rows_mode=mode, options=opts, resident=bool(rng.integers(0, 2)))
+    if rng.random() < 0.4:  # grouped rows, two blocks in flight, expanded on the host
+        ctx = binding.Context(0)
+        try:
+            ctx.set_option("rows_mode", mode)
+            for k, v in opts.items():
+                ctx.set_option(k, v)
+            ctx.set_patterns(ps)
+            h = max(1, blk.n_regions // 2)
+            parts = [blk.slice(0, h, compact=bool(rng.integers(0, 2))), blk.slice(h, blk.n_regions, compact=bool(rng.integers(0, 2)))]
+            for b in parts:
+                ctx.submit_block(b)
+            for b in parts:
+                hp.assert_rows_equal(ctx.collect_grouped(expand=True), hp.run_oracle(ps, b, mode, False))
+        finally:
+            ctx.close()
     if rng.random() < 0.3 and all(p.get("weights") is not None for p in pats):  # the audit: ties and per-haplotype flags
         oa = hp.oracle_audit(ps, blk)
         au, rows, _ = hp.gpu_audit(ps, blk)
