@@ -78,7 +78,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -305,7 +305,9 @@ def main():
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    pipelined(ctx, run, coll, max(2, args.warmup))  # the first block sizes the scratch (it may be repeated once or twice); then steady state
+    # the first two blocks size the scratch (each may be repeated once or twice); the third is the first one enqueued with the
+    # capacities the device asked for (new shared-memory sizes, buffers): steady state starts with the fourth
+    pipelined(ctx, run, coll, max(4, args.warmup))
     ms_total = timed(ctx, stream, lambda: pipelined(ctx, run, coll, args.steps))
     st = ctx.stats()
     launches = st["total_launches"] * args.steps
@@ -483,7 +485,7 @@ def secondary_configs1(args, binding, sharding, device, pk):
         ctx.collect_grouped()
 
     ctx.upload_block(blk)
-    pipelined(ctx.run_resident, 4)
+    pipelined(ctx.run_resident, 5)
     ms_step = timed(lambda: pipelined(ctx.run_resident, steps)) / steps
     st = ctx.stats()
     scan_ms = []

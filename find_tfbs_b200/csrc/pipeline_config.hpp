@@ -570,6 +570,13 @@ struct ConfigPipeline {
             }
             // repeat the block: a hash collision with another seed, an overflow with the capacities the device asked for
             if (++slot->attempts > 16) return fail(ctx, TFBS_ERR_INTERNAL, "the block did not fit after 16 attempts to grow the scratch");
+            if (getenv("TFBS_DEBUG"))
+                fprintf(stderr, "tfbs: block repeated (attempt %d): collided %d, need seq %llu d %llu cfg %llu vd %llu items %llu units %llu dwords %llu rows %llu rowwords %llu capr %u groups %u | caps seq %llu d %llu cfg %llu vd %llu items %llu units %llu dwords %llu rows %llu rowwords %llu capr %u groups %u\n",
+                        slot->attempts, (int)collided, (unsigned long long)hp.need_seq, (unsigned long long)hp.need_d, (unsigned long long)hp.need_cfg, (unsigned long long)hp.need_vd,
+                        (unsigned long long)hp.need_items, (unsigned long long)hp.need_units, (unsigned long long)hp.need_dwords, (unsigned long long)hp.need_rows,
+                        (unsigned long long)hp.need_rowwords, hp.need_capr, hp.need_groups, (unsigned long long)slot->caps.seq, (unsigned long long)slot->caps.d,
+                        (unsigned long long)slot->caps.cfg, (unsigned long long)slot->caps.vd, (unsigned long long)slot->caps.items, (unsigned long long)slot->caps.units,
+                        (unsigned long long)slot->caps.dwords, (unsigned long long)slot->caps.rows, (unsigned long long)slot->caps.rowwords, slot->caps.capr, slot->caps.groups);
             if (collided) slot->seed = slot->seed * 0x9e3779b97f4a7c15ull + 0x7f4a7c15ull;
             int rc = quiesce(ctx);
             if (rc) return rc;

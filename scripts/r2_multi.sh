@@ -7,7 +7,7 @@ O=gpurun_out/${1:-r2multi}
 N=${2:-2}
 mkdir -p $O
 nvidia-smi -L | head -8
-timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -q -x 2>&1 | tail -3
+[ "${3:-}" = "notests" ] || timeout 600 python -m pytest tests/test_multi_gpu.py -m gpu -q -x 2>&1 | tail -3
 timeout 900 python bench.py --gpus 1 --steps 20 --warmup 3 --no-secondary --no-cpu-baseline > $O/bench_n1.json 2> $O/bench_n1.err || tail -3 $O/bench_n1.err
 for n in 2 4 8; do
   [ $n -le $N ] || continue
