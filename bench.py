@@ -44,8 +44,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="configs2", choices=["configs1", "configs2"],
+    ap.add_argument("--workload", default="configs2", choices=["configs1", "configs2", "configs3"],
                     help="configs2 = BASELINE.json configs[2] (the north-star workload, default); configs1 = configs[1]")
+    ap.add_argument("--c3-regions", type=int, default=32, help="configs3: merged regions of a step (the full config has 100k; regions are independent)")
+    ap.add_argument("--c3-samples", type=int, default=100000, help="configs3: samples of the cohort (200k haplotypes)")
+    ap.add_argument("--c3-block", type=int, default=20000, help="configs3: samples per sample block")
     ap.add_argument("--scale", type=float, default=1.0, help="fraction of the regions (debugging only)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="target duration of the CPU baseline sample")
     ap.add_argument("--ref-seconds-per-step", type=float, default=None, help="--impl reference: CPU seconds per step (default: 120 s over all steps, 2-30 s each)")
@@ -288,6 +291,12 @@ def main():
         barrier()
         return allmax(e0.elapsed_time(e1))
 
+    if args.workload == "configs3":
+        if world != 1:
+            raise SystemExit("--workload configs3 runs its sample blocks on one GPU (tests/test_multi_gpu.py covers two)")
+        emit(configs3_line(args, binding, sharding, local_rank, ClockSampler, peaks()))
+        return
+
     pats, blk, config = workload(args.workload, args.scale)
     lmax = max(p["weights"].shape[0] for p in pats)
     shard, r0, i0 = sharding.shard_block(blk, world, rank, lmax=lmax, compact=True)
@@ -507,6 +516,138 @@ def secondary_configs1(args, binding, sharding, device, pk):
             "e2e": {"value": st["nominal_cells"] / (ms_e2e * 1e-3), "ms_per_step": ms_e2e, "h2d_bytes_per_step": st2["h2d_bytes"], "d2h_bytes_per_step": st2["d2h_bytes"]},
             "stages_ms": stages, "evaluated_cells_per_step": st["evaluated_cells"], "executed_cells_per_step": st["executed_cells"],
             "rows_per_step": st["n_rows"], "launches_per_step": st["total_launches"], "roofline": roof}
+
+
+def configs3_line(args, binding, sharding, device, ClockSampler, pk):
+    """BASELINE.json configs[3] (biobank scale, sample-sharded): 200,000 haplotypes, a record every ~4 bp, 50 PWMs, a bounded number
+    of the 100k regions per step.  The cohort is cut into SAMPLE BLOCKS (what a region's fan-out holds in shared memory bounds the
+    distinct haplotypes per block); every block is run with rows_mode = ALL_KEYS and the min != max filter of main.rs:450-458 is
+    applied after the gather by tfbs_merge_sample_blocks.  `value`: every block resident in HBM (one context each); `e2e`: one
+    context, the blocks submitted from pinned host memory two in flight, grouped rows copied out and merged on the host.
+    `roofline_k1` is SURVEY 8(d)'s "K1 / config 4" figure: algorithmic bytes of grouping + build over their device time."""
+    import torch
+    from find_tfbs_b200 import synth
+    pats, blk = synth.config4(n_regions=args.c3_regions, n_samples=args.c3_samples)
+    S = blk.n_samples
+    cuts = [(a, min(S, a + args.c3_block)) for a in range(0, S, args.c3_block)]
+    config = {"workload": "configs[3]: synthetic %d samples (%d haplotypes, a record every ~4 bp, 1/k allele-count spectrum, uniform carriers) x %d of the "
+                          "100k regions (200-2000 bp) x 50 random PWMs (L 8-30, both strands, p=1e-4), in %d sample blocks of <= %d samples"
+                          % (S, 2 * S, blk.n_regions, len(cuts), args.c3_block),
+              "regions": blk.n_regions, "samples": S, "pwms": 50, "patterns": len(pats), "sample_blocks": len(cuts),
+              "sharding": "sample blocks (counts are per sample; min != max over all samples after the gather, tfbs_merge_sample_blocks)",
+              "l2": "inputs larger than L2 (carrier bits of a block: tens of MB; per-haplotype scratch: GBs)"}
+    ps = binding.PatternSet(pats)
+    blocks = [sharding.sample_block(blk, a, b) for a, b in cuts]
+
+    def context():
+        c = binding.Context(device)
+        c.set_option("rows_width", 0)
+        c.set_option("rows_mode", binding.ROWS_ALL_KEYS)
+        for kv in args.option:
+            k, v = kv.split("=")
+            c.set_option(k, int(v))
+        c.set_patterns(ps)
+        return c
+
+    def timed(stream, fn):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        torch.cuda.synchronize()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    # ---- resident: one context per sample block, its block in HBM ----
+    ctxs = [context() for _ in blocks]
+    for c, b in zip(ctxs, blocks):
+        c.upload_block(b)
+    stream = torch.cuda.ExternalStream(ctxs[0].stream(), device=torch.device("cuda", device))
+
+    def step():
+        for c in ctxs:
+            c.run_resident()
+        return [c.collect_grouped() for c in ctxs]
+
+    sampler = ClockSampler(device)
+    sampler.start()
+    for _ in range(max(3, args.warmup)):
+        step()
+    ms_step = timed(stream, lambda: [step() for _ in range(args.steps)]) / args.steps
+    clocks = sampler.stop()
+    sts = [c.stats() for c in ctxs]
+    tot = lambda k: sum(st[k] for st in sts)
+    nominal, executed, evaluated = tot("nominal_cells"), tot("executed_cells"), tot("evaluated_cells")
+    stages = {k: tot(k) for k in ("ms_group", "ms_build", "ms_scan", "ms_scan_kernel", "ms_count", "ms_total")}
+    st_sum = dict(sts[0])
+    for k in ("evaluated_cells", "scan_input_bytes", "scan_launches", "total_launches"):
+        st_sum[k] = tot(k)
+    roofline = roofline_object(st_sum, stages["ms_scan_kernel"], clocks, pk)
+    # K1 roof (HBM): what grouping + build must read -- the carrier bits of every in-window record, the records, the windows
+    H = 2 * S
+    k1_bytes = int(len(blk.variants) * (H / 8 + 32) + len(blk.ref_bases))
+    k1_s = (stages["ms_group"] + stages["ms_build"]) * 1e-3
+    roofline_k1 = {"bound": "hbm", "kernels": "K0 grouping + K1 build (k_signatures .. k_redirect)", "achieved": k1_bytes / k1_s / 1e9, "peak": pk["hbm_gbs"],
+                   "unit": "GB/s", "frac": k1_bytes / k1_s / 1e9 / pk["hbm_gbs"], "algorithmic_bytes_per_step": k1_bytes,
+                   "ms_per_step": k1_s * 1e3, "traffic": None,
+                   "basis": "carrier bits V x H / 8 + 32 B per record + the reference windows, summed over the regions (SURVEY 8d); sequences are never "
+                            "materialised (segments + 3 bits per scored base instead)"}
+    for c in ctxs:
+        c.close()
+
+    # ---- end to end: one context, blocks from pinned host memory, two in flight; rows copied out; merge on the host ----
+    ctx = context()
+    for b in blocks:
+        b.pin()
+    merged_info = {}
+
+    def e2e_step():
+        parts, d2h, h2d = [], 0, 0
+        ctx.submit_block(blocks[0])
+        for i in range(len(blocks)):
+            if i + 1 < len(blocks):
+                ctx.submit_block(blocks[i + 1])
+            g = ctx.collect_grouped()
+            d2h += ctx.stats()["d2h_bytes"]
+            h2d += ctx.stats()["h2d_bytes"]
+            parts.append(binding.own_grouped(g))
+        m = binding.merge_sample_blocks(parts, expand=False)
+        merged_info.update({"rows_all_keys": int(sum(p["n_rows"] for p in parts)), "rows_kept": int(len(m["region"])), "d2h": int(d2h), "h2d": int(h2d),
+                            "vmax_xor": int(np_xor(m["vmax"]))})
+
+    e2e_step()
+    e2e_step()
+    ms_e2e = timed(stream_of(torch, ctx, device), lambda: [e2e_step() for _ in range(args.steps)]) / args.steps
+    launches = ctx.stats()["total_launches"]
+    for b in blocks:
+        b.unpin()
+    ctx.close()
+    out = {"metric": METRIC, "value": nominal / (ms_step * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+           "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+           "config": config, "executed_cells_per_s": executed / (ms_step * 1e-3), "nominal_cells_per_step": nominal,
+           "executed_cells_per_step": executed, "evaluated_cells_per_step": evaluated, "rows_per_step": merged_info["rows_kept"],
+           "stages_ms_summed_over_blocks": stages, "groups": tot("n_groups"), "hits": tot("n_hits"), "haplotypes_truncated": tot("n_truncated"),
+           "groups_dropped": tot("n_dropped"), "roofline": roofline, "roofline_k1": roofline_k1,
+           "e2e": {"value": nominal / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": merged_info["h2d"], "d2h_bytes_per_step": merged_info["d2h"],
+                   "ms_per_step": ms_e2e, "blocks_in_flight": 2, "rows_all_keys": merged_info["rows_all_keys"], "rows_kept": merged_info["rows_kept"],
+                   "vmax_xor": merged_info["vmax_xor"],
+                   "rows": "grouped, ALL_KEYS per sample block; merged on the host by tfbs_merge_sample_blocks (inside the timed region)"},
+           "gpu_launches": int(tot("total_launches")) * args.steps, "launches_per_block": launches, "clocks": clocks}
+    if not args.no_cpu_baseline:
+        small = sharding.sample_block(blk, 0, min(S, 2048))
+        out["cpu_baseline"] = cpu_reference_rate(ps, small, args.cpu_seconds, os.cpu_count() or 1)
+        out["cpu_baseline"]["sample"] = "first %d samples of the cohort; " % small.n_samples + out["cpu_baseline"]["sample"]
+    return out
+
+
+def np_xor(a):
+    import numpy as np
+    return np.bitwise_xor.reduce(a) if len(a) else 0
+
+
+def stream_of(torch, ctx, device):
+    return torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", device))
 
 
 def driver_wall_time(args, world):

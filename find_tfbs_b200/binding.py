@@ -22,7 +22,8 @@ DIR_P, DIR_N = 0, 1
 
 EXPORTS = ["tfbs_abi_version", "tfbs_create", "tfbs_destroy", "tfbs_last_error", "tfbs_set_option", "tfbs_set_patterns",
            "tfbs_submit_block", "tfbs_collect", "tfbs_get_matches", "tfbs_upload_block", "tfbs_run_resident", "tfbs_get_stats",
-           "tfbs_stream", "tfbs_host_register", "tfbs_host_unregister", "tfbs_audit_block", "tfbs_collect_grouped", "tfbs_expand_rows", "tfbs_set_result_arena"]
+           "tfbs_stream", "tfbs_host_register", "tfbs_host_unregister", "tfbs_audit_block", "tfbs_collect_grouped", "tfbs_expand_rows", "tfbs_set_result_arena",
+           "tfbs_merge_sample_blocks"]
 
 
 class TfbsPattern(C.Structure):
@@ -115,6 +116,65 @@ def read_arena(buf, half, expand=False):
     return out
 
 
+_GROUPED_ARRAYS = (("region", C.c_uint32), ("inner", C.c_uint32), ("pattern_id", C.c_uint16), ("vmin", C.c_uint32), ("vmax", C.c_uint32),
+                   ("base", C.c_uint32), ("bits", C.c_uint8), ("offset", C.c_uint64), ("packed", C.c_uint32), ("n_groups", C.c_uint32))
+
+
+def own_grouped(g):
+    """Grouped rows (dict of collect_grouped / read_arena) copied into arrays of their own, with a tfbs_grouped_rows over the copies
+    under "_c": what a caller keeps when the library's buffers are about to be reused (the next collect)."""
+    out = {k: v for k, v in g.items() if k not in ("_c", "_keep")}
+    c = TfbsGroupedRows()
+    c.n_rows, c.n_samples, c.n_regions = int(g["n_rows"]), int(g["n_samples"]), int(g["n_regions"])
+    for name, ct in _GROUPED_ARRAYS:
+        a = np.array(g[name], dtype=np.dtype(ct), copy=True)
+        out[name] = a
+        setattr(c, name, a.ctypes.data_as(C.POINTER(ct)))
+    hg = np.array(g["hap_group"], copy=True)
+    out["hap_group"] = hg
+    c.hap_group = hg.ctypes.data
+    c.hap_group_bytes = hg.dtype.itemsize
+    c.packed_words = len(out["packed"])
+    out["_c"] = c
+    return out
+
+
+def merge_sample_blocks(parts, expand=True):
+    """tfbs_merge_sample_blocks over the grouped rows of the sample blocks (dicts with "_c", in sample order): the keys that survive
+    min != max over ALL samples; with expand=True the blocks' (left, right) are concatenated along the sample axis
+    (tfbs_expand_rows per block and row; a block without the key contributes zeros)."""
+    n_parts = len(parts)
+    arr = (C.POINTER(TfbsGroupedRows) * max(1, n_parts))(*[C.pointer(p["_c"]) for p in parts])
+    n_out = C.c_uint64(0)
+    null32, null16, null64 = C.POINTER(C.c_uint32)(), C.POINTER(C.c_uint16)(), C.POINTER(C.c_uint64)()
+    rc = lib().tfbs_merge_sample_blocks(arr, n_parts, 0, null32, null32, null16, null32, null32, null64, C.byref(n_out))
+    if rc != TFBS_OK:
+        raise TfbsError(rc, "tfbs_merge_sample_blocks failed")
+    n = n_out.value
+    region, inner, pid = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.uint16)
+    vmin, vmax, part_row = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros((max(1, n_parts), n), np.uint64)
+    if n:
+        rc = lib().tfbs_merge_sample_blocks(arr, n_parts, n, _ptr(region, C.c_uint32), _ptr(inner, C.c_uint32), _ptr(pid, C.c_uint16),
+                                            _ptr(vmin, C.c_uint32), _ptr(vmax, C.c_uint32), _ptr(part_row, C.c_uint64), C.byref(n_out))
+        if rc != TFBS_OK or n_out.value != n:
+            raise TfbsError(rc, "tfbs_merge_sample_blocks failed")
+    out = {"region": region, "inner": inner, "pattern_id": pid, "vmin": vmin, "vmax": vmax, "part_row": part_row[:n_parts]}
+    if expand:
+        lefts, rights = [], []
+        for p, part in enumerate(parts):
+            S = int(part["n_samples"])
+            left, right = np.zeros((n, S), np.uint32), np.zeros((n, S), np.uint32)
+            for j in np.nonzero(part_row[p] != np.uint64(0xffffffffffffffff))[0]:
+                rc = lib().tfbs_expand_rows(C.byref(part["_c"]), int(part_row[p, j]), 1, _ptr(left[j], C.c_uint32), _ptr(right[j], C.c_uint32))
+                if rc != TFBS_OK:
+                    raise TfbsError(rc, "tfbs_expand_rows failed")
+            lefts.append(left)
+            rights.append(right)
+        out["left"] = np.concatenate(lefts, axis=1) if lefts else np.zeros((n, 0), np.uint32)
+        out["right"] = np.concatenate(rights, axis=1) if rights else np.zeros((n, 0), np.uint32)
+    return out
+
+
 class TfbsMatches(C.Structure):
     _fields_ = [("n_matches", C.c_uint64), ("region", C.POINTER(C.c_uint32)), ("pattern_index", C.POINTER(C.c_uint32)),
                 ("group", C.POINTER(C.c_uint32)), ("start", C.POINTER(C.c_int64)), ("hap_group", C.POINTER(C.c_uint32)),
@@ -182,6 +242,9 @@ def lib():
         L.tfbs_collect_grouped.argtypes = [C.c_void_p, C.POINTER(TfbsGroupedRows)]
         L.tfbs_expand_rows.argtypes = [C.POINTER(TfbsGroupedRows), C.c_uint64, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
         L.tfbs_set_result_arena.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.tfbs_merge_sample_blocks.argtypes = [C.POINTER(C.POINTER(TfbsGroupedRows)), C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                               C.POINTER(C.c_uint16), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
+                                               C.POINTER(C.c_uint64)]
         L.tfbs_get_matches.argtypes = [C.c_void_p, C.POINTER(TfbsMatches)]
         L.tfbs_get_stats.argtypes = [C.c_void_p, C.POINTER(TfbsStats)]
         L.tfbs_audit_block.argtypes = [C.c_void_p, C.POINTER(TfbsAudit)]

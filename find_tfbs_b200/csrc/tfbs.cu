@@ -373,6 +373,57 @@ int tfbs_expand_rows(const tfbs_grouped_rows* g, uint64_t first_row, uint64_t n_
     return TFBS_OK;
 }
 
+// Sample blocks (BASELINE.json configs[3]): counts are per sample, so the rows of disjoint sample ranges concatenate along
+// the sample axis, but the min != max filter of counts_as_genotypes (main.rs:450-458) needs every sample: it is applied here, after
+// the gather, on the (vmin, vmax) of each block's TFBS_ROWS_ALL_KEYS rows.  A k-way merge over the rows' key order.
+int tfbs_merge_sample_blocks(const tfbs_grouped_rows* const* parts, uint32_t n_parts, uint64_t cap, uint32_t* region, uint32_t* inner,
+                             uint16_t* pattern_id, uint32_t* vmin, uint32_t* vmax, uint64_t* part_row, uint64_t* n_out) {
+    if (!n_out || (n_parts && !parts) || (cap && (!region || !inner || !pattern_id || !vmin || !vmax || !part_row))) return TFBS_ERR_INVALID_ARGUMENT;
+    for (uint32_t p = 0; p < n_parts; ++p)
+        if (!parts[p]) return TFBS_ERR_INVALID_ARGUMENT;
+    struct Key {
+        uint32_t region, inner;
+        uint16_t pid;
+        bool operator<(const Key& o) const { return region != o.region ? region < o.region : (pid != o.pid ? pid < o.pid : inner < o.inner); }
+        bool operator==(const Key& o) const { return region == o.region && pid == o.pid && inner == o.inner; }
+    };
+    auto key_at = [&](uint32_t p, uint64_t i) { return Key{parts[p]->region[i], parts[p]->inner[i], parts[p]->pattern_id[i]}; };
+    std::vector<uint64_t> cur(n_parts, 0);
+    uint64_t n = 0;
+    for (;;) {
+        bool any = false;
+        Key k{};
+        for (uint32_t p = 0; p < n_parts; ++p) {
+            if (cur[p] >= parts[p]->n_rows) continue;
+            const Key kp = key_at(p, cur[p]);
+            if (cur[p] && !(key_at(p, cur[p] - 1) < kp)) return TFBS_ERR_INVALID_ARGUMENT;  // rows are not in key order
+            if (!any || kp < k) k = kp;
+            any = true;
+        }
+        if (!any) break;
+        // a block without the key had no hit for it: all its samples count 0 (main.rs:517-528)
+        uint32_t lo = 0xffffffffu, hi = 0;
+        for (uint32_t p = 0; p < n_parts; ++p) {
+            const bool has = cur[p] < parts[p]->n_rows && key_at(p, cur[p]) == k;
+            const uint32_t a = has ? parts[p]->vmin[cur[p]] : 0u, b = has ? parts[p]->vmax[cur[p]] : 0u;
+            lo = std::min(lo, a);
+            hi = std::max(hi, b);
+        }
+        const bool keep = lo != hi;
+        for (uint32_t p = 0; p < n_parts; ++p) {
+            const bool has = cur[p] < parts[p]->n_rows && key_at(p, cur[p]) == k;
+            if (keep && n < cap) part_row[(uint64_t)p * cap + n] = has ? cur[p] : ~0ull;
+            if (has) ++cur[p];
+        }
+        if (keep) {
+            if (n < cap) { region[n] = k.region; inner[n] = k.inner; pattern_id[n] = k.pid; vmin[n] = lo; vmax[n] = hi; }
+            ++n;
+        }
+    }
+    *n_out = n;
+    return TFBS_OK;
+}
+
 int tfbs_get_matches(tfbs_ctx* ctx, tfbs_matches* out) {
     if (!ctx || !out) return TFBS_ERR_INVALID_ARGUMENT;
     if (ctx->last < 0 || !ctx->slot[ctx->last].full_mode || !ctx->record_matches)

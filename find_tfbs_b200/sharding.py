@@ -90,6 +90,16 @@ def sample_block(block, s0, s1):
     """The same regions and records restricted to samples [s0, s1) (carrier bits re-packed)."""
     from .binding import Block
     H = 2 * block.n_samples
+    if (2 * s0) % 32 == 0:  # the cut falls on a word of the carrier rows: slice the words, clear the bits behind the last haplotype
+        n_h = 2 * (s1 - s0)
+        pitch = max(1, (n_h + 31) // 32)
+        carriers = np.zeros((block.carriers.shape[0], pitch), dtype=np.uint32)
+        src = block.carriers[:, 2 * s0 // 32:2 * s0 // 32 + pitch]
+        carriers[:, :src.shape[1]] = src
+        if n_h % 32:
+            carriers[:, n_h // 32] &= np.uint32((1 << (n_h % 32)) - 1)
+        return Block(s1 - s0, block.region_start, block.region_end, block.ref_off, block.ref_bases, block.inner_off, block.inner,
+                     block.var_off, block.variants, block.allele_bases, carriers)
     bits = np.unpackbits(block.carriers.view(np.uint8), axis=1, bitorder="little")[:, :H]
     sub = bits[:, 2 * s0:2 * s1]
     pitch = max(1, (2 * (s1 - s0) + 31) // 32)

@@ -269,3 +269,13 @@ def config3(scale=1.0, seed=3, n_pwms=401):
     lmax = max(p["weights"].shape[0] for p in pats)
     blk = make_cohort(2504, max(1, int(5000 * scale)), seed=seed, lmax_pattern=lmax, two_beds=True, n_runs=20, bed_b_frac=1.0)
     return pats, blk
+
+
+def config4(n_regions=32, n_samples=100000, seed=4, n_pwms=50):
+    """BASELINE.json configs[3]: biobank scale, 200,000 haplotypes, a record every ~4 bp (1/k allele-count spectrum, uniform
+    carriers), 50 PWMs (L 8-30, both strands).  The full config has 100k regions over chr1; a bench step takes `n_regions` of them
+    (regions are independent, main.rs:395-429) and runs them once per SAMPLE BLOCK (sharding.sample_block)."""
+    pats = make_pwms(n_pwms, seed=4000 + seed)
+    lmax = max(p["weights"].shape[0] for p in pats)
+    blk = make_cohort(n_samples, n_regions, seed=seed, lmax_pattern=lmax, variant_rate=1.0 / 4, gap=(100, 300))
+    return pats, blk

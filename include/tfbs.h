@@ -322,6 +322,19 @@ int tfbs_set_result_arena(tfbs_ctx* ctx, void* base, size_t bytes);
  * code, no CUDA call; thread-safe. */
 int tfbs_expand_rows(const tfbs_grouped_rows* rows, uint64_t first_row, uint64_t n_rows, uint32_t* left, uint32_t* right);
 
+/*
+ * Sample-block sharding (the secondary partition for biobank-scale cohorts, BASELINE.json configs[3]): the same regions and patterns
+ * are run once per block of samples, on any GPU, with "rows_mode" = TFBS_ROWS_ALL_KEYS.  Counts are per sample, so the blocks'
+ * rows concatenate along the sample axis; the min != max filter of counts_as_genotypes (src/main.rs:450-458) needs ALL samples and
+ * is applied by this call after the gather.  parts[p] = the grouped rows of sample block p.  For every key that survives, in row
+ * order: region / inner / pattern_id, vmin / vmax over all samples, and part_row[p * cap + j] = its row in parts[p], or UINT64_MAX
+ * when block p had no hit for the key (every sample of the block counts 0, src/main.rs:517-528); expand block p's share of row j with
+ * tfbs_expand_rows(parts[p], part_row[p * cap + j], 1, ...).  *n_out = surviving keys; when it exceeds `cap` only the first `cap`
+ * were written (call with cap = 0 and NULL arrays to size them).  Pure host code, no CUDA call; thread-safe.
+ */
+int tfbs_merge_sample_blocks(const tfbs_grouped_rows* const* parts, uint32_t n_parts, uint64_t cap, uint32_t* region, uint32_t* inner,
+                             uint16_t* pattern_id, uint32_t* vmin, uint32_t* vmax, uint64_t* part_row, uint64_t* n_out);
+
 /* Matches of the last run when "record_matches" was on (call after tfbs_collect). */
 int tfbs_get_matches(tfbs_ctx* ctx, tfbs_matches* out);
 

@@ -340,6 +340,35 @@ def test_config4_biobank_shape():
     hp.assert_rows_equal(merged, hp.run_oracle(ps, blk, binding.ROWS_VARYING))
 
 
+def test_config4_dense_sample_blocks():
+    """BASELINE.json configs[3] as generated for the bench (synth.config4: a record every ~4 bp, 1/k spectrum, uniform carriers, so
+    nearly every haplotype of a region is distinct and one cluster spans the region), in sample blocks: grouped rows of every block in
+    ALL_KEYS mode, merged by tfbs_merge_sample_blocks (min != max over all samples after the gather), equal to the oracle run block
+    by block and merged in Python -- and to the oracle on the whole cohort where no sequence-keyed overwrite happened (SURVEY A.6 Q4:
+    the winner is chosen per block)."""
+    from find_tfbs_b200 import sharding
+    pats, blk = synth.config4(n_regions=3, n_samples=208, seed=14, n_pwms=4)
+    ps = PatternSet(pats)
+    cuts = ((0, 80), (80, 160), (160, 208))
+    ctx = binding.Context(0)
+    try:
+        ctx.set_option("rows_mode", binding.ROWS_ALL_KEYS)
+        ctx.set_patterns(ps)
+        parts, dropped = [], 0
+        for a, b in cuts:
+            ctx.submit_block(sharding.sample_block(blk, a, b))
+            parts.append(binding.own_grouped(ctx.collect_grouped()))
+            dropped += ctx.stats()["n_dropped"]
+    finally:
+        ctx.close()
+    merged = binding.merge_sample_blocks(parts)
+    o_parts = [hp.run_oracle(ps, sharding.sample_block(blk, a, b), binding.ROWS_ALL_KEYS) for a, b in cuts]
+    hp.assert_rows_equal(merged, sharding.merge_sample_shards(o_parts))
+    assert len(merged["region"]) > 0
+    if dropped == 0:
+        hp.assert_rows_equal(merged, hp.run_oracle(ps, blk, binding.ROWS_VARYING))
+
+
 def test_config2_slice_properties():
     """configs[1] at 3% size against the oracle, plus size-independent properties of the rows."""
     pats, blk = synth.config2(scale=0.03)

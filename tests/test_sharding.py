@@ -60,3 +60,42 @@ def test_two_rank_gloo_shard_and_gather():
         p.join(timeout=60)
     assert ok and n > 0
     assert all(p.exitcode == 0 for p in procs)
+
+
+def _as_grouped(rows, n_regions):
+    """Dense oracle rows -> grouped rows with one group per haplotype (bits = 32), the layout of tfbs_grouped_rows."""
+    from find_tfbs_b200 import binding
+    n, S = rows["left"].shape
+    H = 2 * S
+    packed = np.zeros((n, H), dtype=np.uint32)
+    packed[:, 0::2], packed[:, 1::2] = rows["left"], rows["right"]
+    base = packed.min(axis=1) if n else np.zeros(0, np.uint32)
+    g = {"n_rows": n, "n_samples": S, "n_regions": n_regions, "region": rows["region"], "inner": rows["inner"], "pattern_id": rows["pattern_id"],
+         "vmin": rows["vmin"], "vmax": rows["vmax"], "base": base, "bits": np.full(n, 32, np.uint8), "offset": np.arange(n, dtype=np.uint64) * H,
+         "packed": (packed - base[:, None]).reshape(-1), "n_groups": np.full(n_regions, H, np.uint32),
+         "hap_group": np.tile(np.arange(H, dtype=np.uint32), (n_regions, 1))}
+    return binding.own_grouped(g)
+
+
+def test_merge_sample_blocks_host():
+    """tfbs_merge_sample_blocks (pure host code of the library): sample blocks in ALL_KEYS mode -> the rows counts_as_genotypes keeps
+    over all samples (main.rs:450-458).  The oracle stands in for the device."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import parity_helpers as hp
+    from find_tfbs_b200 import binding
+    pats = synth.make_pwms(5, seed=21, lmin=6, lmax=12, pvalue=2e-3)
+    blk = synth.make_cohort(24, 12, seed=21, lmax_pattern=12, region_len=(60, 300), two_beds=True, variant_rate=0.05)
+    ps = PatternSet(pats)
+    full = hp.run_oracle(ps, blk, binding.ROWS_VARYING, False, 2)
+    cuts = ((0, 7), (7, 16), (16, 24))
+    parts = [hp.run_oracle(ps, sharding.sample_block(blk, a, b), binding.ROWS_ALL_KEYS, False, 2) for a, b in cuts]
+    assert any(len(p["region"]) != len(parts[0]["region"]) for p in parts) or len(full["region"]) < len(parts[0]["region"])
+    merged = binding.merge_sample_blocks([_as_grouped(p, blk.n_regions) for p in parts])
+    for k in ("region", "inner", "pattern_id", "vmin", "vmax", "left", "right"):
+        assert np.array_equal(merged[k], full[k]), k
+    ref = sharding.merge_sample_shards(parts)
+    assert np.array_equal(ref["left"], merged["left"])
+    # no part at all, and parts without rows
+    assert len(binding.merge_sample_blocks([])["region"]) == 0
+    empty = {k: v[:0] for k, v in parts[0].items() if isinstance(v, np.ndarray)}
+    assert len(binding.merge_sample_blocks([_as_grouped(empty, blk.n_regions)])["region"]) == 0
