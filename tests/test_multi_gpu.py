@@ -86,6 +86,63 @@ def test_two_ranks_gather_rows_through_shared_memory_arenas():
     assert all(p.exitcode == 0 for p in procs)
 
 
+def _sample_rank(rank, world, tag, n_dev, q_ready, q_result, done):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from find_tfbs_b200 import binding, sharding
+    import parity_helpers as hp
+    pats, blk = synth.config4(n_regions=3, n_samples=160, seed=15, n_pwms=4)
+    ps = binding.PatternSet(pats)
+    cuts = ((0, 96), (96, 160))
+    mine = sharding.sample_block(blk, *cuts[rank])
+    ctx = binding.Context(rank % n_dev)
+    ctx.set_option("rows_mode", binding.ROWS_ALL_KEYS)
+    ctx.set_patterns(ps)
+    arena = sharding.SharedArena(tag, rank, nbytes=8 << 20, create=True)
+    ctx.set_result_arena(arena.buf)
+    ctx.submit_block(mine)
+    ctx.collect_grouped()
+    q_ready.put(rank)
+    if rank == 0:
+        seen = set()
+        while len(seen) < world:
+            seen.add(q_ready.get(timeout=300))
+        parts = []
+        for k in range(world):
+            a = sharding.SharedArena(tag, k)
+            parts.append(binding.own_grouped(binding.read_arena(a.buf, 0)))
+            a.close()
+        merged = binding.merge_sample_blocks(parts)  # min != max over the samples of BOTH devices, after the gather (main.rs:450-458)
+        want = sharding.merge_sample_shards([hp.run_oracle(ps, sharding.sample_block(blk, a, b), binding.ROWS_ALL_KEYS) for a, b in cuts])
+        ok = all(np.array_equal(merged[key], want[key]) for key in ("region", "inner", "pattern_id", "vmin", "vmax", "left", "right"))
+        q_result.put((ok, len(want["region"]), [int(p["n_rows"]) for p in parts]))
+    done.wait(timeout=600)
+    ctx.set_result_arena(None)
+    ctx.close()
+    arena.close()
+
+
+def test_two_ranks_sample_blocks_merged_after_the_gather():
+    """BASELINE.json configs[3]'s partition: the same regions, one SAMPLE BLOCK per device; the ALL_KEYS rows of both land in rank
+    0's address space and tfbs_merge_sample_blocks applies the filter that needs every sample."""
+    import torch
+    n_dev = max(1, torch.cuda.device_count())
+    ctx = mp.get_context("spawn")
+    q_ready, q_result, done = ctx.Queue(), ctx.Queue(), ctx.Event()
+    tag = "s%d" % os.getpid()
+    procs = [ctx.Process(target=_sample_rank, args=(r, 2, tag, n_dev, q_ready, q_result, done)) for r in range(2)]
+    for p in procs:
+        p.start()
+    try:
+        result = q_result.get(timeout=600)
+    finally:
+        done.set()
+        for p in procs:
+            p.join(timeout=120)
+    assert result[0] and result[1] > 0 and all(n >= result[1] for n in result[2][:1]), result
+    assert all(p.exitcode == 0 for p in procs)
+
+
 def test_driver_one_context_per_device(tmp_path):
     """--devices 0,1 (0,0 on a single-GPU box): chunks of merged regions are dealt to one worker thread + context per device, two
     blocks in flight each; the writer puts the chunks back in order: the output equals the single-device run byte for byte after
