@@ -53,14 +53,21 @@ __device__ __forceinline__ u32 bits_for(u32 span) {  // width that holds 0..span
 }
 
 // Packs the counts of the 32 consecutive groups [g0, g0 + 32) held by the lanes of a warp (lane l: value v of group g0 + l, 0 behind
-// the last group) as `bits`-wide fields: they fill `bits` consecutive words starting at word g0 * bits / 32; word k of them is the OR
-// over the 32 / bits lanes whose group lives in it (REDUX), written by lane k.
+// the last group) as `bits`-wide fields: they fill `bits` consecutive words starting at word g0 * bits / 32.  bits is a power of two,
+// so the lane -> (word, shift) map is shifts and masks.  Narrow fields (1, 2 bits): word k is the OR over the 32 / bits lanes whose
+// group lives in it (REDUX), written by lane k.  Wide fields: a butterfly OR inside each run of 32 / bits lanes, its first lane writes.
 __device__ __forceinline__ void pack_32_groups(u32 v, u32 bits, u32 lane, u32* out, u32 n_out) {  // n_out: words of the row left from `out` on
     if (bits == 32) { if (lane < n_out) out[lane] = v; return; }
-    const u32 per = 32 / bits, mine = lane / per, x = v << ((lane % per) * bits);
-    for (u32 k = 0; k < bits; ++k) {
-        const u32 word = __reduce_or_sync(0xffffffffu, mine == k ? x : 0u);
-        if (lane == k && k < n_out) out[k] = word;
+    const u32 lb = __ffs(bits) - 1, per = 32u >> lb, mine = lane >> (5 - lb);
+    u32 x = v << ((lane & (per - 1)) << lb);
+    if (bits <= 2) {
+        for (u32 k = 0; k < bits; ++k) {
+            const u32 word = __reduce_or_sync(0xffffffffu, mine == k ? x : 0u);
+            if (lane == k && k < n_out) out[k] = word;
+        }
+    } else {
+        for (u32 o = 1; o < per; o <<= 1) x |= __shfl_xor_sync(0xffffffffu, x, o);
+        if ((lane & (per - 1)) == 0 && mine < n_out) out[mine] = x;
     }
 }
 
@@ -80,7 +87,7 @@ constexpr u32 FAN_STAGE_ROWS = 32;
 #ifndef TFBS_FAN_SPLIT
 #define TFBS_FAN_SPLIT 4
 #endif
-constexpr u32 FAN_SPLIT = TFBS_FAN_SPLIT;      // CTAs per region: CTA j takes the rounds j, j + FAN_SPLIT, ... of FAN_THREADS keys
+constexpr u32 FAN_SPLIT = TFBS_FAN_SPLIT;      // smallest number of CTAs per region (gridDim.y): CTA j takes the rounds j, j + gridDim.y, ... of the region's keys
 
 struct FanPair { u32 m0, n, d, cum; };  // members [m0, m0 + n) of the region's member list get the difference d; cum = members of the key's earlier pairs
 
@@ -89,7 +96,7 @@ __host__ __device__ inline size_t fan_smem_bytes(u32 groups_cap, u32 H, bool hg1
     return (size_t)groups_cap * 4 + (size_t)FAN_PAIRS * sizeof(FanPair) + (size_t)FAN_STAGE * 4 + (hg16 ? (((size_t)H * 2 + 15) & ~(size_t)15) : 0);
 }
 
-// FAN_SPLIT CTAs per region, each takes every FAN_SPLIT-th round of FAN_THREADS keys.
+// gridDim.y (>= FAN_SPLIT) CTAs per region, each takes every gridDim.y-th round of at most FAN_THREADS keys.
 //  A. the round's slab of the difference matrix (FAN_THREADS keys x configurations) is read once, coalesced; the few non-zero
 //     entries are counted per key, one block scan gives every key its place, a second pass over the (now cached) slab files the
 //     pairs key by key into shared memory.  A key without a non-zero entry -- the large majority: no hit touched it, or what a
@@ -110,7 +117,10 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
     if (cf.plan->abort) return;
     const u32 r = blockIdx.x;
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if ((u64)blockIdx.y * FAN_THREADS >= (u64)fn.n_pid * (b.inner_off[r + 1] - b.inner_off[r])) return;  // no round for this CTA
+    // the keys of the region go to the gridDim.y CTAs in rounds of `rs` keys: equal shares when they fit one round each
+    const u32 nkeys_all = fn.n_pid * (b.inner_off[r + 1] - b.inner_off[r]);
+    const u32 rs = min((u32)FAN_THREADS, max(1u, (nkeys_all + gridDim.y - 1) / gridDim.y));
+    if ((u64)blockIdx.y * rs >= (u64)nkeys_all) return;  // no round for this CTA
     const u32 ng = (u32)(fn.gbase[r + 1] - fn.gbase[r]);
     if (ng > fn.groups_cap) {  // more distinct haplotypes than the shared-memory vector holds: the host repeats the run
         if (tid == 0) { atomicMax(&cf.plan->need_groups, ng); cf.plan->abort = 1; }
@@ -152,9 +162,9 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
         stage_rows = 0;
     };
 
-    for (u32 k0 = blockIdx.y * FAN_THREADS; k0 < nkeys; k0 += FAN_SPLIT * FAN_THREADS) {
+    for (u32 k0 = blockIdx.y * rs; k0 < nkeys; k0 += gridDim.y * rs) {
         // ---- A: the round's slab of D, coalesced ----
-        const u32 nround = nkeys - k0 < (u32)FAN_THREADS ? nkeys - k0 : (u32)FAN_THREADS;
+        const u32 nround = nkeys - k0 < rs ? nkeys - k0 : rs;
         const u32* slab = Dr + (u64)k0 * ncfg;
         const u32 nwords = nround * ncfg;
         s_cnt[tid] = 0;
@@ -213,6 +223,9 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
             s_href[my_hpos] = ref_mine;
         }
         if (tid == 0 && n_heavy) atomicAdd((unsigned long long*)&cf.plan->fan_keys, (unsigned long long)n_heavy);
+#ifdef TFBS_FAN_STATS
+        if (tid < n_heavy) { atomicAdd((unsigned long long*)&cf.plan->fan_dbg[0], (unsigned long long)s_hcnt[tid]); }
+#endif
         __syncthreads();
         if (tid < n_heavy && s_hfirst[tid] + s_hcnt[tid] <= FAN_PAIRS) {  // members before every pair of the key: the scatter below is flat
             u32 cum = 0;
@@ -235,13 +248,25 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
                     const FanPair pr = pairs[first + j];
                     atomicAdd(&val[members[pr.m0 + (x - pr.cum)]], pr.d);
                 }
-            } else {  // more pairs in this round than shared memory holds: this key reads its row again
+            } else {  // more pairs in this round than shared memory holds: this key reads its row again, a lane per configuration;
+                      // long member lists are shared out over the warp
                 const u32* drow = Dr + (u64)hkey * ncfg;
-                for (u32 c = wid; c < ncfg; c += NW) {
-                    const u32 d = drow[c];
-                    if (!d) continue;
-                    const u64 m0 = cf.moff[cb + c], m1 = cf.moff[cb + c + 1];
-                    for (u64 m = m0 + lane; m < m1; m += 32) atomicAdd(&val[cf.members[m]], d);
+                for (u32 c0 = wid * 32; c0 < ncfg; c0 += NW * 32) {
+                    const u32 c = c0 + lane;
+                    const u32 d = c < ncfg ? drow[c] : 0u;
+                    u64 m0 = 0, m1 = 0;
+                    if (d) { m0 = cf.moff[cb + c]; m1 = cf.moff[cb + c + 1]; }
+                    const bool longlist = m1 - m0 > 8;
+                    if (d && !longlist)
+                        for (u64 m = m0; m < m1; ++m) atomicAdd(&val[cf.members[m]], d);
+                    u32 todo = __ballot_sync(0xffffffffu, longlist);
+                    while (todo) {
+                        const int src = __ffs(todo) - 1;
+                        todo &= todo - 1;
+                        const u64 a0 = __shfl_sync(0xffffffffu, m0, src), a1 = __shfl_sync(0xffffffffu, m1, src);
+                        const u32 dd = __shfl_sync(0xffffffffu, d, src);
+                        for (u64 m = a0 + lane; m < a1; m += 32) atomicAdd(&val[cf.members[m]], dd);
+                    }
                 }
             }
             __syncthreads();
@@ -252,6 +277,16 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
                 gmin = min(gmin, c);
                 gmax = max(gmax, c);
             }
+#ifdef TFBS_FAN_STATS
+            {
+                u32 tg = 0, ts = 0;
+                for (u32 g = tid; g < ng; g += FAN_THREADS) tg += val[g] != 0;
+                for (u32 s = tid; s < b.S; s += FAN_THREADS) ts += (val[hg[2 * s]] | val[hg[2 * s + 1]]) != 0;
+                atomicAdd((unsigned long long*)&cf.plan->fan_dbg[2], (unsigned long long)tg);
+                atomicAdd((unsigned long long*)&cf.plan->fan_dbg[3], (unsigned long long)ts);
+                if (tid == 0 && first + hcnt <= FAN_PAIRS) atomicAdd((unsigned long long*)&cf.plan->fan_dbg[1], (unsigned long long)s_htot[a]);
+            }
+#endif
             if (fn.hg16) {
                 for (u32 s = tid; s < b.S; s += FAN_THREADS) {
                     const u32 two = reinterpret_cast<const u32*>(hg16)[s];  // both haplotypes of the sample

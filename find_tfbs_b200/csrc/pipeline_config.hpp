@@ -518,7 +518,10 @@ struct ConfigPipeline {
                                                                 std::to_string(c.groups) + "): use sample blocks");
             CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fan_smem));
             CK(cudaFuncSetAttribute(k_fanout, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-            TFBS_LAUNCH(k_fanout, dim3(R, FAN_SPLIT), FAN_THREADS, fan_smem, st)(db, cf, fn);
+            // CTAs per region: FAN_SPLIT when there are many regions, more when few regions would leave SMs idle (sample blocks of a
+            // biobank cohort: few regions, tens of thousands of groups each)
+            const uint32_t split = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(FAN_SPLIT, (8ull * slot->stats.sm_count + R - 1) / R));
+            TFBS_LAUNCH(k_fanout, dim3(R, split), FAN_THREADS, fan_smem, st)(db, cf, fn);
             ++launches();
             if ((rc = scan(fn.flag, n_keys, nullptr, ctx->d_rowidx.as<u64>()))) return rc;
             gate(ctx->d_rowidx.as<u64>() + n_keys, 0, c.rows, &plan->n_rows, &plan->need_rows);
@@ -640,6 +643,10 @@ struct ConfigPipeline {
         s.n_dropped = hs.n_dropped;
         s.n_truncated = hs.n_truncated;
         s.reserved = (uint32_t)std::min<uint64_t>(hp.fan_keys, 0xffffffffu);
+        if (getenv("TFBS_DEBUG") && hp.fan_dbg[0])
+            fprintf(stderr, "tfbs: fan-out: %llu keys with a count vector, %llu pairs, %llu member updates, %llu groups / %llu samples with a non-zero difference\n",
+                    (unsigned long long)hp.fan_keys, (unsigned long long)hp.fan_dbg[0], (unsigned long long)hp.fan_dbg[1], (unsigned long long)hp.fan_dbg[2],
+                    (unsigned long long)hp.fan_dbg[3]);
         uint64_t table_bytes = 0;
         for (const ChunkDesc& cd : ctx->cp.chunks) table_bytes += (uint64_t)cd.tbl_words * 8 * s.scan_ctas;
         s.scan_input_bytes = (R && S) ? hp.n_units * 12 * ctx->cp.chunks.size() + table_bytes : 0;

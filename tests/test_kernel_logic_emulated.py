@@ -83,8 +83,8 @@ def test_bench_control_flow_dry_run(emu_env):
     line carries every contract key and internally consistent counters: the north-star workload (configs[2], strong scaling), the
     shared-memory gather of the grouped rows, the sustained run, the configs[1] secondary object.  The numbers themselves mean nothing."""
     import json
-    r = subprocess.run([sys.executable, os.path.join(EMU, "run_bench_emulated.py"), "--scale", "0.001", "--steps", "2", "--warmup", "1",
-                        "--cpu-seconds", "0.5", "--no-full-scan", "--sustain-seconds", "0.01", "--no-driver"], cwd=ROOT, env=emu_env,
+    r = subprocess.run([sys.executable, os.path.join(EMU, "run_bench_emulated.py"), "--scale", "0.0004", "--steps", "2", "--warmup", "1",
+                        "--cpu-seconds", "0.2", "--no-full-scan", "--sustain-seconds", "0.01", "--no-driver"], cwd=ROOT, env=emu_env,
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
     lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
@@ -108,8 +108,8 @@ def test_bench_control_flow_dry_run(emu_env):
 def test_bench_reference_arm():
     """`bench.py --impl reference` needs no GPU: the CPU restatement on the host cores, same metric / config keys, impl = reference."""
     import json
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scale", "0.004", "--steps", "2", "--warmup", "1",
-                        "--ref-seconds-per-step", "0.3"], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--scale", "0.0004", "--steps", "1", "--warmup", "1",
+                        "--ref-seconds-per-step", "0.2"], cwd=ROOT, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     d = json.loads([ln for ln in r.stdout.splitlines() if ln.strip()][-1])
     assert d["impl"] == "reference" and d["metric"] == "pwm_cells_per_s" and d["value"] > 0 and d["gpu_launches"] == 0

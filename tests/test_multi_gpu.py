@@ -21,7 +21,8 @@ DRIVER = os.environ.get("TFBS_B200_DRIVER") or os.path.join(ROOT, "find_tfbs_b20
 
 def _cohort():
     pats = synth.make_pwms(10, seed=71, lmin=8, lmax=22)
-    blk = synth.make_cohort(40, 120, seed=71, lmax_pattern=22, region_len=(150, 700), two_beds=True, n_runs=3, frac_ins=0.08, frac_del=0.08)
+    n_regions = 24 if os.environ.get("TFBS_TEST_SCALE") else 120  # TFBS_TEST_SCALE is set by the emulated run (host fibers are slow)
+    blk = synth.make_cohort(40, n_regions, seed=71, lmax_pattern=22, region_len=(150, 700), two_beds=True, n_runs=3, frac_ins=0.08, frac_del=0.08)
     return pats, blk
 
 
