@@ -86,9 +86,21 @@ __device__ __forceinline__ u64 mix64(u64 x) {
 constexpr u64 HASH_B = 0x9e3779b97f4a7c15ULL;      // odd => invertible mod 2^64
 constexpr u64 HASH_BINV = 0xf1de83e19937733dULL;   // HASH_B * HASH_BINV == 1 (mod 2^64), checked at start-up
 __device__ __forceinline__ u64 hash_val(u32 code, int rel) { return mix64(((u64)(u32)rel << 3) | code) | 1ULL; }
-__device__ __forceinline__ u64 hash_pow(long long e) {  // HASH_B ^ e, negative exponents through the inverse
-    u64 base = e < 0 ? HASH_BINV : HASH_B;
-    u64 n = (u64)(e < 0 ? -e : e), r = 1;
+// HASH_B ^ e for |e| < HASH_POW_N from a table (filled once per device by k_hash_pow_init; segment offsets and indel shifts of a
+// window are almost always below it), by squaring beyond; negative exponents through the inverse.
+constexpr u32 HASH_POW_N = 4096;
+__device__ u64 g_hash_pow[2][HASH_POW_N];
+__global__ void k_hash_pow_init() {
+    if (blockIdx.x == 0 && threadIdx.x < 2) {
+        const u64 base = threadIdx.x ? HASH_BINV : HASH_B;
+        u64 r = 1;
+        for (u32 e = 0; e < HASH_POW_N; ++e) { g_hash_pow[threadIdx.x][e] = r; r *= base; }
+    }
+}
+__device__ __forceinline__ u64 hash_pow(long long e) {
+    const u64 a = (u64)(e < 0 ? -e : e);
+    if (a < HASH_POW_N) return g_hash_pow[e < 0 ? 1 : 0][a];
+    u64 base = e < 0 ? HASH_BINV : HASH_B, n = a, r = 1;
     while (n) {
         if (n & 1) r *= base;
         base *= base;

@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
     if (fn.hg16)
         for (u32 h = tid; h < b.H; h += FAN_THREADS) hg16[h] = (u16)hg[h];
     for (u32 g = tid; g < ng; g += FAN_THREADS) val[g] = 0;
+    for (u32 w = tid; w < FAN_STAGE; w += FAN_THREADS) stage[w] = 0;  // rows are XORed into the staging buffer: it is all zero between rows
     u32 row_max = 0;
     u32 stage_used = 0, stage_rows = 0;  // the same in every thread: every decision about the staging buffer is uniform
 
@@ -153,8 +154,11 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
             if (tid == 0) s_base = atomicAdd((unsigned long long*)&cf.plan->rowwords_alloc, (unsigned long long)stage_used);
             __syncthreads();
             const u64 base = s_base;
-            if (base + stage_used <= fn.words_cap)  // beyond the capacity: the gate behind this kernel raises abort
-                for (u32 w = tid; w < stage_used; w += FAN_THREADS) fn.o_packed[base + w] = stage[w];
+            const bool fits = base + stage_used <= fn.words_cap;  // beyond the capacity: the gate behind this kernel raises abort
+            for (u32 w = tid; w < stage_used; w += FAN_THREADS) {
+                if (fits) fn.o_packed[base + w] = stage[w];
+                stage[w] = 0;
+            }
             for (u32 i = tid; i < stage_rows; i += FAN_THREADS) fn.k_off[kb + s_stage_key[i]] = base + s_stage_rel[i];
             __syncthreads();
         }
@@ -239,14 +243,25 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
         // ---- B: the whole CTA per key that needs the count vector (val is all zero on entry) ----
         for (u32 a = 0; a < n_heavy; ++a) {
             const u32 hkey = s_hkey[a], first = s_hfirst[a], hcnt = s_hcnt[a], ref = s_href[a];
-            if (first + hcnt <= FAN_PAIRS) {
+            // sparse = the key's pairs sit in shared memory: every later pass visits only the groups a pair touches (a few hundred of
+            // the region's thousands), found again through the pairs; the others keep the reference haplotype's count
+            const bool sparse = first + hcnt <= FAN_PAIRS;
+            const u32 tot = sparse ? s_htot[a] : 0u;
+            auto touched = [&](u32 x, u32& d) {  // group of the x-th (configuration, member) of the key
+                u32 j = 0;
+                while (j + 1 < hcnt && pairs[first + j + 1].cum <= x) ++j;
+                const FanPair pr = pairs[first + j];
+                d = pr.d;
+                return members[pr.m0 + (x - pr.cum)];
+            };
+            u32 g_mine = 0;  // the group of x = tid, kept for the later passes
+            if (sparse) {
                 // a thread per (configuration, member group) of the key: two configurations of different clusters can meet in a group
-                const u32 tot = s_htot[a];
                 for (u32 x = tid; x < tot; x += FAN_THREADS) {
-                    u32 j = 0;
-                    while (j + 1 < hcnt && pairs[first + j + 1].cum <= x) ++j;
-                    const FanPair pr = pairs[first + j];
-                    atomicAdd(&val[members[pr.m0 + (x - pr.cum)]], pr.d);
+                    u32 d;
+                    const u32 g = touched(x, d);
+                    if (x == tid) g_mine = g;
+                    atomicAdd(&val[g], d);
                 }
             } else {  // more pairs in this round than shared memory holds: this key reads its row again, a lane per configuration;
                       // long member lists are shared out over the warp
@@ -272,10 +287,19 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
             __syncthreads();
             // smallest / largest count over the groups (the packing base and width), min / max of left + right over the samples
             u32 gmin = ref, gmax = ref, lo = 0xffffffffu, hi = 0;
-            for (u32 g = tid; g < ng; g += FAN_THREADS) {
-                const u32 c = ref + val[g];
-                gmin = min(gmin, c);
-                gmax = max(gmax, c);
+            if (sparse) {
+                for (u32 x = tid; x < tot; x += FAN_THREADS) {
+                    u32 d;
+                    const u32 c = ref + val[x == tid ? g_mine : touched(x, d)];
+                    gmin = min(gmin, c);
+                    gmax = max(gmax, c);
+                }
+            } else {
+                for (u32 g = tid; g < ng; g += FAN_THREADS) {
+                    const u32 c = ref + val[g];
+                    gmin = min(gmin, c);
+                    gmax = max(gmax, c);
+                }
             }
 #ifdef TFBS_FAN_STATS
             {
@@ -347,11 +371,27 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
             if (f && bits && words <= FAN_STAGE) {
                 if (stage_used + words > FAN_STAGE || stage_rows == FAN_STAGE_ROWS) flush();
                 const u32 rel = stage_used;
-                for (u32 g = tid; g < ng32; g += FAN_THREADS) {
-                    u32 v = 0;
-                    if (g < ng) { v = ref + val[g] - gmin; val[g] = 0; }
-                    const u32 w0 = (g - lane) / 32 * bits;
-                    pack_32_groups(v, bits, lane, stage + rel + w0, words - w0);
+                if (sparse) {
+                    // every field holds the reference haplotype's offset, except those of the touched groups: XORed into the zeroed
+                    // staging words in any order.  atomicExch hands a group that two pairs touch to one thread and clears the vector.
+                    const u32 f0 = ref - gmin;
+                    const u32 pat = bits == 32 ? f0 : f0 * (0xffffffffu / ((1u << bits) - 1u));
+                    const u32 tail = (ng * bits) & 31u;
+                    for (u32 w = tid; w < words; w += FAN_THREADS)
+                        atomicXor(&stage[rel + w], (w + 1 == words && tail) ? (pat & ((1u << tail) - 1u)) : pat);
+                    for (u32 x = tid; x < tot; x += FAN_THREADS) {
+                        u32 d;
+                        const u32 g = x == tid ? g_mine : touched(x, d);
+                        const u32 old = atomicExch(&val[g], 0u);
+                        if (old) atomicXor(&stage[rel + ((g * bits) >> 5)], ((f0 + old) ^ f0) << ((g * bits) & 31u));
+                    }
+                } else {
+                    for (u32 g = tid; g < ng32; g += FAN_THREADS) {
+                        u32 v = 0;
+                        if (g < ng) { v = ref + val[g] - gmin; val[g] = 0; }
+                        const u32 w0 = (g - lane) / 32 * bits;
+                        pack_32_groups(v, bits, lane, stage + rel + w0, words - w0);
+                    }
                 }
                 if (tid == 0) { s_stage_key[stage_rows] = hkey; s_stage_rel[stage_rows] = rel; }
                 stage_used = rel + words;
@@ -367,6 +407,11 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
                     if (g < ng) { v = ref + val[g] - gmin; val[g] = 0; }
                     const u32 w0 = (g - lane) / 32 * bits;
                     if (fits) pack_32_groups(v, bits, lane, fn.o_packed + base + w0, words - w0);
+                }
+            } else if (sparse) {
+                for (u32 x = tid; x < tot; x += FAN_THREADS) {
+                    u32 d;
+                    val[x == tid ? g_mine : touched(x, d)] = 0;
                 }
             } else {
                 for (u32 g = tid; g < ng; g += FAN_THREADS) val[g] = 0;

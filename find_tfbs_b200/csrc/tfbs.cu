@@ -171,6 +171,12 @@ int tfbs_create(int device, tfbs_ctx** out) {
         cudaEventCreate(&s.ev_done);
         for (auto& ev : s.ev_t) cudaEventCreate(&ev);
     }
+    TFBS_LAUNCH(k_hash_pow_init, 1, 32, 0, ctx->stream)();  // ordered before every pipeline: they are enqueued on the same stream
+    if ((e = cudaGetLastError()) != cudaSuccess) {
+        g_create_error = std::string("CUDA initialisation failed: ") + cudaGetErrorString(e);
+        tfbs_destroy(ctx);
+        return TFBS_ERR_CUDA;
+    }
     *out = ctx;
     return TFBS_OK;
 }

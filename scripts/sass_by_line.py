@@ -5,6 +5,7 @@ usage: sass_by_line.py <source.csv> <nvdisasm.txt> <mangled-kernel-substring> [t
 import csv, re, sys, collections
 src_csv, dis, kern = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+kern_plain = sys.argv[5] if len(sys.argv) > 5 else ""  # substring of the demangled name in the csv (several kernels in one report)
 lines = open(dis).read().split("\n")
 start = [i for i, l in enumerate(lines) if l.startswith(".text.") and kern in l][0]
 insn_line = []
@@ -19,10 +20,16 @@ for l in lines[start + 1:]:
     if re.match(r"\s*/\*[0-9a-f]{4,}\*/", l):
         insn_line.append(cur)
 rows = list(csv.reader(open(src_csv)))
-hdr = [i for i, r in enumerate(rows) if r and r[0] == "Address"][0]
+# one section per profiled launch: "Kernel Name" line, header line, one row per SASS instruction; the first launch of the kernel is used
+sec = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and kern_plain in r[1]]
+hdr = [i for i, r in enumerate(rows) if r and r[0] == "Address" and i > sec[0]][0]
 h = rows[hdr]
 ci, cs = h.index("Instructions Executed"), h.index("# Samples")
-body = rows[hdr + 1:]
+body = []
+for r in rows[hdr + 1:]:
+    if not r or r[0] == "Kernel Name":
+        break
+    body.append(r)
 assert len(body) == len(insn_line), (len(body), len(insn_line))
 inst, samp = collections.Counter(), collections.Counter()
 for r, ln in zip(body, insn_line):

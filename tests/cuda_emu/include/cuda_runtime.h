@@ -301,6 +301,12 @@ template <class T, class U>
 inline T atomicMax(T* p, U v) { T old = *p; if ((T)v > old) *p = (T)v; return old; }
 template <class T, class U, class V>
 inline T atomicCAS(T* p, U cmp, V val) { T old = *p; if (old == (T)cmp) *p = (T)val; return old; }
+template <class T, class U>
+inline T atomicXor(T* p, U v) { T old = *p; *p = (T)(old ^ (T)v); return old; }
+template <class T, class U>
+inline T atomicOr(T* p, U v) { T old = *p; *p = (T)(old | (T)v); return old; }
+template <class T, class U>
+inline T atomicExch(T* p, U v) { T old = *p; *p = (T)v; return old; }
 
 inline unsigned min(unsigned a, unsigned b) { return a < b ? a : b; }
 inline unsigned max(unsigned a, unsigned b) { return a > b ? a : b; }
