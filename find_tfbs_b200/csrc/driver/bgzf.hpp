@@ -131,16 +131,17 @@ std::vector<uint8_t> gunzip_bgzf(const uint8_t* in, size_t n_in, const std::stri
 // BGZF writer: independent gzip members of <= 64 KiB with the BC extra field, terminated by the empty EOF block.
 class BgzfWriter {
 public:
-    BgzfWriter(const std::string& path, unsigned threads) : f_(path, std::ios::binary), threads_(std::max(1u, threads)) {
+    BgzfWriter(const std::string& path, unsigned threads, int level = 6) : f_(path, std::ios::binary), threads_(std::max(1u, threads)), level_(level) {
         if (!f_) die("Could not create output file");
     }
-    void write(const std::string& s) {
-        buf_ += s;
+    void write(const std::string& s) { write(s.data(), s.size()); }
+    void write(const char* p, size_t n) {  // pieces of a line go straight into the block buffer
+        buf_.append(p, n);
         if (buf_.size() >= kBlock * 8 * threads_) flush(false);
     }
     void finish() {
         flush(true);
-        const std::string eof = compress(nullptr, 0);  // EOF marker
+        const std::string eof = compress(nullptr, 0, 6);  // EOF marker
         f_.write(eof.data(), (std::streamsize)eof.size());
         f_.close();
     }
@@ -157,7 +158,7 @@ private:
             for (;;) {
                 size_t k = next.fetch_add(1);
                 if (k >= n) return;
-                out[k] = compress(buf_.data() + k * kBlock, std::min(kBlock, buf_.size() - k * kBlock));
+                out[k] = compress(buf_.data() + k * kBlock, std::min(kBlock, buf_.size() - k * kBlock), level_);
             }
         };
         const unsigned nt = (unsigned)std::min<size_t>(threads_, n);
@@ -170,12 +171,12 @@ private:
         for (const std::string& blk : out) f_.write(blk.data(), (std::streamsize)blk.size());
         buf_.erase(0, std::min(buf_.size(), n * kBlock));
     }
-    static std::string compress(const char* data, size_t n) {
+    static std::string compress(const char* data, size_t n, int level) {
         std::string out(0x10000 + 64, '\0');
         uint8_t* o = (uint8_t*)&out[0];
         z_stream zs;
         memset(&zs, 0, sizeof zs);
-        deflateInit2(&zs, 6, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
+        deflateInit2(&zs, level, Z_DEFLATED, -15, 8, Z_DEFAULT_STRATEGY);
         zs.next_in = (Bytef*)data;
         zs.avail_in = (uInt)n;
         zs.next_out = o + 18;
@@ -198,6 +199,7 @@ private:
     std::ofstream f_;
     std::string buf_;
     unsigned threads_;
+    int level_;
 };
 
 }  // namespace

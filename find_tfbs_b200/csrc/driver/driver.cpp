@@ -112,7 +112,7 @@ int main(int argc, char** argv) {
     }
 
     const std::string part = o.output + ".part";
-    BgzfWriter* gz = o.plain_text ? nullptr : new BgzfWriter(part, o.threads);
+    BgzfWriter* gz = o.plain_text ? nullptr : new BgzfWriter(part, o.threads, o.compression_level);
     std::ofstream plain;
     if (o.plain_text) { plain.open(part, std::ios::binary); if (!plain) die("Could not create output file"); }
     auto emit = [&](const std::string& s) { if (gz) gz->write(s); else plain << s; };
@@ -147,7 +147,11 @@ int main(int argc, char** argv) {
                 done_chunks.erase(it);
             }
             auto tw = std::chrono::steady_clock::now();
-            for (const std::string& row : t.rows) emit(chr + "\t" + std::to_string(fake_position++) + row);
+            for (const std::string& row : t.rows) {  // CHROM, POS, then the row as the worker formatted it: no copy of the row on the way
+                const std::string head = chr + "\t" + std::to_string(fake_position++);
+                if (gz) { gz->write(head.data(), head.size()); gz->write(row.data(), row.size()); }
+                else plain << head << row;
+            }
             secs_write += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw).count();
             {
                 std::lock_guard<std::mutex> lk(out_mu);

@@ -15,6 +15,7 @@ struct Options {
     float pwm_threshold = 0;
     bool forward_only = false, tabix = false, verbose = false, has_samples = false, plain_text = false;
     uint32_t min_maf = 0, threads = 1, chunk = 2000;
+    int compression_level = 3;  // zlib level of the BGZF blocks: the byte stream is not part of the contract (outputs are compared after gunzip)
     uint64_t after_position = 0;
     std::vector<int> devices{0};
     bool use_index = true;   // --no_index: ignore <bcf>.csi and scan the whole BCF
@@ -37,7 +38,7 @@ void usage() {
          "USAGE: find-tfbs-b200 --chromosome CHROM --input IN.bcf --output OUT.vcf.gz --reference REF.fa --bed A.bed[,B.bed]\n"
          "         --pwm_names NAME[,NAME] --pwm_file PWM.txt --pwm_threshold_directory DIR --pwm_threshold P\n"
          "         [--forward_only] [--threads N] [--min_maf N] [--after_position POS] [--samples FILE] [--tabix] [--verbose]\n"
-         "         [--devices 0,1,...] [--chunk REGIONS_PER_BLOCK] [--plain] [--audit AUDIT.tsv] [--no_index]");
+         "         [--devices 0,1,...] [--chunk REGIONS_PER_BLOCK] [--plain] [--audit AUDIT.tsv] [--no_index] [--compression_level 1..9]");
 }
 
 Options parse_args(int argc, char** argv) {
@@ -99,6 +100,7 @@ Options parse_args(int argc, char** argv) {
     if (kv.count("threads") && o.threads < 1) die("Wrong number of threads");
     o.after_position = num("after_position", 0, "Cannot parse after_position");
     o.chunk = (uint32_t)std::max<uint64_t>(1, num("chunk", 2000, "Cannot parse chunk"));
+    o.compression_level = (int)std::min<uint64_t>(9, std::max<uint64_t>(1, num("compression_level", 3, "Cannot parse compression_level")));
     if (kv.count("samples")) { o.has_samples = true; o.samples_file = kv["samples"]; }
     if (kv.count("audit")) o.audit_file = kv["audit"];
     if (kv.count("devices")) {

@@ -48,34 +48,50 @@ __device__ __forceinline__ bool carries(const DevBlock& b, u32 v, u32 h) {
     return (b.carriers[(size_t)b.variants[v].carrier_row * b.pitch + (h >> 5)] >> (h & 31)) & 1u;
 }
 
-// Thread per (region, haplotype): hash of the ordered list of carried Diff classes; 0 = no diff
-// (such a haplotype stays in the reference set, main.rs:74-81,103-105).
+// Transpose of a 32 x 32 bit matrix held one row per lane: lane l returns column l (bit j = bit l of lane j's row); five butterfly
+// exchanges.
+__device__ __forceinline__ u32 warp_transpose32(u32 a, u32 lane) {
+    u32 m = 0x0000ffffu;
+#pragma unroll
+    for (u32 j = 16; j; j >>= 1, m ^= m << j) {
+        const u32 other = __shfl_xor_sync(0xffffffffu, a, j);
+        if ((lane & j) == 0) a ^= (((a >> j) ^ other) & m) << j;
+        else a ^= ((other >> j) ^ a) & m;
+    }
+    return a;
+}
+
+// Warp per (region, 32 consecutive haplotypes), lane = haplotype: hash of the ordered list of carried Diff classes; 0 = no diff
+// (such a haplotype stays in the reference set, main.rs:74-81,103-105).  Launch with nr * ceil(H / 32) * 32 threads.
 __global__ void k_signatures(DevBlock b, u32 r0, u32 nr, u64 seed, u64* sig, u32* nd_in) {
-    u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (u64)nr * b.H) return;
-    u32 r = r0 + (u32)(idx / b.H), h = (u32)(idx % b.H);
+    const u64 idx = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const u32 HW = (b.H + 31) / 32, lane = threadIdx.x & 31;
+    const u64 wg = idx >> 5;
+    if (wg >= (u64)nr * HW) return;  // whole warps leave together
+    const u32 r = r0 + (u32)(wg / HW), hw = (u32)(wg % HW), h = hw * 32 + lane;
+    const bool valid = h < b.H;
     u64 s = seed;
     u32 carried = 0, inw = 0;
     const u32 v0 = b.var_off[r], v1 = b.var_off[r + 1];
     if (b.hap_mask) {
-        // first the mask, 32 records per word (the loads are the same for the 32 haplotypes of a warp: one carrier word per record),
-        // then the hash over its set bits: a haplotype carries a few records out of dozens
+        // first the mask, 32 records per word: lane j fetches the carrier word of record vb + j for these 32 haplotypes (one load
+        // instruction for 32 records), a bit-matrix transpose turns record-major into haplotype-major; then the hash over the set
+        // bits: a haplotype carries a few records out of dozens
         u32* mask = b.hap_mask + b.mask_base[r] + h;  // word w of haplotype h sits at w * H + h: a warp writes 32 consecutive words
-        const u32 hw = h >> 5, hb = h & 31;
         for (u32 vb = v0, w = 0; vb < v1; vb += 32, ++w) {
-            const u32 ve = vb + 32 < v1 ? vb + 32 : v1;
-            u32 word = 0;
-            for (u32 v = vb; v < ve; ++v)
-                word |= ((b.carriers[(size_t)b.var_row[v] * b.pitch + hw] >> hb) & 1u) << (v - vb);
+            const u32 v = vb + lane;
+            const u32 cw = v < v1 ? b.carriers[(size_t)b.var_row[v] * b.pitch + hw] : 0u;
+            const u32 word = warp_transpose32(cw, lane);
+            if (!valid) continue;
             mask[(u64)w * b.H] = word;
             for (u32 m = word; m; m &= m - 1) {
-                const u32 v = vb + (u32)__ffs((int)m) - 1;
-                s = mix64(s + b.var_class[v] + 1) * 0x9e3779b97f4a7c15ULL + carried;
+                const u32 vv = vb + (u32)__ffs((int)m) - 1;
+                s = mix64(s + b.var_class[vv] + 1) * 0x9e3779b97f4a7c15ULL + carried;
                 ++carried;
-                inw += b.var_inwin[v];
+                inw += b.var_inwin[vv];
             }
         }
-    } else {
+    } else if (valid) {
         for (u32 v = v0; v < v1; ++v)
             if (carries(b, v, h)) {
                 s = mix64(s + b.var_class[v] + 1) * 0x9e3779b97f4a7c15ULL + carried;
@@ -83,6 +99,7 @@ __global__ void k_signatures(DevBlock b, u32 r0, u32 nr, u64 seed, u64* sig, u32
                 inw += b.var_inwin[v];
             }
     }
+    if (!valid) return;
     sig[(size_t)r * b.H + h] = carried ? (mix64(s) | 1ULL) : 0ULL;
     nd_in[(size_t)r * b.H + h] = inw;
 }

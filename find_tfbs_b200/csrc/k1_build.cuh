@@ -119,7 +119,8 @@ struct WalkOut {
     u32 ns, len, ntake;
     bool trunc;
 };
-__device__ __forceinline__ WalkOut walk_diffs(const DevBlock& b, u32 r, const u32* dl, u32 nd, Seg* sg, DevStatus* st, u64 q_report) {
+template <class Sink>
+__device__ __forceinline__ WalkOut walk_diffs_to(const DevBlock& b, u32 r, const u32* dl, u32 nd, Sink&& put, DevStatus* st, u64 q_report) {
     const i64 start = b.region_start[r], end = b.region_end[r];
     const u64 ro = b.ref_off[r];
     const i64 n_ref = (i64)(b.ref_off[r + 1] - ro);
@@ -131,7 +132,7 @@ __device__ __forceinline__ WalkOut walk_diffs(const DevBlock& b, u32 r, const u3
         if (a < start) a = start;
         if (e2 > avail_end) e2 = avail_end;
         if (e2 >= a) {
-            sg[ns++] = Seg{out, (u32)(a - start), (int)(a - start), 0u};
+            put(ns++, Seg{out, (u32)(a - start), (int)(a - start), 0u});
             out += (u32)(e2 - a + 1);
         }
     };
@@ -148,12 +149,12 @@ __device__ __forceinline__ WalkOut walk_diffs(const DevBlock& b, u32 r, const u3
         } else if (d.pos == rp && d.ref_len == 1) {  // :115-135 SNV or insertion
             u8 at = (rp >= start && rp <= avail_end) ? b.ref_codes[ro + (u64)(rp - start)] : (u8)4;
             if (b.allele_codes[d.ref_off] != at) { if (st) report(st, q_report, rp - start, DEV_REF_MISMATCH); break; }
-            sg[ns++] = Seg{out, d.alt_off, (int)(rp - start), 1u};
+            put(ns++, Seg{out, d.alt_off, (int)(rp - start), 1u});
             out += d.alt_len;
             rp += 1;
             ++k;
         } else if (d.pos == rp && d.alt_len == 1) {  // :136-140 deletion
-            sg[ns++] = Seg{out, d.alt_off, (int)(rp - start), 1u};
+            put(ns++, Seg{out, d.alt_off, (int)(rp - start), 1u});
             out += 1;
             rp += d.ref_len;
             ++k;
@@ -171,12 +172,17 @@ __device__ __forceinline__ WalkOut walk_diffs(const DevBlock& b, u32 r, const u3
             break;
         }
     }
-    sg[ns] = Seg{out, 0u, 0, 2u};  // terminator
+    put(ns, Seg{out, 0u, 0, 2u});  // terminator
     return WalkOut{ns, out, k, trunc};
+}
+__device__ __forceinline__ WalkOut walk_diffs(const DevBlock& b, u32 r, const u32* dl, u32 nd, Seg* sg, DevStatus* st, u64 q_report) {
+    return walk_diffs_to(b, r, dl, nd, [sg](u32 i, const Seg& x) { sg[i] = x; }, st, q_report);
 }
 
 // Thread per sequence: gathers the carried in-window diffs (haplotype.rs:95), sorts them (:96) and walks them.
-__global__ void k_walk(DevBlock b, DevSeqs sq, u64 d_cap, DevStatus* st) {
+// store_segs = 0: the segment lists are not kept (the configuration path scans virtual sequences, k_cfg_walk; only k_seq_resolve
+// looks at a haplotype's own segments, for the few candidates of the sequence-keyed map, and walks those again).
+__global__ void k_walk(DevBlock b, DevSeqs sq, u64 d_cap, DevStatus* st, u32 store_segs) {
     u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= seq_count(sq)) return;
     u32 r = sq.seq_region[q];
@@ -203,25 +209,27 @@ __global__ void k_walk(DevBlock b, DevSeqs sq, u64 d_cap, DevStatus* st) {
         for (u32 v = b.var_off[r]; v < b.var_off[r + 1]; ++v)
             if (b.var_inwin[v] && carries(b, v, h)) take(v);
     }
-    const WalkOut w = walk_diffs(b, r, dl, nd, sg, st, q);
-    const u32 ns = w.ns;
-    sq.seq_nseg[q] = ns;
+    // hash of the (nuc, pos) vector, segment by segment as the walk emits them (a segment's length is known when the next one starts)
+    const u64* P = b.ref_prefix + b.ref_off[r] + r;
+    u64 hsh = 0;
+    Seg prev{0u, 0u, 0, 2u};
+    const WalkOut w = walk_diffs_to(b, r, dl, nd, [&](u32 i, const Seg& x) {
+        if (store_segs) sg[i] = x;
+        if (i) {
+            const u32 n = x.out_start - prev.out_start;
+            if (prev.kind == 0) hsh += hash_pow((long long)prev.out_start - (long long)prev.src) * (P[prev.src + n] - P[prev.src]);
+            else {
+                u64 pw = hash_pow(prev.out_start);
+                for (u32 t = 0; t < n; ++t) { hsh += hash_val(b.allele_codes[prev.src + t], prev.relpos) * pw; pw *= HASH_B; }
+            }
+        }
+        prev = x;
+    }, st, q);
+    sq.seq_nseg[q] = w.ns;
     sq.seq_len[q] = w.len;
     sq.seq_flags[q] = w.trunc ? 1 : 0;
     sq.seq_ntake[q] = w.ntake;
-    {   // hash of the (nuc, pos) vector from the segments
-        const u64* P = b.ref_prefix + b.ref_off[r] + r;
-        u64 hsh = 0;
-        for (u32 s = 0; s < ns; ++s) {
-            const u32 n = sg[s + 1].out_start - sg[s].out_start;
-            if (sg[s].kind == 0) hsh += hash_pow((long long)sg[s].out_start - (long long)sg[s].src) * (P[sg[s].src + n] - P[sg[s].src]);
-            else {
-                u64 pw = hash_pow(sg[s].out_start);
-                for (u32 x = 0; x < n; ++x) { hsh += hash_val(b.allele_codes[sg[s].src + x], sg[s].relpos) * pw; pw *= HASH_B; }
-            }
-        }
-        sq.seq_hash[q] = hsh;
-    }
+    sq.seq_hash[q] = hsh;
     if (w.trunc) atomicAdd(&st->n_truncated, 1u);
 }
 
@@ -284,7 +292,7 @@ __device__ __forceinline__ void base_at(const DevBlock& b, const DevSeqs& sq, u3
 // A later insert with an equal key overwrites the earlier one in the reference (haplotype.rs:84); the
 // winner there depends on HashMap order, here the group with the smallest first haplotype wins (same rule
 // as the oracle).  The losers are dropped: their haplotypes stay in the reference set (main.rs:103-105).
-__global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32* vals, u32 mask, u32 seg, u32 r0, DevStatus* st) {
+__global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32* vals, u32 mask, u32 seg, u32 r0, DevStatus* st, u32 have_segs) {
     u32 q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= seq_count(sq)) return;
     u32 g = seq_group(sq, q);
@@ -299,8 +307,13 @@ __global__ void k_seq_resolve(DevBlock b, DevSeqs sq, const u64* keys, const u32
     // walk the two segment lists over the union of their breakpoints: two reference-copy pieces at the same position are equal by
     // construction, anything else is compared base by base (nuc and pos)
     if (same) {
-        const Seg* sa = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
-        const Seg* sb = sq.segs + 2 * sq.seq_doff[qw] + 2 * (u64)qw;
+        Seg* sa = sq.segs + 2 * sq.seq_doff[q] + 2 * (u64)q;
+        Seg* sb = sq.segs + 2 * sq.seq_doff[qw] + 2 * (u64)qw;
+        if (!have_segs) {  // k_walk did not keep them: walk the two candidates again into their own slots (several losers of one winner
+                           // write the same values to the winner's slot)
+            walk_diffs(b, sq.seq_region[q], sq.dlist + sq.seq_doff[q], sq.seq_nd[q], sa, nullptr, 0);
+            walk_diffs(b, sq.seq_region[qw], sq.dlist + sq.seq_doff[qw], sq.seq_nd[qw], sb, nullptr, 0);
+        }
         const u8* refc = b.ref_codes + b.ref_off[sq.seq_region[q]];
         const u32 len = sq.seq_len[q];
         u32 ia = 0, ib = 0, i = 0;

@@ -301,7 +301,7 @@ struct ConfigPipeline {
                 const uint32_t nr = std::min(regions_per_super, R - r0);
                 const uint64_t pairs = (uint64_t)nr * H;
                 if ((rc = table_slots((uint64_t)nr * seg))) return rc;
-                TFBS_LAUNCH(k_signatures, grid_for(pairs, 256), 256, 0, st)(db, r0, nr, slot->seed, ctx->d_sig.as<u64>(), ctx->d_nd_in.as<u32>());
+                TFBS_LAUNCH(k_signatures, grid_for((uint64_t)nr * ((H + 31) / 32) * 32, 256), 256, 0, st)(db, r0, nr, slot->seed, ctx->d_sig.as<u64>(), ctx->d_nd_in.as<u32>());
                 TFBS_LAUNCH(k_group_insert, grid_for(pairs, 256), 256, 0, st)(H, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), 0u, seg);
                 TFBS_LAUNCH(k_group_lookup, grid_for(pairs, 256), 256, 0, st)(db, r0, nr, ctx->d_sig.as<u64>(), ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), 0u, seg,
                                                                      ctx->d_leader.as<u32>(), dst);
@@ -339,13 +339,13 @@ struct ConfigPipeline {
         // the total sits behind the last sequence; k_gate reads it through the clamped count
         TFBS_LAUNCH(k_gate_at, 1, 1, 0, st)(sq.seq_doff, &plan->n_seq, (u64)c.d, &plan->n_d, &plan->need_d, &plan->abort);
         ++launches();
-        TFBS_LAUNCH(k_walk, grid_for(c.seq, 128), 128, 0, st)(db, sq, (u64)c.d, dst);
+        TFBS_LAUNCH(k_walk, grid_for(c.seq, 128), 128, 0, st)(db, sq, (u64)c.d, dst, 0u);
         ++launches();
         {
             if ((rc = table_slots((uint64_t)R * seg))) return rc;  // at most H + 1 distinct haplotypes per region
             CK(cudaMemsetAsync(ctx->d_ref_used.p, 0, (size_t)R * 4, st));
             TFBS_LAUNCH(k_seq_insert, grid_for(c.seq, 256), 256, 0, st)(sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), 0u, seg, 0u);
-            TFBS_LAUNCH(k_seq_resolve, grid_for(c.seq, 128), 128, 0, st)(db, sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), 0u, seg, 0u, dst);
+            TFBS_LAUNCH(k_seq_resolve, grid_for(c.seq, 128), 128, 0, st)(db, sq, ctx->d_keys.as<u64>(), ctx->d_vals.as<u32>(), 0u, seg, 0u, dst, 0u);
             TFBS_LAUNCH(k_redirect, grid_for(RH, 256), 256, 0, st)(H, 0, R, sq, hap_group, ctx->d_ref_used.as<u32>(), (u8*)nullptr, (u64*)&dst->nominal_cells,
                                                                    ctx->dpat.max_len, ctx->dpat.sum_len, (u64)ctx->dpat.sum_len_sq, ctx->dpat.n_patterns, ctx->dpat.pat_len);
             launches() += 3;
