@@ -35,6 +35,7 @@ struct DevBlock {
     // derived per variant
     const u32* var_class;       // index (inside the region) of the first record with the same Diff
     const u8* var_inwin;        // region_start <= pos <= region_end (haplotype.rs:95)
+    u64* var_althash;           // sum_t val(alt[t], pos - region_start) * B^t: what the record's ALT bases add to a haplotype's hash, up to B^out_start
     const u64* ref_prefix;      // polynomial prefix hash of every window: entry ref_off[r] + r + j = sum_{t<j} val(code_t, t) * B^t
     // carried-record masks (NULL = not kept): word w of haplotype h of region r sits at mask_base[r] + w * H + h (ceil(V_r / 32) words per
     // haplotype), bit v of the mask = it carries record var_off[r] + v.  Written by k_signatures; they make the exact check of a group and the gather of a

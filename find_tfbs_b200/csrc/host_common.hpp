@@ -166,7 +166,7 @@ struct tfbs_ctx {
     size_t arena_bytes = 0;
 
     // scratch shared by consecutive blocks (their kernels are serialised on `stream`)
-    DevBuf d_ref_codes, d_allele_codes, d_var_class, d_var_inwin, d_ref_prefix;
+    DevBuf d_ref_codes, d_allele_codes, d_var_class, d_var_inwin, d_var_althash, d_ref_prefix;
     DevBuf d_sig, d_nd_in, d_leader, d_hap_group, d_ngroups, d_sum_nd, d_ref_used;
     DevBuf d_keys, d_vals, d_scanwork;
     DevBuf d_kbase, d_hap_mask, d_mask_base, d_region_dups, d_var_row;
@@ -336,6 +336,7 @@ int reserve_encoding(tfbs_ctx* ctx, const BlockDev& B) {
     if ((rc = grow(ctx, ctx->d_allele_codes, std::max<uint64_t>(1, B.n_allele_bytes)))) return rc;
     if ((rc = grow(ctx, ctx->d_var_class, std::max<uint64_t>(1, B.n_var) * 4))) return rc;
     if ((rc = grow(ctx, ctx->d_var_inwin, std::max<uint64_t>(1, B.n_var)))) return rc;
+    if ((rc = grow(ctx, ctx->d_var_althash, std::max<uint64_t>(1, B.n_var) * 8))) return rc;
     if ((rc = grow(ctx, ctx->d_ref_prefix, (B.n_ref_bytes + B.R + 1) * 8))) return rc;
     return TFBS_OK;
 }
@@ -358,6 +359,7 @@ DevBlock dev_block(const tfbs_ctx* ctx, const BlockDev& B) {
     b.pitch = B.pitch;
     b.var_class = ctx->d_var_class.as<u32>();
     b.var_inwin = ctx->d_var_inwin.as<u8>();
+    b.var_althash = ctx->d_var_althash.as<u64>();
     b.ref_prefix = ctx->d_ref_prefix.as<u64>();
     return b;
 }

@@ -132,7 +132,7 @@ __device__ __forceinline__ WalkOut walk_diffs_to(const DevBlock& b, u32 r, const
         if (a < start) a = start;
         if (e2 > avail_end) e2 = avail_end;
         if (e2 >= a) {
-            put(ns++, Seg{out, (u32)(a - start), (int)(a - start), 0u});
+            put(ns++, Seg{out, (u32)(a - start), (int)(a - start), 0u}, 0xffffffffu);
             out += (u32)(e2 - a + 1);
         }
     };
@@ -149,12 +149,12 @@ __device__ __forceinline__ WalkOut walk_diffs_to(const DevBlock& b, u32 r, const
         } else if (d.pos == rp && d.ref_len == 1) {  // :115-135 SNV or insertion
             u8 at = (rp >= start && rp <= avail_end) ? b.ref_codes[ro + (u64)(rp - start)] : (u8)4;
             if (b.allele_codes[d.ref_off] != at) { if (st) report(st, q_report, rp - start, DEV_REF_MISMATCH); break; }
-            put(ns++, Seg{out, d.alt_off, (int)(rp - start), 1u});
+            put(ns++, Seg{out, d.alt_off, (int)(rp - start), 1u}, dl[k]);
             out += d.alt_len;
             rp += 1;
             ++k;
         } else if (d.pos == rp && d.alt_len == 1) {  // :136-140 deletion
-            put(ns++, Seg{out, d.alt_off, (int)(rp - start), 1u});
+            put(ns++, Seg{out, d.alt_off, (int)(rp - start), 1u}, dl[k]);
             out += 1;
             rp += d.ref_len;
             ++k;
@@ -172,11 +172,11 @@ __device__ __forceinline__ WalkOut walk_diffs_to(const DevBlock& b, u32 r, const
             break;
         }
     }
-    put(ns, Seg{out, 0u, 0, 2u});  // terminator
+    put(ns, Seg{out, 0u, 0, 2u}, 0xffffffffu);  // terminator
     return WalkOut{ns, out, k, trunc};
 }
 __device__ __forceinline__ WalkOut walk_diffs(const DevBlock& b, u32 r, const u32* dl, u32 nd, Seg* sg, DevStatus* st, u64 q_report) {
-    return walk_diffs_to(b, r, dl, nd, [sg](u32 i, const Seg& x) { sg[i] = x; }, st, q_report);
+    return walk_diffs_to(b, r, dl, nd, [sg](u32 i, const Seg& x, u32) { sg[i] = x; }, st, q_report);
 }
 
 // Thread per sequence: gathers the carried in-window diffs (haplotype.rs:95), sorts them (:96) and walks them.
@@ -213,17 +213,19 @@ __global__ void k_walk(DevBlock b, DevSeqs sq, u64 d_cap, DevStatus* st, u32 sto
     const u64* P = b.ref_prefix + b.ref_off[r] + r;
     u64 hsh = 0;
     Seg prev{0u, 0u, 0, 2u};
-    const WalkOut w = walk_diffs_to(b, r, dl, nd, [&](u32 i, const Seg& x) {
+    u32 prev_v = 0xffffffffu;  // the record of an ALT segment: its bases' share of the hash is known per record (k_variant_prep)
+    const WalkOut w = walk_diffs_to(b, r, dl, nd, [&](u32 i, const Seg& x, u32 v) {
         if (store_segs) sg[i] = x;
         if (i) {
-            const u32 n = x.out_start - prev.out_start;
-            if (prev.kind == 0) hsh += hash_pow((long long)prev.out_start - (long long)prev.src) * (P[prev.src + n] - P[prev.src]);
-            else {
-                u64 pw = hash_pow(prev.out_start);
-                for (u32 t = 0; t < n; ++t) { hsh += hash_val(b.allele_codes[prev.src + t], prev.relpos) * pw; pw *= HASH_B; }
+            if (prev.kind == 0) {
+                const u32 n = x.out_start - prev.out_start;
+                hsh += hash_pow((long long)prev.out_start - (long long)prev.src) * (P[prev.src + n] - P[prev.src]);
+            } else {
+                hsh += hash_pow(prev.out_start) * b.var_althash[prev_v];
             }
         }
         prev = x;
+        prev_v = v;
     }, st, q);
     sq.seq_nseg[q] = w.ns;
     sq.seq_len[q] = w.len;
