@@ -23,7 +23,7 @@ DIR_P, DIR_N = 0, 1
 EXPORTS = ["tfbs_abi_version", "tfbs_create", "tfbs_destroy", "tfbs_last_error", "tfbs_set_option", "tfbs_set_patterns",
            "tfbs_submit_block", "tfbs_collect", "tfbs_get_matches", "tfbs_upload_block", "tfbs_run_resident", "tfbs_get_stats",
            "tfbs_stream", "tfbs_host_register", "tfbs_host_unregister", "tfbs_audit_block", "tfbs_collect_grouped", "tfbs_expand_rows", "tfbs_set_result_arena",
-           "tfbs_merge_sample_blocks"]
+           "tfbs_merge_sample_blocks", "tfbs_merge_regions"]
 
 
 class TfbsPattern(C.Structure):
@@ -245,6 +245,8 @@ def lib():
         L.tfbs_merge_sample_blocks.argtypes = [C.POINTER(C.POINTER(TfbsGroupedRows)), C.c_uint32, C.c_uint64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
                                                C.POINTER(C.c_uint16), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64),
                                                C.POINTER(C.c_uint64)]
+        L.tfbs_merge_regions.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(C.c_uint64),
+                                         C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         L.tfbs_get_matches.argtypes = [C.c_void_p, C.POINTER(TfbsMatches)]
         L.tfbs_get_stats.argtypes = [C.c_void_p, C.POINTER(TfbsStats)]
         L.tfbs_audit_block.argtypes = [C.c_void_p, C.POINTER(TfbsAudit)]
@@ -482,6 +484,17 @@ class Context:
                     raise TfbsError(rc, "tfbs_expand_rows failed")
             out["left"], out["right"] = left, right
         return out
+
+    def merge_regions(self, ranges):
+        """tfbs_merge_regions: the merged regions of the concatenated BED ranges [(start, end)], ascending (bed.rs:37-45)."""
+        a = np.ascontiguousarray(np.array(ranges, dtype=np.uint64).reshape(-1, 2))
+        n = len(a)
+        start, end = np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1])
+        o_s, o_e = np.zeros(max(1, n), np.uint64), np.zeros(max(1, n), np.uint64)
+        n_out = C.c_uint64(0)
+        self._check(self._lib.tfbs_merge_regions(self._h, _ptr(start, C.c_uint64), _ptr(end, C.c_uint64), n, _ptr(o_s, C.c_uint64),
+                                                 _ptr(o_e, C.c_uint64), C.byref(n_out)))
+        return [(int(o_s[i]), int(o_e[i])) for i in range(n_out.value)]
 
     def matches(self, n_regions):
         m = TfbsMatches()

@@ -69,8 +69,6 @@ int main(int argc, char** argv) {
         peak_map.push_back(kept);
         bed_names.push_back(basename_of(b));
     }
-    std::vector<Range> merged = merge_ranges(all);
-    printf("Merged all region files: %zu merged regions\n", merged.size());
 
     // one context per device; chunks of merged regions are dealt round-robin (regions are independent, main.rs:395-429)
     std::vector<tfbs_pattern> cpat(pwms.size());
@@ -102,6 +100,22 @@ int main(int argc, char** argv) {
     Cohort co = load_bcf(o);
     const double t_after_bcf = since();
     for (auto& t : pre) t.join();
+    // the merged regions (bed.rs:37-45): on the first device; ranges with end < start only fold in file order, on the host
+    std::vector<Range> merged;
+    {
+        std::vector<uint64_t> bs(all.size()), be(all.size()), ms(all.size()), me(all.size());
+        for (size_t i = 0; i < all.size(); ++i) { bs[i] = all[i].start; be[i] = all[i].end; }
+        uint64_t nm = 0;
+        const int rc = ctxs[0] ? tfbs_merge_regions(ctxs[0], bs.data(), be.data(), all.size(), ms.data(), me.data(), &nm) : TFBS_ERR_INVALID_ARGUMENT;
+        if (rc == TFBS_OK) {
+            for (uint64_t i = 0; i < nm; ++i) merged.push_back(Range{ms[i], me[i]});
+        } else if (rc == TFBS_ERR_INVALID_ARGUMENT) {
+            merged = merge_ranges(all);
+        } else {
+            die(std::string(tfbs_last_error(ctxs[0])));
+        }
+    }
+    printf("Merged all region files: %zu merged regions\n", merged.size());
     const uint32_t S = (uint32_t)co.samples.size();
 
     // main.rs:402 chromosome.replace("chr", ""): one left-to-right pass over non-overlapping matches

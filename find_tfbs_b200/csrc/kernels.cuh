@@ -8,6 +8,7 @@
 //       scan          k_scan                replaces matches / apply_pwm              (pattern.rs:119-171)
 //                                           + the hit -> inner-region test            (main.rs:500-505)
 //       finish        k_group_finish        inherited / lost reference hits, shared item counts -> per-group count rows
+//   BED merge         k_bed_rank/merge      merged regions of all BED files          (bed.rs:37-45, range.rs:43-87)
 //   K3  count/rows    k_rows_*              count_matches_by_sample fan-out           (main.rs:506-531)
 //                                           + min/max filter of counts_as_genotypes   (main.rs:439-458)
 //
@@ -25,3 +26,4 @@
 #include "k2_finish.cuh"
 #include "k3_rows.cuh"
 #include "k3_fanout.cuh"
+#include "k_bed.cuh"

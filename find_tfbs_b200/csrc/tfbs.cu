@@ -430,6 +430,38 @@ int tfbs_merge_sample_blocks(const tfbs_grouped_rows* const* parts, uint32_t n_p
     return TFBS_OK;
 }
 
+// load_peak_files' merge (bed.rs:37-45 -> RangeStack, range.rs:43-87) on the device: stable rank by start, prefix maximum of the ends.
+int tfbs_merge_regions(tfbs_ctx* ctx, const uint64_t* start, const uint64_t* end, uint64_t n, uint64_t* out_start, uint64_t* out_end, uint64_t* n_out) {
+    if (!ctx || !n_out || (n && (!start || !end || !out_start || !out_end))) return TFBS_ERR_INVALID_ARGUMENT;
+    *n_out = 0;
+    if (n == 0) return TFBS_OK;
+    if (n > 0x7fffffffull) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "too many ranges");
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    DevBuf d_in, d_out, d_order, d_misc;
+    CK(d_in.reserve(n * 16));
+    CK(d_out.reserve(n * 16));
+    CK(d_order.reserve(n * 4));
+    CK(d_misc.reserve(16));
+    u64* ds = d_in.as<u64>();
+    u64* de = ds + n;
+    CK(cudaMemcpyAsync(ds, start, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(de, end, n * 8, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(d_misc.p, 0, 16, st));
+    TFBS_LAUNCH(k_bed_rank, grid_for(n, BED_THREADS), BED_THREADS, 0, st)(ds, (u64)n, d_order.as<u32>());
+    TFBS_LAUNCH(k_bed_merge, 1, BED_THREADS, 0, st)(ds, de, d_order.as<u32>(), (u64)n, d_out.as<u64>(), d_out.as<u64>() + n, d_misc.as<u64>(),
+                                                    reinterpret_cast<u32*>(d_misc.as<u64>() + 1));
+    uint64_t misc[2] = {0, 0};
+    CK(cudaMemcpyAsync(misc, d_misc.p, 16, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    if ((uint32_t)misc[1]) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "a range has end < start");
+    CK(cudaMemcpyAsync(out_start, d_out.p, misc[0] * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(out_end, d_out.as<u64>() + n, misc[0] * 8, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    *n_out = misc[0];
+    return TFBS_OK;
+}
+
 int tfbs_get_matches(tfbs_ctx* ctx, tfbs_matches* out) {
     if (!ctx || !out) return TFBS_ERR_INVALID_ARGUMENT;
     if (ctx->last < 0 || !ctx->slot[ctx->last].full_mode || !ctx->record_matches)

@@ -335,6 +335,17 @@ int tfbs_expand_rows(const tfbs_grouped_rows* rows, uint64_t first_row, uint64_t
 int tfbs_merge_sample_blocks(const tfbs_grouped_rows* const* parts, uint32_t n_parts, uint64_t cap, uint32_t* region, uint32_t* inner,
                              uint16_t* pattern_id, uint32_t* vmin, uint32_t* vmax, uint64_t* part_row, uint64_t* n_out);
 
+/*
+ * Merged regions of all BED files on the device: load_peak_files' RangeStack (src/bed.rs:37-45, src/range.rs:43-87) -- the ranges
+ * sorted by start (stable) and folded from the left with Range::overlaps / Range::merge (range.rs:18-36) -- as a stable rank, a
+ * prefix maximum of the ends and a compaction.  start / end: the concatenated inclusive ranges of every BED file (bed.rs:15);
+ * out_start / out_end: room for n ranges; *n_out = merged ranges, ascending by start (bed.rs:40-44).  A range with end < start
+ * fails with TFBS_ERR_INVALID_ARGUMENT (the fold is then order-dependent; fold such input on the host with the literal rule).
+ * Synchronous; independent of the blocks in flight.
+ */
+int tfbs_merge_regions(tfbs_ctx* ctx, const uint64_t* start, const uint64_t* end, uint64_t n, uint64_t* out_start, uint64_t* out_end,
+                       uint64_t* n_out);
+
 /* Matches of the last run when "record_matches" was on (call after tfbs_collect). */
 int tfbs_get_matches(tfbs_ctx* ctx, tfbs_matches* out);
 

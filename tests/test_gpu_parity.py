@@ -590,3 +590,24 @@ def test_grouped_rows_two_blocks_in_flight_and_scratch_growth():
                     ctx.collect()  # nothing in flight any more
             finally:
                 ctx.close()
+
+
+def test_bed_merge_on_device():
+    """tfbs_merge_regions == load_peak_files' merge (bed.rs:37-45, range.rs:43-87): the reference's own vector (bed.rs:67-95), random
+    range sets against the literal fold (synth.merge_regions), ties in start, touching and nested ranges, sizes around the tile."""
+    ctx = binding.Context(0)
+    try:
+        ref = [(100, 110), (120, 130), (150, 160), (180, 190), (200, 210), (110, 115), (118, 125), (161, 165), (190, 200)]
+        assert ctx.merge_regions(ref) == [(100, 115), (118, 130), (150, 160), (161, 165), (180, 210)]
+        assert ctx.merge_regions([]) == [] and ctx.merge_regions([(5, 5)]) == [(5, 5)]
+        assert ctx.merge_regions([(0, 0), (0, 0), (1, 1)]) == [(0, 0), (1, 1)]  # equal ranges join, start = end + 1 does not (inclusive ends)
+        rng = np.random.default_rng(7)
+        for n, span, width in ((2, 10, 5), (255, 3000, 20), (256, 3000, 20), (257, 1000, 3), (700, 200000, 400), (5000, 10 ** 7, 3000), (3000, 500, 50)):
+            s = rng.integers(0, span, size=n)
+            e = s + rng.integers(0, width, size=n)
+            ranges = list(zip(s.tolist(), e.tolist()))
+            assert ctx.merge_regions(ranges) == synth.merge_regions(ranges), n
+        with pytest.raises(binding.TfbsError):
+            ctx.merge_regions([(10, 5), (1, 2)])
+    finally:
+        ctx.close()
