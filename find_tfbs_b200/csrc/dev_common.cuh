@@ -45,6 +45,7 @@ struct DevBlock {
     u32* var_row_out;           // the same array, written by k_variant_prep
     const u64* mask_base;
     const u32* region_dups;     // 1 = the region holds two records with the same Diff value (equal lists may then have different masks)
+    u64 hash_seed;              // seed of the sequence hash (hash_val): a block whose sequence-keyed map met a hash collision is repeated with another one
 };
 
 // Error / status word: the smallest key wins so that the reported failure is deterministic.
@@ -86,7 +87,7 @@ __device__ __forceinline__ u64 mix64(u64 x) {
 // region's window, so the hash of a patched haplotype costs O(segments), not O(bases).  Equal hashes are verified exactly.
 constexpr u64 HASH_B = 0x9e3779b97f4a7c15ULL;      // odd => invertible mod 2^64
 constexpr u64 HASH_BINV = 0xf1de83e19937733dULL;   // HASH_B * HASH_BINV == 1 (mod 2^64), checked at start-up
-__device__ __forceinline__ u64 hash_val(u32 code, int rel) { return mix64(((u64)(u32)rel << 3) | code) | 1ULL; }
+__device__ __forceinline__ u64 hash_val(u32 code, int rel, u64 seed) { return mix64((((u64)(u32)rel << 3) | code) ^ seed) | 1ULL; }
 // HASH_B ^ e for |e| < HASH_POW_N from a table (filled once per device by k_hash_pow_init; segment offsets and indel shifts of a
 // window are almost always below it), by squaring beyond; negative exponents through the inverse.
 constexpr u32 HASH_POW_N = 4096;

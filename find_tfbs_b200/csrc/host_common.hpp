@@ -146,6 +146,7 @@ struct tfbs_ctx {
     int rows_width = 32;        // 32: counts are returned as u32; 0: narrowest of u8 / u16 / u32 that holds every count of the block
     int audit = 0;              // set by tfbs_audit_block: per-haplotype flags are kept
     int64_t tiny_caps = 0;      // testing: start the configuration path with minimal scratch so that every growth path runs
+    int64_t test_reseed = 0;    // testing: the first attempt of every block is treated as a hash collision (repeated with another seed)
 
     // patterns
     bool have_patterns = false;

@@ -37,7 +37,7 @@ __global__ void k_variant_prep(DevBlock b, u32 r0, u32* var_class, u8* var_inwin
         if (b.var_row_out) b.var_row_out[v] = x.carrier_row;
         if (b.var_althash) {  // patch_haplotype gives every ALT base the record's position (haplotype.rs:130-132,136-137)
             u64 a = 0, pw = 1;
-            for (u32 t = 0; t < x.alt_len; ++t) { a += hash_val(b.allele_codes[x.alt_off + t], (int)(x.pos - s)) * pw; pw *= HASH_B; }
+            for (u32 t = 0; t < x.alt_len; ++t) { a += hash_val(b.allele_codes[x.alt_off + t], (int)(x.pos - s), b.hash_seed) * pw; pw *= HASH_B; }
             b.var_althash[v] = a;
         }
     }

@@ -255,7 +255,7 @@ __global__ void k_ref_prefix(DevBlock b, u32 r0, u64* prefix) {
     __syncthreads();
     for (u32 t0 = 0; t0 < n; t0 += SCAN_THREADS) {
         const u32 t = t0 + threadIdx.x;
-        u64 term = t < n ? hash_val(b.ref_codes[ro + t], (int)t) * hash_pow(t) : 0ULL;
+        u64 term = t < n ? hash_val(b.ref_codes[ro + t], (int)t, b.hash_seed) * hash_pow(t) : 0ULL;
         u64 tot;
         u64 ex = block_exclusive_scan(term, &tot);
         const u64 carry = s_carry;

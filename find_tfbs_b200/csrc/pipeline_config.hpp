@@ -280,6 +280,7 @@ struct ConfigPipeline {
         db.mask_base = ctx->d_mask_base.as<u64>();
         db.region_dups = ctx->d_region_dups.as<u32>();
         db.var_row = db.var_row_out = ctx->d_var_row.as<u32>();
+        db.hash_seed = slot->seed;
         TFBS_LAUNCH(k_mask_words, grid_for(R, 256), 256, 0, st)(db, ctx->d_dwords.as<u32>());
         ++launches();
         if ((rc = scan(ctx->d_dwords.as<u32>(), R, nullptr, ctx->d_mask_base.as<u64>()))) return rc;
@@ -556,7 +557,8 @@ struct ConfigPipeline {
                             std::string("Unknown nucleotide at byte ") + std::to_string(hs.bad_ref_base != ~0ull ? hs.bad_ref_base : hs.bad_allele_base) +
                                 (hs.bad_ref_base != ~0ull ? " of ref_bases" : " of allele_bases"));
             }
-            const bool collided = (hs.sig_collision && ctx->verify_groups) || hp.cfg_collision;
+            const bool collided = (hs.sig_collision && ctx->verify_groups) || hp.cfg_collision || hs.seq_collision ||  // every hash is seeded by slot->seed
+                                  (ctx->test_reseed && slot->attempts == 0 && !hp.abort);
             if (!hp.abort && !collided) {
                 if (hs.err_key != ~0ull) {
                     // region of sequence q: the status word carries the sequence; its region comes from the device's gbase
@@ -567,7 +569,6 @@ struct ConfigPipeline {
                     const uint32_t r = (uint32_t)(std::upper_bound(gb.begin(), gb.begin() + R, (uint64_t)q) - gb.begin() - 1);
                     return patch_panic(ctx, hs.err_key, r, B.h_region_start[r]);
                 }
-                if (hs.seq_collision) return fail(ctx, TFBS_ERR_INTERNAL, "sequence hash collision between distinct haplotypes");
                 note_needs(hp);
                 return publish(hs, hp);
             }

@@ -611,3 +611,14 @@ def test_bed_merge_on_device():
             ctx.merge_regions([(10, 5), (1, 2)])
     finally:
         ctx.close()
+
+
+def test_repeat_with_another_seed():
+    """A hash collision (signature, configuration or sequence hash) repeats the block with another seed; option test_reseed makes the
+    first attempt of every block count as one: the rows of the repeated run equal the oracle's, sequence-keyed overwrites included."""
+    pats = synth.make_pwms(4, seed=77, lmin=8, lmax=14, pvalue=2e-3)
+    blk = synth.make_cohort(30, 10, seed=77, lmax_pattern=14, region_len=(80, 400), variant_rate=0.08, frac_del=0.2, same_pos_frac=0.1)
+    ps = PatternSet(pats)
+    g = hp.run_gpu(ps, blk, options={"test_reseed": 1})
+    hp.assert_rows_equal(g, hp.run_oracle(ps, blk, 0))
+    assert g["stats"]["n_dropped"] == hp.run_gpu(ps, blk)["stats"]["n_dropped"]
