@@ -1,6 +1,7 @@
 // host_common.hpp -- the context behind the C ABI: device / pinned buffers, a block on the device, the two slots of blocks in flight
 // Host side of libtfbs_b200.so (tfbs.cu is the map); one translation unit.
 #pragma once
+#include <deque>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -197,6 +198,16 @@ struct tfbs_ctx {
     bool matches_truncated = false;
 
     cudaEvent_t ev[10]{};
+
+    // option "dual_stream": a second, complete context on the same device (own streams and scratch); blocks alternate between the
+    // two, so the kernels of consecutive blocks overlap on the device instead of queueing on one stream
+    tfbs_ctx* twin = nullptr;
+    bool is_twin = false, bypass = false;
+    int dual = 0;
+    int next_target = 0, last_target = 0;   // 0 = this context, 1 = the twin
+    std::deque<int> order;                  // targets of the blocks in flight, oldest first
+    int fixed_half = -1;                    // result arena: this context always writes this half (blocks alternate between the twins)
+    std::vector<std::pair<std::string, int64_t>> opt_log;
 };
 
 namespace {

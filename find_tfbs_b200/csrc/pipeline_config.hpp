@@ -690,7 +690,7 @@ struct ConfigPipeline {
         tfbs_arena_header* hdr = nullptr;
         slot->stats.d2h_bytes = 0;
         if (ctx->arena) {
-            uint8_t* half = ctx->arena + (size_t)(slot - ctx->slot) * (ctx->arena_bytes / 2);
+            uint8_t* half = ctx->arena + (size_t)(ctx->fixed_half >= 0 ? ctx->fixed_half : (int)(slot - ctx->slot)) * (ctx->arena_bytes / 2);
             hdr = reinterpret_cast<tfbs_arena_header*>(half);
             tfbs_arena_header h = *hdr;
             if (h.magic != TFBS_ARENA_MAGIC) { memset(&h, 0, sizeof h); h.magic = TFBS_ARENA_MAGIC; }

@@ -120,6 +120,26 @@ int drain(tfbs_ctx* ctx) {
     return rc;
 }
 
+// ---- option "dual_stream": routing between a context and its twin ----
+bool dual_active(const tfbs_ctx* ctx) { return ctx->dual && ctx->twin && !ctx->bypass && !wants_full(ctx); }
+void share_hints(tfbs_ctx* a, tfbs_ctx* b) {  // what one twin learnt about the blocks' sizes serves the other
+    Caps& x = a->hint;
+    Caps& y = b->hint;
+#define TFBS_BOTH(f) x.f = y.f = std::max(x.f, y.f)
+    TFBS_BOTH(seq); TFBS_BOTH(d); TFBS_BOTH(cfg); TFBS_BOTH(vd); TFBS_BOTH(items); TFBS_BOTH(units); TFBS_BOTH(dwords); TFBS_BOTH(rows);
+    TFBS_BOTH(rowwords); TFBS_BOTH(capr); TFBS_BOTH(groups);
+#undef TFBS_BOTH
+}
+int twin_failed(tfbs_ctx* ctx, int rc) {
+    if (rc != TFBS_OK) ctx->err = ctx->twin->err;
+    return rc;
+}
+struct Bypass {  // the public entry points call themselves once more for "this context itself"
+    tfbs_ctx* c;
+    explicit Bypass(tfbs_ctx* ctx) : c(ctx) { c->bypass = true; }
+    ~Bypass() { c->bypass = false; }
+};
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------------
@@ -183,6 +203,8 @@ int tfbs_create(int device, tfbs_ctx** out) {
 
 void tfbs_destroy(tfbs_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->twin) { tfbs_destroy(ctx->twin); ctx->twin = nullptr; }
+    if (ctx->is_twin) ctx->arena = nullptr;  // the arena is page-locked by the owner of the pair
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream_in);
     cudaStreamSynchronize(ctx->stream);
@@ -225,7 +247,26 @@ int tfbs_set_option(tfbs_ctx* ctx, const char* key, int64_t value) {
         if (value != 0 && value != 32) return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "rows_width must be 32 or 0 (automatic)");
         ctx->rows_width = (int)value;
     }
+    else if (k == "dual_stream") {
+        if (ctx->is_twin) return TFBS_OK;
+        if (!ctx->order.empty() || ctx->in_flight) return fail(ctx, TFBS_ERR_STATE, "dual_stream with blocks in flight: call tfbs_collect first");
+        if (value && !ctx->twin) {
+            tfbs_ctx* t = nullptr;
+            int rc = tfbs_create(ctx->device, &t);
+            if (rc != TFBS_OK) return fail(ctx, rc, g_create_error);
+            t->is_twin = true;
+            for (const auto& kv : ctx->opt_log) tfbs_set_option(t, kv.first.c_str(), kv.second);
+            ctx->twin = t;
+            if (ctx->have_patterns && (rc = twin_failed(ctx, tfbs_set_patterns(t, ctx->orig_patterns.data(), (uint32_t)ctx->orig_patterns.size())))) return rc;
+            if (ctx->arena) return fail(ctx, TFBS_ERR_STATE, "set dual_stream before tfbs_set_result_arena");
+        }
+        ctx->dual = value != 0;
+        ctx->next_target = 0;
+        return TFBS_OK;
+    }
     else return fail(ctx, TFBS_ERR_INVALID_ARGUMENT, "unknown option " + k);
+    ctx->opt_log.emplace_back(k, value);
+    if (ctx->twin) return twin_failed(ctx, tfbs_set_option(ctx->twin, key, value));
     return TFBS_OK;
 }
 
@@ -243,6 +284,7 @@ int tfbs_set_patterns(tfbs_ctx* ctx, const tfbs_pattern* patterns, uint32_t n_pa
         } else {
             ctx->orig_patterns[i].weights = nullptr;
         }
+    if (ctx->twin) return twin_failed(ctx, tfbs_set_patterns(ctx->twin, patterns, n_patterns));
     return TFBS_OK;
 }
 
@@ -255,11 +297,23 @@ int tfbs_upload_block(tfbs_ctx* ctx, const tfbs_block* block) {
     if (rc) return rc;
     CK(cudaStreamSynchronize(ctx->stream_in));
     ctx->last_block = &ctx->resident;
+    if (ctx->twin && ctx->dual) return twin_failed(ctx, tfbs_upload_block(ctx->twin, block));
     return TFBS_OK;
 }
 
 int tfbs_run_resident(tfbs_ctx* ctx) {
     if (!ctx) return TFBS_ERR_INVALID_ARGUMENT;
+    if (dual_active(ctx)) {
+        if (ctx->order.size() >= 2) return fail(ctx, TFBS_ERR_STATE, "two blocks are already in flight on this context: call tfbs_collect first");
+        const int tgt = ctx->next_target;
+        int rc;
+        if (tgt) rc = twin_failed(ctx, tfbs_run_resident(ctx->twin));
+        else { Bypass by(ctx); rc = tfbs_run_resident(ctx); }
+        if (rc) return rc;
+        ctx->order.push_back(tgt);
+        ctx->next_target ^= 1;
+        return TFBS_OK;
+    }
     CK(cudaSetDevice(ctx->device));
     if (!ctx->resident.valid) return fail(ctx, TFBS_ERR_STATE, "no block has been uploaded");
     return start_block(ctx, &ctx->resident, false);
@@ -267,6 +321,17 @@ int tfbs_run_resident(tfbs_ctx* ctx) {
 
 int tfbs_submit_block(tfbs_ctx* ctx, const tfbs_block* block) {
     if (!ctx) return TFBS_ERR_INVALID_ARGUMENT;
+    if (dual_active(ctx)) {
+        if (ctx->order.size() >= 2) return fail(ctx, TFBS_ERR_STATE, "two blocks are already in flight on this context: call tfbs_collect first");
+        const int tgt = ctx->next_target;
+        int rc;
+        if (tgt) rc = twin_failed(ctx, tfbs_submit_block(ctx->twin, block));
+        else { Bypass by(ctx); rc = tfbs_submit_block(ctx, block); }
+        if (rc) return rc;
+        ctx->order.push_back(tgt);
+        ctx->next_target ^= 1;
+        return TFBS_OK;
+    }
     CK(cudaSetDevice(ctx->device));
     if (!ctx->have_patterns) return fail(ctx, TFBS_ERR_STATE, "tfbs_set_patterns has not been called");
     if (ctx->in_flight >= 2) return fail(ctx, TFBS_ERR_STATE, "two blocks are already in flight on this context: call tfbs_collect first");
@@ -278,6 +343,16 @@ int tfbs_submit_block(tfbs_ctx* ctx, const tfbs_block* block) {
 
 int tfbs_collect(tfbs_ctx* ctx, tfbs_rows* out) {
     if (!ctx || !out) return TFBS_ERR_INVALID_ARGUMENT;
+    if (ctx->twin && !ctx->bypass && !ctx->order.empty()) {  // the oldest block in flight, whichever twin has it
+        const int tgt = ctx->order.front();
+        ctx->order.pop_front();
+        ctx->last_target = tgt;
+        int rc;
+        if (tgt) rc = twin_failed(ctx, tfbs_collect(ctx->twin, out));
+        else { Bypass by(ctx); rc = tfbs_collect(ctx, out); }
+        share_hints(ctx, ctx->twin);
+        return rc;
+    }
     CK(cudaSetDevice(ctx->device));
     Slot* slot = nullptr;
     int rc = finish_oldest(ctx, &slot);
@@ -300,6 +375,16 @@ int tfbs_collect(tfbs_ctx* ctx, tfbs_rows* out) {
 
 int tfbs_collect_grouped(tfbs_ctx* ctx, tfbs_grouped_rows* out) {
     if (!ctx || !out) return TFBS_ERR_INVALID_ARGUMENT;
+    if (ctx->twin && !ctx->bypass && !ctx->order.empty()) {
+        const int tgt = ctx->order.front();
+        ctx->order.pop_front();
+        ctx->last_target = tgt;
+        int rc;
+        if (tgt) rc = twin_failed(ctx, tfbs_collect_grouped(ctx->twin, out));
+        else { Bypass by(ctx); rc = tfbs_collect_grouped(ctx, out); }
+        share_hints(ctx, ctx->twin);
+        return rc;
+    }
     CK(cudaSetDevice(ctx->device));
     Slot* slot = nullptr;
     int rc = finish_oldest(ctx, &slot);
@@ -336,7 +421,19 @@ int tfbs_set_result_arena(tfbs_ctx* ctx, void* base, size_t bytes) {
     CK(cudaSetDevice(ctx->device));
     int rc = quiesce(ctx);
     if (rc) return rc;
-    if (ctx->in_flight) return fail(ctx, TFBS_ERR_STATE, "tfbs_set_result_arena with blocks in flight: call tfbs_collect first");
+    if (ctx->in_flight || !ctx->order.empty()) return fail(ctx, TFBS_ERR_STATE, "tfbs_set_result_arena with blocks in flight: call tfbs_collect first");
+    if (ctx->twin) {  // the twin writes the second half of the same arena (page-locked once, by this context)
+        tfbs_ctx* t = ctx->twin;
+        if ((rc = quiesce(t))) return twin_failed(ctx, rc);
+        for (Slot& s : t->slot)
+            for (HostBuf* hb : {&s.res.h_region, &s.res.h_inner, &s.res.h_pid, &s.res.h_vmin, &s.res.h_vmax, &s.res.h_base, &s.res.h_bits, &s.res.h_off,
+                                &s.res.h_packed, &s.res.h_ngroups, &s.res.h_hg})
+                if (!hb->owned) hb->bind(nullptr, 0);
+        t->arena = nullptr;
+        t->arena_bytes = 0;
+        t->fixed_half = ctx->fixed_half = -1;
+        ctx->next_target = 0;
+    }
     if (ctx->arena) {
         cudaHostUnregister(ctx->arena);
         for (Slot& s : ctx->slot)
@@ -353,6 +450,12 @@ int tfbs_set_result_arena(tfbs_ctx* ctx, void* base, size_t bytes) {
     ctx->arena_bytes = bytes;
     memset(base, 0, sizeof(tfbs_arena_header));
     memset((uint8_t*)base + bytes / 2, 0, sizeof(tfbs_arena_header));
+    if (ctx->twin && ctx->dual) {
+        ctx->twin->arena = ctx->arena;
+        ctx->twin->arena_bytes = bytes;
+        ctx->twin->fixed_half = 1;
+        ctx->fixed_half = 0;
+    }
     return TFBS_OK;
 }
 
@@ -576,6 +679,7 @@ int tfbs_audit_block(tfbs_ctx* ctx, tfbs_audit* out) {
 
 int tfbs_get_stats(const tfbs_ctx* ctx, tfbs_stats* out) {
     if (!ctx || !out) return TFBS_ERR_INVALID_ARGUMENT;
+    if (ctx->twin && ctx->last_target == 1) return tfbs_get_stats(ctx->twin, out);
     if (ctx->last < 0) memset(out, 0, sizeof *out);
     else *out = ctx->slot[ctx->last].stats;
     return TFBS_OK;

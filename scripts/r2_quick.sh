@@ -4,7 +4,7 @@ set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out/${1:-r2q}
 mkdir -p $O
-B="python bench.py --no-driver --no-cpu-baseline --no-secondary --sustain-seconds 0"
+B="python bench.py --no-driver --no-cpu-baseline --no-secondary --sustain-seconds 0 ${EXTRA:-}"
 timeout 300 $B --steps 10 --warmup 2 > $O/bench.json 2> $O/bench.err || tail -3 $O/bench.err
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/launches_c2.csv $B --steps 2 --warmup 2 > $O/ncu_list_c2.log 2>&1
 python - "$O" <<'PY'

@@ -564,32 +564,47 @@ def test_grouped_rows_two_blocks_in_flight_and_scratch_growth():
             d = hp.run_gpu(ps, blk, mode, False, {"tiny_caps": 1})
             hp.assert_rows_equal(d, o)
             hp.check_stats(d["stats"], o)
-            ctx = binding.Context(0)
-            try:
-                ctx.set_option("rows_mode", mode)
-                ctx.set_patterns(ps)
-                half = blk.n_regions // 2
-                b1, b2 = blk.slice(0, half), blk.slice(half, blk.n_regions)
-                ctx.submit_block(b1)
-                ctx.submit_block(b2)
-                with pytest.raises(binding.TfbsError) as e:
+            for dual in (0, 1):  # option dual_stream: the blocks alternate between the context and its twin (own streams and scratch)
+                ctx = binding.Context(0)
+                try:
+                    ctx.set_option("rows_mode", mode)
+                    ctx.set_patterns(ps)
+                    ctx.set_option("dual_stream", dual)
+                    half = blk.n_regions // 2
+                    b1, b2 = blk.slice(0, half), blk.slice(half, blk.n_regions)
                     ctx.submit_block(b1)
-                assert e.value.code == binding.ERR_STATE
-                g1 = ctx.collect_grouped(expand=True)
-                g1 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in g1.items()}
-                g2 = ctx.collect_grouped(expand=True)
-                hp.assert_rows_equal(g1, hp.run_oracle(ps, b1, mode, False))
-                hp.assert_rows_equal(g2, hp.run_oracle(ps, b2, mode, False))
-                assert set(np.unique(g2["bits"]).tolist()) <= {0, 1, 2, 4, 8, 16, 32}
-                ctx.upload_block(blk)
-                ctx.run_resident()
-                ctx.run_resident()
-                hp.assert_rows_equal(ctx.collect(), o)
-                hp.assert_rows_equal(ctx.collect_grouped(expand=True), o)
-                with pytest.raises(binding.TfbsError):
-                    ctx.collect()  # nothing in flight any more
-            finally:
-                ctx.close()
+                    ctx.submit_block(b2)
+                    with pytest.raises(binding.TfbsError) as e:
+                        ctx.submit_block(b1)
+                    assert e.value.code == binding.ERR_STATE
+                    g1 = ctx.collect_grouped(expand=True)
+                    g1 = {k: (v.copy() if isinstance(v, np.ndarray) else v) for k, v in g1.items()}
+                    g2 = ctx.collect_grouped(expand=True)
+                    hp.assert_rows_equal(g1, hp.run_oracle(ps, b1, mode, False))
+                    hp.assert_rows_equal(g2, hp.run_oracle(ps, b2, mode, False))
+                    assert set(np.unique(g2["bits"]).tolist()) <= {0, 1, 2, 4, 8, 16, 32}
+                    ctx.upload_block(blk)
+                    ctx.run_resident()
+                    ctx.run_resident()
+                    hp.assert_rows_equal(ctx.collect(), o)
+                    hp.assert_rows_equal(ctx.collect_grouped(expand=True), o)
+                    with pytest.raises(binding.TfbsError):
+                        ctx.collect()  # nothing in flight any more
+                    if dual:  # result arena: the context writes the first half, its twin the second
+                        raw = np.zeros((4 << 20) + 64, dtype=np.uint8)
+                        arena = raw[(-raw.ctypes.data) % 64:][:4 << 20]  # 64-byte aligned
+                        ctx.set_result_arena(arena)
+                        for b in (b1, b2, b1):
+                            ctx.submit_block(b)
+                            ctx.collect_grouped()
+                        h0, h1 = binding.read_arena(arena, 0, expand=True), binding.read_arena(arena, 1, expand=True)
+                        assert h0["sequence"] == 2 and h1["sequence"] == 1
+                        hp.assert_rows_equal(h0, hp.run_oracle(ps, b1, mode, False))
+                        hp.assert_rows_equal(h1, hp.run_oracle(ps, b2, mode, False))
+                        ctx.set_result_arena(None)
+                        assert ctx.stats()["n_regions"] == b1.n_regions
+                finally:
+                    ctx.close()
 
 
 def test_bed_merge_on_device():
