@@ -132,6 +132,7 @@ def workload(name, scale):
         cfg = {"workload": "configs[1]: synthetic 100 samples x %d DHS regions (200-2000 bp) x 50 random PWMs (L 8-30, both strands, p=1e-4); ONE fixed block"
                            % blk.n_regions, "regions": blk.n_regions, "samples": 100, "pwms": 50, "patterns": 100}
     cfg["sharding"] = "contiguous region ranges balanced by scan work, one context per GPU, no collective; rows land in rank 0's address space by DMA into shared memory"
+    cfg["streams"] = "option dual_stream: the blocks of consecutive steps alternate between two contexts (streams + scratch) on the same GPU"
     cfg["l2"] = "inputs larger than L2 (carrier bits + reference windows + per-haplotype scratch of a step: hundreds of MB to GB)"
     return pats, blk, cfg
 
@@ -304,6 +305,7 @@ def main():
     ps = binding.PatternSet(pats)
     ctx = binding.Context(local_rank)
     ctx.set_option("rows_width", 0)
+    ctx.set_option("dual_stream", 1)  # consecutive blocks run on two streams of the same GPU (a twin context): their kernels overlap
     options(ctx)
     ctx.set_patterns(ps)
     stream = torch.cuda.ExternalStream(ctx.stream(), device=torch.device("cuda", local_rank))
@@ -352,7 +354,7 @@ def main():
     tag = "%s_%d" % (os.environ.get("MASTER_PORT", "0"), os.getppid() if world > 1 else os.getpid())
     arena = sharding.SharedArena(tag, rank, nbytes=2 * (int(probe["bytes"] * 1.3) + (1 << 20)), create=True)
     ctx.set_result_arena(arena.buf)
-    pipelined(ctx, lambda: ctx.submit_block(shard), coll, 2)
+    pipelined(ctx, lambda: ctx.submit_block(shard), coll, 4)  # every slot of both twins has received a block from host memory once
     barrier()
     others = [sharding.SharedArena(tag, k) for k in range(world)] if rank == 0 else []
     gathered = {}
@@ -470,6 +472,7 @@ def secondary_configs1(args, binding, sharding, device, pk):
     ps = binding.PatternSet(pats)
     ctx = binding.Context(device)
     ctx.set_option("rows_width", 0)
+    ctx.set_option("dual_stream", 1)
     for kv in args.option:
         k, v = kv.split("=")
         ctx.set_option(k, int(v))
@@ -494,7 +497,7 @@ def secondary_configs1(args, binding, sharding, device, pk):
         ctx.collect_grouped()
 
     ctx.upload_block(blk)
-    pipelined(ctx.run_resident, 5)
+    pipelined(ctx.run_resident, 6)
     ms_step = timed(lambda: pipelined(ctx.run_resident, steps)) / steps
     st = ctx.stats()
     scan_ms = []
@@ -504,7 +507,7 @@ def secondary_configs1(args, binding, sharding, device, pk):
         scan_ms.append(ctx.stats()["ms_scan_kernel"])
     stages = {k: ctx.stats()[k] for k in ("ms_group", "ms_build", "ms_scan", "ms_scan_kernel", "ms_count", "ms_total")}
     blk.pin()
-    pipelined(lambda: ctx.submit_block(blk), 3)
+    pipelined(lambda: ctx.submit_block(blk), 4)
     ms_e2e = timed(lambda: pipelined(lambda: ctx.submit_block(blk), steps)) / steps
     st2 = ctx.stats()
     blk.unpin()
