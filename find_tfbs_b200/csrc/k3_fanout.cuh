@@ -119,9 +119,12 @@ __global__ void __launch_bounds__(FAN_THREADS) k_fanout(DevBlock b, DevConfigs c
     const u32 tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     // the keys of the region go to the gridDim.y CTAs in rounds of `rs` keys: equal shares when they fit one round each
     const u32 nkeys_all = fn.n_pid * (b.inner_off[r + 1] - b.inner_off[r]);
-    const u32 rs = min((u32)FAN_THREADS, max(1u, (nkeys_all + gridDim.y - 1) / gridDim.y));
-    if ((u64)blockIdx.y * rs >= (u64)nkeys_all) return;  // no round for this CTA
+    // (a CTA has a fixed cost -- the haplotype -> group map, the zeroed vector -- that only pays when a key is expensive, i.e. when
+    // the region has many groups: small regions keep their few keys in one CTA)
     const u32 ng = (u32)(fn.gbase[r + 1] - fn.gbase[r]);
+    const u32 kmin = ng >= 8192 ? 1u : (ng >= 1024 ? 16u : 64u);
+    const u32 rs = min((u32)FAN_THREADS, max(kmin, (nkeys_all + gridDim.y - 1) / gridDim.y));
+    if ((u64)blockIdx.y * rs >= (u64)nkeys_all) return;  // no round for this CTA
     if (ng > fn.groups_cap) {  // more distinct haplotypes than the shared-memory vector holds: the host repeats the run
         if (tid == 0) { atomicMax(&cf.plan->need_groups, ng); cf.plan->abort = 1; }
         return;
