@@ -40,6 +40,17 @@ namespace {
 
 int main(int argc, char** argv) {
     Options o = parse_args(argc, argv);
+    if (!o.write_thresholds.empty()) {  // threshold tooling: exact score distribution of every (wanted) PWM -> <DIR>/<name>.thr
+        size_t n = 0;
+        for (const auto& def : read_pwm_definitions(o.pwm_file)) {
+            if (!o.pwm_names.empty() && std::find(o.pwm_names.begin(), o.pwm_names.end(), def.first) == o.pwm_names.end()) continue;
+            if (def.second.empty()) continue;
+            write_threshold_file(o.write_thresholds + "/" + def.first + ".thr", def.second, o.pvalues);
+            ++n;
+        }
+        printf("Wrote %zu threshold files to %s\n", n, o.write_thresholds.c_str());
+        return 0;
+    }
     if (o.tabix && system("command -v tabix > /dev/null 2>&1") != 0) die("tabix cannot in found in PATH");  // main.rs:220-223
     auto t_start = std::chrono::steady_clock::now();
     auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };

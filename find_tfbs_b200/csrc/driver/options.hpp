@@ -15,6 +15,8 @@ struct Options {
     float pwm_threshold = 0;
     bool forward_only = false, tabix = false, verbose = false, has_samples = false, plain_text = false;
     uint32_t min_maf = 0, threads = 1, chunk = 2000;
+    std::string write_thresholds;  // --write_thresholds DIR: write <name>.thr for the PWMs of --pwm_file (exact DP), then exit
+    std::vector<double> pvalues{1e-2, 1e-3, 5e-4, 1e-4, 1e-5};
     int compression_level = 3;  // zlib level of the BGZF blocks: the byte stream is not part of the contract (outputs are compared after gunzip)
     uint64_t after_position = 0;
     std::vector<int> devices{0};
@@ -38,7 +40,8 @@ void usage() {
          "USAGE: find-tfbs-b200 --chromosome CHROM --input IN.bcf --output OUT.vcf.gz --reference REF.fa --bed A.bed[,B.bed]\n"
          "         --pwm_names NAME[,NAME] --pwm_file PWM.txt --pwm_threshold_directory DIR --pwm_threshold P\n"
          "         [--forward_only] [--threads N] [--min_maf N] [--after_position POS] [--samples FILE] [--tabix] [--verbose]\n"
-         "         [--devices 0,1,...] [--chunk REGIONS_PER_BLOCK] [--plain] [--audit AUDIT.tsv] [--no_index] [--compression_level 1..9]");
+         "         [--devices 0,1,...] [--chunk REGIONS_PER_BLOCK] [--plain] [--audit AUDIT.tsv] [--no_index] [--compression_level 1..9]\n"
+         "       find-tfbs-b200 --write_thresholds DIR --pwm_file PWM.txt [--pwm_names NAME[,NAME]] [--pvalues P[,P]]   (exact .thr files)");
 }
 
 Options parse_args(int argc, char** argv) {
@@ -65,6 +68,17 @@ Options parse_args(int argc, char** argv) {
         kv[key] = val;
     }
     if (kv.count("help")) { usage(); exit(0); }
+    if (kv.count("write_thresholds")) {  // threshold tooling: needs the PWM definitions only
+        o.write_thresholds = kv["write_thresholds"];
+        if (!kv.count("pwm_file")) { usage(); die("error: The following required argument was not provided: --pwm_file"); }
+        o.pwm_file = kv["pwm_file"];
+        if (kv.count("pwm_names")) o.pwm_names = split(kv["pwm_names"], ',');
+        if (kv.count("pvalues")) {
+            o.pvalues.clear();
+            for (auto& t : split(kv["pvalues"], ',')) o.pvalues.push_back(atof(t.c_str()));
+        }
+        return o;
+    }
     auto req = [&](const char* k) -> std::string {
         if (!kv.count(k)) { usage(); die(std::string("error: The following required argument was not provided: --") + k); }
         return kv[k];

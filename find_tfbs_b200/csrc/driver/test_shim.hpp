@@ -17,6 +17,14 @@ int drv_parse_threshold_file(const char* path, float thr, int32_t* out) {
     try { return parse_threshold_file(path, thr, out) ? 1 : 0; } catch (const std::exception& e) { g_shim_err = e.what(); return -1; }
 }
 
+int drv_score_threshold(const int32_t* w, uint32_t len, double pvalue, int32_t* out) {
+    try { *out = score_threshold(std::vector<int32_t>(w, w + 4 * (size_t)len), pvalue); return 0; } catch (const std::exception& e) { g_shim_err = e.what(); return -1; }
+}
+int drv_write_threshold_file(const char* path, const int32_t* w, uint32_t len, const double* pvalues, uint32_t n) {
+    try { write_threshold_file(path, std::vector<int32_t>(w, w + 4 * (size_t)len), std::vector<double>(pvalues, pvalues + n)); return 0; }
+    catch (const std::exception& e) { g_shim_err = e.what(); return -1; }
+}
+
 // merge_ranges: returns the number of merged ranges written to out_s / out_e (capacity n)
 int drv_merge_ranges(const uint64_t* s, const uint64_t* e, uint32_t n, uint64_t* out_s, uint64_t* out_e) {
     std::vector<Range> raw;

@@ -198,3 +198,22 @@ def test_bgzf_writer(drv, tmp_path):
         assert out == text and n_members > 5
         assert raw.endswith(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))  # the BGZF EOF block
         assert ora.gunzip_file(path).encode() == text
+
+
+def test_threshold_tooling_is_exact(drv, tmp_path):
+    """score_threshold / write_threshold_file of the driver (--write_thresholds): the exact DP equals the harness's
+    (synth.score_threshold), and a written .thr file read back with the reference's rule (pattern.rs:18-35, the last line whose
+    p-value exceeds the threshold) gives the same score for every listed p-value."""
+    pats = [p for p in synth.make_pwms(12, seed=8, lmin=5, lmax=30) if p["direction"] == 0]
+    pvals = [1e-2, 1e-3, 5e-4, 1e-4, 1e-5]
+    for i, p in enumerate(pats):
+        w = np.ascontiguousarray(p["weights"], dtype=np.int32)
+        for pv in pvals + [0.3, 1e-7]:
+            out = C.c_int32()
+            assert drv.drv_score_threshold(w.ctypes.data_as(C.POINTER(C.c_int32)), w.shape[0], C.c_double(pv), C.byref(out)) == 0
+            assert out.value == synth.score_threshold(w, pv), (i, pv)
+        path = str(tmp_path / ("P%d.thr" % i))
+        arr = (C.c_double * len(pvals))(*pvals)
+        assert drv.drv_write_threshold_file(path.encode(), w.ctypes.data_as(C.POINTER(C.c_int32)), w.shape[0], arr, len(pvals)) == 0
+        for pv in pvals:
+            assert ora.parse_threshold_file(path, pv) == synth.score_threshold(w, pv), (i, pv)
