@@ -139,6 +139,18 @@ public:
         buf_.append(p, n);
         if (buf_.size() >= kBlock * 8 * threads_) flush(false);
     }
+    // text -> complete BGZF blocks (thread-safe: no state); blocks compressed elsewhere are appended with write_blocks
+    static std::string compress_blocks(const char* p, size_t n, int level) {
+        std::string out;
+        out.reserve(n / 8 + 64);
+        for (size_t a = 0; a < n; a += kBlock) out += compress(p + a, std::min(kBlock, n - a), level);
+        return out;
+    }
+    int level() const { return level_; }
+    void write_blocks(const std::string& blocks) {  // whatever text is pending goes out first, as blocks of its own
+        flush(true);
+        f_.write(blocks.data(), (std::streamsize)blocks.size());
+    }
     void finish() {
         flush(true);
         const std::string eof = compress(nullptr, 0, 6);  // EOF marker

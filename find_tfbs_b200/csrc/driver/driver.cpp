@@ -172,10 +172,38 @@ int main(int argc, char** argv) {
                 done_chunks.erase(it);
             }
             auto tw = std::chrono::steady_clock::now();
-            for (const std::string& row : t.rows) {  // CHROM, POS, then the row as the worker formatted it: no copy of the row on the way
-                const std::string head = chr + "\t" + std::to_string(fake_position++);
-                if (gz) { gz->write(head.data(), head.size()); gz->write(row.data(), row.size()); }
-                else plain << head << row;
+            // CHROM, POS, then the row as the worker formatted it.  The rows of the chunk are cut into one range per host thread;
+            // every range is assembled and compressed into BGZF blocks of its own (the blocks of a BGZF file are independent gzip
+            // members), the writer only appends the finished blocks in order.
+            const size_t n = t.rows.size();
+            const uint64_t first = fake_position;
+            fake_position += n;
+            const size_t nt = std::max<size_t>(1, std::min<size_t>(o.threads, n / 64 + 1));
+            std::vector<std::string> piece(nt);
+            auto assemble = [&](size_t k) {
+                const size_t a = n * k / nt, b = n * (k + 1) / nt;
+                size_t bytes = 0;
+                for (size_t i = a; i < b; ++i) bytes += t.rows[i].size() + chr.size() + 24;
+                std::string text;
+                text.reserve(bytes);
+                for (size_t i = a; i < b; ++i) {
+                    text += chr;
+                    text += '\t';
+                    text += std::to_string(first + i);
+                    text += t.rows[i];
+                    std::string().swap(t.rows[i]);  // the row's memory goes back as soon as it has been copied
+                }
+                piece[k] = gz ? BgzfWriter::compress_blocks(text.data(), text.size(), gz->level()) : std::move(text);
+            };
+            if (nt == 1) assemble(0);
+            else {
+                std::vector<std::thread> th;
+                for (size_t k = 0; k < nt; ++k) th.emplace_back(assemble, k);
+                for (auto& x : th) x.join();
+            }
+            for (const std::string& pc : piece) {
+                if (gz) gz->write_blocks(pc);
+                else plain << pc;
             }
             secs_write += std::chrono::duration<double>(std::chrono::steady_clock::now() - tw).count();
             {
