@@ -468,10 +468,12 @@ int tfbs_expand_rows(const tfbs_grouped_rows* g, uint64_t first_row, uint64_t n_
         const uint32_t r = g->region[row], base = g->base[row], bits = g->bits[row];
         if (r >= g->n_regions || (bits != 0 && bits != 1 && bits != 2 && bits != 4 && bits != 8 && bits != 16 && bits != 32)) return TFBS_ERR_INVALID_ARGUMENT;
         const uint32_t* pk = g->packed + g->offset[row];
-        const uint32_t per = bits ? 32 / bits : 0, mask = bits == 32 ? 0xffffffffu : ((1u << bits) - 1);
+        // bits is a power of two: entry g sits in word g >> (5 - log2 bits) at bit (g mod (32 / bits)) << log2 bits
+        const uint32_t lb = bits ? (uint32_t)__builtin_ctz(bits) : 0, wshift = 5 - lb, per_mask = bits ? (32u >> lb) - 1 : 0;
+        const uint32_t mask = bits == 32 ? 0xffffffffu : ((1u << bits) - 1);
         uint32_t* l = left + i * S;
         uint32_t* rt = right + i * S;
-        auto count = [&](uint32_t grp) { return bits ? base + ((pk[grp / per] >> ((grp % per) * bits)) & mask) : base; };
+        auto count = [&](uint32_t grp) { return bits ? base + ((pk[grp >> wshift] >> ((grp & per_mask) << lb)) & mask) : base; };
         if (g->hap_group_bytes == 2) {
             const uint16_t* hg = (const uint16_t*)g->hap_group + (uint64_t)r * H;
             for (uint32_t s = 0; s < S; ++s) { l[s] = count(hg[2 * s]); rt[s] = count(hg[2 * s + 1]); }
