@@ -210,14 +210,9 @@ __global__ void __launch_bounds__(SCAN_CTA, 1)
             }
             if (lane == 0) { ws->piece_vstart[np] = vtot; ws->n_pieces = np; }
             __syncwarp();
-#if TFBS_SCAN_KEEP_PIECE
-            u32 k = 0;  // a lane's start only moves forward inside a round: the piece search resumes where it stopped
-#endif
             for (u32 v0 = 0; v0 < vtot; v0 += 32) {
                 const u32 v = v0 + lane;
-#if !TFBS_SCAN_KEEP_PIECE
                 u32 k = 0;
-#endif
                 while (k + 1 < np && v >= ws->piece_vstart[k + 1]) ++k;
                 const bool valid = v < vtot;
                 const u32 off = valid ? v - ws->piece_vstart[k] : 0u;
@@ -226,23 +221,8 @@ __global__ void __launch_bounds__(SCAN_CTA, 1)
                 const u32 item_index = ws->piece_item[k];
                 const u8* pl = &ws->plane[j & 1][j >> 1];
                 u32 idx[kMaxGroups];
-#if TFBS_SCAN_IDX_WORDS
-                {   // the 16 pair codes of this start as five aligned 32-bit words instead of 16 byte loads
-                    const u32* pw = reinterpret_cast<const u32*>(reinterpret_cast<uintptr_t>(pl) & ~(uintptr_t)3);
-                    const u32 sh = (u32)(reinterpret_cast<uintptr_t>(pl) & 3) * 8;
-                    u32 w[kMaxGroups / 4 + 1];
-#pragma unroll
-                    for (int x = 0; x < kMaxGroups / 4 + 1; ++x) w[x] = pw[x];
-#pragma unroll
-                    for (int gg = 0; gg < kMaxGroups; ++gg) {
-                        const u64 two = ((u64)w[gg / 4 + 1] << 32) | w[gg / 4];
-                        idx[gg] = (u32)(two >> (sh + 8 * (gg & 3))) & 0xffu;
-                    }
-                }
-#else
 #pragma unroll
                 for (int gg = 0; gg < kMaxGroups; ++gg) idx[gg] = pl[gg];
-#endif
                 const u8* tb = tbl;
                 u32 t0 = 0;
                 for (u32 rn = 0; rn < n_runs; ++rn) {

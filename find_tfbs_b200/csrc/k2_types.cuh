@@ -62,15 +62,8 @@ constexpr int MAX_PIECES = TFBS_MAX_PIECES;          // items (or tiles of a lon
 #ifndef TFBS_MERGE_GAP
 #define TFBS_MERGE_GAP 0   /* measured on B200 (configs[1]): 0 -> 8.02 ms/step, 8 -> 8.26, 24 -> 9.05, 64 -> 12.5: short items are shared more */
 #endif
-// Variants of the scan's per-iteration bookkeeping, off by default until timed on a B200 (build one with `make variant`):
-// KEEP_PIECE resumes the piece search instead of restarting it every 32 starts; IDX_WORDS reads the 16 pair codes of a start as
-// aligned 32-bit words (5 LDS.32 + shifts) instead of 16 LDS.U8 -- both take load off the shared-memory pipe the kernel is bound by.
-#ifndef TFBS_SCAN_KEEP_PIECE
-#define TFBS_SCAN_KEEP_PIECE 0
-#endif
-#ifndef TFBS_SCAN_IDX_WORDS
-#define TFBS_SCAN_IDX_WORDS 0
-#endif
+// (Two variants of the per-iteration bookkeeping -- resuming the piece search, reading the pair codes as aligned words -- were timed
+// on the B200 at the start of round 2: within 1.5 % of this code on both workloads, removed.)
 #ifndef TFBS_PER_GRAB
 #define TFBS_PER_GRAB 8
 #endif

@@ -7,11 +7,9 @@
 set -u
 cd "$(dirname "$0")/.."
 declare -A VARIANTS=(
-  [keep]="-DTFBS_SCAN_KEEP_PIECE=1"
-  [words]="-DTFBS_SCAN_IDX_WORDS=1"
-  [keepwords]="-DTFBS_SCAN_KEEP_PIECE=1 -DTFBS_SCAN_IDX_WORDS=1"
   [tile2k]="-DTFBS_TILE_POS=2048 -DTFBS_MAX_PIECES=32"
-  [finishlanes]="-DTFBS_FINISH_LANES=1"
+  [fan512]="-DTFBS_FAN_THREADS=512"
+  [fansplit8]="-DTFBS_FAN_SPLIT=8"
   [warps28]="-DTFBS_SCAN_WARPS=28"
   [grab16]="-DTFBS_PER_GRAB=16"
 )
