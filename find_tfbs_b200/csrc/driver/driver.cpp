@@ -147,6 +147,10 @@ int main(int argc, char** argv) {
         emit(hdr + "\n");
     }
 
+    // Regions per block: the reference hands out chunks of 50 (main.rs:375-381); a block here should keep a GPU busy for milliseconds
+    // (thousands of regions for a small cohort) yet leave several blocks per run, so that row text, compression and the GPU overlap
+    // (a region of a 2,504-sample cohort already gives ~75 rows of 25 KB).
+    if (o.chunk == 0) o.chunk = (uint32_t)std::min<uint64_t>(2000, std::max<uint64_t>(50, 2000000ull / std::max<uint32_t>(1, S)));
     const size_t n_chunks = (merged.size() + o.chunk - 1) / o.chunk;
     // The writer (main.rs:264-290 has a writer thread fed through a channel): chunks finish in any order on the devices and are
     // written in chunk order as soon as every earlier chunk is there; a finished chunk's text is freed once written, so the

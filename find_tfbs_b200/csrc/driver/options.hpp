@@ -14,7 +14,7 @@ struct Options {
     std::vector<std::string> beds, pwm_names;
     float pwm_threshold = 0;
     bool forward_only = false, tabix = false, verbose = false, has_samples = false, plain_text = false;
-    uint32_t min_maf = 0, threads = 1, chunk = 2000;
+    uint32_t min_maf = 0, threads = 1, chunk = 0;  // chunk: merged regions per block (0 = automatic)
     std::string write_thresholds;  // --write_thresholds DIR: write <name>.thr for the PWMs of --pwm_file (exact DP), then exit
     std::vector<double> pvalues{1e-2, 1e-3, 5e-4, 1e-4, 1e-5};
     int compression_level = 3;  // zlib level of the BGZF blocks: the byte stream is not part of the contract (outputs are compared after gunzip)
@@ -113,7 +113,7 @@ Options parse_args(int argc, char** argv) {
     o.threads = (uint32_t)num("threads", 1, "Cannot parse thread number");
     if (kv.count("threads") && o.threads < 1) die("Wrong number of threads");
     o.after_position = num("after_position", 0, "Cannot parse after_position");
-    o.chunk = (uint32_t)std::max<uint64_t>(1, num("chunk", 2000, "Cannot parse chunk"));
+    o.chunk = (uint32_t)num("chunk", 0, "Cannot parse chunk");  // 0 = chosen from the cohort size once the BCF header is read
     o.compression_level = (int)std::min<uint64_t>(9, std::max<uint64_t>(1, num("compression_level", 3, "Cannot parse compression_level")));
     if (kv.count("samples")) { o.has_samples = true; o.samples_file = kv["samples"]; }
     if (kv.count("audit")) o.audit_file = kv["audit"];
