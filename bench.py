@@ -17,7 +17,10 @@ strands, per-haplotype counts, min/max row filter) over the whole block.
   cpu_baseline  the C++ oracle (a restatement of the reference: the Rust binary cannot be built here) on the host cores
   wall_s    chromosome wall time of the C++ driver (find-tfbs-b200) on the same cohort written as files, --devices 0..N-1 (rank 0)
 
-`--impl reference` times the CPU restatement alone on the same workload.
+`--impl reference` times the CPU restatement alone on the same workload.  Every context runs with option dual_stream (a twin context
+on the same GPU: the blocks of consecutive steps alternate between two sets of streams and scratch and overlap on the device).
+`--workload configs3` prints the line of BASELINE.json configs[3] instead: 200,000 haplotypes in SAMPLE BLOCKS, merged on the host by
+tfbs_merge_sample_blocks (min != max over all samples after the gather), with `roofline_k1` for grouping + build.
 """
 import argparse
 import json
