@@ -229,7 +229,8 @@ BcfFile read_bcf(const std::string& path) {
 
 // bio::io::fasta::IndexedReader::fetch(chrom, start, stop) + read: bases [start, stop) of the
 // contig through the .fai offsets (name, length, offset, line_bases, line_bytes).  A stop past the
-// contig end is clipped here (the reference errors out; generators avoid it, SURVEY 8c "unpinned").
+// contig end is an error in bio 0.28's IndexedReader::read ("FASTA read interval was out of bounds"), which
+// process_peak turns into a panic (main.rs:157-159); no reference test pins it (SURVEY 8c "unpinned").
 std::vector<uint8_t> fasta_fetch(const std::string& fasta_path, const std::string& chrom, uint64_t start, uint64_t stop) {
     std::ifstream fai(fasta_path + ".fai");
     if (!fai) throw OracleError{TFBS_ERR_INVALID_ARGUMENT, "Error while opening the reference genome index '" + fasta_path + ".fai'"};
@@ -248,7 +249,8 @@ std::vector<uint8_t> fasta_fetch(const std::string& fasta_path, const std::strin
         }
     }
     if (!found) throw OracleError{TFBS_ERR_INVALID_ARGUMENT, "Error while seeking in reference genome file: unknown sequence " + chrom};
-    if (stop > len) stop = len;
+    if (stop > len)
+        throw OracleError{TFBS_ERR_INVALID_ARGUMENT, "Error while reading in reference genome file: FASTA read interval was out of bounds"};
     std::vector<uint8_t> out;
     if (start >= stop) return out;
     std::ifstream f(fasta_path, std::ios::binary);
