@@ -319,6 +319,49 @@ int main(int argc, char** argv) {
                 printf("\nChunk %zu/%zu\t%llu haplotypes\t%llu hits\n", c + 1, n_chunks, (unsigned long long)st.n_groups, (unsigned long long)st.n_hits);
         };
         if (o.audit_file.empty()) {
+            // The rows of a collected block are copied out of the library's buffers (they are reused by the next collect) and handed
+            // to a formatter thread: sorting and row text of block c run while this thread submits and collects the next blocks.
+            struct OwnedRows {
+                std::vector<uint32_t> region, inner, vmin, vmax, base, packed, n_groups;
+                std::vector<uint16_t> pid;
+                std::vector<uint8_t> bits, hap_group;
+                std::vector<uint64_t> offset;
+                tfbs_grouped_rows g{};
+                explicit OwnedRows(const tfbs_grouped_rows& s) {
+                    const uint64_t n = s.n_rows, RH = (uint64_t)s.n_regions * 2 * s.n_samples;
+                    region.assign(s.region, s.region + n); inner.assign(s.inner, s.inner + n); pid.assign(s.pattern_id, s.pattern_id + n);
+                    vmin.assign(s.vmin, s.vmin + n); vmax.assign(s.vmax, s.vmax + n); base.assign(s.base, s.base + n);
+                    bits.assign(s.bits, s.bits + n); offset.assign(s.offset, s.offset + n);
+                    packed.assign(s.packed, s.packed + s.packed_words);
+                    n_groups.assign(s.n_groups, s.n_groups + s.n_regions);
+                    hap_group.assign((const uint8_t*)s.hap_group, (const uint8_t*)s.hap_group + RH * s.hap_group_bytes);
+                    g = s;
+                    g.region = region.data(); g.inner = inner.data(); g.pattern_id = pid.data(); g.vmin = vmin.data(); g.vmax = vmax.data();
+                    g.base = base.data(); g.bits = bits.data(); g.offset = offset.data(); g.packed = packed.data();
+                    g.n_groups = n_groups.data(); g.hap_group = hap_group.data();
+                }
+            };
+            struct Collected { size_t c; std::unique_ptr<BlockData> bd; std::unique_ptr<OwnedRows> rows; };
+            std::mutex fmu;
+            std::condition_variable fcv;
+            std::deque<Collected> to_format;
+            bool collected_all = false;
+            std::thread formatter([&] {
+                for (;;) {
+                    Collected it;
+                    {
+                        std::unique_lock<std::mutex> lk(fmu);
+                        fcv.wait(lk, [&] { return !to_format.empty() || collected_all; });
+                        if (to_format.empty()) return;
+                        it = std::move(to_format.front());
+                        to_format.pop_front();
+                        fcv.notify_all();
+                    }
+                    const tfbs_grouped_rows& g = it.rows->g;
+                    rows_to_text(it.c, *it.bd, g.n_rows, g.region, g.inner, g.pattern_id, g.vmin, g.vmax,
+                                 [&](uint64_t i, uint32_t* l, uint32_t* r) { tfbs_expand_rows(&g, i, 1, l, r); });
+                }
+            });
             // two blocks in flight per device: the copies and the host work of one overlap the kernels of the other
             std::deque<Ready> flying;
             for (;;) {
@@ -339,9 +382,18 @@ int main(int argc, char** argv) {
                 TF(tfbs_collect_grouped(ctx, &g));
                 us_gpu += now_us() - tg;
                 note_stats(item.c);
-                rows_to_text(item.c, *item.bd, g.n_rows, g.region, g.inner, g.pattern_id, g.vmin, g.vmax,
-                             [&](uint64_t i, uint32_t* l, uint32_t* r) { tfbs_expand_rows(&g, i, 1, l, r); });
+                std::unique_ptr<OwnedRows> own(new OwnedRows(g));
+                std::unique_lock<std::mutex> lk(fmu);
+                fcv.wait(lk, [&] { return to_format.size() < 2; });  // bounded: at most two collected blocks wait for their text
+                to_format.push_back(Collected{item.c, std::move(item.bd), std::move(own)});
+                fcv.notify_all();
             }
+            {
+                std::lock_guard<std::mutex> lk(fmu);
+                collected_all = true;
+            }
+            fcv.notify_all();
+            formatter.join();
         } else {
             for (;;) {
                 Ready item;
