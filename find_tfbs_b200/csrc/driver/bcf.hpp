@@ -3,6 +3,9 @@
 #pragma once
 #include "options.hpp"
 #include "bgzf.hpp"
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 namespace {
 
@@ -159,6 +162,14 @@ CsiSpan csi_contig_span(const std::string& bcf_path, int rid) {
 }
 
 Cohort load_bcf(const Options& o) {
+    const bool timing = getenv("TFBS_DRIVER_TIMING") != nullptr;  // stderr: where the time of the BCF phase goes
+    auto t_mark = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "load_bcf: %-28s %.3f s\n", what, std::chrono::duration<double>(now - t_mark).count());
+        t_mark = now;
+    };
     MappedFile file(o.bcf, "Error while opening the bcf file");
     Cohort co;
     std::vector<std::string> contigs;
@@ -213,6 +224,7 @@ Cohort load_bcf(const Options& o) {
     } else if (!indexed) {
         raw = gunzip_bgzf(file.data(), file.size(), o.bcf, std::max(1u, o.threads));
     }
+    lap("header + inflate");
     if (first_record > raw.size()) die("truncated BCF");
     Cursor c{raw.data() + first_record, raw.data() + raw.size()};
     // pass 1 (serial, a few bytes per record): positions, alleles, carrier rows; the genotype blocks are only located
@@ -260,6 +272,9 @@ Cohort load_bcf(const Options& o) {
         co.max_rlen = std::max(co.max_rlen, std::max(1, r.rlen));
         co.records.push_back(std::move(r));
     }
+    lap("pass 1 (records, serial)");
+    bool all_samples_in_order = true;
+    for (size_t k = 0; k < co.sample_positions.size(); ++k) all_samples_in_order = all_samples_in_order && co.sample_positions[k] == k;
     // pass 2 (--threads host threads): GT of the selected samples -> carrier bits (haplotype.rs:30-51), the O(records x samples) part
     co.carriers.assign(pending.size() * (size_t)co.pitch, 0);
     std::atomic<size_t> next_rec{0};
@@ -287,6 +302,44 @@ Cohort load_bcf(const Options& o) {
                             have_gt = true;
                             if (vl != 2 && S) { problem = "Inconsistent number of alleles"; d.p += bytes; continue; }  // haplotype.rs:32
                             const size_t es = Cursor::tsize(vt);
+                            if (vt == 1) {
+                                // 8-bit GT vectors (every cohort with fewer than 63 alleles per record): the same rule without the
+                                // generic cursor.  Bit 2k of the row = (first value of sample k == 4 = Unphased(1)), bit 2k + 1 =
+                                // (second value == 5 = Phased(1)), haplotype.rs:34-41.
+                                const int8_t* gp = (const int8_t*)d.p;
+                                bool vend_seen = false;
+                                if (all_samples_in_order) {
+                                    // every sample, in file order: the row is the byte-wise comparison of the GT vector with 04 05 04 05 ...
+                                    if ((size_t)S * 2 > bytes) die("truncated BCF");
+                                    const size_t nb = (size_t)S * 2;
+                                    size_t j = 0;
+#if defined(__SSE2__)
+                                    const __m128i pat = _mm_set1_epi16(0x0504), vend = _mm_set1_epi8((char)-127);
+                                    __m128i any_vend = _mm_setzero_si128();
+                                    for (; j + 32 <= nb; j += 32) {
+                                        const __m128i a = _mm_loadu_si128((const __m128i*)(gp + j)), b = _mm_loadu_si128((const __m128i*)(gp + j + 16));
+                                        any_vend = _mm_or_si128(any_vend, _mm_or_si128(_mm_cmpeq_epi8(a, vend), _mm_cmpeq_epi8(b, vend)));
+                                        row[j >> 5] = (uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(a, pat)) | ((uint32_t)_mm_movemask_epi8(_mm_cmpeq_epi8(b, pat)) << 16);
+                                    }
+                                    vend_seen = _mm_movemask_epi8(any_vend) != 0;
+#endif
+                                    for (; j < nb; ++j) {
+                                        vend_seen |= gp[j] == -127;
+                                        row[j >> 5] |= (uint32_t)(gp[j] == (int8_t)(4 + (j & 1))) << (j & 31);
+                                    }
+                                } else {
+                                    for (uint32_t k = 0; k < S; ++k) {
+                                        const size_t sp = co.sample_positions[k] * 2;
+                                        if (sp + 2 > bytes) die("truncated BCF");
+                                        const int8_t g0 = gp[sp], g1 = gp[sp + 1];
+                                        vend_seen |= (g0 == -127) | (g1 == -127);
+                                        row[k >> 4] |= ((uint32_t)(g0 == 4) | ((uint32_t)(g1 == 5) << 1)) << ((2 * k) & 31);
+                                    }
+                                }
+                                if (vend_seen && problem.empty()) problem = "Inconsistent number of alleles";
+                                d.p += bytes;
+                                continue;
+                            }
                             for (uint32_t k = 0; k < S; ++k) {
                                 Cursor g{d.p + co.sample_positions[k] * 2 * es, d.p + bytes};
                                 int32_t g0 = g.tint(vt), g1 = g.tint(vt);
@@ -318,6 +371,7 @@ Cohort load_bcf(const Options& o) {
         }
         if (!err.empty()) die(err);
     }
+    lap("pass 2 (GT -> carrier bits)");
     if (!std::is_sorted(co.records.begin(), co.records.end(), [](const Record& a, const Record& b) { return a.pos < b.pos; }))
         die("the BCF is not sorted by position (an indexed BCF always is)");
     return co;

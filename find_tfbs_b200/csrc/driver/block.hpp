@@ -20,6 +20,8 @@ struct BlockData {
     std::vector<tfbs_variant> variants;
     std::vector<uint8_t> alleles;
     std::vector<uint32_t> n_records;  // all records of the window, incl. non-biallelic ("variants" of main.rs:435)
+    std::vector<uint32_t> carriers;   // the carrier rows of this block's records only ([rows][pitch]): a block does not ship the cohort's matrix
+    std::unordered_map<uint32_t, uint32_t> row_of;  // cohort row -> row of this block (windows of neighbouring regions share records)
     tfbs_block view(const Cohort& co) const {
         tfbs_block b;
         memset(&b, 0, sizeof b);
@@ -35,8 +37,8 @@ struct BlockData {
         b.variants = variants.data();
         b.allele_bases = alleles.data();
         b.allele_bytes = alleles.size();
-        b.carriers = co.carriers.data();
-        b.n_carrier_rows = (uint32_t)(co.carriers.size() / co.pitch);
+        b.carriers = carriers.data();
+        b.n_carrier_rows = (uint32_t)(carriers.size() / co.pitch);
         b.carrier_pitch = co.pitch;
         return b;
     }
@@ -83,7 +85,13 @@ void build_block(const std::vector<Range>& merged, size_t m0, size_t m1, const s
             v.alt_off = (uint32_t)bd->alleles.size();
             v.alt_len = (uint32_t)it->alt.size();
             bd->alleles.insert(bd->alleles.end(), it->alt.begin(), it->alt.end());
-            v.carrier_row = it->carrier_row;
+            auto found = bd->row_of.find(it->carrier_row);
+            if (found == bd->row_of.end()) {
+                found = bd->row_of.emplace(it->carrier_row, (uint32_t)(bd->carriers.size() / co.pitch)).first;
+                const uint32_t* src = co.carriers.data() + (size_t)it->carrier_row * co.pitch;
+                bd->carriers.insert(bd->carriers.end(), src, src + co.pitch);
+            }
+            v.carrier_row = found->second;
             bd->variants.push_back(v);
         }
         bd->n_records.push_back(nrec);
