@@ -128,7 +128,7 @@ CsiSpan csi_contig_span(const std::string& bcf_path, int rid) {
     if (!probe) return sp;
     probe.close();
     MappedFile f(bcf_path + ".csi", "Error while opening the index");
-    std::vector<uint8_t> d = gunzip_bgzf(f.data(), f.size(), bcf_path + ".csi", 1);
+    const RawBytes d = gunzip_bgzf(f.data(), f.size(), bcf_path + ".csi", 1);
     Cursor c{d.data(), d.data() + d.size()};
     auto u64 = [&] { c.need(8); uint64_t v; memcpy(&v, c.p, 8); c.p += 8; return v; };
     if (d.size() < 16 || memcmp(c.p, "CSI\1", 4) != 0) return sp;
@@ -210,7 +210,7 @@ Cohort load_bcf(const Options& o) {
     const uint32_t S = (uint32_t)co.samples.size();
     co.pitch = std::max<uint32_t>(1, (2 * S + 31) / 32);
     // With a CSI index only the BGZF members that hold the wanted contig are read and inflated; without one the whole file is.
-    std::vector<uint8_t> raw;
+    RawBytes raw;
     size_t first_record = header_bytes;
     const CsiSpan span = o.use_index ? csi_contig_span(o.bcf, rid) : CsiSpan();
     const bool indexed = span.found && (span.empty || ((span.vbeg >> 16) < file.size() && bgzf_member_size(file.data(), file.size(), span.vbeg >> 16)));

@@ -83,20 +83,38 @@ size_t bgzf_member_size(const uint8_t* in, size_t n_in, size_t off) {
     return bsize;
 }
 
-std::vector<uint8_t> gunzip_bgzf(const uint8_t* in, size_t n_in, const std::string& what, unsigned threads) {
+// Bytes that are not zeroed when the vector is sized: the inflated BCF of a cohort is gigabytes that every inflate thread
+// overwrites anyway (zero-filling them first costs a serial pass over the whole buffer).
+template <class T>
+struct NoInit {
+    using value_type = T;
+    NoInit() = default;
+    template <class U> NoInit(const NoInit<U>&) {}
+    T* allocate(size_t n) { return static_cast<T*>(::operator new(n * sizeof(T))); }
+    void deallocate(T* p, size_t) { ::operator delete(p); }
+    template <class U, class... A> void construct(U* p, A&&... a) {
+        if constexpr (sizeof...(A) == 0) ::new ((void*)p) U;
+        else ::new ((void*)p) U(std::forward<A>(a)...);
+    }
+    template <class U> bool operator==(const NoInit<U>&) const { return true; }
+    template <class U> bool operator!=(const NoInit<U>&) const { return false; }
+};
+using RawBytes = std::vector<uint8_t, NoInit<uint8_t>>;
+
+RawBytes gunzip_bgzf(const uint8_t* in, size_t n_in, const std::string& what, unsigned threads) {
     struct Member { size_t off, csize, uoff; uint32_t isize; };
     std::vector<Member> ms;
     size_t off = 0, total = 0;
     while (off < n_in) {
         const size_t bsize = bgzf_member_size(in, n_in, off);
-        if (!bsize) return gunzip_members(in, n_in, what);
+        if (!bsize) { const std::vector<uint8_t> v = gunzip_members(in, n_in, what); return RawBytes(v.begin(), v.end()); }
         uint32_t isize;
         memcpy(&isize, in + off + bsize - 4, 4);
         ms.push_back(Member{off, bsize, total, isize});
         total += isize;
         off += bsize;
     }
-    std::vector<uint8_t> out(total);
+    RawBytes out(total);
     std::atomic<size_t> next{0};
     std::atomic<bool> bad{false};
     auto work = [&] {
