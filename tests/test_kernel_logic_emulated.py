@@ -115,3 +115,23 @@ def test_bench_reference_arm():
     assert d["impl"] == "reference" and d["metric"] == "pwm_cells_per_s" and d["value"] > 0 and d["gpu_launches"] == 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] == d["value"]
+
+
+def test_bench_configs3_dry_run(emu_env):
+    """`bench.py --workload configs3` (sample blocks, tfbs_merge_sample_blocks, roofline_k1) end to end on the emulated library with a
+    tiny cohort: control flow and the contract keys only."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(EMU, "run_bench_emulated.py"), "--workload", "configs3", "--c3-regions", "2", "--c3-samples", "96",
+                        "--c3-block", "48", "--steps", "1", "--warmup", "1", "--cpu-seconds", "0.2"], cwd=ROOT, env=emu_env,
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, lines
+    d = json.loads(lines[0])
+    for k in CONTRACT_KEYS:
+        assert k in d, k
+    assert d["config"]["workload"].startswith("configs[3]") and d["config"]["sample_blocks"] == 2
+    k1 = d["roofline_k1"]
+    assert k1["bound"] == "hbm" and k1["algorithmic_bytes_per_step"] > 0 and 0 < k1["frac"]
+    assert d["e2e"]["rows_all_keys"] >= d["e2e"]["rows_kept"] == d["rows_per_step"] and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert d["nominal_cells_per_step"] >= d["executed_cells_per_step"] >= d["evaluated_cells_per_step"] > 0
